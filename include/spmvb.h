@@ -1,0 +1,168 @@
+/*
+ * spmvb.h - C ABI of the B200-native SpMV engine (drop-in boundary).
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ * Every entry point names the interface of euroexa/spmv-fpga it replaces
+ * (paths relative to the reference's src/).  The C++ host API of the reference
+ * (create_csr_hw_matrix / create_csr_hw_x_vector / spmv_hw / delete_*) is
+ * re-exported on top of this ABI by include/spmv_fpga_compat.h.
+ *
+ * All functions returning int return SPMVB_OK (0) or a negative SPMVB_E_* code;
+ * spmvb_last_error() gives the message for the calling thread.  There is no CPU
+ * fallback: engine calls fail with SPMVB_E_CUDA when no sm_100 device is usable.
+ *
+ * Threading: handles are not thread-safe; different handles may be used from
+ * different threads.  One engine drives one GPU; multi-GPU = one engine (and
+ * normally one process) per GPU over a row partition (spmvb_partition_rows).
+ */
+#ifndef SPMVB_H
+#define SPMVB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPMVB_OK 0
+#define SPMVB_E_ARG (-1)    /* invalid argument / unsupported CU, VF */
+#define SPMVB_E_NOMEM (-2)  /* host allocation failed */
+#define SPMVB_E_CUDA (-3)   /* CUDA error or no device */
+#define SPMVB_E_IO (-4)     /* matrix-file error */
+#define SPMVB_E_RANGE (-5)  /* a count does not fit the reference's 32-bit IndexType */
+
+typedef struct spmvb_layout spmvb_layout; /* host hw_matrix layout: all (CU, block) pieces + bitmap + device aux */
+typedef struct spmvb_engine spmvb_engine; /* device-resident copy of a layout + x / y + stream */
+
+const char *spmvb_last_error(void);
+int spmvb_version(void);
+
+/* ------------------------------------------------------------------ layout (host) */
+
+/* Replaces create_csr_hw_matrix (csr_hw_wrapper.cpp:3-80 -> csr_hw.cpp:377-429, 496-554, ... 1277-1395):
+ * scan_matrix (csr_hw.cpp:7-146), prepare_balanced_hw_matrix (:327-361, 432-484), hw_matrix_alloc (:151-183),
+ * create_block_matrix (:190-265) and generate_balanced_hw_submatrix (:270-318), in O(nnz + rows) and in
+ * parallel.  n_cu in {1,2,4,8,10,12} (any n_cu >= 1 is accepted), vf in {1,2,4,8}, is_double 1 = fp64
+ * values, 0 = fp32.  cols_div_blocks 0 = reference default for that CU (util.h:41-59: 32768, or 16384 for
+ * CU 10/12); otherwise a multiple of 4 that is <= 32768.  row_ptr has rows+1 entries. */
+int spmvb_layout_build(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, const uint32_t *col_ind,
+                       const void *values, int n_cu, int vf, int is_double, uint32_t cols_div_blocks,
+                       spmvb_layout **out);
+/* Same with the reference's 32-bit row_ptr (csr.h:15-24 csr_matrix). */
+int spmvb_layout_build_u32(uint32_t rows, uint32_t cols, const uint32_t *row_ptr, const uint32_t *col_ind,
+                           const void *values, int n_cu, int vf, int is_double, uint32_t cols_div_blocks,
+                           spmvb_layout **out);
+/* Replaces delete_csr_hw_matrix (csr_hw_wrapper.cpp:291-296 -> csr_hw.cpp:1414-1431). */
+void spmvb_layout_free(spmvb_layout *l);
+
+/* csr_hw_matrix fields (csr_hw.h:16-26). */
+int spmvb_layout_blocks(const spmvb_layout *l);       /* hw_matrix[k]->blocks */
+int spmvb_layout_n_cu(const spmvb_layout *l);
+uint32_t spmvb_layout_rows(const spmvb_layout *l);
+uint32_t spmvb_layout_cols(const spmvb_layout *l);
+uint32_t spmvb_layout_expanded_cols(const spmvb_layout *l); /* csr_hw_header.expanded_nr_cols, csr_hw.cpp:30-33 */
+uint64_t spmvb_layout_real_nnz(const spmvb_layout *l);      /* non-zeros of the input (no padding) */
+uint64_t spmvb_layout_padded_nnz(const spmvb_layout *l);    /* sum of nr_nzeros over all pieces */
+uint64_t spmvb_layout_pairs(const spmvb_layout *l);         /* non-empty (row, block) pairs = bitmap zeros */
+uint64_t spmvb_layout_stream_bytes(const spmvb_layout *l);  /* bytes of the device image of all pieces */
+/* out[5] = nr_rows, nr_cols, nr_nzeros, nr_ci, nr_val of hw_matrix[cu]->...[block]; nr_val floors like
+ * hw_matrix_alloc (csr_hw.cpp:179) although ceil(nr_nzeros/RATIO_v) value words are stored. */
+int spmvb_layout_piece_info(const spmvb_layout *l, int cu, int block, uint32_t *out);
+/* hw_matrix[cu]->submatrix[block]: nr_ci + ceil(nr_nzeros/RATIO_v) 128-bit words, bit-exact with
+ * generate_balanced_hw_submatrix (csr_hw.cpp:270-318); unused index slots are zero. */
+const void *spmvb_layout_piece_words(const spmvb_layout *l, int cu, int block);
+/* empty_rows_bitmap[block][0..rows) (csr_hw.cpp:340-345, 391-393) expanded from the compact row map. */
+int spmvb_layout_bitmap_row(const spmvb_layout *l, int block, uint8_t *out_rows_bytes);
+/* storage_overhead (csr_hw.cpp:1401-1409): MB of hw_matrix[cu]. */
+double spmvb_layout_storage_mb(const spmvb_layout *l, int cu);
+/* write_csr_hw_vector (csr_hw.cpp:1470-1488): x -> expanded_nr_cols zero-padded values. */
+int spmvb_layout_pack_x(const spmvb_layout *l, const void *x, uint32_t n, void *out_expanded);
+
+/* Row partition for multi-GPU (the CU dimension mapped to GPUs, SURVEY 8e mapping A): `parts` contiguous row
+ * ranges balanced by non-zero count with the reference's split rule S1/S2/S3 (csr_hw.cpp:459-460) applied
+ * to whole rows.  bounds has parts+1 entries. */
+int spmvb_partition_rows(uint32_t rows, const uint64_t *row_ptr, int parts, int ratio_v, uint32_t *bounds);
+
+/* ------------------------------------------------------------------ engine (device) */
+
+/* Uploads the layout to GPU `device` (the analogue of sds_alloc_non_cacheable buffers, csr_hw.cpp:180).
+ * variant: 0 = default, otherwise a kernel variant id. */
+int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_engine **out);
+void spmvb_engine_free(spmvb_engine *e);
+int spmvb_engine_set_variant(spmvb_engine *e, int variant);
+int spmvb_engine_variant(const spmvb_engine *e);
+/* number of kernel launches issued by this engine so far (bench.py's gpu_launches) */
+uint64_t spmvb_engine_launches(const spmvb_engine *e);
+/* algorithmic bytes of one SpMV with this engine: nnz*(2+vb) + rows*vb + cols*vb */
+uint64_t spmvb_engine_algorithmic_bytes(const spmvb_engine *e);
+/* engine-owned device vectors: x has expanded_nr_cols values, y has rows values */
+void *spmvb_engine_x_dev(spmvb_engine *e);
+void *spmvb_engine_y_dev(spmvb_engine *e);
+void *spmvb_engine_stream(spmvb_engine *e); /* cudaStream_t */
+
+/* Replaces create_csr_hw_x_vector (csr_hw_wrapper.cpp:187-191): host x[n] -> device hw_x (zero padded). */
+int spmvb_engine_set_x(spmvb_engine *e, const void *x_host, uint32_t n);
+/* Replaces the per-block spmv() loop (csr_hw_wrapper.cpp:202-271; spmv.cpp:6-205) fused with accum_results
+ * (csr_hw.cpp:1531-1565): y_dev (+)= A * x_dev on `stream` (NULL = engine stream).  x_dev must hold
+ * expanded_nr_cols values (or NULL = engine x), y_dev rows values (or NULL = engine y).  accumulate 1 keeps
+ * the reference's `+=` semantics, 0 zeroes y first.  Asynchronous. */
+int spmvb_engine_spmv_dev(spmvb_engine *e, const void *x_dev, void *y_dev, int accumulate, void *stream);
+int spmvb_engine_sync(spmvb_engine *e);
+/* device y -> host; accumulate 1: y_host[i] += y_dev[i] (spmv_hw semantics), 0: overwrite */
+int spmvb_engine_get_y(spmvb_engine *e, void *y_host, uint32_t n, int accumulate);
+/* Replaces spmv_hw (csr_hw_wrapper.cpp:193-288) end to end with HOST buffers: H2D x, SpMV, D2H y,
+ * y_host (+)= result.  Synchronous. */
+int spmvb_engine_spmv_host(spmvb_engine *e, const void *x_host, uint32_t n, void *y_host, int accumulate);
+/* Times `iters` device SpMVs (y = A x, engine vectors) with CUDA events on the engine stream;
+ * ms_out[iters] per-iteration milliseconds.  flush_l2 1 writes a >L2 scratch buffer between iterations. */
+int spmvb_engine_time_spmv(spmvb_engine *e, int iters, int flush_l2, float *ms_out);
+/* Iterated SpMV on one GPU (square matrices): x <- A x / ||A x||_2, `iters` times, all on device.
+ * Returns the last norm in *norm_out.  The multi-GPU version lives in the host driver (NCCL all-gather). */
+int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
+/* x_dev[i] = y_dev[i] * scale for i < n (the normalisation step of the iterated caller) */
+int spmvb_engine_scale_copy(spmvb_engine *e, const void *src_dev, void *dst_dev, uint32_t n, double scale,
+                            void *stream);
+/* sum of squares of y_dev[0..n) into a device double (for the norm all-reduce) */
+int spmvb_engine_sumsq(spmvb_engine *e, const void *src_dev, uint32_t n, double *out_dev, void *stream);
+
+/* ------------------------------------------------------------------ matrix files and synthetic inputs */
+
+/* A CSR matrix owned by the library (csr.h:15-24 csr_matrix with 64-bit row offsets). */
+typedef struct spmvb_csr spmvb_csr;
+void spmvb_csr_free(spmvb_csr *m);
+uint32_t spmvb_csr_rows(const spmvb_csr *m);
+uint32_t spmvb_csr_cols(const spmvb_csr *m);
+uint64_t spmvb_csr_nnz(const spmvb_csr *m);
+int spmvb_csr_is_double(const spmvb_csr *m);
+const uint64_t *spmvb_csr_row_ptr(const spmvb_csr *m); /* rows + 1 */
+const uint32_t *spmvb_csr_col_ind(const spmvb_csr *m);
+const void *spmvb_csr_values(const spmvb_csr *m);       /* fp64 or fp32 */
+/* create_csr_hw_matrix on a library-owned CSR */
+int spmvb_layout_build_csr(const spmvb_csr *m, int n_cu, int vf, uint32_t cols_div_blocks, spmvb_layout **out);
+
+/* Matrix-file format of the reference (read_csr_header / read_csr_matrix, csr.cpp:10-46, 87-136):
+ * "rows cols nnz" then one "row col value" line per entry, 1-based, sorted by row.  Trailing empty rows get
+ * row_ptr = nnz (the reference leaves them uninitialised). */
+int spmvb_csr_read(const char *path, int is_double, spmvb_csr **out);
+int spmvb_csr_write(const spmvb_csr *m, const char *path);
+
+/* Synthetic inputs of BASELINE.json's configs; values are U(-1,1) from a counter-based hash of (seed, row, col)
+ * unless stated.  [row_begin,row_end) selects a row slice of the same global matrix (multi-GPU shards);
+ * row_end == 0 means all rows. */
+int spmvb_csr_gen_band(uint32_t n, int half_bandwidth, uint64_t seed, int is_double, spmvb_csr **out);
+/* 5-point Laplacian on an nx x ny grid: 4 on the diagonal, -1 for the (up to) four neighbours */
+int spmvb_csr_gen_laplacian2d(uint32_t nx, uint32_t ny, uint32_t row_begin, uint32_t row_end, int is_double,
+                              spmvb_csr **out);
+/* nnz_per_row distinct uniformly random columns per row, sorted */
+int spmvb_csr_gen_uniform(uint32_t rows, uint32_t cols, int nnz_per_row, uint64_t seed, uint32_t row_begin,
+                          uint32_t row_end, int is_double, spmvb_csr **out);
+/* R-MAT with 2^scale rows/cols and edge_factor * 2^scale edges before de-duplication, probabilities
+ * (a, b, c, 1-a-b-c), no vertex permutation (keeps the empty-row tail); the last row is made non-empty. */
+int spmvb_csr_gen_rmat(int scale, int edge_factor, double a, double b, double c, uint64_t seed, uint32_t row_begin,
+                       uint32_t row_end, int is_double, spmvb_csr **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPMVB_H */

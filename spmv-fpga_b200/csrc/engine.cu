@@ -1,0 +1,316 @@
+// Device side of the C ABI (include/spmvb.h): upload of the hw_matrix image, kernel launches, host<->device
+// vector traffic.  Replaces the body of spmv_hw (reference src/csr_hw_wrapper.cpp:193-288): the per-block
+// spmv() round trips and the host accum_results loop become ONE kernel launch over all (CU, block) pieces.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/spmvb.h"
+#include "layout.h"
+#include "spmv_kernels.cuh"
+
+namespace spmvb {
+
+enum Variant { kVariantDefault = 0, kVariantDirect = 1, kVariantRing = 2, kVariantXsmem = 3 };
+
+struct Engine {
+  int device = 0, is_double = 1, vb = 8, variant = kVariantRing;
+  uint32_t rows = 0, cols = 0, expanded_cols = 0, cdb = 32768;
+  int blocks = 0;
+  uint64_t real_nnz = 0, n_chunks = 0, n_pairs = 0, stream_bytes = 0, x_len = 0;
+  uint8_t *d_stream = nullptr;
+  ChunkMeta *d_chunks = nullptr;
+  uint32_t *d_rowmap = nullptr;
+  void *d_x = nullptr, *d_y = nullptr;
+  double *d_scalar = nullptr;
+  uint4 *d_flush = nullptr;
+  size_t flush_words = 0;
+  void *h_stage = nullptr;  // pinned staging for get_y(accumulate)
+  size_t h_stage_bytes = 0;
+  cudaStream_t stream = nullptr;
+  int sms = 148;
+  uint64_t launches = 0;
+};
+
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(SPMVB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+  } while (0)
+
+template <typename VT>
+static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st) {
+  const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
+  constexpr int WARPS = 8;
+  int variant = E->variant == kVariantDefault ? kVariantRing : E->variant;
+  if (E->n_chunks == 0) return SPMVB_OK;
+  if (variant == kVariantDirect) {
+    auto kern = spmv_direct_kernel<VT, WARPS>;
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    int grid = E->sms * per_sm;
+    kern<<<grid, WARPS * 32, 0, st>>>(stream, E->d_chunks, E->d_rowmap, x, y, E->n_chunks, E->cdb);
+  } else {
+    constexpr int STAGES = 4;
+    auto kern = spmv_ring_kernel<VT, WARPS, STAGES>;
+    const size_t smem = (size_t)WARPS * STAGES * (VTraits<VT>::kGroupWords * 16 * 32) + (size_t)WARPS * STAGES * 8;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[sizeof(VT) == 8]) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set[sizeof(VT) == 8] = true;
+    }
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = E->sms * per_sm;
+    kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_chunks, E->d_rowmap, x, y, E->n_chunks, E->cdb);
+  }
+  E->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SPMVB_OK;
+}
+
+static int do_spmv(Engine *E, const void *x_dev, void *y_dev, int accumulate, cudaStream_t st) {
+  const void *x = x_dev ? x_dev : E->d_x;
+  void *y = y_dev ? y_dev : E->d_y;
+  if (!accumulate) CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)E->rows * E->vb, st));
+  if (E->is_double) return launch_spmv<double>(E, (const double *)x, (double *)y, st);
+  return launch_spmv<float>(E, (const float *)x, (float *)y, st);
+}
+
+}  // namespace spmvb
+
+using namespace spmvb;
+
+extern "C" {
+
+int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_engine **out) {
+  const Layout *L = (const Layout *)l;
+  if (!L || !out) return fail(SPMVB_E_ARG, "engine_create: NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(SPMVB_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(SPMVB_E_ARG, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(SPMVB_E_CUDA, "an sm_100-class GPU (B200) is required; there is no fallback path");
+  Engine *E = new Engine();
+  E->device = device; E->is_double = L->is_double; E->vb = L->vb;
+  E->rows = L->rows; E->cols = L->cols; E->expanded_cols = L->expanded_cols; E->cdb = L->cdb; E->blocks = L->blocks;
+  E->real_nnz = L->real_nnz; E->n_chunks = L->n_chunks; E->n_pairs = L->n_pairs; E->stream_bytes = L->stream_bytes;
+  E->variant = variant;
+  E->sms = prop.multiProcessorCount;
+  E->x_len = (uint64_t)L->blocks * L->cdb;  // >= expanded_cols: any 15-bit index of any block stays in range
+  cudaError_t e = cudaSuccess;
+  auto chk = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; };
+  chk(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+  chk(cudaMalloc((void **)&E->d_stream, std::max<uint64_t>(L->stream_bytes, 16)));
+  chk(cudaMalloc((void **)&E->d_chunks, std::max<uint64_t>(L->n_chunks, 1) * sizeof(ChunkMeta)));
+  chk(cudaMalloc((void **)&E->d_rowmap, (std::max<uint64_t>(L->n_pairs, 1) + 1) * 4));
+  chk(cudaMalloc(&E->d_x, E->x_len * E->vb));
+  chk(cudaMalloc(&E->d_y, (size_t)E->rows * E->vb));
+  chk(cudaMalloc((void **)&E->d_scalar, 64));
+  if (e == cudaSuccess) {
+    chk(cudaMemcpyAsync(E->d_stream, L->stream, L->stream_bytes, cudaMemcpyHostToDevice, E->stream));
+    chk(cudaMemcpyAsync(E->d_chunks, L->chunks, L->n_chunks * sizeof(ChunkMeta), cudaMemcpyHostToDevice, E->stream));
+    chk(cudaMemcpyAsync(E->d_rowmap, L->rowmap, L->n_pairs * 4, cudaMemcpyHostToDevice, E->stream));
+    chk(cudaMemsetAsync(E->d_x, 0, E->x_len * E->vb, E->stream));
+    chk(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
+    chk(cudaStreamSynchronize(E->stream));
+  }
+  if (e != cudaSuccess) {
+    std::string msg = std::string("engine_create: ") + cudaGetErrorString(e);
+    spmvb_engine_free((spmvb_engine *)E);
+    return fail(SPMVB_E_CUDA, msg);
+  }
+  *out = (spmvb_engine *)E;
+  return SPMVB_OK;
+}
+
+void spmvb_engine_free(spmvb_engine *e) {
+  Engine *E = (Engine *)e;
+  if (!E) return;
+  cudaSetDevice(E->device);
+  if (E->stream) cudaStreamSynchronize(E->stream);
+  cudaFree(E->d_stream); cudaFree(E->d_chunks); cudaFree(E->d_rowmap);
+  cudaFree(E->d_x); cudaFree(E->d_y); cudaFree(E->d_scalar); cudaFree(E->d_flush);
+  if (E->h_stage) cudaFreeHost(E->h_stage);
+  if (E->stream) cudaStreamDestroy(E->stream);
+  delete E;
+}
+
+int spmvb_engine_set_variant(spmvb_engine *e, int variant) {
+  if (!e || variant < 0 || variant > 3) return fail(SPMVB_E_ARG, "variant");
+  ((Engine *)e)->variant = variant;
+  return SPMVB_OK;
+}
+int spmvb_engine_variant(const spmvb_engine *e) { return ((const Engine *)e)->variant; }
+uint64_t spmvb_engine_launches(const spmvb_engine *e) { return ((const Engine *)e)->launches; }
+uint64_t spmvb_engine_algorithmic_bytes(const spmvb_engine *e) {
+  const Engine *E = (const Engine *)e;
+  return E->real_nnz * (2 + (uint64_t)E->vb) + (uint64_t)E->rows * E->vb + (uint64_t)E->cols * E->vb;
+}
+void *spmvb_engine_x_dev(spmvb_engine *e) { return ((Engine *)e)->d_x; }
+void *spmvb_engine_y_dev(spmvb_engine *e) { return ((Engine *)e)->d_y; }
+void *spmvb_engine_stream(spmvb_engine *e) { return (void *)((Engine *)e)->stream; }
+
+int spmvb_engine_set_x(spmvb_engine *e, const void *x_host, uint32_t n) {
+  Engine *E = (Engine *)e;
+  if (!E || !x_host) return fail(SPMVB_E_ARG, "set_x");
+  CUDA_TRY(cudaSetDevice(E->device));
+  const uint32_t m = std::min<uint32_t>(n, E->expanded_cols);
+  CUDA_TRY(cudaMemcpyAsync(E->d_x, x_host, (size_t)m * E->vb, cudaMemcpyHostToDevice, E->stream));
+  if (m < E->x_len)  // zero-pad the remaining columns (csr_hw.cpp:1478-1481)
+    CUDA_TRY(cudaMemsetAsync((uint8_t *)E->d_x + (size_t)m * E->vb, 0, (E->x_len - m) * E->vb, E->stream));
+  return SPMVB_OK;
+}
+
+int spmvb_engine_spmv_dev(spmvb_engine *e, const void *x_dev, void *y_dev, int accumulate, void *stream) {
+  Engine *E = (Engine *)e;
+  if (!E) return fail(SPMVB_E_ARG, "spmv_dev");
+  CUDA_TRY(cudaSetDevice(E->device));
+  return do_spmv(E, x_dev, y_dev, accumulate, stream ? (cudaStream_t)stream : E->stream);
+}
+
+int spmvb_engine_sync(spmvb_engine *e) {
+  Engine *E = (Engine *)e;
+  if (!E) return fail(SPMVB_E_ARG, "sync");
+  CUDA_TRY(cudaSetDevice(E->device));
+  CUDA_TRY(cudaStreamSynchronize(E->stream));
+  return SPMVB_OK;
+}
+
+int spmvb_engine_get_y(spmvb_engine *e, void *y_host, uint32_t n, int accumulate) {
+  Engine *E = (Engine *)e;
+  if (!E || !y_host) return fail(SPMVB_E_ARG, "get_y");
+  CUDA_TRY(cudaSetDevice(E->device));
+  const uint32_t m = std::min<uint32_t>(n, E->rows);
+  const size_t bytes = (size_t)m * E->vb;
+  if (!accumulate) {
+    CUDA_TRY(cudaMemcpyAsync(y_host, E->d_y, bytes, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    return SPMVB_OK;
+  }
+  if (E->h_stage_bytes < bytes) {
+    if (E->h_stage) cudaFreeHost(E->h_stage);
+    E->h_stage = nullptr; E->h_stage_bytes = 0;
+    CUDA_TRY(cudaMallocHost(&E->h_stage, bytes));
+    E->h_stage_bytes = bytes;
+  }
+  CUDA_TRY(cudaMemcpyAsync(E->h_stage, E->d_y, bytes, cudaMemcpyDeviceToHost, E->stream));
+  CUDA_TRY(cudaStreamSynchronize(E->stream));
+  // y_fpga[row] += partial, csr_hw.cpp:1557 (the per-block partials were already summed on the device)
+  if (E->is_double) {
+    double *dst = (double *)y_host; const double *src = (const double *)E->h_stage;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)m; i++) dst[i] += src[i];
+  } else {
+    float *dst = (float *)y_host; const float *src = (const float *)E->h_stage;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)m; i++) dst[i] += src[i];
+  }
+  return SPMVB_OK;
+}
+
+int spmvb_engine_spmv_host(spmvb_engine *e, const void *x_host, uint32_t n, void *y_host, int accumulate) {
+  Engine *E = (Engine *)e;
+  if (!E) return fail(SPMVB_E_ARG, "spmv_host");
+  int rc = spmvb_engine_set_x(e, x_host, n);
+  if (rc) return rc;
+  rc = do_spmv(E, nullptr, nullptr, 0, E->stream);
+  if (rc) return rc;
+  return spmvb_engine_get_y(e, y_host, E->rows, accumulate);
+}
+
+int spmvb_engine_time_spmv(spmvb_engine *e, int iters, int flush_l2, float *ms_out) {
+  Engine *E = (Engine *)e;
+  if (!E || iters < 1 || !ms_out) return fail(SPMVB_E_ARG, "time_spmv");
+  CUDA_TRY(cudaSetDevice(E->device));
+  if (flush_l2 && !E->d_flush) {
+    E->flush_words = (size_t)256 * 1024 * 1024 / 16;  // 256 MiB > 126 MB L2
+    CUDA_TRY(cudaMalloc((void **)&E->d_flush, E->flush_words * 16));
+  }
+  std::vector<cudaEvent_t> ev(2 * (size_t)iters);
+  for (auto &x : ev) CUDA_TRY(cudaEventCreate(&x));
+  int rc = SPMVB_OK;
+  for (int i = 0; i < iters && rc == SPMVB_OK; i++) {
+    if (flush_l2) l2_flush_kernel<<<E->sms * 4, 256, 0, E->stream>>>(E->d_flush, E->flush_words);
+    cudaEventRecord(ev[2 * i], E->stream);
+    rc = do_spmv(E, nullptr, nullptr, 0, E->stream);
+    cudaEventRecord(ev[2 * i + 1], E->stream);
+  }
+  cudaError_t ce = cudaStreamSynchronize(E->stream);
+  for (int i = 0; i < iters; i++) {
+    ms_out[i] = 0.f;
+    if (ce == cudaSuccess && rc == SPMVB_OK) cudaEventElapsedTime(&ms_out[i], ev[2 * i], ev[2 * i + 1]);
+  }
+  for (auto &x : ev) cudaEventDestroy(x);
+  if (rc) return rc;
+  if (ce != cudaSuccess) return fail(SPMVB_E_CUDA, std::string("time_spmv: ") + cudaGetErrorString(ce));
+  return SPMVB_OK;
+}
+
+int spmvb_engine_scale_copy(spmvb_engine *e, const void *src_dev, void *dst_dev, uint32_t n, double scale,
+                            void *stream) {
+  Engine *E = (Engine *)e;
+  if (!E || !src_dev || !dst_dev) return fail(SPMVB_E_ARG, "scale_copy");
+  CUDA_TRY(cudaSetDevice(E->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : E->stream;
+  if (E->is_double)
+    scale_copy_kernel<double><<<E->sms * 4, 256, 0, st>>>((const double *)src_dev, (double *)dst_dev, n, scale);
+  else
+    scale_copy_kernel<float><<<E->sms * 4, 256, 0, st>>>((const float *)src_dev, (float *)dst_dev, n, scale);
+  E->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SPMVB_OK;
+}
+
+int spmvb_engine_sumsq(spmvb_engine *e, const void *src_dev, uint32_t n, double *out_dev, void *stream) {
+  Engine *E = (Engine *)e;
+  if (!E || !src_dev || !out_dev) return fail(SPMVB_E_ARG, "sumsq");
+  CUDA_TRY(cudaSetDevice(E->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : E->stream;
+  CUDA_TRY(cudaMemsetAsync(out_dev, 0, sizeof(double), st));
+  if (E->is_double)
+    sumsq_kernel<double><<<E->sms * 2, 256, 0, st>>>((const double *)src_dev, n, out_dev);
+  else
+    sumsq_kernel<float><<<E->sms * 2, 256, 0, st>>>((const float *)src_dev, n, out_dev);
+  E->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SPMVB_OK;
+}
+
+int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out) {
+  Engine *E = (Engine *)e;
+  if (!E || iters < 1) return fail(SPMVB_E_ARG, "power_iter");
+  if (E->rows != E->cols) return fail(SPMVB_E_ARG, "power_iter needs a square matrix");
+  CUDA_TRY(cudaSetDevice(E->device));
+  double nrm = 0.0;
+  for (int it = 0; it < iters; it++) {
+    int rc = do_spmv(E, nullptr, nullptr, 0, E->stream);
+    if (rc) return rc;
+    rc = spmvb_engine_sumsq(e, E->d_y, E->rows, E->d_scalar, E->stream);
+    if (rc) return rc;
+    double ss = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(&ss, E->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    nrm = std::sqrt(ss);
+    rc = spmvb_engine_scale_copy(e, E->d_y, E->d_x, E->rows, nrm > 0 ? 1.0 / nrm : 0.0, E->stream);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(E->stream));
+  if (norm_out) *norm_out = nrm;
+  return SPMVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// Internal C++ view of the hw_matrix layout shared by the host builder and the CUDA engine.
+// The public boundary is include/spmvb.h; nothing here is exported.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace spmvb {
+
+constexpr int kBusBytes = 16;        // BUS_BIT_WIDTH / 8, reference src/util.h:61
+constexpr int kRatioCi = 8;          // 16-bit index slots per bus word, src/util.h:65
+constexpr int kGroupsPerChunk = 32;  // one warp lane per 8-entry group
+constexpr int kChunkEntries = kRatioCi * kGroupsPerChunk;  // 256 stream entries per chunk
+
+// Per-chunk device metadata (16 bytes per 2560 B (fp64) / 1536 B (fp32) of stream).
+struct ChunkMeta {
+  uint32_t rank0;      // global row-map index of the segment that contains the chunk's first entry
+  uint32_t block;      // column block: x slice starts at block * cols_div_blocks
+  uint32_t valid;      // real entries in this chunk (padding rows / tail padding excluded), 0..256
+  uint32_t row_first;  // rowmap[rank0] (row of the first segment), for the consecutive-rows fast path
+};
+
+constexpr uint32_t kChunkRowsConsecutive = 0x80000000u;  // flag in ChunkMeta::valid
+
+struct Layout {
+  int cu = 1, vf = 1, is_double = 1, blocks = 0;
+  uint32_t rows = 0, cols = 0, expanded_cols = 0, cdb = 32768;
+  int ratio_v = 2, ratio_col_val = 5, vb = 8, group_bytes = 80, chunk_bytes = 2560;
+  uint64_t real_nnz = 0, padded_nnz = 0, n_pairs = 0;
+
+  // [k * blocks + b]
+  std::vector<uint32_t> nr_rows, nr_nzeros, nr_ci, nr_val;
+  std::vector<uint32_t> nr_cols;         // [b]
+  // [b * cu + k] (device order: block-major so that rows ascend through a block)
+  std::vector<uint64_t> piece_off;       // byte offset into stream
+  std::vector<uint64_t> piece_chunk0;    // first chunk index
+  std::vector<uint32_t> piece_real_nnz;  // entries before the padding rows
+
+  uint8_t *stream = nullptr;  // all pieces, each zero-padded to whole chunks
+  uint64_t stream_bytes = 0;
+  std::vector<uint64_t> rank_base;  // [blocks + 1] into rowmap
+  uint32_t *rowmap = nullptr;       // rank -> row id; the compact form of empty_rows_bitmap
+  ChunkMeta *chunks = nullptr;
+  uint64_t n_chunks = 0;
+
+  ~Layout();
+};
+
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+}  // namespace spmvb

@@ -1,0 +1,447 @@
+// Host builder of the hw_matrix layout: O(nnz + rows) work, OpenMP-parallel over row ranges,
+// bit-exact with the reference's create_csr_hw_matrix wherever the reference is well defined.
+//
+// What it reproduces (reference = /root/reference/src):
+//   scan_matrix                      csr_hw.cpp:7-146    column blocks, expanded_nr_cols, padded row lengths
+//   prepare_balanced_hw_matrix       csr_hw.cpp:327-361 (CU=1), 432-484 (CU=2), same rule for 4/8/10/12
+//   hw_matrix_alloc                  csr_hw.cpp:151-183  nr_ci / nr_val
+//   create_block_matrix              csr_hw.cpp:190-265  per-block rows, rebased columns, VF / row padding
+//   generate_balanced_hw_submatrix   csr_hw.cpp:270-318  the 128-bit word packing
+// How it differs in method: the reference keeps blocks x (rows+1) prefix tables and re-walks the whole matrix once
+// per block; here three passes over the CSR (count, [segment lengths], scatter) with per-thread per-block cursors
+// write every entry straight to its final byte, and the empty_rows_bitmap is kept as a rank -> row map.
+#include <omp.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/spmvb.h"
+#include "layout.h"
+
+namespace spmvb {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+const char *last_error_cstr() { return g_err.c_str(); }
+
+Layout::~Layout() {
+  free(stream);
+  free(rowmap);
+  free(chunks);
+}
+
+static inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+namespace {
+
+struct BlockOf {  // col -> block, shift when cols_div_blocks is a power of two
+  uint32_t cdb;
+  int shift;
+  explicit BlockOf(uint32_t c) : cdb(c), shift(-1) {
+    if ((c & (c - 1)) == 0) { shift = 0; while ((1u << shift) != c) shift++; }
+  }
+  inline uint32_t operator()(uint32_t col) const { return shift >= 0 ? col >> shift : col / cdb; }
+};
+
+template <typename RP>
+int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *col_ind, const void *values, int cu,
+               int vf, int is_double, uint32_t cdb_in, Layout **out) {
+  if (!out) return fail(SPMVB_E_ARG, "out is NULL");
+  *out = nullptr;
+  if (cu < 1 || cu > 4096) return fail(SPMVB_E_ARG, "n_cu must be >= 1");
+  if (!(vf == 1 || vf == 2 || vf == 4 || vf == 8)) return fail(SPMVB_E_ARG, "vf must be 1, 2, 4 or 8");
+  if (rows == 0 || cols == 0 || !row_ptr) return fail(SPMVB_E_ARG, "empty matrix");
+  uint32_t cdb = cdb_in ? cdb_in : ((cu == 10 || cu == 12) ? 16384u : 32768u);  // util.h:41-59
+  if (cdb > 32768 || cdb % 4 != 0) return fail(SPMVB_E_ARG, "cols_div_blocks must be a multiple of 4 and <= 32768");
+  const uint64_t nnz = (uint64_t)row_ptr[rows];
+  if (nnz && (!col_ind || !values)) return fail(SPMVB_E_ARG, "col_ind/values are NULL");
+
+  Layout *L = new Layout();
+  L->cu = cu; L->vf = vf; L->is_double = is_double ? 1 : 0;
+  L->rows = rows; L->cols = cols; L->cdb = cdb;
+  L->ratio_v = is_double ? 2 : 4;
+  L->ratio_col_val = kRatioCi / L->ratio_v + 1;
+  L->vb = is_double ? 8 : 4;
+  L->group_bytes = L->ratio_col_val * kBusBytes;
+  L->chunk_bytes = L->group_bytes * kGroupsPerChunk;
+  L->real_nnz = nnz;
+  const int vb = L->vb;
+  const uint32_t ratio_v = (uint32_t)L->ratio_v;
+
+  // scan_matrix, csr_hw.cpp:25-33: blocks and expanded_nr_cols
+  int blocks = (int)(cols / cdb) + 1;
+  if (cols % cdb == 0) blocks--;
+  L->blocks = blocks;
+  {
+    uint64_t N = (uint64_t)ratio_v * (uint64_t)blocks;
+    uint64_t ec = cols;
+    if (ec % N) ec += N - ec % N;
+    if (ec > 0xFFFFFFFFull) { delete L; return fail(SPMVB_E_RANGE, "expanded_nr_cols overflows IndexType"); }
+    L->expanded_cols = (uint32_t)ec;
+  }
+  L->nr_cols.resize(blocks);
+  for (int b = 0; b < blocks; b++)  // thres_h - thres_l + 1, csr_hw.cpp:64-76,167
+    L->nr_cols[b] = (b == blocks - 1) ? L->expanded_cols - (uint32_t)b * cdb : cdb;
+  const BlockOf block_of(cdb);
+
+  // row ranges of (almost) equal non-zero count, one per thread
+  int T = omp_get_max_threads();
+  if (T < 1) T = 1;
+  if ((uint64_t)T > (uint64_t)rows) T = (int)rows;
+  std::vector<uint32_t> rb(T + 1);
+  rb[0] = 0; rb[T] = rows;
+  for (int t = 1; t < T; t++) {
+    uint64_t target = nnz / T * t;
+    const RP *p = std::lower_bound(row_ptr, row_ptr + rows + 1, (RP)target);
+    uint32_t r = (uint32_t)(p - row_ptr);
+    if (r > rows) r = rows;
+    rb[t] = std::max(r, rb[t - 1]);
+  }
+
+  // ---- pass 1: per (thread, block) counts of non-empty (row, block) pairs and padded entries (csr_hw.cpp:87-119)
+  const size_t TB = (size_t)T * blocks;
+  std::vector<uint64_t> pairs_t(TB, 0), zpad_t(TB, 0);
+  int bad_col = 0;
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    std::vector<uint32_t> cnt(blocks, 0), touched;
+    uint64_t *pt = &pairs_t[(size_t)t * blocks], *zt = &zpad_t[(size_t)t * blocks];
+    for (uint32_t r = rb[t]; r < rb[t + 1]; r++) {
+      for (uint64_t j = row_ptr[r]; j < (uint64_t)row_ptr[r + 1]; j++) {
+        uint32_t c = col_ind[j];
+        if (c >= cols) { bad_col = 1; continue; }
+        uint32_t b = block_of(c);
+        if (cnt[b]++ == 0) touched.push_back(b);
+      }
+      for (uint32_t b : touched) { pt[b]++; zt[b] += round_up(cnt[b], (uint32_t)vf); cnt[b] = 0; }
+      touched.clear();
+    }
+  }
+  if (bad_col) { delete L; return fail(SPMVB_E_ARG, "column index out of range"); }
+
+  // exclusive scan over threads per block -> per-thread starting rank / position inside each block
+  std::vector<uint64_t> P(blocks), Z(blocks);
+  for (int b = 0; b < blocks; b++) {
+    uint64_t pr = 0, zp = 0;
+    for (int t = 0; t < T; t++) {
+      uint64_t a = pairs_t[(size_t)t * blocks + b], z = zpad_t[(size_t)t * blocks + b];
+      pairs_t[(size_t)t * blocks + b] = pr; zpad_t[(size_t)t * blocks + b] = zp;
+      pr += a; zp += z;
+    }
+    P[b] = pr; Z[b] = zp;
+    if (zp + (uint64_t)ratio_v * vf > 0xFFFFFFFFull) { delete L; return fail(SPMVB_E_RANGE, "block nnz overflows IndexType"); }
+  }
+  L->rank_base.assign(blocks + 1, 0);
+  for (int b = 0; b < blocks; b++) L->rank_base[b + 1] = L->rank_base[b] + P[b];
+  L->n_pairs = L->rank_base[blocks];
+  if (L->n_pairs >= 0xFFFFFFF0ull) { delete L; return fail(SPMVB_E_RANGE, "too many (row, block) pairs for a 32-bit rank"); }
+  L->rowmap = (uint32_t *)malloc((size_t)std::max<uint64_t>(L->n_pairs, 1) * 4);
+  if (!L->rowmap) { delete L; return fail(SPMVB_E_NOMEM, "rowmap"); }
+
+  // ---- pass 2 (CU > 1 only): row map + padded segment lengths, needed by the sequential split rule
+  std::vector<uint32_t> seglen;
+  if (cu > 1) {
+    seglen.resize((size_t)L->n_pairs);
+#pragma omp parallel num_threads(T)
+    {
+      const int t = omp_get_thread_num();
+      std::vector<uint32_t> cnt(blocks, 0), touched;
+      std::vector<uint64_t> rank(blocks);
+      for (int b = 0; b < blocks; b++) rank[b] = L->rank_base[b] + pairs_t[(size_t)t * blocks + b];
+      for (uint32_t r = rb[t]; r < rb[t + 1]; r++) {
+        for (uint64_t j = row_ptr[r]; j < (uint64_t)row_ptr[r + 1]; j++) {
+          uint32_t b = block_of(col_ind[j]);
+          if (cnt[b]++ == 0) touched.push_back(b);
+        }
+        for (uint32_t b : touched) {
+          L->rowmap[rank[b]] = r; seglen[rank[b]] = round_up(cnt[b], (uint32_t)vf);
+          rank[b]++; cnt[b] = 0;
+        }
+        touched.clear();
+      }
+    }
+  }
+
+  // ---- prepare_balanced_hw_matrix: S1 && S2 && S3 split per block (csr_hw.cpp:459-468), leftovers + row padding to
+  //      the last CU (:474-482).  fp[b*(cu+1)+k] = first block position of piece k (real entries only).
+  const size_t KB = (size_t)cu * blocks;
+  L->nr_rows.assign(KB, 0); L->nr_nzeros.assign(KB, 0); L->nr_ci.assign(KB, 0); L->nr_val.assign(KB, 0);
+  std::vector<uint64_t> fp((size_t)blocks * (cu + 1), 0);
+  std::vector<uint32_t> pad_rows(blocks, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < blocks; b++) {
+    uint64_t *f = &fp[(size_t)b * (cu + 1)];
+    uint64_t nz = 0, rc = 0, pos = 0;
+    int fired = 0;
+    if (cu > 1) {
+      const uint64_t thr = Z[b] / (uint64_t)cu;
+      const uint64_t base = L->rank_base[b];
+      for (uint64_t i = 0; i < P[b]; i++) {
+        uint32_t len = seglen[base + i];
+        nz += len; rc++; pos += len;
+        if (nz > thr && nz % ratio_v == 0 && rc % ratio_v == 0 && fired < cu - 1) {
+          L->nr_rows[(size_t)fired * blocks + b] = (uint32_t)rc;
+          L->nr_nzeros[(size_t)fired * blocks + b] = (uint32_t)nz;
+          fired++;
+          f[fired] = pos;
+          nz = 0; rc = 0;
+        }
+      }
+    } else {
+      nz = Z[b]; rc = P[b];
+    }
+    for (int k = fired + 1; k < cu; k++) f[k] = f[fired];  // un-fired middle CUs stay empty (reference: garbage, Q2)
+    f[cu] = Z[b];
+    uint32_t mod = (uint32_t)(rc % ratio_v);
+    if (mod) { pad_rows[b] = ratio_v - mod; rc += pad_rows[b]; nz += (uint64_t)pad_rows[b] * vf; }
+    L->nr_rows[(size_t)(cu - 1) * blocks + b] = (uint32_t)rc;
+    L->nr_nzeros[(size_t)(cu - 1) * blocks + b] = (uint32_t)nz;
+  }
+  std::vector<uint32_t>().swap(seglen);
+
+  // ---- hw_matrix_alloc (csr_hw.cpp:174-180) + device image offsets (each piece padded to whole chunks)
+  L->piece_off.assign(KB, 0); L->piece_chunk0.assign(KB, 0); L->piece_real_nnz.assign(KB, 0);
+  uint64_t off = 0, chunk0 = 0, padded = 0;
+  for (int b = 0; b < blocks; b++)
+    for (int k = 0; k < cu; k++) {
+      const size_t kb = (size_t)k * blocks + b, bk = (size_t)b * cu + k;
+      uint32_t n = L->nr_nzeros[kb];
+      L->nr_ci[kb] = (n + kRatioCi - 1) / kRatioCi;
+      L->nr_val[kb] = n / ratio_v;  // floors like the reference (Q1); ceil(n / ratio_v) words are stored
+      uint64_t nchunks = ((uint64_t)L->nr_ci[kb] + kGroupsPerChunk - 1) / kGroupsPerChunk;
+      L->piece_off[bk] = off; L->piece_chunk0[bk] = chunk0;
+      L->piece_real_nnz[bk] = (uint32_t)(fp[(size_t)b * (cu + 1) + k + 1] - fp[(size_t)b * (cu + 1) + k]);
+      off += nchunks * (uint64_t)L->chunk_bytes;
+      chunk0 += nchunks;
+      padded += n;
+    }
+  L->stream_bytes = off; L->n_chunks = chunk0; L->padded_nnz = padded;
+  L->stream = (uint8_t *)calloc((size_t)std::max<uint64_t>(off, 16), 1);
+  L->chunks = (ChunkMeta *)calloc((size_t)std::max<uint64_t>(chunk0, 1), sizeof(ChunkMeta));
+  if (!L->stream || !L->chunks) { delete L; return fail(SPMVB_E_NOMEM, "stream"); }
+#pragma omp parallel for schedule(static)
+  for (int64_t bk = 0; bk < (int64_t)KB; bk++) {
+    const int b = (int)(bk / cu);
+    uint64_t c0 = L->piece_chunk0[bk];
+    uint64_t c1 = (bk + 1 < (int64_t)KB) ? L->piece_chunk0[bk + 1] : L->n_chunks;
+    uint32_t real = L->piece_real_nnz[bk];
+    for (uint64_t c = c0; c < c1; c++) {
+      uint64_t first = (c - c0) * kChunkEntries;
+      L->chunks[c].block = (uint32_t)b;
+      L->chunks[c].valid = first >= real ? 0u : (uint32_t)std::min<uint64_t>(kChunkEntries, real - first);
+    }
+  }
+
+  // ---- pass 3: scatter every entry to its final byte (create_block_matrix + generate_balanced_hw_submatrix)
+  const uint8_t *vals = (const uint8_t *)values;
+  const int gb = L->group_bytes;
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    std::vector<uint32_t> cnt(blocks, 0), fill(blocks, 0), touched;
+    std::vector<uint64_t> rank(blocks), pos(blocks);
+    for (int b = 0; b < blocks; b++) {
+      rank[b] = L->rank_base[b] + pairs_t[(size_t)t * blocks + b];
+      pos[b] = zpad_t[(size_t)t * blocks + b];
+    }
+    std::vector<int> piece_k(blocks, 0);  // monotone cursor: CU piece that holds pos[b]
+    for (uint32_t r = rb[t]; r < rb[t + 1]; r++) {
+      const uint64_t j0 = row_ptr[r], j1 = row_ptr[r + 1];
+      for (uint64_t j = j0; j < j1; j++) {
+        uint32_t b = block_of(col_ind[j]);
+        if (cnt[b]++ == 0) touched.push_back(b);
+      }
+      // a segment never straddles pieces: resolve the piece once per (row, block)
+      for (uint32_t b : touched) {
+        const uint64_t *f = &fp[(size_t)b * (cu + 1)];
+        int k = piece_k[b];
+        while (k < cu - 1 && pos[b] >= f[k + 1]) k++;
+        piece_k[b] = k;
+      }
+      for (uint64_t j = j0; j < j1; j++) {
+        const uint32_t c = col_ind[j];
+        const uint32_t b = block_of(c);
+        const int k = piece_k[b];
+        const uint64_t e = pos[b] + fill[b] - fp[(size_t)b * (cu + 1) + k];
+        const uint32_t is_last = (++fill[b] == cnt[b]) && (cnt[b] % (uint32_t)vf == 0);
+        uint8_t *grp = L->stream + L->piece_off[(size_t)b * cu + k] + (e / kRatioCi) * (uint64_t)gb;
+        const uint32_t s = (uint32_t)(e % kRatioCi);
+        const uint16_t ci = (uint16_t)((c - b * cdb) | (is_last ? 0x8000u : 0u));  // csr_hw.cpp:220, :288-292
+        memcpy(grp + 2 * s, &ci, 2);
+        memcpy(grp + kBusBytes + (size_t)s * vb, vals + (size_t)j * vb, vb);       // csr_hw.cpp:300-310
+      }
+      for (uint32_t b : touched) {
+        const int k = piece_k[b];
+        const size_t bk = (size_t)b * cu + k;
+        const uint64_t pstart = fp[(size_t)b * (cu + 1) + k];
+        const uint64_t s_e = pos[b] - pstart;
+        const uint64_t t_e = s_e + round_up(cnt[b], (uint32_t)vf);  // VF padding: (col 0, val 0), csr_hw.cpp:229-238
+        if (cnt[b] % (uint32_t)vf != 0) {
+          const uint64_t e = t_e - 1;
+          uint8_t *grp = L->stream + L->piece_off[bk] + (e / kRatioCi) * (uint64_t)gb;
+          const uint16_t ci = 0x8000u;
+          memcpy(grp + 2 * (e % kRatioCi), &ci, 2);
+        }
+        L->rowmap[rank[b]] = r;
+        // chunks whose first entry lies inside this segment start at this rank
+        for (uint64_t c = (s_e + kChunkEntries - 1) / kChunkEntries; c * kChunkEntries < t_e; c++)
+          L->chunks[L->piece_chunk0[bk] + c].rank0 = (uint32_t)rank[b];
+        pos[b] = pstart + t_e;
+        rank[b]++;
+        cnt[b] = 0; fill[b] = 0;
+      }
+      touched.clear();
+    }
+  }
+
+  // padding rows of the last CU: VF x (col 0, val 0) with the end-of-row bit on the last (csr_hw.cpp:246-255)
+  for (int b = 0; b < blocks; b++) {
+    const size_t bk = (size_t)b * cu + (cu - 1);
+    const uint64_t real = L->piece_real_nnz[bk];
+    for (uint32_t i = 0; i < pad_rows[b]; i++) {
+      const uint64_t e = real + (uint64_t)i * vf + (vf - 1);
+      uint8_t *grp = L->stream + L->piece_off[bk] + (e / kRatioCi) * (uint64_t)gb;
+      const uint16_t ci = 0x8000u;
+      memcpy(grp + 2 * (e % kRatioCi), &ci, 2);
+    }
+  }
+
+  // consecutive-rows fast path: rows of a block ascend, so first/last rank spanning equal row distance <=> consecutive
+#pragma omp parallel for schedule(static)
+  for (int64_t bk = 0; bk < (int64_t)KB; bk++) {
+    const int b = (int)(bk / cu);
+    uint64_t c0 = L->piece_chunk0[bk];
+    uint64_t c1 = (bk + 1 < (int64_t)KB) ? L->piece_chunk0[bk + 1] : L->n_chunks;
+    // last rank owned by this piece
+    uint64_t last_piece_rank = 0;
+    bool have = false;
+    for (uint64_t c = c1; c > c0; c--)
+      if (L->chunks[c - 1].valid) { have = true; break; }
+    if (!have) continue;
+    {
+      // rank of the segment holding the last real entry = rank0 of a virtual chunk after the piece - 1:
+      // count pieces' pairs: ranks are contiguous per block in CU order
+      uint64_t rows_before = 0;
+      for (int k = 0; k < (int)(bk % cu); k++) rows_before += L->nr_rows[(size_t)k * blocks + b];
+      uint64_t real_rows = L->nr_rows[(size_t)(bk % cu) * blocks + b];
+      if ((int)(bk % cu) == cu - 1) real_rows -= pad_rows[b];
+      last_piece_rank = L->rank_base[b] + rows_before + real_rows - 1;
+    }
+    for (uint64_t c = c0; c < c1; c++) {
+      ChunkMeta &m = L->chunks[c];
+      if (!m.valid) continue;
+      m.row_first = L->rowmap[m.rank0];
+      uint64_t last_rank = (c + 1 < c1 && L->chunks[c + 1].valid) ? L->chunks[c + 1].rank0 : last_piece_rank;
+      if ((uint64_t)L->rowmap[last_rank] - m.row_first == last_rank - m.rank0) m.valid |= kChunkRowsConsecutive;
+    }
+  }
+
+  *out = L;
+  return SPMVB_OK;
+}
+
+}  // namespace
+}  // namespace spmvb
+
+using namespace spmvb;
+
+extern "C" {
+
+const char *spmvb_last_error(void) { return last_error_cstr(); }
+int spmvb_version(void) { return 100; }
+
+int spmvb_layout_build(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, const uint32_t *col_ind,
+                       const void *values, int n_cu, int vf, int is_double, uint32_t cols_div_blocks,
+                       spmvb_layout **out) {
+  return build_impl<uint64_t>(rows, cols, row_ptr, col_ind, values, n_cu, vf, is_double, cols_div_blocks,
+                              (Layout **)out);
+}
+
+int spmvb_layout_build_u32(uint32_t rows, uint32_t cols, const uint32_t *row_ptr, const uint32_t *col_ind,
+                           const void *values, int n_cu, int vf, int is_double, uint32_t cols_div_blocks,
+                           spmvb_layout **out) {
+  return build_impl<uint32_t>(rows, cols, row_ptr, col_ind, values, n_cu, vf, is_double, cols_div_blocks,
+                              (Layout **)out);
+}
+
+void spmvb_layout_free(spmvb_layout *l) { delete (Layout *)l; }
+
+int spmvb_layout_blocks(const spmvb_layout *l) { return ((const Layout *)l)->blocks; }
+int spmvb_layout_n_cu(const spmvb_layout *l) { return ((const Layout *)l)->cu; }
+uint32_t spmvb_layout_rows(const spmvb_layout *l) { return ((const Layout *)l)->rows; }
+uint32_t spmvb_layout_cols(const spmvb_layout *l) { return ((const Layout *)l)->cols; }
+uint32_t spmvb_layout_expanded_cols(const spmvb_layout *l) { return ((const Layout *)l)->expanded_cols; }
+uint64_t spmvb_layout_real_nnz(const spmvb_layout *l) { return ((const Layout *)l)->real_nnz; }
+uint64_t spmvb_layout_padded_nnz(const spmvb_layout *l) { return ((const Layout *)l)->padded_nnz; }
+uint64_t spmvb_layout_pairs(const spmvb_layout *l) { return ((const Layout *)l)->n_pairs; }
+uint64_t spmvb_layout_stream_bytes(const spmvb_layout *l) { return ((const Layout *)l)->stream_bytes; }
+
+int spmvb_layout_piece_info(const spmvb_layout *l, int cu, int block, uint32_t *out) {
+  const Layout *L = (const Layout *)l;
+  if (!L || !out || cu < 0 || cu >= L->cu || block < 0 || block >= L->blocks) return fail(SPMVB_E_ARG, "piece index");
+  const size_t kb = (size_t)cu * L->blocks + block;
+  out[0] = L->nr_rows[kb]; out[1] = L->nr_cols[block]; out[2] = L->nr_nzeros[kb];
+  out[3] = L->nr_ci[kb];   out[4] = L->nr_val[kb];
+  return SPMVB_OK;
+}
+
+const void *spmvb_layout_piece_words(const spmvb_layout *l, int cu, int block) {
+  const Layout *L = (const Layout *)l;
+  if (!L || cu < 0 || cu >= L->cu || block < 0 || block >= L->blocks) return nullptr;
+  return L->stream + L->piece_off[(size_t)block * L->cu + cu];
+}
+
+int spmvb_layout_bitmap_row(const spmvb_layout *l, int block, uint8_t *out) {
+  const Layout *L = (const Layout *)l;
+  if (!L || !out || block < 0 || block >= L->blocks) return fail(SPMVB_E_ARG, "block index");
+  memset(out, 1, L->rows);  // 1 = row has no non-zero in this block (csr_hw.cpp:340-345)
+  for (uint64_t i = L->rank_base[block]; i < L->rank_base[block + 1]; i++) out[L->rowmap[i]] = 0;
+  return SPMVB_OK;
+}
+
+double spmvb_layout_storage_mb(const spmvb_layout *l, int cu) {
+  const Layout *L = (const Layout *)l;
+  if (!L || cu < 0 || cu >= L->cu) return -1.0;
+  // storage_overhead, csr_hw.cpp:1401-1409 (its IndexType accumulator wraps at 2^32 bits; this one does not)
+  double bits = (double)L->blocks * 5 * 32;
+  for (int b = 0; b < L->blocks; b++) {
+    const size_t kb = (size_t)cu * L->blocks + b;
+    bits += ((double)L->nr_ci[kb] + (double)L->nr_val[kb]) * 128.0;
+  }
+  return bits / (8.0 * 1024 * 1024);
+}
+
+int spmvb_layout_pack_x(const spmvb_layout *l, const void *x, uint32_t n, void *out) {
+  const Layout *L = (const Layout *)l;
+  if (!L || !x || !out) return fail(SPMVB_E_ARG, "pack_x");
+  const uint32_t m = std::min(n, L->expanded_cols);
+  memcpy(out, x, (size_t)m * L->vb);
+  memset((uint8_t *)out + (size_t)m * L->vb, 0, (size_t)(L->expanded_cols - m) * L->vb);
+  return SPMVB_OK;
+}
+
+int spmvb_partition_rows(uint32_t rows, const uint64_t *row_ptr, int parts, int ratio_v, uint32_t *bounds) {
+  if (!row_ptr || !bounds || parts < 1 || ratio_v < 1) return fail(SPMVB_E_ARG, "partition_rows");
+  const uint64_t total = row_ptr[rows];
+  const uint64_t thr = total / (uint64_t)parts;
+  bounds[0] = 0;
+  int fired = 0;
+  uint64_t nz = 0, rc = 0;
+  for (uint32_t r = 0; r < rows && fired < parts - 1; r++) {
+    nz += row_ptr[r + 1] - row_ptr[r];
+    rc++;
+    if (nz > thr && nz % (uint64_t)ratio_v == 0 && rc % (uint64_t)ratio_v == 0) {  // S1 && S2 && S3
+      bounds[++fired] = r + 1;
+      nz = 0; rc = 0;
+    }
+  }
+  for (int k = fired + 1; k <= parts; k++) bounds[k] = rows;
+  return SPMVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,373 @@
+"""ctypes binding of the C ABI (include/spmvb.h) for tests, bench.py and the multi-GPU host driver.
+
+This module is plumbing only: every compute call goes into lib/libspmvb.so (hand-written sm_100a CUDA).  It never
+falls back to a CPU implementation - a missing library or a missing GPU raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libspmvb.so")
+
+_vp = ctypes.c_void_p
+_u32 = ctypes.c_uint32
+_u64 = ctypes.c_uint64
+_int = ctypes.c_int
+
+# every symbol include/spmvb.h declares: (restype, argtypes)
+SYMBOLS = {
+    "spmvb_last_error": (ctypes.c_char_p, []),
+    "spmvb_version": (_int, []),
+    "spmvb_layout_build": (_int, [_u32, _u32, _vp, _vp, _vp, _int, _int, _int, _u32, _vp]),
+    "spmvb_layout_build_u32": (_int, [_u32, _u32, _vp, _vp, _vp, _int, _int, _int, _u32, _vp]),
+    "spmvb_layout_free": (None, [_vp]),
+    "spmvb_layout_blocks": (_int, [_vp]),
+    "spmvb_layout_n_cu": (_int, [_vp]),
+    "spmvb_layout_rows": (_u32, [_vp]),
+    "spmvb_layout_cols": (_u32, [_vp]),
+    "spmvb_layout_expanded_cols": (_u32, [_vp]),
+    "spmvb_layout_real_nnz": (_u64, [_vp]),
+    "spmvb_layout_padded_nnz": (_u64, [_vp]),
+    "spmvb_layout_pairs": (_u64, [_vp]),
+    "spmvb_layout_stream_bytes": (_u64, [_vp]),
+    "spmvb_layout_piece_info": (_int, [_vp, _int, _int, _vp]),
+    "spmvb_layout_piece_words": (_vp, [_vp, _int, _int]),
+    "spmvb_layout_bitmap_row": (_int, [_vp, _int, _vp]),
+    "spmvb_layout_storage_mb": (ctypes.c_double, [_vp, _int]),
+    "spmvb_layout_pack_x": (_int, [_vp, _vp, _u32, _vp]),
+    "spmvb_partition_rows": (_int, [_u32, _vp, _int, _int, _vp]),
+    "spmvb_engine_create": (_int, [_vp, _int, _int, _vp]),
+    "spmvb_engine_free": (None, [_vp]),
+    "spmvb_engine_set_variant": (_int, [_vp, _int]),
+    "spmvb_engine_variant": (_int, [_vp]),
+    "spmvb_engine_launches": (_u64, [_vp]),
+    "spmvb_engine_algorithmic_bytes": (_u64, [_vp]),
+    "spmvb_engine_x_dev": (_vp, [_vp]),
+    "spmvb_engine_y_dev": (_vp, [_vp]),
+    "spmvb_engine_stream": (_vp, [_vp]),
+    "spmvb_engine_set_x": (_int, [_vp, _vp, _u32]),
+    "spmvb_engine_spmv_dev": (_int, [_vp, _vp, _vp, _int, _vp]),
+    "spmvb_engine_sync": (_int, [_vp]),
+    "spmvb_engine_get_y": (_int, [_vp, _vp, _u32, _int]),
+    "spmvb_engine_spmv_host": (_int, [_vp, _vp, _u32, _vp, _int]),
+    "spmvb_engine_time_spmv": (_int, [_vp, _int, _int, _vp]),
+    "spmvb_engine_power_iter": (_int, [_vp, _int, _vp]),
+    "spmvb_engine_scale_copy": (_int, [_vp, _vp, _vp, _u32, ctypes.c_double, _vp]),
+    "spmvb_engine_sumsq": (_int, [_vp, _vp, _u32, _vp, _vp]),
+    "spmvb_csr_free": (None, [_vp]),
+    "spmvb_csr_rows": (_u32, [_vp]),
+    "spmvb_csr_cols": (_u32, [_vp]),
+    "spmvb_csr_nnz": (_u64, [_vp]),
+    "spmvb_csr_is_double": (_int, [_vp]),
+    "spmvb_csr_row_ptr": (_vp, [_vp]),
+    "spmvb_csr_col_ind": (_vp, [_vp]),
+    "spmvb_csr_values": (_vp, [_vp]),
+    "spmvb_layout_build_csr": (_int, [_vp, _int, _int, _u32, _vp]),
+    "spmvb_csr_read": (_int, [ctypes.c_char_p, _int, _vp]),
+    "spmvb_csr_write": (_int, [_vp, ctypes.c_char_p]),
+    "spmvb_csr_gen_band": (_int, [_u32, _int, _u64, _int, _vp]),
+    "spmvb_csr_gen_laplacian2d": (_int, [_u32, _u32, _u32, _u32, _int, _vp]),
+    "spmvb_csr_gen_uniform": (_int, [_u32, _u32, _int, _u64, _u32, _u32, _int, _vp]),
+    "spmvb_csr_gen_rmat": (_int, [_int, _int, ctypes.c_double, ctypes.c_double, ctypes.c_double, _u64, _u32, _u32,
+                                  _int, _vp]),
+}
+
+_lib = None
+
+
+class SpmvbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("spmvb error %d: %s" % (code, msg))
+        self.code = code
+
+
+def build_library(force=False):
+    """Compile lib/libspmvb.so in-tree (nvcc, sm_100a)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SpmvbError(-3, "libspmvb.so is not built (run `make -C spmv-fpga_b200` or __graft_entry__.build()); "
+                                 "there is no fallback path")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise SpmvbError(rc, lib().spmvb_last_error().decode(errors="replace"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp) if a is not None else None
+
+
+def vdtype(is_double):
+    return np.float64 if is_double else np.float32
+
+
+class Csr:
+    """Library-owned CSR matrix (numpy views are zero-copy and valid while the object lives)."""
+
+    def __init__(self, handle):
+        self.h = _vp(handle)
+        L = lib()
+        self.rows = L.spmvb_csr_rows(self.h)
+        self.cols = L.spmvb_csr_cols(self.h)
+        self.nnz = L.spmvb_csr_nnz(self.h)
+        self.is_double = bool(L.spmvb_csr_is_double(self.h))
+
+    def _view(self, p, n, dt):
+        if n == 0:
+            return np.zeros(0, dt)
+        buf = (ctypes.c_uint8 * (n * np.dtype(dt).itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=dt, count=n)
+
+    @property
+    def row_ptr(self):
+        return self._view(lib().spmvb_csr_row_ptr(self.h), self.rows + 1, np.uint64)
+
+    @property
+    def col_ind(self):
+        return self._view(lib().spmvb_csr_col_ind(self.h), self.nnz, np.uint32)
+
+    @property
+    def values(self):
+        return self._view(lib().spmvb_csr_values(self.h), self.nnz, vdtype(self.is_double))
+
+    def write(self, path):
+        _check(lib().spmvb_csr_write(self.h, path.encode()))
+
+    def free(self):
+        if self.h:
+            lib().spmvb_csr_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # ---- constructors
+    @staticmethod
+    def _new(fn, *args):
+        out = _vp()
+        _check(fn(*args, ctypes.byref(out)))
+        return Csr(out.value)
+
+    @staticmethod
+    def read(path, is_double=True):
+        return Csr._new(lib().spmvb_csr_read, path.encode(), int(is_double))
+
+    @staticmethod
+    def band(n, half_bw=5, seed=1, is_double=True):
+        return Csr._new(lib().spmvb_csr_gen_band, n, half_bw, seed, int(is_double))
+
+    @staticmethod
+    def laplacian2d(nx, ny, row_begin=0, row_end=0, is_double=True):
+        return Csr._new(lib().spmvb_csr_gen_laplacian2d, nx, ny, row_begin, row_end, int(is_double))
+
+    @staticmethod
+    def uniform(rows, cols, nnz_per_row, seed=1, row_begin=0, row_end=0, is_double=True):
+        return Csr._new(lib().spmvb_csr_gen_uniform, rows, cols, nnz_per_row, seed, row_begin, row_end, int(is_double))
+
+    @staticmethod
+    def rmat(scale, edge_factor=16, a=0.57, b=0.19, c=0.19, seed=1, row_begin=0, row_end=0, is_double=True):
+        return Csr._new(lib().spmvb_csr_gen_rmat, scale, edge_factor, a, b, c, seed, row_begin, row_end, int(is_double))
+
+
+class Layout:
+    """Host hw_matrix layout (create_csr_hw_matrix)."""
+
+    def __init__(self, handle, is_double):
+        self.h = _vp(handle)
+        self.is_double = bool(is_double)
+        L = lib()
+        self.blocks = L.spmvb_layout_blocks(self.h)
+        self.n_cu = L.spmvb_layout_n_cu(self.h)
+        self.rows = L.spmvb_layout_rows(self.h)
+        self.cols = L.spmvb_layout_cols(self.h)
+        self.expanded_cols = L.spmvb_layout_expanded_cols(self.h)
+        self.real_nnz = L.spmvb_layout_real_nnz(self.h)
+        self.padded_nnz = L.spmvb_layout_padded_nnz(self.h)
+        self.pairs = L.spmvb_layout_pairs(self.h)
+        self.stream_bytes = L.spmvb_layout_stream_bytes(self.h)
+
+    @staticmethod
+    def build(rows, cols, row_ptr, col_ind, values, n_cu=1, vf=1, is_double=True, cols_div_blocks=0):
+        rp = np.ascontiguousarray(row_ptr, np.uint64)
+        ci = np.ascontiguousarray(col_ind, np.uint32)
+        va = np.ascontiguousarray(values, vdtype(is_double))
+        out = _vp()
+        _check(lib().spmvb_layout_build(rows, cols, _ptr(rp), _ptr(ci), _ptr(va), n_cu, vf, int(is_double),
+                                        cols_div_blocks, ctypes.byref(out)))
+        return Layout(out.value, is_double)
+
+    @staticmethod
+    def build_u32(rows, cols, row_ptr, col_ind, values, n_cu=1, vf=1, is_double=True, cols_div_blocks=0):
+        rp = np.ascontiguousarray(row_ptr, np.uint32)
+        ci = np.ascontiguousarray(col_ind, np.uint32)
+        va = np.ascontiguousarray(values, vdtype(is_double))
+        out = _vp()
+        _check(lib().spmvb_layout_build_u32(rows, cols, _ptr(rp), _ptr(ci), _ptr(va), n_cu, vf, int(is_double),
+                                            cols_div_blocks, ctypes.byref(out)))
+        return Layout(out.value, is_double)
+
+    @staticmethod
+    def from_csr(csr, n_cu=1, vf=1, cols_div_blocks=0):
+        out = _vp()
+        _check(lib().spmvb_layout_build_csr(csr.h, n_cu, vf, cols_div_blocks, ctypes.byref(out)))
+        return Layout(out.value, csr.is_double)
+
+    def piece_info(self, cu, block):
+        info = (ctypes.c_uint32 * 5)()
+        _check(lib().spmvb_layout_piece_info(self.h, cu, block, info))
+        return tuple(int(v) for v in info)
+
+    def piece_words(self, cu, block):
+        nr_rows, nr_cols, nnz, nr_ci, nr_val = self.piece_info(cu, block)
+        ratio_v = 2 if self.is_double else 4
+        nwords = nr_ci + (nnz + ratio_v - 1) // ratio_v
+        p = lib().spmvb_layout_piece_words(self.h, cu, block)
+        if nwords == 0:
+            return np.zeros(0, np.uint8)
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(nwords * 16,)).copy()
+
+    def bitmap_row(self, block):
+        out = np.zeros(self.rows, np.uint8)
+        _check(lib().spmvb_layout_bitmap_row(self.h, block, _ptr(out)))
+        return out
+
+    def storage_mb(self, cu):
+        return lib().spmvb_layout_storage_mb(self.h, cu)
+
+    def pack_x(self, x):
+        xx = np.ascontiguousarray(x, vdtype(self.is_double))
+        out = np.empty(self.expanded_cols, vdtype(self.is_double))
+        _check(lib().spmvb_layout_pack_x(self.h, _ptr(xx), len(xx), _ptr(out)))
+        return out
+
+    def free(self):
+        if self.h:
+            lib().spmvb_layout_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def partition_rows(rows, row_ptr, parts, ratio_v=2):
+    rp = np.ascontiguousarray(row_ptr, np.uint64)
+    bounds = np.zeros(parts + 1, np.uint32)
+    _check(lib().spmvb_partition_rows(rows, _ptr(rp), parts, ratio_v, _ptr(bounds)))
+    return bounds
+
+
+VARIANT_DEFAULT, VARIANT_DIRECT, VARIANT_RING, VARIANT_XSMEM = 0, 1, 2, 3
+
+
+class Engine:
+    """Device-resident hw_matrix + the SpMV kernels (spmv_hw)."""
+
+    def __init__(self, layout, device=0, variant=VARIANT_DEFAULT):
+        out = _vp()
+        _check(lib().spmvb_engine_create(layout.h, device, variant, ctypes.byref(out)))
+        self.h = _vp(out.value)
+        self.is_double = layout.is_double
+        self.rows, self.cols, self.expanded_cols = layout.rows, layout.cols, layout.expanded_cols
+        self.real_nnz = layout.real_nnz
+
+    def set_variant(self, v):
+        _check(lib().spmvb_engine_set_variant(self.h, v))
+
+    @property
+    def launches(self):
+        return lib().spmvb_engine_launches(self.h)
+
+    @property
+    def algorithmic_bytes(self):
+        return lib().spmvb_engine_algorithmic_bytes(self.h)
+
+    @property
+    def x_dev(self):
+        return lib().spmvb_engine_x_dev(self.h)
+
+    @property
+    def y_dev(self):
+        return lib().spmvb_engine_y_dev(self.h)
+
+    @property
+    def stream(self):
+        return lib().spmvb_engine_stream(self.h)
+
+    def set_x(self, x):
+        xx = np.ascontiguousarray(x, vdtype(self.is_double))
+        _check(lib().spmvb_engine_set_x(self.h, _ptr(xx), len(xx)))
+        _check(lib().spmvb_engine_sync(self.h))
+
+    def spmv_dev(self, x_dev=None, y_dev=None, accumulate=False, stream=None):
+        _check(lib().spmvb_engine_spmv_dev(self.h, x_dev, y_dev, int(accumulate), stream))
+
+    def sync(self):
+        _check(lib().spmvb_engine_sync(self.h))
+
+    def get_y(self, out=None, accumulate=False):
+        if out is None:
+            out = np.zeros(self.rows, vdtype(self.is_double))
+        _check(lib().spmvb_engine_get_y(self.h, _ptr(out), len(out), int(accumulate)))
+        return out
+
+    def spmv_host(self, x, y, accumulate=True):
+        """spmv_hw: y (+)= A x with host buffers (x, y numpy arrays or raw host pointers)."""
+        if isinstance(x, np.ndarray):
+            assert x.dtype == vdtype(self.is_double) and x.flags.c_contiguous
+            xp, n = _ptr(x), len(x)
+        else:
+            xp, n = x
+        yp = _ptr(y) if isinstance(y, np.ndarray) else y
+        _check(lib().spmvb_engine_spmv_host(self.h, xp, n, yp, int(accumulate)))
+        return y
+
+    def time_spmv(self, iters, flush_l2=False):
+        ms = np.zeros(iters, np.float32)
+        _check(lib().spmvb_engine_time_spmv(self.h, iters, int(flush_l2), _ptr(ms)))
+        return ms
+
+    def power_iter(self, iters):
+        nrm = ctypes.c_double()
+        _check(lib().spmvb_engine_power_iter(self.h, iters, ctypes.byref(nrm)))
+        return nrm.value
+
+    def scale_copy(self, src_dev, dst_dev, n, scale, stream=None):
+        _check(lib().spmvb_engine_scale_copy(self.h, src_dev, dst_dev, n, scale, stream))
+
+    def sumsq(self, src_dev, n, out_dev, stream=None):
+        _check(lib().spmvb_engine_sumsq(self.h, src_dev, n, out_dev, stream))
+
+    def free(self):
+        if self.h:
+            lib().spmvb_engine_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
