@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the hw_matrix SpMV hot path on B200 (metric of BASELINE.json: SpMV GFLOP/s + effective GB/s
+against the HBM roofline, reference CPU path timed beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload laplacian|rmat|uniform|band] [--impl reference]
+
+A "step" is one SpMV y = A x over the whole (per-rank) matrix: zero y, one kernel launch.  At N>1 (torchrun, one rank
+per GPU) the rows are sharded over the ranks (the reference's CU dimension), x is replicated, there is no data-path
+collective; per-GPU work is fixed as N grows (weak scaling).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "spmv-fpga_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="laplacian", choices=["laplacian", "rmat", "uniform", "band"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--scale", type=int, default=0, help="log2(rows per GPU) for rmat/uniform (default 24 / 23)")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--flush-l2", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (default min(steps, 20))")
+    return ap.parse_args()
+
+
+def workload_spec(args, world):
+    """Global shape of the synthetic matrix and this job's config dict (weak scaling: fixed rows per GPU)."""
+    if args.workload == "laplacian":
+        nx, ny = 2048, 2048 * world
+        return dict(kind="laplacian", nx=nx, ny=ny, rows=nx * ny, cols=nx * ny,
+                    name="2D 5-point Laplacian %dx%d grid (BASELINE configs[1]: 4M rows/GPU, ~21M nnz/GPU)" % (nx, ny))
+    if args.workload == "rmat":
+        s = (args.scale or 24) + int(np.log2(world))
+        return dict(kind="rmat", scale=s, rows=1 << s, cols=1 << s,
+                    name="R-MAT scale %d ef16 (0.57,0.19,0.19,0.05), many empty rows (BASELINE configs[2])" % s)
+    if args.workload == "uniform":
+        s = (args.scale or 23) + int(np.log2(world))
+        return dict(kind="uniform", rows=1 << s, cols=1 << s, k=16,
+                    name="uniform random %d rows x 16 nnz/row (BASELINE configs[3] shape)" % (1 << s))
+    return dict(kind="band", rows=10000 * world, cols=10000 * world, name="band 10k rows (BASELINE configs[0])")
+
+
+def make_matrix(spmvb, spec, is_double, rank, world):
+    rows = spec["rows"]
+    per = rows // world
+    rb, re = rank * per, (rank + 1) * per if rank < world - 1 else rows
+    if spec["kind"] == "laplacian":
+        return spmvb.Csr.laplacian2d(spec["nx"], spec["ny"], rb, re, is_double), rb, re
+    if spec["kind"] == "rmat":
+        return spmvb.Csr.rmat(spec["scale"], 16, 0.57, 0.19, 0.19, 1, rb, re, is_double), rb, re
+    if spec["kind"] == "uniform":
+        return spmvb.Csr.uniform(rows, spec["cols"], spec["k"], 1, rb, re, is_double), rb, re
+    assert world == 1
+    return spmvb.Csr.band(rows, 5, 1, is_double), 0, rows
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake_slowdown"}
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def start(self):
+        def loop():
+            while not self._stop.is_set():
+                self.sample()
+                time.sleep(0.002)
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        self.sample()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_spmv(csr, is_double, budget_s=12.0, min_reps=3, max_reps=50):
+    """Times the reference's CPU SpMV (spmv_gold, csr.cpp:184-194) single-threaded, exactly as the reference runs it:
+    oracle/_ref (the unmodified reference compiled here) when present, else the oracle port."""
+    import ctypes
+    import oracle_api as oa
+    vt = np.float64 if is_double else np.float32
+    rows, cols, nnz = csr.rows, csr.cols, csr.nnz
+    x = np.random.default_rng(1).random(cols).astype(vt)
+    y = np.zeros(rows, vt)
+    ci, va = csr.col_ind, csr.values
+    kind = "port"
+    fn = None
+    if nnz < 2 ** 32 and oa.have_ref(1, 1, is_double):
+        try:
+            R = oa.RefLib(1, 1, is_double)
+            rp32 = csr.row_ptr.astype(np.uint32)
+            args = (rows, cols, nnz, oa._ptr(rp32), oa._ptr(ci), oa._ptr(va), oa._ptr(x), oa._ptr(y))
+            fn = lambda: R.L.ref_spmv_gold(*args)
+            kind = "reference"
+        except OSError:
+            fn = None
+    if fn is None:
+        O = oa.OracleLib()
+        rp = csr.row_ptr
+        args = (rows, oa._ptr(rp), oa._ptr(ci), oa._ptr(va), oa._ptr(x), oa._ptr(y), int(is_double))
+        fn = lambda: O.L.orc_spmv_gold(*args)
+    fn()  # warm
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < max_reps and (len(times) < min_reps or time.perf_counter() < t_end):
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+    return kind, times, y, x
+
+
+def run_reference(args, spec, world, rank):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, same config/metric."""
+    if rank != 0:
+        return
+    import spmvb
+    is_double = args.dtype == "f64"
+    csr, _, _ = make_matrix(spmvb, spec, is_double, 0, 1)  # the whole job's matrix on rank 0
+    kind, _, _, _ = cpu_reference_spmv(csr, is_double, budget_s=0.0, min_reps=max(args.warmup, 1), max_reps=max(args.warmup, 1))
+    kind, times, _, _ = cpu_reference_spmv(csr, is_double, budget_s=0.0, min_reps=args.steps, max_reps=args.steps)
+    total = float(np.sum(times))
+    gflops = 2.0 * csr.nnz * len(times) / total / 1e9
+    vb = 8 if is_double else 4
+    alg = csr.nnz * (2 + vb) + csr.rows * vb + csr.cols * vb
+    sample = "whole %s, %d nnz, %d passes of spmv_gold (csr.cpp:184-194), single thread as the reference runs it" % (
+        spec["name"], csr.nnz, len(times))
+    line = {
+        "impl": "reference", "metric": "SpMV GFLOP/s (2*nnz/t)", "value": gflops, "unit": "GFLOP/s", "n_gpus": world,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": spec["name"], "rows": csr.rows, "cols": csr.cols, "nnz": int(csr.nnz)},
+        "effective_gbs": alg * len(times) / total / 1e9,
+        "cpu_baseline": {"value": gflops, "unit": "GFLOP/s", "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    spec = workload_spec(args, world)
+    if args.impl == "reference":
+        run_reference(args, spec, world, rank)
+        return
+
+    import torch
+    import spmvb
+    spmvb.lib()  # fails loudly when the CUDA library is missing: there is no fallback
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200; no CUDA device is visible (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    is_double = args.dtype == "f64"
+    vt = np.float64 if is_double else np.float32
+    vb = 8 if is_double else 4
+
+    t0 = time.perf_counter()
+    csr, rb, re = make_matrix(spmvb, spec, is_double, rank, world)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lay = spmvb.Layout.from_csr(csr, 1, 1)
+    t_layout = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng = spmvb.Engine(lay, local_rank, args.variant)
+    t_upload = time.perf_counter() - t0
+    nnz_local = int(csr.nnz)
+    alg_bytes_local = int(eng.algorithmic_bytes)
+
+    # x replicated on every rank (pinned host copy for the e2e leg), y sharded by rows
+    x_host = torch.empty(csr.cols, dtype=torch.float64 if is_double else torch.float32).pin_memory()
+    x_np = x_host.numpy()
+    x_np[:] = np.random.default_rng(1).random(csr.cols).astype(vt)
+    y_host = torch.zeros(csr.rows, dtype=x_host.dtype).pin_memory()
+    eng.set_x(x_np)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.sync()
+
+    # ---- warm-up
+    eng.enqueue_steps(max(args.warmup, 3), args.flush_l2)
+    eng.collect_steps()
+
+    # ---- timed region: K steps, device-timed, clocks sampled while it runs
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = eng.launches
+    sampler.start()
+    eng.enqueue_steps(args.steps, args.flush_l2)
+    total_ms, kernel_ms = eng.collect_steps()
+    sampler.stop()
+    barrier()
+    launches = eng.launches - launches0
+    t_job_ms = total_ms
+    if args.flush_l2:  # the flush kernels are not part of a step: count kernel + memset only
+        t_job_ms = float(np.sum(kernel_ms))
+    nnz_total = nnz_local
+    if dist is not None:
+        t = torch.tensor([t_job_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_job_ms = float(t.item())
+        n = torch.tensor([nnz_local, alg_bytes_local, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        nnz_total, alg_total, launches_total = int(n[0].item()), int(n[1].item()), int(n[2].item())
+    else:
+        alg_total, launches_total = alg_bytes_local, launches
+    ms_per_step = t_job_ms / args.steps
+    gflops = 2.0 * nnz_total / (ms_per_step * 1e-3) / 1e9
+    eff_gbs = alg_total / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the C-ABI call with host buffers (spmv_hw semantics: H2D x, SpMV, D2H y, y_host += y)
+    e2e_steps = args.e2e_steps or min(args.steps, 20)
+    xp = (x_host.data_ptr(), csr.cols)
+    yp = y_host.data_ptr()
+    for _ in range(2):
+        eng.spmv_host(xp, yp, accumulate=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.spmv_host(xp, yp, accumulate=True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_gflops = 2.0 * nnz_total * e2e_steps / e2e_s / 1e9
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    k_ms = float(np.mean(kernel_ms))
+    achieved = alg_bytes_local / (k_ms * 1e-3) / 1e9
+    line = {
+        "metric": "SpMV GFLOP/s (2*nnz/t)", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": spec["name"], "rows": spec["rows"], "cols": spec["cols"], "nnz": nnz_total,
+                   "layout": "hw_matrix CU=1 VF=1 per GPU (rows sharded over GPUs, x replicated)",
+                   "l2": "flushed between steps" if args.flush_l2 else "inputs larger than L2 (no flush)",
+                   "variant": int(args.variant), "step": "zero y + one SpMV kernel launch"},
+        "effective_gbs": eff_gbs,
+        "roofline_nominal_frac": eff_gbs / (8000.0 * world),
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": int(csr.cols * vb) * world,
+                "d2h_bytes_per_step": int(spec["rows"] * vb), "steps": e2e_steps,
+                "what": "spmvb_engine_spmv_host: pinned x -> GPU, kernel, y -> pinned host, y_host += y (spmv_hw semantics)"},
+        "gpu_launches": launches_total,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "spmv_ring_kernel" if args.variant in (0, 2) else "variant %d" % args.variant,
+                     "kernel_ms_avg": k_ms, "kernel_ms_min": float(np.min(kernel_ms)),
+                     "algorithmic_bytes_per_launch": alg_bytes_local},
+        "setup_s": {"generate": t_gen, "layout_build": t_layout, "upload": t_upload},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        kind, times, y_cpu, x_cpu = cpu_reference_spmv(csr, is_double)
+        # the same x: check the GPU result of the bench matrix against the CPU reference while we are here
+        eng.set_x(x_cpu)
+        eng.spmv_dev()
+        y_gpu = eng.get_y()
+        scale = np.abs(y_cpu).max() + 1e-300
+        line["check_vs_cpu_reference_max_abs_err_over_max_abs_y"] = float(np.abs(y_gpu - y_cpu).max() / scale)
+        t = float(np.mean(times))
+        line["cpu_baseline"] = {"value": 2.0 * nnz_local / t / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": kind,
+                                "sample": "whole workload matrix, %d passes of spmv_gold (csr.cpp:184-194), single thread"
+                                          % len(times), "ms_per_pass": t * 1e3}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

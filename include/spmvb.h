@@ -117,6 +117,12 @@ int spmvb_engine_spmv_host(spmvb_engine *e, const void *x_host, uint32_t n, void
 /* Times `iters` device SpMVs (y = A x, engine vectors) with CUDA events on the engine stream;
  * ms_out[iters] per-iteration milliseconds.  flush_l2 1 writes a >L2 scratch buffer between iterations. */
 int spmvb_engine_time_spmv(spmvb_engine *e, int iters, int flush_l2, float *ms_out);
+/* Asynchronous version for the benchmark: enqueues `steps` x (zero y; SpMV kernel) on the engine stream with
+ * CUDA events around the whole region and around every kernel launch, and returns at once so the caller can
+ * sample clocks while the GPU works.  collect waits and returns the region time and per-launch kernel times. */
+int spmvb_engine_enqueue_steps(spmvb_engine *e, int steps, int flush_l2);
+int spmvb_engine_steps_done(spmvb_engine *e);
+int spmvb_engine_collect_steps(spmvb_engine *e, float *total_ms, float *kernel_ms);
 /* Iterated SpMV on one GPU (square matrices): x <- A x / ||A x||_2, `iters` times, all on device.
  * Returns the last norm in *norm_out.  The multi-GPU version lives in the host driver (NCCL all-gather). */
 int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);

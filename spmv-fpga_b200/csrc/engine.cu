@@ -35,6 +35,10 @@ struct Engine {
   cudaStream_t stream = nullptr;
   int sms = 148;
   uint64_t launches = 0;
+  int grid_cache[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [variant][is_double] -> grid size
+  // asynchronous step timing (bench): events of the last enqueue_steps()
+  std::vector<cudaEvent_t> ev;
+  int ev_steps = 0;
 };
 
 #define CUDA_TRY(expr)                                                                       \
@@ -52,24 +56,24 @@ static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st) {
   if (E->n_chunks == 0) return SPMVB_OK;
   if (variant == kVariantDirect) {
     auto kern = spmv_direct_kernel<VT, WARPS>;
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, 0));
-    if (per_sm < 1) per_sm = 1;
-    int grid = E->sms * per_sm;
+    int &grid = E->grid_cache[kVariantDirect][sizeof(VT) == 8];
+    if (grid == 0) {
+      int per_sm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, 0));
+      grid = E->sms * std::max(per_sm, 1);
+    }
     kern<<<grid, WARPS * 32, 0, st>>>(stream, E->d_chunks, E->d_rowmap, x, y, E->n_chunks, E->cdb);
   } else {
     constexpr int STAGES = 4;
     auto kern = spmv_ring_kernel<VT, WARPS, STAGES>;
     const size_t smem = (size_t)WARPS * STAGES * (VTraits<VT>::kGroupWords * 16 * 32) + (size_t)WARPS * STAGES * 8;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[sizeof(VT) == 8]) {
+    int &grid = E->grid_cache[kVariantRing][sizeof(VT) == 8];
+    if (grid == 0) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set[sizeof(VT) == 8] = true;
+      int per_sm = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+      grid = E->sms * std::max(per_sm, 1);
     }
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
-    if (per_sm < 1) per_sm = 1;
-    int grid = E->sms * per_sm;
     kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_chunks, E->d_rowmap, x, y, E->n_chunks, E->cdb);
   }
   E->launches++;
@@ -145,6 +149,7 @@ void spmvb_engine_free(spmvb_engine *e) {
   cudaFree(E->d_stream); cudaFree(E->d_chunks); cudaFree(E->d_rowmap);
   cudaFree(E->d_x); cudaFree(E->d_y); cudaFree(E->d_scalar); cudaFree(E->d_flush);
   if (E->h_stage) cudaFreeHost(E->h_stage);
+  for (auto &x : E->ev) cudaEventDestroy(x);
   if (E->stream) cudaStreamDestroy(E->stream);
   delete E;
 }
@@ -257,6 +262,53 @@ int spmvb_engine_time_spmv(spmvb_engine *e, int iters, int flush_l2, float *ms_o
   for (auto &x : ev) cudaEventDestroy(x);
   if (rc) return rc;
   if (ce != cudaSuccess) return fail(SPMVB_E_CUDA, std::string("time_spmv: ") + cudaGetErrorString(ce));
+  return SPMVB_OK;
+}
+
+int spmvb_engine_enqueue_steps(spmvb_engine *e, int steps, int flush_l2) {
+  Engine *E = (Engine *)e;
+  if (!E || steps < 1) return fail(SPMVB_E_ARG, "enqueue_steps");
+  CUDA_TRY(cudaSetDevice(E->device));
+  if (flush_l2 && !E->d_flush) {
+    E->flush_words = (size_t)256 * 1024 * 1024 / 16;
+    CUDA_TRY(cudaMalloc((void **)&E->d_flush, E->flush_words * 16));
+  }
+  for (auto &x : E->ev) cudaEventDestroy(x);
+  E->ev.assign(2 * (size_t)steps + 2, nullptr);
+  for (auto &x : E->ev) CUDA_TRY(cudaEventCreate(&x));
+  E->ev_steps = steps;
+  const void *x = E->d_x;
+  void *y = E->d_y;
+  CUDA_TRY(cudaEventRecord(E->ev[0], E->stream));
+  for (int i = 0; i < steps; i++) {
+    if (flush_l2) l2_flush_kernel<<<E->sms * 4, 256, 0, E->stream>>>(E->d_flush, E->flush_words);
+    CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)E->rows * E->vb, E->stream));
+    CUDA_TRY(cudaEventRecord(E->ev[2 + 2 * i], E->stream));
+    int rc = E->is_double ? launch_spmv<double>(E, (const double *)x, (double *)y, E->stream)
+                          : launch_spmv<float>(E, (const float *)x, (float *)y, E->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(E->ev[3 + 2 * i], E->stream));
+  }
+  CUDA_TRY(cudaEventRecord(E->ev[1], E->stream));
+  return SPMVB_OK;
+}
+
+int spmvb_engine_steps_done(spmvb_engine *e) {
+  Engine *E = (Engine *)e;
+  if (!E || E->ev.empty()) return 1;
+  return cudaEventQuery(E->ev[1]) == cudaSuccess ? 1 : 0;
+}
+
+int spmvb_engine_collect_steps(spmvb_engine *e, float *total_ms, float *kernel_ms) {
+  Engine *E = (Engine *)e;
+  if (!E || E->ev.empty()) return fail(SPMVB_E_ARG, "collect_steps: nothing enqueued");
+  CUDA_TRY(cudaSetDevice(E->device));
+  CUDA_TRY(cudaEventSynchronize(E->ev[1]));
+  if (total_ms) CUDA_TRY(cudaEventElapsedTime(total_ms, E->ev[0], E->ev[1]));
+  if (kernel_ms)
+    for (int i = 0; i < E->ev_steps; i++) CUDA_TRY(cudaEventElapsedTime(&kernel_ms[i], E->ev[2 + 2 * i], E->ev[3 + 2 * i]));
+  for (auto &x : E->ev) cudaEventDestroy(x);
+  E->ev.clear();
   return SPMVB_OK;
 }
 

@@ -54,6 +54,9 @@ SYMBOLS = {
     "spmvb_engine_get_y": (_int, [_vp, _vp, _u32, _int]),
     "spmvb_engine_spmv_host": (_int, [_vp, _vp, _u32, _vp, _int]),
     "spmvb_engine_time_spmv": (_int, [_vp, _int, _int, _vp]),
+    "spmvb_engine_enqueue_steps": (_int, [_vp, _int, _int]),
+    "spmvb_engine_steps_done": (_int, [_vp]),
+    "spmvb_engine_collect_steps": (_int, [_vp, _vp, _vp]),
     "spmvb_engine_power_iter": (_int, [_vp, _int, _vp]),
     "spmvb_engine_scale_copy": (_int, [_vp, _vp, _vp, _u32, ctypes.c_double, _vp]),
     "spmvb_engine_sumsq": (_int, [_vp, _vp, _u32, _vp, _vp]),
@@ -349,6 +352,19 @@ class Engine:
         ms = np.zeros(iters, np.float32)
         _check(lib().spmvb_engine_time_spmv(self.h, iters, int(flush_l2), _ptr(ms)))
         return ms
+
+    def enqueue_steps(self, steps, flush_l2=False):
+        self._steps = steps
+        _check(lib().spmvb_engine_enqueue_steps(self.h, steps, int(flush_l2)))
+
+    def steps_done(self):
+        return bool(lib().spmvb_engine_steps_done(self.h))
+
+    def collect_steps(self):
+        total = ctypes.c_float()
+        ker = np.zeros(self._steps, np.float32)
+        _check(lib().spmvb_engine_collect_steps(self.h, ctypes.byref(total), _ptr(ker)))
+        return total.value, ker
 
     def power_iter(self, iters):
         nrm = ctypes.c_double()

@@ -1,0 +1,130 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the oracle on the same seeded inputs.
+
+Tolerances are the north-star's: |y - y_ref| <= 1e-12 (fp64) / 1e-5 (fp32) x row-wise |A||x|.
+"""
+import numpy as np
+import pytest
+
+import matgen
+import oracle_api as oa
+
+pytestmark = pytest.mark.gpu
+
+TOL = {True: 1e-12, False: 1e-5}
+
+CASES = {
+    "kat6x6": lambda: (6, 6, np.array([0, 3, 4, 4, 6, 7, 9]), np.array([0, 2, 5, 1, 0, 3, 4, 0, 5]),
+                       np.arange(1, 10, dtype=float)),
+    "band10k": lambda: matgen.band(10000, 5, seed=1),             # BASELINE config 1
+    "lap256": lambda: matgen.laplacian2d(256, 256),                # 2 column blocks
+    "lap_wide": lambda: matgen.laplacian2d(700, 150),              # 4 column blocks, partial last block
+    "ragged": lambda: matgen.ragged(5000, 100000, seed=7),         # empty rows, unsorted columns, 4 blocks
+    "uniform": lambda: matgen.uniform(4000, 200000, 16, seed=3),   # ~1 entry per (row, block) pair
+    "rmat13": lambda: matgen.rmat(13, 8, seed=5),                  # power law, long rows, empty rows
+    "longrow": lambda: matgen.uniform(40, 30000, 9000, seed=9),    # rows spanning many chunks / warps
+    "onerow": lambda: matgen.uniform(1, 5000, 3000, seed=11),
+}
+
+CONFIGS = [(1, 1, True), (1, 1, False), (2, 2, True), (8, 4, True), (8, 4, False), (12, 8, False), (4, 1, True)]
+
+
+def _check(spmvb, oracle, M, cu, vf, isd, variant, cdb=0):
+    rows, cols, rp, ci, va = M
+    vt = oa.vdtype(isd)
+    va = va.astype(vt)
+    rng = np.random.default_rng(1234)
+    x = rng.random(cols).astype(vt)
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, cu, vf, isd, cdb)
+    eng = spmvb.Engine(lay, 0, variant)
+    y = np.zeros(rows, vt)
+    eng.spmv_host(x, y, accumulate=True)
+    gold = oracle.spmv_gold(rows, rp, ci, va, x, isd)
+    scale = oracle.abs_ax(rows, rp, ci, va, x, isd)
+    ho = oracle.build(rows, cols, rp, ci, va, cu, vf, isd, cdb)
+    y_emu = np.zeros(rows, vt)
+    assert oracle.spmv_emu(ho, x, y_emu, isd) == 0
+    oracle.free(ho)
+    tol = TOL[isd]
+    tiny = np.finfo(vt).tiny
+    err_gold = np.abs(y.astype(np.float64) - gold.astype(np.float64))
+    err_emu = np.abs(y.astype(np.float64) - y_emu.astype(np.float64))
+    assert np.all(err_gold <= tol * scale + tiny), "vs gold: max ratio %g" % np.max(err_gold / (scale + tiny))
+    assert np.all(err_emu <= tol * scale + tiny), "vs emu: max ratio %g" % np.max(err_emu / (scale + tiny))
+    # spmv_hw accumulates into y_fpga (csr_hw.cpp:1557): a second call doubles the result
+    eng.spmv_host(x, y, accumulate=True)
+    assert np.all(np.abs(y.astype(np.float64) - 2 * gold.astype(np.float64)) <= 4 * tol * scale + tiny)
+    assert eng.launches >= 2
+    eng.free()
+    lay.free()
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: "cu%d_vf%d_%s" % (c[0], c[1], "f64" if c[2] else "f32"))
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_spmv_matches_oracle(spmvb, oracle, case, cfg, variant):
+    cu, vf, isd = cfg
+    _check(spmvb, oracle, CASES[case](), cu, vf, isd, variant)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_small_column_blocks(spmvb, oracle, variant):
+    """cols_div_blocks = 16384 (the reference's CU=10/12 setting) and a tiny block width: many blocks."""
+    _check(spmvb, oracle, matgen.ragged(3000, 50000, seed=2), 1, 1, True, variant, cdb=16384)
+    _check(spmvb, oracle, matgen.uniform(3000, 9000, 12, seed=4), 2, 2, True, variant, cdb=256)
+
+
+def test_device_api_and_determinism_of_inputs(spmvb, oracle):
+    rows, cols, rp, ci, va = matgen.laplacian2d(512, 512)
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True)
+    eng = spmvb.Engine(lay, 0)
+    x = np.random.default_rng(0).random(cols)
+    eng.set_x(x)
+    eng.spmv_dev()
+    y1 = eng.get_y()
+    eng.spmv_dev(accumulate=True)
+    y2 = eng.get_y()
+    gold = oracle.spmv_gold(rows, rp, ci, va, x, True)
+    scale = oracle.abs_ax(rows, rp, ci, va, x, True)
+    assert np.all(np.abs(y1 - gold) <= 1e-12 * scale)
+    assert np.all(np.abs(y2 - 2 * gold) <= 4e-12 * scale)
+    ms = eng.time_spmv(3, flush_l2=True)
+    assert np.all(ms > 0)
+
+
+def test_linearity_at_scale(spmvb):
+    """Size-independent property on a matrix too big for the O(blocks x rows) oracle: A(ax+bz) = aAx + bAz."""
+    A = spmvb.Csr.laplacian2d(2048, 2048)  # BASELINE config 2: 4 194 304 rows, 20 963 328 nnz
+    assert A.nnz == 20963328
+    lay = spmvb.Layout.from_csr(A)
+    eng = spmvb.Engine(lay, 0)
+    rng = np.random.default_rng(5)
+    x, z = rng.random(A.cols), rng.random(A.cols)
+    y = {}
+    for name, v in (("x", x), ("z", z), ("c", 2.0 * x - 3.0 * z)):
+        out = np.zeros(A.rows)
+        eng.spmv_host(v, out, accumulate=False)
+        y[name] = out
+    # |A||v| <= 8 * max|v| for this operator
+    assert np.max(np.abs(y["c"] - (2.0 * y["x"] - 3.0 * y["z"]))) <= 1e-12 * 8 * 5
+    # interior rows of the Laplacian applied to a constant vector vanish; row sums are known exactly
+    ones = np.ones(A.cols)
+    out = np.zeros(A.rows)
+    eng.spmv_host(ones, out, accumulate=False)
+    deg = np.diff(A.row_ptr.astype(np.int64)) - 1
+    assert np.array_equal(out, 4.0 - deg)
+
+
+def test_power_iteration_matches_numpy(spmvb, oracle):
+    rows, cols, rp, ci, va = matgen.rmat(11, 8, seed=3)
+    va = np.abs(va).astype(np.float32)
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, False)
+    eng = spmvb.Engine(lay, 0)
+    x0 = np.full(cols, 1.0 / np.sqrt(cols), np.float32)
+    eng.set_x(x0)
+    nrm = eng.power_iter(20)
+    x = x0.astype(np.float64)
+    for _ in range(20):
+        yv = oracle.spmv_gold(rows, rp, ci, va.astype(np.float64), x, True)
+        n = np.linalg.norm(yv)
+        x = yv / n
+    assert abs(nrm - n) <= 1e-3 * n
