@@ -66,6 +66,8 @@ uint64_t spmvb_layout_real_nnz(const spmvb_layout *l);      /* non-zeros of the 
 uint64_t spmvb_layout_padded_nnz(const spmvb_layout *l);    /* sum of nr_nzeros over all pieces */
 uint64_t spmvb_layout_pairs(const spmvb_layout *l);         /* non-empty (row, block) pairs = bitmap zeros */
 uint64_t spmvb_layout_stream_bytes(const spmvb_layout *l);  /* bytes of the device image of all pieces */
+/* rows cleared before each y = A x (rows updated with atomics or not at all); -1 = all of y is cleared */
+int64_t spmvb_layout_zero_rows(const spmvb_layout *l);
 /* out[5] = nr_rows, nr_cols, nr_nzeros, nr_ci, nr_val of hw_matrix[cu]->...[block]; nr_val floors like
  * hw_matrix_alloc (csr_hw.cpp:179) although ceil(nr_nzeros/RATIO_v) value words are stored. */
 int spmvb_layout_piece_info(const spmvb_layout *l, int cu, int block, uint32_t *out);

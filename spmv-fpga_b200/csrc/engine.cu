@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,6 +27,9 @@ struct Engine {
   uint8_t *d_stream = nullptr;
   ChunkMeta *d_chunks = nullptr;
   uint32_t *d_rowmap = nullptr;
+  uint32_t *d_zero_rows = nullptr;
+  uint32_t n_zero_rows = 0, run_log2 = 2;
+  bool zero_all = true;
   void *d_x = nullptr, *d_y = nullptr;
   double *d_scalar = nullptr;
   uint4 *d_flush = nullptr;
@@ -34,8 +38,9 @@ struct Engine {
   size_t h_stage_bytes = 0;
   cudaStream_t stream = nullptr;
   int sms = 148;
+  uint32_t dbg = 0;  // profiling experiments (SPMVB_DEBUG_MODE env), 0 in production
   uint64_t launches = 0;
-  int grid_cache[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [variant][is_double] -> grid size
+  int grid_cache[8][2] = {};  // [variant][is_double] -> grid size
   // asynchronous step timing (bench): events of the last enqueue_steps()
   std::vector<cudaEvent_t> ev;
   int ev_steps = 0;
@@ -48,14 +53,35 @@ struct Engine {
       return fail(SPMVB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
   } while (0)
 
+// Kernel variants (spmvb_engine_set_variant): 1 = DIRECT (ld.global per lane, no prefetch); RING (TMA ring + x prefetch)
+// with (stages per warp, min CTAs/SM): 2 = (4, 2) default, 4 = (4, 3), 5 = (2, 3).  0 = default.
+template <typename VT, int STAGES, int MINB>
+static int launch_ring(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
+  constexpr int WARPS = 8;
+  const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
+  auto kern = spmv_ring_kernel<VT, WARPS, STAGES, MINB>;
+  const size_t smem = (size_t)WARPS * STAGES * (VTraits<VT>::kGroupWords * 16 * 32) + (size_t)WARPS * STAGES * 8;
+  int &grid = E->grid_cache[slot][sizeof(VT) == 8];
+  if (grid == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    grid = E->sms * std::max(per_sm, 1);
+  }
+  kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_chunks, E->d_rowmap, x, y, E->n_chunks, E->cdb, E->run_log2,
+                                       E->dbg | (accumulate ? 4u : 0u));
+  return SPMVB_OK;
+}
+
 template <typename VT>
-static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st) {
+static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
   constexpr int WARPS = 8;
   int variant = E->variant == kVariantDefault ? kVariantRing : E->variant;
   if (E->n_chunks == 0) return SPMVB_OK;
+  int rc = SPMVB_OK;
   if (variant == kVariantDirect) {
-    auto kern = spmv_direct_kernel<VT, WARPS>;
+    auto kern = spmv_direct_kernel<VT, WARPS, 4>;
     int &grid = E->grid_cache[kVariantDirect][sizeof(VT) == 8];
     if (grid == 0) {
       int per_sm = 0;
@@ -63,30 +89,41 @@ static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st) {
       grid = E->sms * std::max(per_sm, 1);
     }
     kern<<<grid, WARPS * 32, 0, st>>>(stream, E->d_chunks, E->d_rowmap, x, y, E->n_chunks, E->cdb);
+  } else if (variant == 5) {
+    rc = launch_ring<VT, 4, 3>(E, x, y, st, 5, accumulate);
   } else {
-    constexpr int STAGES = 4;
-    auto kern = spmv_ring_kernel<VT, WARPS, STAGES>;
-    const size_t smem = (size_t)WARPS * STAGES * (VTraits<VT>::kGroupWords * 16 * 32) + (size_t)WARPS * STAGES * 8;
-    int &grid = E->grid_cache[kVariantRing][sizeof(VT) == 8];
-    if (grid == 0) {
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int per_sm = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
-      grid = E->sms * std::max(per_sm, 1);
-    }
-    kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_chunks, E->d_rowmap, x, y, E->n_chunks, E->cdb);
+    rc = launch_ring<VT, 4, 2>(E, x, y, st, 2, accumulate);
   }
+  if (rc) return rc;
   E->launches++;
   CUDA_TRY(cudaGetLastError());
+  return SPMVB_OK;
+}
+
+// y = A x needs y prepared only where the kernel uses atomics or writes nothing: either the listed rows or all of y
+static int zero_y(Engine *E, void *y, cudaStream_t st) {
+  const int variant = E->variant == kVariantDefault ? kVariantRing : E->variant;
+  if (E->zero_all || variant == kVariantDirect) {
+    CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)E->rows * E->vb, st));
+  } else if (E->n_zero_rows) {
+    const int grid = (int)std::min<uint64_t>(((uint64_t)E->n_zero_rows + 255) / 256, (uint64_t)E->sms * 8);
+    if (E->is_double) zero_rows_kernel<double><<<grid, 256, 0, st>>>((double *)y, E->d_zero_rows, E->n_zero_rows);
+    else zero_rows_kernel<float><<<grid, 256, 0, st>>>((float *)y, E->d_zero_rows, E->n_zero_rows);
+    E->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
   return SPMVB_OK;
 }
 
 static int do_spmv(Engine *E, const void *x_dev, void *y_dev, int accumulate, cudaStream_t st) {
   const void *x = x_dev ? x_dev : E->d_x;
   void *y = y_dev ? y_dev : E->d_y;
-  if (!accumulate) CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)E->rows * E->vb, st));
-  if (E->is_double) return launch_spmv<double>(E, (const double *)x, (double *)y, st);
-  return launch_spmv<float>(E, (const float *)x, (float *)y, st);
+  if (!accumulate) {
+    int rc = zero_y(E, y, st);
+    if (rc) return rc;
+  }
+  if (E->is_double) return launch_spmv<double>(E, (const double *)x, (double *)y, st, accumulate);
+  return launch_spmv<float>(E, (const float *)x, (float *)y, st, accumulate);
 }
 
 }  // namespace spmvb
@@ -113,6 +150,7 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   E->rows = L->rows; E->cols = L->cols; E->expanded_cols = L->expanded_cols; E->cdb = L->cdb; E->blocks = L->blocks;
   E->real_nnz = L->real_nnz; E->n_chunks = L->n_chunks; E->n_pairs = L->n_pairs; E->stream_bytes = L->stream_bytes;
   E->variant = variant;
+  if (const char *dm = getenv("SPMVB_DEBUG_MODE")) E->dbg = (uint32_t)atoi(dm);
   E->sms = prop.multiProcessorCount;
   E->x_len = (uint64_t)L->blocks * L->cdb;  // >= expanded_cols: any 15-bit index of any block stays in range
   cudaError_t e = cudaSuccess;
@@ -121,6 +159,8 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   chk(cudaMalloc((void **)&E->d_stream, std::max<uint64_t>(L->stream_bytes, 16)));
   chk(cudaMalloc((void **)&E->d_chunks, std::max<uint64_t>(L->n_chunks, 1) * sizeof(ChunkMeta)));
   chk(cudaMalloc((void **)&E->d_rowmap, (std::max<uint64_t>(L->n_pairs, 1) + 1) * 4));
+  E->zero_all = L->zero_all; E->n_zero_rows = (uint32_t)L->zero_rows.size(); E->run_log2 = (uint32_t)L->run_log2;
+  chk(cudaMalloc((void **)&E->d_zero_rows, std::max<size_t>(L->zero_rows.size(), 1) * 4));
   chk(cudaMalloc(&E->d_x, E->x_len * E->vb));
   chk(cudaMalloc(&E->d_y, (size_t)E->rows * E->vb));
   chk(cudaMalloc((void **)&E->d_scalar, 64));
@@ -128,6 +168,7 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
     chk(cudaMemcpyAsync(E->d_stream, L->stream, L->stream_bytes, cudaMemcpyHostToDevice, E->stream));
     chk(cudaMemcpyAsync(E->d_chunks, L->chunks, L->n_chunks * sizeof(ChunkMeta), cudaMemcpyHostToDevice, E->stream));
     chk(cudaMemcpyAsync(E->d_rowmap, L->rowmap, L->n_pairs * 4, cudaMemcpyHostToDevice, E->stream));
+    chk(cudaMemcpyAsync(E->d_zero_rows, L->zero_rows.data(), L->zero_rows.size() * 4, cudaMemcpyHostToDevice, E->stream));
     chk(cudaMemsetAsync(E->d_x, 0, E->x_len * E->vb, E->stream));
     chk(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
     chk(cudaStreamSynchronize(E->stream));
@@ -146,7 +187,7 @@ void spmvb_engine_free(spmvb_engine *e) {
   if (!E) return;
   cudaSetDevice(E->device);
   if (E->stream) cudaStreamSynchronize(E->stream);
-  cudaFree(E->d_stream); cudaFree(E->d_chunks); cudaFree(E->d_rowmap);
+  cudaFree(E->d_stream); cudaFree(E->d_chunks); cudaFree(E->d_rowmap); cudaFree(E->d_zero_rows);
   cudaFree(E->d_x); cudaFree(E->d_y); cudaFree(E->d_scalar); cudaFree(E->d_flush);
   if (E->h_stage) cudaFreeHost(E->h_stage);
   for (auto &x : E->ev) cudaEventDestroy(x);
@@ -155,7 +196,7 @@ void spmvb_engine_free(spmvb_engine *e) {
 }
 
 int spmvb_engine_set_variant(spmvb_engine *e, int variant) {
-  if (!e || variant < 0 || variant > 3) return fail(SPMVB_E_ARG, "variant");
+  if (!e || variant < 0 || variant > 7) return fail(SPMVB_E_ARG, "variant");
   ((Engine *)e)->variant = variant;
   return SPMVB_OK;
 }
@@ -282,10 +323,11 @@ int spmvb_engine_enqueue_steps(spmvb_engine *e, int steps, int flush_l2) {
   CUDA_TRY(cudaEventRecord(E->ev[0], E->stream));
   for (int i = 0; i < steps; i++) {
     if (flush_l2) l2_flush_kernel<<<E->sms * 4, 256, 0, E->stream>>>(E->d_flush, E->flush_words);
-    CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)E->rows * E->vb, E->stream));
+    int rc = zero_y(E, y, E->stream);
+    if (rc) return rc;
     CUDA_TRY(cudaEventRecord(E->ev[2 + 2 * i], E->stream));
-    int rc = E->is_double ? launch_spmv<double>(E, (const double *)x, (double *)y, E->stream)
-                          : launch_spmv<float>(E, (const float *)x, (float *)y, E->stream);
+    rc = E->is_double ? launch_spmv<double>(E, (const double *)x, (double *)y, E->stream, 0)
+                      : launch_spmv<float>(E, (const float *)x, (float *)y, E->stream, 0);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(E->ev[3 + 2 * i], E->stream));
   }

@@ -21,7 +21,10 @@ struct ChunkMeta {
   uint32_t row_first;  // rowmap[rank0] (row of the first segment), for the consecutive-rows fast path
 };
 
-constexpr uint32_t kChunkRowsConsecutive = 0x80000000u;  // flag in ChunkMeta::valid
+// flags in ChunkMeta::valid (the entry count lives in the low 10 bits)
+constexpr uint32_t kChunkRowsConsecutive = 0x80000000u;  // rows of the chunk's segments are row_first, row_first+1, ...
+constexpr uint32_t kChunkSole = 0x40000000u;       // every row touched by the chunk lives in exactly one column block
+constexpr uint32_t kChunkStartsMid = 0x20000000u;  // the chunk's first entry continues a row begun in the previous chunk
 
 struct Layout {
   int cu = 1, vf = 1, is_double = 1, blocks = 0;
@@ -43,6 +46,12 @@ struct Layout {
   uint32_t *rowmap = nullptr;       // rank -> row id; the compact form of empty_rows_bitmap
   ChunkMeta *chunks = nullptr;
   uint64_t n_chunks = 0;
+  // Warps walk runs of 2^run_log2 consecutive chunks (carry in registers inside a run, atomics across runs).
+  int run_log2 = 3;
+  // Rows that must be zero before the kernel runs: rows no chunk writes (empty rows), rows updated with atomics
+  // (several column blocks, or split across a run boundary).  zero_all: too many to list -> clear all of y.
+  std::vector<uint32_t> zero_rows;
+  bool zero_all = true;
 
   ~Layout();
 };

@@ -105,6 +105,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   // ---- pass 1: per (thread, block) counts of non-empty (row, block) pairs and padded entries (csr_hw.cpp:87-119)
   const size_t TB = (size_t)T * blocks;
   std::vector<uint64_t> pairs_t(TB, 0), zpad_t(TB, 0);
+  std::vector<uint8_t> rowkind(rows, 0);  // column blocks touched by the row: 0 = none, 1 = one, 2 = several
   int bad_col = 0;
 #pragma omp parallel num_threads(T)
   {
@@ -119,6 +120,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
         if (cnt[b]++ == 0) touched.push_back(b);
       }
       for (uint32_t b : touched) { pt[b]++; zt[b] += round_up(cnt[b], (uint32_t)vf); cnt[b] = 0; }
+      rowkind[r] = touched.size() > 1 ? 2 : (uint8_t)touched.size();
       touched.clear();
     }
   }
@@ -289,8 +291,11 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
         }
         L->rowmap[rank[b]] = r;
         // chunks whose first entry lies inside this segment start at this rank
-        for (uint64_t c = (s_e + kChunkEntries - 1) / kChunkEntries; c * kChunkEntries < t_e; c++)
-          L->chunks[L->piece_chunk0[bk] + c].rank0 = (uint32_t)rank[b];
+        for (uint64_t c = (s_e + kChunkEntries - 1) / kChunkEntries; c * kChunkEntries < t_e; c++) {
+          ChunkMeta &cm = L->chunks[L->piece_chunk0[bk] + c];
+          cm.rank0 = (uint32_t)rank[b];
+          if (c * kChunkEntries > s_e) cm.valid |= kChunkStartsMid;
+        }
         pos[b] = pstart + t_e;
         rank[b]++;
         cnt[b] = 0; fill[b] = 0;
@@ -312,6 +317,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   }
 
   // consecutive-rows fast path: rows of a block ascend, so first/last rank spanning equal row distance <=> consecutive
+  std::vector<uint64_t> piece_last_rank(KB, 0);
 #pragma omp parallel for schedule(static)
   for (int64_t bk = 0; bk < (int64_t)KB; bk++) {
     const int b = (int)(bk / cu);
@@ -321,7 +327,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     uint64_t last_piece_rank = 0;
     bool have = false;
     for (uint64_t c = c1; c > c0; c--)
-      if (L->chunks[c - 1].valid) { have = true; break; }
+      if (L->chunks[c - 1].valid & 0x3FFu) { have = true; break; }
     if (!have) continue;
     {
       // rank of the segment holding the last real entry = rank0 of a virtual chunk after the piece - 1:
@@ -331,13 +337,54 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
       uint64_t real_rows = L->nr_rows[(size_t)(bk % cu) * blocks + b];
       if ((int)(bk % cu) == cu - 1) real_rows -= pad_rows[b];
       last_piece_rank = L->rank_base[b] + rows_before + real_rows - 1;
+      piece_last_rank[bk] = last_piece_rank;
     }
     for (uint64_t c = c0; c < c1; c++) {
       ChunkMeta &m = L->chunks[c];
-      if (!m.valid) continue;
+      if (!(m.valid & 0x3FFu)) continue;
       m.row_first = L->rowmap[m.rank0];
-      uint64_t last_rank = (c + 1 < c1 && L->chunks[c + 1].valid) ? L->chunks[c + 1].rank0 : last_piece_rank;
+      uint64_t last_rank = (c + 1 < c1 && (L->chunks[c + 1].valid & 0x3FFu)) ? L->chunks[c + 1].rank0 : last_piece_rank;
       if ((uint64_t)L->rowmap[last_rank] - m.row_first == last_rank - m.rank0) m.valid |= kChunkRowsConsecutive;
+      bool sole = true;
+      for (uint64_t rk = m.rank0; rk <= last_rank && sole; rk++) sole = rowkind[L->rowmap[rk]] == 1;
+      if (sole) m.valid |= kChunkSole;
+    }
+  }
+
+  // Rows to clear before every SpMV (see Layout::zero_rows).  Marks are idempotent byte stores.
+  {
+    if (const char *e = getenv("SPMVB_RUN_LOG2")) L->run_log2 = std::max(0, std::min(8, atoi(e)));
+    const uint64_t R = 1ull << L->run_log2;
+    std::vector<uint8_t> needz(rows, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < (int64_t)rows; r++) needz[r] = rowkind[r] == 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t bk = 0; bk < (int64_t)KB; bk++) {
+      uint64_t c0 = L->piece_chunk0[bk];
+      uint64_t c1 = (bk + 1 < (int64_t)KB) ? L->piece_chunk0[bk + 1] : L->n_chunks;
+      for (uint64_t c = c0; c < c1; c++) {
+        const ChunkMeta &m = L->chunks[c];
+        if (!(m.valid & 0x3FFu)) continue;
+        if ((m.valid & kChunkStartsMid) && (c % R) == 0) needz[m.row_first] = 1;  // row split across two runs
+        if (m.valid & kChunkSole) continue;
+        // every row with a segment (or part of one) in an atomics-only chunk
+        uint64_t rk = m.rank0;
+        uint64_t end_rank;
+        if (c + 1 < c1 && (L->chunks[c + 1].valid & 0x3FFu))
+          end_rank = L->chunks[c + 1].rank0;  // inclusive: also covers a row that spills into the next chunk
+        else
+          end_rank = piece_last_rank[bk];
+        for (; rk <= end_rank; rk++) needz[L->rowmap[rk]] = 1;
+      }
+    }
+    uint64_t nz = 0;
+    for (uint32_t r = 0; r < rows; r++) nz += needz[r];
+    L->zero_all = nz > (uint64_t)rows / 3;
+    if (getenv("SPMVB_ZERO_ALL")) L->zero_all = true;
+    if (!L->zero_all) {
+      L->zero_rows.reserve(nz);
+      for (uint32_t r = 0; r < rows; r++)
+        if (needz[r]) L->zero_rows.push_back(r);
     }
   }
 
@@ -380,6 +427,10 @@ uint64_t spmvb_layout_real_nnz(const spmvb_layout *l) { return ((const Layout *)
 uint64_t spmvb_layout_padded_nnz(const spmvb_layout *l) { return ((const Layout *)l)->padded_nnz; }
 uint64_t spmvb_layout_pairs(const spmvb_layout *l) { return ((const Layout *)l)->n_pairs; }
 uint64_t spmvb_layout_stream_bytes(const spmvb_layout *l) { return ((const Layout *)l)->stream_bytes; }
+int64_t spmvb_layout_zero_rows(const spmvb_layout *l) {
+  const Layout *L = (const Layout *)l;
+  return L->zero_all ? -1 : (int64_t)L->zero_rows.size();
+}
 
 int spmvb_layout_piece_info(const spmvb_layout *l, int cu, int block, uint32_t *out) {
   const Layout *L = (const Layout *)l;

@@ -60,6 +60,16 @@ __device__ __forceinline__ uint32_t idx16(const uint4 &iw, int s) {
 __device__ __forceinline__ void y_add(double *p, double v) { atomicAdd(p, v); }
 __device__ __forceinline__ void y_add(float *p, float v) { atomicAdd(p, v); }
 
+// predicated variant: the RED is the only instruction under the predicate (no branch, no reconvergence barrier)
+__device__ __forceinline__ void y_add_if(double *p, double v, uint32_t e) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(e)
+               : "memory");
+}
+__device__ __forceinline__ void y_add_if(float *p, float v, uint32_t e) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"(e)
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -88,113 +98,165 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// bulk prefetch global -> L2 (no shared memory, no completion tracking): deepens the bytes in flight to DRAM beyond
+// what the shared-memory ring can hold
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One chunk for one warp: lane `lane` owns group `lane`.  iw / vw already hold the lane's index word and value
-// words.  XS: x slice addressable at xs[col] (global pointer to the block's slice, or shared memory).
-// `carry` (warp-uniform) is the open row sum entering the chunk; `open` says whether entries after the last
-// end-of-row bit exist (so a flush at the end of the warp's range is due).  Returns through references.
-template <typename VT, typename XS>
-__device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 *vw, const ChunkMeta &m, XS xs,
+// One chunk for one warp: lane `lane` owns group `lane`.  iw / vw hold the lane's index word and value words.
+// xs points at the column block's x slice (global or shared).  `carry` (warp-uniform) is the open row sum entering
+// the chunk; `open` says whether entries after the last end-of-row bit exist (a flush is due at the end of the
+// warp's range); `next_rank` is the rank of that open row.
+// FULLC: all 256 entries are real (no per-entry validity predicates) - every chunk but the last of a piece.
+template <typename VT, bool FULLC>
+__device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 *vw, const ChunkMeta &m, const VT *xv,
                                               const uint32_t *__restrict__ rowmap, VT *__restrict__ y, int lane,
-                                              VT &carry, bool &open, uint32_t &next_rank, bool &first_head_pending) {
+                                              VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red) {
   const uint32_t FULL = 0xFFFFFFFFu;
-  const uint32_t valid = m.valid & 0x3FFu;
   const bool consecutive = (m.valid & kChunkRowsConsecutive) != 0;
-  const int nvalid = min(8, max(0, (int)valid - lane * 8));
+  int nvalid = 8;
+  if (!FULLC) nvalid = min(8, max(0, (int)(m.valid & 0x3FFu) - lane * 8));
 
-  // end-of-row bits of this lane's valid entries
-  uint32_t eor = 0;
-#pragma unroll
-  for (int s = 0; s < 8; s++) eor |= ((idx16(iw, s) >> 15) & 1u) << s;
-  eor &= (1u << nvalid) - 1u;
+  // end-of-row bits: gather the high byte of the 8 slots, then compress bit 7 of each byte with a multiply
+  const uint32_t h0 = __byte_perm(iw.x, iw.y, 0x7531), h1 = __byte_perm(iw.z, iw.w, 0x7531);
+  uint32_t eor = ((((h0 >> 7) & 0x01010101u) * 0x01020408u) >> 24) | (((((h1 >> 7) & 0x01010101u) * 0x01020408u) >> 24) << 4);
+  eor &= FULLC ? 0xFFu : ((1u << nvalid) - 1u);
   const int n_eor = __popc(eor);
 
-  // exclusive prefix of n_eor across lanes -> rank of this lane's first segment end
+  // multiply by the gathered x (mul and add separately rounded, like the HLS cores: spmv.cpp:84-97)
+  VT prod[8];
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    if (FULLC) {
+      prod[s] = vmul(value_of<VT>(vw, s), xv[s]);
+    } else {
+      const bool ok = s < nvalid;
+      prod[s] = vmul(ok ? value_of<VT>(vw, s) : VT(0), ok ? xv[s] : VT(0));
+    }
+  }
+
+  // inclusive prefix of n_eor across lanes -> rank of this lane's first segment end
   int pre = n_eor;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    int o = __shfl_up_sync(FULL, pre, d);
+    const int o = __shfl_up_sync(FULL, pre, d);
     if (lane >= d) pre += o;
   }
   const int total_eor = __shfl_sync(FULL, pre, 31);
   const uint32_t rank_t = m.rank0 + (uint32_t)(pre - n_eor);
 
-  // gather + multiply; products of invalid slots are exactly 0
-  VT prod[8];
-#pragma unroll
-  for (int s = 0; s < 8; s++) {
-    const uint32_t ci = idx16(iw, s) & 0x7FFFu;
-    VT xv = (s < nvalid) ? xs[ci] : VT(0);
-    VT v = (s < nvalid) ? value_of<VT>(vw, s) : VT(0);
-    prod[s] = vmul(v, xv);
-  }
-
-  // per-lane sequential segmented sum (compute_results order inside a lane)
+  // branch-free per-lane running sums with resets after each end-of-row bit
+  VT seg[8];
   VT acc = (lane == 0) ? carry : VT(0);
-  VT head = VT(0);
-  bool seen = false;
-  int seg = 0;
 #pragma unroll
   for (int s = 0; s < 8; s++) {
     acc = vadd(acc, prod[s]);
-    if ((eor >> s) & 1u) {
-      if (!seen) {
-        head = acc;
-        seen = true;
-      } else {
-        const uint32_t rk = rank_t + (uint32_t)seg;
-        const uint32_t row = consecutive ? m.row_first + (rk - m.rank0) : rowmap[rk];
-        y_add(&y[row], acc);
-      }
-      seg++;
-      acc = VT(0);
-    }
+    seg[s] = acc;
+    acc = ((eor >> s) & 1u) ? VT(0) : acc;
   }
-
-  // warp segmented inclusive scan of the open tails; a lane with an end-of-row bit restarts the segment
-  VT v = acc;
-  bool f = seen;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    VT pv = __shfl_up_sync(FULL, v, d);
-    int pf = __shfl_up_sync(FULL, (int)f, d);
-    if (lane >= d && !f) {
-      v = vadd(pv, v);
-      f = pf != 0;
-    }
-  }
-  VT cin = __shfl_up_sync(FULL, v, 1);
-  if (lane == 0) cin = VT(0);  // lane 0 already absorbed `carry`
-
+  const bool seen = eor != 0;
   const uint32_t seen_mask = __ballot_sync(FULL, seen);
-  if (seen) {
-    const VT tot = vadd(cin, head);
-    const uint32_t row = consecutive ? m.row_first + (rank_t - m.rank0) : rowmap[rank_t];
-    (void)first_head_pending;
-    y_add(&y[row], tot);
+
+  // carry-in of every lane = open tails of the lanes before it back to the last lane that closed a row
+  VT cin;
+  if (seen_mask == FULL) {  // short rows: every lane closes at least one row
+    cin = __shfl_up_sync(FULL, acc, 1);
+    carry = __shfl_sync(FULL, acc, 31);
+  } else {
+    VT v = acc;
+    bool f = seen;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const VT pv = __shfl_up_sync(FULL, v, d);
+      const int pf = __shfl_up_sync(FULL, (int)f, d);
+      if (lane >= d && !f) {
+        v = vadd(pv, v);
+        f = pf != 0;
+      }
+    }
+    cin = __shfl_up_sync(FULL, v, 1);
+    carry = __shfl_sync(FULL, v, 31);
   }
-  carry = __shfl_sync(FULL, v, 31);
+  if (lane == 0) cin = VT(0);  // lane 0 already absorbed the incoming carry
+
+  // emit one y update per end-of-row bit; only the guarded RED sits under the predicate
+  // `sole` chunks (every row lives in one column block only) write y with plain stores: nothing else ever touches
+  // those rows, so they need no zero-fill and no read-modify-write.  The one exception is the chunk's first row when
+  // the run starts in the middle of it (head_red): the previous run flushed its share with an atomic.
+  const uint32_t upto_first = eor ^ (eor - 1u);  // bits 0..first end-of-row bit (all ones when eor == 0)
+  uint32_t redm = 0xFFu;
+  if (sole) redm = (head_red && seen && (seen_mask & ((1u << lane) - 1u)) == 0) ? (eor & (0u - eor)) : 0u;
+  if (seen_mask) head_red = false;  // the row the run started in is closed by this chunk
+  if (consecutive) {
+    uint32_t row = m.row_first + (rank_t - m.rank0);
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const uint32_t e = (eor >> s) & 1u;
+      const VT v = ((upto_first >> s) & 1u) ? vadd(cin, seg[s]) : seg[s];
+      if (e) {
+        if ((redm >> s) & 1u) y_add(y + row, v);
+        else y[row] = v;
+      }
+      row += e;
+    }
+  } else {
+    uint32_t rk = rank_t;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const uint32_t e = (eor >> s) & 1u;
+      const VT v = ((upto_first >> s) & 1u) ? vadd(cin, seg[s]) : seg[s];
+      if (e) {
+        const uint32_t row = rowmap[rk];
+        if ((redm >> s) & 1u) y_add(y + row, v);
+        else y[row] = v;
+      }
+      rk += e;
+    }
+  }
 
   // is a row still open after this chunk?
-  const int trail = nvalid - (eor ? (32 - __clz(eor)) : 0);  // valid entries after the lane's last end-of-row bit
-  const uint32_t trail_mask = __ballot_sync(FULL, trail > 0);
-  if (trail_mask | seen_mask) {
-    const int hi_trail = trail_mask ? 31 - __clz(trail_mask) : -1;
-    const int hi_seen = seen_mask ? 31 - __clz(seen_mask) : -1;
-    open = hi_trail >= 0 && hi_trail >= hi_seen;
+  if (FULLC) {
+    open = ((__shfl_sync(FULL, eor, 31) >> 7) & 1u) == 0;
+  } else {
+    const int trail = nvalid - (eor ? (32 - __clz(eor)) : 0);  // valid entries after the lane's last end-of-row bit
+    const uint32_t trail_mask = __ballot_sync(FULL, trail > 0);
+    if (trail_mask | seen_mask) {
+      const int hi_trail = trail_mask ? 31 - __clz(trail_mask) : -1;
+      const int hi_seen = seen_mask ? 31 - __clz(seen_mask) : -1;
+      open = hi_trail >= 0 && hi_trail >= hi_seen;
+    }
   }
   next_rank = m.rank0 + (uint32_t)total_eor;
 }
 
+// The 8 x gathers of a lane.  Index 0 of a zero-padded slot is a valid address (x holds blocks * cols_div_blocks
+// values), so the loads are unconditional and partial chunks mask the products instead.
+template <typename VT>
+__device__ __forceinline__ void gather_x(const uint4 &iw, const VT *__restrict__ x, uint32_t xbase, VT *xv) {
+#pragma unroll
+  for (int s = 0; s < 8; s++) xv[s] = x[xbase + (idx16(iw, s) & 0x7FFFu)];  // 32-bit element index: one IMAD.WIDE each
+}
+
+template <typename VT>
+__device__ __forceinline__ void process_any(const uint4 &iw, const uint4 *vw, const ChunkMeta &m, const VT *xv,
+                                            const uint32_t *__restrict__ rowmap, VT *__restrict__ y, int lane,
+                                            VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red) {
+  if ((m.valid & 0x3FFu) == (uint32_t)kChunkEntries)
+    process_chunk<VT, true>(iw, vw, m, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red);
+  else
+    process_chunk<VT, false>(iw, vw, m, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Variant DIRECT: every lane loads its group straight from global memory (5 / 3 x ld.global.v4).
-template <typename VT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <typename VT, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
     spmv_direct_kernel(const uint4 *__restrict__ stream, const ChunkMeta *__restrict__ meta,
                        const uint32_t *__restrict__ rowmap, const VT *__restrict__ x, VT *__restrict__ y,
                        unsigned long long n_chunks, uint32_t cdb) {
@@ -205,7 +267,7 @@ __global__ void __launch_bounds__(WARPS * 32)
   const unsigned long long W = (unsigned long long)gridDim.x * WARPS;
   const unsigned long long c0 = n_chunks * w / W, c1 = n_chunks * (w + 1) / W;
   VT carry = VT(0);
-  bool open = false, fhp = true;
+  bool open = false;
   uint32_t next_rank = 0;
   for (unsigned long long c = c0; c < c1; c++) {
     const uint4 mraw = __ldg(reinterpret_cast<const uint4 *>(meta) + c);
@@ -216,8 +278,10 @@ __global__ void __launch_bounds__(WARPS * 32)
     uint4 vw[VW];
 #pragma unroll
     for (int i = 0; i < VW; i++) vw[i] = __ldg(g + 1 + i);
-    const VT *xs = x + (size_t)m.block * cdb;
-    process_chunk<VT, const VT *>(iw, vw, m, xs, rowmap, y, lane, carry, open, next_rank, fhp);
+    VT xv[8];
+    gather_x<VT>(iw, x, m.block * cdb, xv);
+    bool head_red = false;
+    process_any<VT>(iw, vw, m, xv, rowmap, y, lane, carry, open, next_rank, false, head_red);
   }
   if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
 }
@@ -225,11 +289,28 @@ __global__ void __launch_bounds__(WARPS * 32)
 // ------------------------------------------------------------------------------------------------------------------
 // Variant RING: per-warp ring of STAGES chunks filled by cp.async.bulk (one elected lane issues, an mbarrier per
 // stage counts the bytes); lanes read their group with conflict-free LDS.128 (lane stride 80 B / 48 B).
-template <typename VT, int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32)
+// Software pipeline per warp, chunk i being summed while chunk i+1's x values are in flight:
+//   iteration i:  wait stage(i+1) -> LDS its index word -> issue its 8 x gathers (not consumed until i+1)
+//                 LDS chunk i's value words -> refill stage(i-1) with chunk i-1+STAGES -> segmented sums of chunk i
+template <typename VT>
+struct ChunkRegs {  // what is carried from the prefetch of a chunk to its processing
+  uint4 iw;
+  uint4 mraw;
+  VT xv[8];
+};
+
+// Chunk assignment: warp w of W walks runs of R = 2^run_log2 consecutive chunks, run q of the warp being global run
+// q*W + w.  All warps therefore sweep one contiguous window of the stream together (DRAM page locality; contiguous
+// per-warp ranges measured ~25 % slower), while inside a run the open row sum stays in registers.
+template <typename VT, int WARPS, int STAGES, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
     spmv_ring_kernel(const uint4 *__restrict__ stream, const ChunkMeta *__restrict__ meta,
                      const uint32_t *__restrict__ rowmap, const VT *__restrict__ x, VT *__restrict__ y,
-                     unsigned long long n_chunks, uint32_t cdb) {
+                     unsigned long long n_chunks, uint32_t cdb, uint32_t run_log2, uint32_t dbg) {
+  // dbg: bit 0 = no y updates, bit 1 = no x gathers (profiling experiments only); bit 2 = atomics everywhere
+  // (y += A x semantics: plain stores would overwrite the caller's y)
+  static_assert((STAGES & (STAGES - 1)) == 0 && STAGES >= 4,
+                "prefetch one chunk ahead + refill one chunk behind needs >= 3 stages (power of two: 4)");
   constexpr int GW = VTraits<VT>::kGroupWords;
   constexpr int VW = VTraits<VT>::kValWords;
   constexpr uint32_t CHUNK_BYTES = GW * 16 * 32;
@@ -240,7 +321,21 @@ __global__ void __launch_bounds__(WARPS * 32)
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)WARPS * STAGES * CHUNK_BYTES) + warp * STAGES;
   const unsigned long long w = (unsigned long long)blockIdx.x * WARPS + warp;
   const unsigned long long W = (unsigned long long)gridDim.x * WARPS;
-  const unsigned long long c0 = n_chunks * w / W, c1 = n_chunks * (w + 1) / W;
+  const uint32_t R = 1u << run_log2;
+  const unsigned long long total_runs = (n_chunks + R - 1) >> run_log2;
+  if (w >= total_runs) return;
+  const unsigned long long my_runs = (total_runs - w + W - 1) / W;
+  uint32_t n = (uint32_t)(my_runs << run_log2);  // chunks this warp walks
+  {
+    const unsigned long long last_run = (my_runs - 1) * W + w;  // a partial last run can only be the global last one
+    const unsigned long long over = ((last_run + 1) << run_log2);
+    if (over > n_chunks) n -= (uint32_t)(over - n_chunks);
+  }
+  // global chunk index of the warp's i-th chunk
+  auto chunk_of = [&](uint32_t i) -> unsigned long long {
+    return ((((unsigned long long)(i >> run_log2)) * W + w) << run_log2) + (i & (R - 1));
+  };
+  const bool force_red = (dbg & 4u) != 0;
 
   if (lane == 0) {
 #pragma unroll
@@ -251,40 +346,88 @@ __global__ void __launch_bounds__(WARPS * 32)
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; s++) {
-      if (c0 + s < c1) {
+      if ((uint32_t)s < n) {
         const uint32_t bar = smem_u32(&bars[s]);
         mbar_expect_tx(bar, CHUNK_BYTES);
-        bulk_g2s(smem_u32(ring + (size_t)s * CHUNK_BYTES), stream + (c0 + s) * 32 * GW, CHUNK_BYTES, bar);
+        bulk_g2s(smem_u32(ring + (size_t)s * CHUNK_BYTES), stream + chunk_of(s) * 32 * GW, CHUNK_BYTES, bar);
       }
     }
   }
+
   VT carry = VT(0);
-  bool open = false, fhp = true;
+  bool open = false, head_red = false;
   uint32_t next_rank = 0;
-  int stage = 0;
-  uint32_t parity = 0;
-  uint4 mraw = (c0 < c1) ? __ldg(reinterpret_cast<const uint4 *>(meta) + c0) : make_uint4(0, 0, 0, 0);
-  for (unsigned long long c = c0; c < c1; c++) {
-    ChunkMeta m;
-    m.rank0 = mraw.x; m.block = mraw.y; m.valid = mraw.z; m.row_first = mraw.w;
-    if (c + 1 < c1) mraw = __ldg(reinterpret_cast<const uint4 *>(meta) + c + 1);
-    const uint32_t bar = smem_u32(&bars[stage]);
-    mbar_wait(bar, parity);
+  const uint4 *mp = reinterpret_cast<const uint4 *>(meta);
+  uint4 m_ahead = __ldg(mp + chunk_of(0));  // meta of the next chunk to prefetch
+
+  // prefetch chunk i: its stage must have landed; leaves the gathers in flight
+  auto prefetch = [&](ChunkRegs<VT> &r, uint32_t i) {
+    r.mraw = m_ahead;
+    if (i + 1 < n) m_ahead = __ldg(mp + chunk_of(i + 1));
+    const uint32_t stage = i & (STAGES - 1);
+    mbar_wait(smem_u32(&bars[stage]), (i / STAGES) & 1u);
+    r.iw = *(reinterpret_cast<const uint4 *>(ring + (size_t)stage * CHUNK_BYTES) + lane * GW);
+    if (dbg & 2u) {
+#pragma unroll
+      for (int s = 0; s < 8; s++) r.xv[s] = VT(1);
+    } else {
+      gather_x<VT>(r.iw, x, r.mraw.y * cdb, r.xv);
+    }
+  };
+  // finish chunk i (prefetched into r) while `nx` receives chunk i+1
+  auto step = [&](ChunkRegs<VT> &r, ChunkRegs<VT> &nx, uint32_t i) {
+    if (i + 1 < n) prefetch(nx, i + 1);
+    const uint32_t stage = i & (STAGES - 1);
     const uint4 *g = reinterpret_cast<const uint4 *>(ring + (size_t)stage * CHUNK_BYTES) + lane * GW;
-    uint4 iw = g[0];
     uint4 vw[VW];
 #pragma unroll
-    for (int i = 0; i < VW; i++) vw[i] = g[1 + i];
-    __syncwarp();  // every lane has its group in registers: the stage may be refilled
-    if (lane == 0 && c + STAGES < c1) {
-      mbar_expect_tx(bar, CHUNK_BYTES);
-      bulk_g2s(smem_u32(ring + (size_t)stage * CHUNK_BYTES), stream + (c + STAGES) * 32 * GW, CHUNK_BYTES, bar);
+    for (int k = 0; k < VW; k++) vw[k] = g[1 + k];
+    // Refill the stage consumed in the PREVIOUS iteration: its registers went through process_chunk, whose warp
+    // shuffles order every lane's LDS before this point.  (Refilling the stage just read is a race: the bulk copy
+    // runs in the async proxy and can overtake LDS still queued in the LSU - seen as rare wrong rows on B200.)
+    __syncwarp();
+    if (lane == 0 && i >= 1 && i - 1 + STAGES < n) {
+      const uint32_t ps = (i - 1) & (STAGES - 1);
+      const uint32_t pbar = smem_u32(&bars[ps]);
+      mbar_expect_tx(pbar, CHUNK_BYTES);
+      bulk_g2s(smem_u32(ring + (size_t)ps * CHUNK_BYTES), stream + chunk_of(i - 1 + STAGES) * 32 * GW, CHUNK_BYTES, pbar);
     }
-    if (++stage == STAGES) { stage = 0; parity ^= 1; }
-    const VT *xs = x + (size_t)m.block * cdb;
-    process_chunk<VT, const VT *>(iw, vw, m, xs, rowmap, y, lane, carry, open, next_rank, fhp);
+    ChunkMeta m;
+    m.rank0 = r.mraw.x; m.block = r.mraw.y; m.valid = r.mraw.z; m.row_first = r.mraw.w;
+    const bool run_start = (i & (R - 1)) == 0;
+    const bool run_end = (i & (R - 1)) == R - 1 || i + 1 == n;
+    if (dbg & 1u) {  // consume the registers without touching y
+      VT t = VT(0);
+#pragma unroll
+      for (int s = 0; s < 8; s++) t = vadd(t, vmul(value_of<VT>(vw, s), r.xv[s]));
+      if (t == VT(123.456) && r.iw.x == 0x12345u) y_add(&y[0], t);
+    } else {
+      const bool sole = (m.valid & kChunkSole) != 0 && !force_red;
+      if (run_start) head_red = (m.valid & kChunkStartsMid) != 0;  // stays set until the run's first row end
+      process_any<VT>(r.iw, vw, m, r.xv, rowmap, y, lane, carry, open, next_rank, sole, head_red);
+      if (run_end) {  // the row left open continues in another warp's run: hand over through an atomic
+        if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
+        carry = VT(0);
+        open = false;
+      }
+    }
+  };
+
+  ChunkRegs<VT> A, B;
+  prefetch(A, 0);
+  uint32_t i = 0;
+  for (; i + 1 < n; i += 2) {  // two chunks per trip: the register sets swap roles without moves
+    step(A, B, i);
+    step(B, A, i + 1);
   }
-  if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
+  if (i < n) step(A, B, i);
+}
+
+// y[rows[i]] = 0 for the rows that receive atomics or no update at all (Layout::zero_rows)
+template <typename VT>
+__global__ void zero_rows_kernel(VT *__restrict__ y, const uint32_t *__restrict__ rows, uint32_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[rows[i]] = VT(0);
 }
 
 // zero-fill / scale helpers for the iterated caller

@@ -33,6 +33,7 @@ SYMBOLS = {
     "spmvb_layout_padded_nnz": (_u64, [_vp]),
     "spmvb_layout_pairs": (_u64, [_vp]),
     "spmvb_layout_stream_bytes": (_u64, [_vp]),
+    "spmvb_layout_zero_rows": (ctypes.c_int64, [_vp]),
     "spmvb_layout_piece_info": (_int, [_vp, _int, _int, _vp]),
     "spmvb_layout_piece_words": (_vp, [_vp, _int, _int]),
     "spmvb_layout_bitmap_row": (_int, [_vp, _int, _vp]),
@@ -209,6 +210,7 @@ class Layout:
         self.padded_nnz = L.spmvb_layout_padded_nnz(self.h)
         self.pairs = L.spmvb_layout_pairs(self.h)
         self.stream_bytes = L.spmvb_layout_stream_bytes(self.h)
+        self.zero_rows = L.spmvb_layout_zero_rows(self.h)
 
     @staticmethod
     def build(rows, cols, row_ptr, col_ind, values, n_cu=1, vf=1, is_double=True, cols_div_blocks=0):
