@@ -17,7 +17,7 @@
 
 namespace spmvb {
 
-enum Variant { kVariantDefault = 0, kVariantDirect = 1, kVariantRing = 2, kVariantXsmem = 3 };
+enum Variant { kVariantDefault = 0, kVariantDirect = 1, kVariantRing = 2, kVariantOcc4 = 6, kVariantOcc3 = 7 };
 
 struct Engine {
   int device = 0, is_double = 1, vb = 8, variant = kVariantRing;
@@ -25,7 +25,6 @@ struct Engine {
   int blocks = 0;
   uint64_t real_nnz = 0, n_chunks = 0, n_pairs = 0, stream_bytes = 0, x_len = 0;
   uint8_t *d_stream = nullptr;
-  ChunkMeta *d_chunks = nullptr;
   uint32_t *d_rowmap = nullptr;
   uint32_t *d_zero_rows = nullptr;
   uint32_t n_zero_rows = 0, run_log2 = 2;
@@ -53,14 +52,15 @@ struct Engine {
       return fail(SPMVB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
   } while (0)
 
-// Kernel variants (spmvb_engine_set_variant): 1 = DIRECT (ld.global per lane, no prefetch); RING (TMA ring + x prefetch)
-// with (stages per warp, min CTAs/SM): 2 = (4, 2) default, 4 = (4, 3), 5 = (2, 3).  0 = default.
+// Kernel variants (spmvb_engine_set_variant): 0 = default (= 7); 1 = DIRECT (ld.global per lane, contiguous chunk
+// ranges, atomics only); 2 = RING (4-stage TMA ring + x prefetched one chunk ahead in registers, 2 CTAs/SM);
+// 5 = RING with 3 CTAs/SM (spills); 6 / 7 = OCC (2-stage TMA ring, no register prefetch, 4 / 3 CTAs per SM).
 template <typename VT, int STAGES, int MINB>
 static int launch_ring(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
   constexpr int WARPS = 8;
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
   auto kern = spmv_ring_kernel<VT, WARPS, STAGES, MINB>;
-  const size_t smem = (size_t)WARPS * STAGES * (VTraits<VT>::kGroupWords * 16 * 32) + (size_t)WARPS * STAGES * 8;
+  const size_t smem = (size_t)WARPS * STAGES * (VTraits<VT>::kGroupWords * 16 * 32 + 16) + (size_t)WARPS * STAGES * 8;
   int &grid = E->grid_cache[slot][sizeof(VT) == 8];
   if (grid == 0) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -68,8 +68,26 @@ static int launch_ring(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot,
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     grid = E->sms * std::max(per_sm, 1);
   }
-  kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_chunks, E->d_rowmap, x, y, E->n_chunks, E->cdb, E->run_log2,
-                                       E->dbg | (accumulate ? 4u : 0u));
+  kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_rowmap, x, y, (uint32_t)E->n_chunks, E->cdb, E->run_log2,
+                                       accumulate ? 4u : 0u);
+  return SPMVB_OK;
+}
+
+template <typename VT, int MINB>
+static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
+  constexpr int WARPS = 8;
+  const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
+  auto kern = spmv_occ_kernel<VT, WARPS, MINB>;
+  const size_t smem = (size_t)WARPS * 2 * (VTraits<VT>::kGroupWords * 16 * 32 + 16) + (size_t)WARPS * 2 * 8;
+  int &grid = E->grid_cache[slot][sizeof(VT) == 8];
+  if (grid == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    grid = E->sms * std::max(per_sm, 1);
+  }
+  kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_rowmap, x, y, (uint32_t)E->n_chunks, E->cdb, E->run_log2,
+                                       accumulate ? 4u : 0u);
   return SPMVB_OK;
 }
 
@@ -77,8 +95,9 @@ template <typename VT>
 static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
   constexpr int WARPS = 8;
-  int variant = E->variant == kVariantDefault ? kVariantRing : E->variant;
+  int variant = E->variant == kVariantDefault ? kVariantOcc3 : E->variant;
   if (E->n_chunks == 0) return SPMVB_OK;
+  if (E->n_chunks >= 0x7FFFFFFFull) return fail(SPMVB_E_RANGE, "too many chunks for one engine");
   int rc = SPMVB_OK;
   if (variant == kVariantDirect) {
     auto kern = spmv_direct_kernel<VT, WARPS, 4>;
@@ -88,7 +107,11 @@ static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accum
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, 0));
       grid = E->sms * std::max(per_sm, 1);
     }
-    kern<<<grid, WARPS * 32, 0, st>>>(stream, E->d_chunks, E->d_rowmap, x, y, E->n_chunks, E->cdb);
+    kern<<<grid, WARPS * 32, 0, st>>>(stream, E->d_rowmap, x, y, E->n_chunks, E->cdb);
+  } else if (variant == 6) {
+    rc = launch_occ<VT, 4>(E, x, y, st, 6, accumulate);
+  } else if (variant == 7) {
+    rc = launch_occ<VT, 3>(E, x, y, st, 7, accumulate);
   } else if (variant == 5) {
     rc = launch_ring<VT, 4, 3>(E, x, y, st, 5, accumulate);
   } else {
@@ -102,7 +125,7 @@ static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accum
 
 // y = A x needs y prepared only where the kernel uses atomics or writes nothing: either the listed rows or all of y
 static int zero_y(Engine *E, void *y, cudaStream_t st) {
-  const int variant = E->variant == kVariantDefault ? kVariantRing : E->variant;
+  const int variant = E->variant == kVariantDefault ? kVariantOcc3 : E->variant;
   if (E->zero_all || variant == kVariantDirect) {
     CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)E->rows * E->vb, st));
   } else if (E->n_zero_rows) {
@@ -156,8 +179,10 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   cudaError_t e = cudaSuccess;
   auto chk = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; };
   chk(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
-  chk(cudaMalloc((void **)&E->d_stream, std::max<uint64_t>(L->stream_bytes, 16)));
-  chk(cudaMalloc((void **)&E->d_chunks, std::max<uint64_t>(L->n_chunks, 1) * sizeof(ChunkMeta)));
+  // device image: one slot per chunk = the chunk's words (bit-exact hw_matrix bytes) followed by its 16-byte ChunkMeta,
+  // so that a single bulk copy brings both into shared memory
+  const size_t slot = (size_t)L->chunk_bytes + sizeof(ChunkMeta);
+  chk(cudaMalloc((void **)&E->d_stream, std::max<uint64_t>(L->n_chunks * slot, 16)));
   chk(cudaMalloc((void **)&E->d_rowmap, (std::max<uint64_t>(L->n_pairs, 1) + 1) * 4));
   E->zero_all = L->zero_all; E->n_zero_rows = (uint32_t)L->zero_rows.size(); E->run_log2 = (uint32_t)L->run_log2;
   chk(cudaMalloc((void **)&E->d_zero_rows, std::max<size_t>(L->zero_rows.size(), 1) * 4));
@@ -165,8 +190,12 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   chk(cudaMalloc(&E->d_y, (size_t)E->rows * E->vb));
   chk(cudaMalloc((void **)&E->d_scalar, 64));
   if (e == cudaSuccess) {
-    chk(cudaMemcpyAsync(E->d_stream, L->stream, L->stream_bytes, cudaMemcpyHostToDevice, E->stream));
-    chk(cudaMemcpyAsync(E->d_chunks, L->chunks, L->n_chunks * sizeof(ChunkMeta), cudaMemcpyHostToDevice, E->stream));
+    if (L->n_chunks) {
+      chk(cudaMemcpy2DAsync(E->d_stream, slot, L->stream, L->chunk_bytes, L->chunk_bytes, L->n_chunks,
+                            cudaMemcpyHostToDevice, E->stream));
+      chk(cudaMemcpy2DAsync(E->d_stream + L->chunk_bytes, slot, L->chunks, sizeof(ChunkMeta), sizeof(ChunkMeta),
+                            L->n_chunks, cudaMemcpyHostToDevice, E->stream));
+    }
     chk(cudaMemcpyAsync(E->d_rowmap, L->rowmap, L->n_pairs * 4, cudaMemcpyHostToDevice, E->stream));
     chk(cudaMemcpyAsync(E->d_zero_rows, L->zero_rows.data(), L->zero_rows.size() * 4, cudaMemcpyHostToDevice, E->stream));
     chk(cudaMemsetAsync(E->d_x, 0, E->x_len * E->vb, E->stream));
@@ -187,7 +216,7 @@ void spmvb_engine_free(spmvb_engine *e) {
   if (!E) return;
   cudaSetDevice(E->device);
   if (E->stream) cudaStreamSynchronize(E->stream);
-  cudaFree(E->d_stream); cudaFree(E->d_chunks); cudaFree(E->d_rowmap); cudaFree(E->d_zero_rows);
+  cudaFree(E->d_stream); cudaFree(E->d_rowmap); cudaFree(E->d_zero_rows);
   cudaFree(E->d_x); cudaFree(E->d_y); cudaFree(E->d_scalar); cudaFree(E->d_flush);
   if (E->h_stage) cudaFreeHost(E->h_stage);
   for (auto &x : E->ev) cudaEventDestroy(x);

@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "layout.h"
 
 namespace spmvb {
@@ -109,56 +111,53 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One chunk for one warp: lane `lane` owns group `lane`.  iw / vw hold the lane's index word and value words.
-// xs points at the column block's x slice (global or shared).  `carry` (warp-uniform) is the open row sum entering
-// the chunk; `open` says whether entries after the last end-of-row bit exist (a flush is due at the end of the
-// warp's range); `next_rank` is the rank of that open row.
-// FULLC: all 256 entries are real (no per-entry validity predicates) - every chunk but the last of a piece.
-template <typename VT, bool FULLC>
-__device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 *vw, const ChunkMeta &m, const VT *xv,
+// One chunk for one warp: lane `lane` owns group `lane`.  iw holds the lane's index word, vw its value words and xv
+// its 8 gathered x values (MUL) or its 8 products value * x[col] (!MUL, vw unused).  Warp-uniform state threaded through the chunks of a run:
+//   carry      open row sum entering the chunk (absorbed by lane 0)
+//   open       entries after the last end-of-row bit exist (a hand-over is due at the end of the run)
+//   next_rank  rank of that open row
+//   head_red   the run began in the middle of a row: that row's end must be an atomic even in a `sole` chunk
+// A chunk with fewer than 256 real entries is the last one of its piece: only its end-of-row bits need masking (the
+// padding slots follow every real entry of their lane, so they never reach a row sum that is written) and it always
+// ends closed.  `consec`: the chunk's rows are row_first, row_first + 1, ... (no row-map loads).
+// `sole` chunks (every row lives in one column block only) write y with plain stores: nothing else ever touches
+// those rows, so they need no zero-fill and no read-modify-write.
+template <typename VT, bool MUL>
+__device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw, const uint4 *vw, const VT *xv,
                                               const uint32_t *__restrict__ rowmap, VT *__restrict__ y, int lane,
                                               VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red) {
   const uint32_t FULL = 0xFFFFFFFFu;
-  const bool consecutive = (m.valid & kChunkRowsConsecutive) != 0;
-  int nvalid = 8;
-  if (!FULLC) nvalid = min(8, max(0, (int)(m.valid & 0x3FFu) - lane * 8));
+  const uint32_t rank0 = mraw.x, valid = mraw.z & 0x3FFu, row_first = mraw.w;
+  const bool consec = (mraw.z & kChunkRowsConsecutive) != 0;
+  const bool partial = valid != (uint32_t)kChunkEntries;
 
   // end-of-row bits: gather the high byte of the 8 slots, then compress bit 7 of each byte with a multiply
   const uint32_t h0 = __byte_perm(iw.x, iw.y, 0x7531), h1 = __byte_perm(iw.z, iw.w, 0x7531);
-  uint32_t eor = ((((h0 >> 7) & 0x01010101u) * 0x01020408u) >> 24) | (((((h1 >> 7) & 0x01010101u) * 0x01020408u) >> 24) << 4);
-  eor &= FULLC ? 0xFFu : ((1u << nvalid) - 1u);
+  uint32_t eor = ((((h0 >> 7) & 0x01010101u) * 0x01020408u) >> 24) | (((((h1 >> 7) & 0x01010101u) * 0x01020408u) >> 20) & 0xF0u);
+  if (partial) eor &= (1u << min(8, max(0, (int)valid - lane * 8))) - 1u;
   const int n_eor = __popc(eor);
 
-  // multiply by the gathered x (mul and add separately rounded, like the HLS cores: spmv.cpp:84-97)
-  VT prod[8];
-#pragma unroll
-  for (int s = 0; s < 8; s++) {
-    if (FULLC) {
-      prod[s] = vmul(value_of<VT>(vw, s), xv[s]);
-    } else {
-      const bool ok = s < nvalid;
-      prod[s] = vmul(ok ? value_of<VT>(vw, s) : VT(0), ok ? xv[s] : VT(0));
-    }
-  }
-
-  // inclusive prefix of n_eor across lanes -> rank of this lane's first segment end
+  // inclusive prefix of n_eor across lanes -> rank of this lane's first row end
   int pre = n_eor;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const int o = __shfl_up_sync(FULL, pre, d);
     if (lane >= d) pre += o;
   }
-  const int total_eor = __shfl_sync(FULL, pre, 31);
-  const uint32_t rank_t = m.rank0 + (uint32_t)(pre - n_eor);
+  const uint32_t total_eor = (uint32_t)__shfl_sync(FULL, pre, 31);
+  const uint32_t rank_t = rank0 + (uint32_t)(pre - n_eor);
 
-  // branch-free per-lane running sums with resets after each end-of-row bit
+  // per-lane running sums of the products that restart after each end-of-row bit (add separately rounded from the
+  // multiply, like the HLS cores: spmv.cpp:84-97)
   VT seg[8];
   VT acc = (lane == 0) ? carry : VT(0);
 #pragma unroll
   for (int s = 0; s < 8; s++) {
-    acc = vadd(acc, prod[s]);
+    // MUL: xv holds the gathered x values and the multiply happens here, after the index work and the rank
+    // shuffles above, which gives the gathers that much more time to land; otherwise xv already holds products
+    acc = vadd(acc, MUL ? vmul(value_of<VT>(vw, s), xv[s]) : xv[s]);
     seg[s] = acc;
-    acc = ((eor >> s) & 1u) ? VT(0) : acc;
+    if ((eor >> s) & 1u) acc = VT(0);
   }
   const bool seen = eor != 0;
   const uint32_t seen_mask = __ballot_sync(FULL, seen);
@@ -185,79 +184,75 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 *vw, 
   }
   if (lane == 0) cin = VT(0);  // lane 0 already absorbed the incoming carry
 
-  // emit one y update per end-of-row bit; only the guarded RED sits under the predicate
-  // `sole` chunks (every row lives in one column block only) write y with plain stores: nothing else ever touches
-  // those rows, so they need no zero-fill and no read-modify-write.  The one exception is the chunk's first row when
-  // the run starts in the middle of it (head_red): the previous run flushed its share with an atomic.
-  const uint32_t upto_first = eor ^ (eor - 1u);  // bits 0..first end-of-row bit (all ones when eor == 0)
+  const uint32_t first_bit = eor & (0u - eor);  // the lane's first row end also closes what earlier lanes left open
+
+  // which row ends must be atomics: all of them unless the chunk is `sole`; then only the run's dangling first row
   uint32_t redm = 0xFFu;
-  if (sole) redm = (head_red && seen && (seen_mask & ((1u << lane) - 1u)) == 0) ? (eor & (0u - eor)) : 0u;
+  if (sole) redm = (head_red && (seen_mask & ((2u << lane) - 1u)) == (1u << lane)) ? first_bit : 0u;
   if (seen_mask) head_red = false;  // the row the run started in is closed by this chunk
-  if (consecutive) {
-    uint32_t row = m.row_first + (rank_t - m.rank0);
+
+  // Two copies of the emission loop on purpose: with a single loop and `consec ? row : rowmap[row]` the compiler
+  // emits a predicated-off LDG whose scoreboard slot is shared with the x gathers already in flight for the next
+  // chunk, and every store then waits for them (measured: +20 % kernel time).
+  if (consec) {
+    uint32_t row = row_first + (rank_t - rank0);
 #pragma unroll
     for (int s = 0; s < 8; s++) {
-      const uint32_t e = (eor >> s) & 1u;
-      const VT v = ((upto_first >> s) & 1u) ? vadd(cin, seg[s]) : seg[s];
-      if (e) {
+      if ((eor >> s) & 1u) {
+        VT v = seg[s];
+        if ((first_bit >> s) & 1u) v = vadd(cin, v);
         if ((redm >> s) & 1u) y_add(y + row, v);
         else y[row] = v;
+        row++;
       }
-      row += e;
     }
   } else {
     uint32_t rk = rank_t;
 #pragma unroll
     for (int s = 0; s < 8; s++) {
-      const uint32_t e = (eor >> s) & 1u;
-      const VT v = ((upto_first >> s) & 1u) ? vadd(cin, seg[s]) : seg[s];
-      if (e) {
+      if ((eor >> s) & 1u) {
         const uint32_t row = rowmap[rk];
+        VT v = seg[s];
+        if ((first_bit >> s) & 1u) v = vadd(cin, v);
         if ((redm >> s) & 1u) y_add(y + row, v);
         else y[row] = v;
+        rk++;
       }
-      rk += e;
     }
   }
 
-  // is a row still open after this chunk?
-  if (FULLC) {
-    open = ((__shfl_sync(FULL, eor, 31) >> 7) & 1u) == 0;
-  } else {
-    const int trail = nvalid - (eor ? (32 - __clz(eor)) : 0);  // valid entries after the lane's last end-of-row bit
-    const uint32_t trail_mask = __ballot_sync(FULL, trail > 0);
-    if (trail_mask | seen_mask) {
-      const int hi_trail = trail_mask ? 31 - __clz(trail_mask) : -1;
-      const int hi_seen = seen_mask ? 31 - __clz(seen_mask) : -1;
-      open = hi_trail >= 0 && hi_trail >= hi_seen;
-    }
-  }
-  next_rank = m.rank0 + (uint32_t)total_eor;
+  // is a row still open after this chunk?  (a partial chunk ends its piece, and pieces end on a row end)
+  open = !partial && ((__shfl_sync(FULL, eor, 31) >> 7) & 1u) == 0;
+  if (partial) carry = VT(0);
+  next_rank = rank0 + total_eor;
 }
 
 // The 8 x gathers of a lane.  Index 0 of a zero-padded slot is a valid address (x holds blocks * cols_div_blocks
 // values), so the loads are unconditional and partial chunks mask the products instead.
+// The loads are volatile asm so that they stay where they are written: issued one chunk ahead of their use.  (As plain
+// loads the compiler sank them to the multiply when registers got tight, which silently removed the prefetch.)
+__device__ __forceinline__ double ldg_x(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_x(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 template <typename VT>
 __device__ __forceinline__ void gather_x(const uint4 &iw, const VT *__restrict__ x, uint32_t xbase, VT *xv) {
 #pragma unroll
-  for (int s = 0; s < 8; s++) xv[s] = x[xbase + (idx16(iw, s) & 0x7FFFu)];  // 32-bit element index: one IMAD.WIDE each
-}
-
-template <typename VT>
-__device__ __forceinline__ void process_any(const uint4 &iw, const uint4 *vw, const ChunkMeta &m, const VT *xv,
-                                            const uint32_t *__restrict__ rowmap, VT *__restrict__ y, int lane,
-                                            VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red) {
-  if ((m.valid & 0x3FFu) == (uint32_t)kChunkEntries)
-    process_chunk<VT, true>(iw, vw, m, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red);
-  else
-    process_chunk<VT, false>(iw, vw, m, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red);
+  for (int s = 0; s < 8; s++) xv[s] = ldg_x(x + (xbase + (idx16(iw, s) & 0x7FFFu)));  // 32-bit element index
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Variant DIRECT: every lane loads its group straight from global memory (5 / 3 x ld.global.v4).
+// Variant DIRECT: every lane loads its group straight from global memory (5 / 3 x ld.global.v4); contiguous chunk
+// range per warp, atomics for every row end.  Kept as the simple baseline the RING kernel is measured against.
 template <typename VT, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-    spmv_direct_kernel(const uint4 *__restrict__ stream, const ChunkMeta *__restrict__ meta,
+    spmv_direct_kernel(const uint4 *__restrict__ stream,
                        const uint32_t *__restrict__ rowmap, const VT *__restrict__ x, VT *__restrict__ y,
                        unsigned long long n_chunks, uint32_t cdb) {
   constexpr int GW = VTraits<VT>::kGroupWords;
@@ -270,18 +265,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   bool open = false;
   uint32_t next_rank = 0;
   for (unsigned long long c = c0; c < c1; c++) {
-    const uint4 mraw = __ldg(reinterpret_cast<const uint4 *>(meta) + c);
-    ChunkMeta m;
-    m.rank0 = mraw.x; m.block = mraw.y; m.valid = mraw.z; m.row_first = mraw.w;
-    const uint4 *g = stream + (c * 32 + lane) * GW;
+    const uint4 *slot = stream + c * (32 * GW + 1);  // device slot = chunk words + its ChunkMeta
+    const uint4 mraw = __ldg(slot + 32 * GW);
+    const uint4 *g = slot + lane * GW;
     uint4 iw = __ldg(g);
     uint4 vw[VW];
 #pragma unroll
     for (int i = 0; i < VW; i++) vw[i] = __ldg(g + 1 + i);
     VT xv[8];
-    gather_x<VT>(iw, x, m.block * cdb, xv);
+    gather_x<VT>(iw, x, mraw.y * cdb, xv);
     bool head_red = false;
-    process_any<VT>(iw, vw, m, xv, rowmap, y, lane, carry, open, next_rank, false, head_red);
+    process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, false, head_red);
   }
   if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
 }
@@ -292,135 +286,215 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 // Software pipeline per warp, chunk i being summed while chunk i+1's x values are in flight:
 //   iteration i:  wait stage(i+1) -> LDS its index word -> issue its 8 x gathers (not consumed until i+1)
 //                 LDS chunk i's value words -> refill stage(i-1) with chunk i-1+STAGES -> segmented sums of chunk i
-template <typename VT>
-struct ChunkRegs {  // what is carried from the prefetch of a chunk to its processing
-  uint4 iw;
-  uint4 mraw;
-  VT xv[8];
-};
-
 // Chunk assignment: warp w of W walks runs of R = 2^run_log2 consecutive chunks, run q of the warp being global run
 // q*W + w.  All warps therefore sweep one contiguous window of the stream together (DRAM page locality; contiguous
 // per-warp ranges measured ~25 % slower), while inside a run the open row sum stays in registers.
 template <typename VT, int WARPS, int STAGES, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-    spmv_ring_kernel(const uint4 *__restrict__ stream, const ChunkMeta *__restrict__ meta,
+    spmv_ring_kernel(const uint4 *__restrict__ stream,
                      const uint32_t *__restrict__ rowmap, const VT *__restrict__ x, VT *__restrict__ y,
-                     unsigned long long n_chunks, uint32_t cdb, uint32_t run_log2, uint32_t dbg) {
-  // dbg: bit 0 = no y updates, bit 1 = no x gathers (profiling experiments only); bit 2 = atomics everywhere
-  // (y += A x semantics: plain stores would overwrite the caller's y)
+                     uint32_t n_chunks, uint32_t cdb, uint32_t run_log2, uint32_t flags) {
+  // flags bit 2: atomics everywhere (y += A x semantics: plain stores would overwrite the caller's y)
   static_assert((STAGES & (STAGES - 1)) == 0 && STAGES >= 4,
                 "prefetch one chunk ahead + refill one chunk behind needs >= 3 stages (power of two: 4)");
   constexpr int GW = VTraits<VT>::kGroupWords;
   constexpr int VW = VTraits<VT>::kValWords;
   constexpr uint32_t CHUNK_BYTES = GW * 16 * 32;
+  constexpr uint32_t SLOT = CHUNK_BYTES + 16;  // a device slot: the chunk's words followed by its ChunkMeta
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  uint8_t *ring = smem + (size_t)warp * STAGES * CHUNK_BYTES;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)WARPS * STAGES * CHUNK_BYTES) + warp * STAGES;
-  const unsigned long long w = (unsigned long long)blockIdx.x * WARPS + warp;
-  const unsigned long long W = (unsigned long long)gridDim.x * WARPS;
+  const uint32_t ring = smem_u32(smem) + (uint32_t)warp * STAGES * SLOT;   // shared-window addresses
+  const uint32_t bars = smem_u32(smem) + WARPS * STAGES * SLOT + (uint32_t)warp * STAGES * 8;
+  const uint32_t my = ring + lane * (GW * 16);                                    // this lane's group in stage 0
+  const uint32_t w = blockIdx.x * WARPS + warp, W = gridDim.x * WARPS;
   const uint32_t R = 1u << run_log2;
-  const unsigned long long total_runs = (n_chunks + R - 1) >> run_log2;
+  const uint32_t total_runs = (n_chunks + R - 1) >> run_log2;
   if (w >= total_runs) return;
-  const unsigned long long my_runs = (total_runs - w + W - 1) / W;
-  uint32_t n = (uint32_t)(my_runs << run_log2);  // chunks this warp walks
+  const uint32_t my_runs = (total_runs - w + W - 1) / W;
+  uint32_t n = my_runs << run_log2;  // chunks this warp walks
   {
-    const unsigned long long last_run = (my_runs - 1) * W + w;  // a partial last run can only be the global last one
-    const unsigned long long over = ((last_run + 1) << run_log2);
-    if (over > n_chunks) n -= (uint32_t)(over - n_chunks);
+    const uint32_t over = ((my_runs - 1) * W + w + 1) << run_log2;  // a partial last run can only be the global last
+    if (over > n_chunks) n -= over - n_chunks;
   }
-  // global chunk index of the warp's i-th chunk
-  auto chunk_of = [&](uint32_t i) -> unsigned long long {
-    return ((((unsigned long long)(i >> run_log2)) * W + w) << run_log2) + (i & (R - 1));
+  const uint32_t jump = (W - 1) << run_log2;  // extra chunk distance when stepping from one run into the next
+  // global chunk index of the warp's (i + k)-th chunk, given ci = index of its i-th, for 0 <= k <= R
+  auto ahead = [&](uint32_t ci, uint32_t i, uint32_t k) -> uint32_t {
+    return ci + k + ((((i & (R - 1)) + k) >> run_log2) ? jump : 0u);
   };
-  const bool force_red = (dbg & 4u) != 0;
+  const bool force_red = (flags & 4u) != 0;
+  auto lds128 = [](uint32_t a) -> uint4 {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+  };
+  auto issue = [&](uint32_t stage, uint32_t chunk) {  // lane 0 only
+    const uint32_t bar = bars + stage * 8;
+    mbar_expect_tx(bar, SLOT);
+    bulk_g2s(ring + stage * SLOT, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar);
+  };
 
+  uint32_t c_cur = w << run_log2;  // global index of chunk i (i = 0)
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; s++) mbar_init(smem_u32(&bars[s]), 1);
+    for (int s = 0; s < STAGES; s++) mbar_init(bars + s * 8, 1);
     fence_barrier_init();
   }
   __syncwarp();
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; s++) {
-      if ((uint32_t)s < n) {
-        const uint32_t bar = smem_u32(&bars[s]);
-        mbar_expect_tx(bar, CHUNK_BYTES);
-        bulk_g2s(smem_u32(ring + (size_t)s * CHUNK_BYTES), stream + chunk_of(s) * 32 * GW, CHUNK_BYTES, bar);
-      }
-    }
+    for (int s = 0; s < STAGES; s++)
+      if ((uint32_t)s < n) issue(s, ahead(c_cur, 0, s));
   }
 
   VT carry = VT(0);
   bool open = false, head_red = false;
   uint32_t next_rank = 0;
-  const uint4 *mp = reinterpret_cast<const uint4 *>(meta);
-  uint4 m_ahead = __ldg(mp + chunk_of(0));  // meta of the next chunk to prefetch
 
-  // prefetch chunk i: its stage must have landed; leaves the gathers in flight
-  auto prefetch = [&](ChunkRegs<VT> &r, uint32_t i) {
-    r.mraw = m_ahead;
-    if (i + 1 < n) m_ahead = __ldg(mp + chunk_of(i + 1));
-    const uint32_t stage = i & (STAGES - 1);
-    mbar_wait(smem_u32(&bars[stage]), (i / STAGES) & 1u);
-    r.iw = *(reinterpret_cast<const uint4 *>(ring + (size_t)stage * CHUNK_BYTES) + lane * GW);
-    if (dbg & 2u) {
-#pragma unroll
-      for (int s = 0; s < 8; s++) r.xv[s] = VT(1);
-    } else {
-      gather_x<VT>(r.iw, x, r.mraw.y * cdb, r.xv);
+  // registers of the chunk being prefetched / processed: [i & 1]
+  uint4 iw[2], mr[2];
+  VT xv[2][8];
+  // prologue: prefetch chunk 0
+  {
+    mbar_wait(bars, 0);
+    mr[0] = lds128(ring + CHUNK_BYTES);
+    iw[0] = lds128(my);
+    gather_x<VT>(iw[0], x, mr[0].y * cdb, xv[0]);
+  }
+  // one pipeline step; CUR is a compile-time 0/1 so that the double-buffered registers are never indexed dynamically
+  auto step = [&](auto CUR, uint32_t i) {
+    constexpr int cur = decltype(CUR)::value, nxt = cur ^ 1;
+    // ---- prefetch chunk i+1: its stage has landed or is about to; leaves the 8 gathers in flight
+    if (i + 1 < n) {
+      const uint32_t st = (i + 1) & (STAGES - 1);
+      mbar_wait(bars + st * 8, ((i + 1) / STAGES) & 1u);
+      mr[nxt] = lds128(ring + st * SLOT + CHUNK_BYTES);  // the chunk's meta travels with it: no separate global load
+      iw[nxt] = lds128(my + st * SLOT);
+      gather_x<VT>(iw[nxt], x, mr[nxt].y * cdb, xv[nxt]);
     }
-  };
-  // finish chunk i (prefetched into r) while `nx` receives chunk i+1
-  auto step = [&](ChunkRegs<VT> &r, ChunkRegs<VT> &nx, uint32_t i) {
-    if (i + 1 < n) prefetch(nx, i + 1);
-    const uint32_t stage = i & (STAGES - 1);
-    const uint4 *g = reinterpret_cast<const uint4 *>(ring + (size_t)stage * CHUNK_BYTES) + lane * GW;
-    uint4 vw[VW];
+    // ---- values of chunk i and its products with the x values gathered one step ago
+    VT prod[8];
+    {
+      uint4 vw[VW];
+      const uint32_t a = my + (i & (STAGES - 1)) * SLOT + 16;
 #pragma unroll
-    for (int k = 0; k < VW; k++) vw[k] = g[1 + k];
+      for (int k = 0; k < VW; k++) vw[k] = lds128(a + k * 16);
+#pragma unroll
+      for (int s = 0; s < 8; s++) prod[s] = vmul(value_of<VT>(vw, s), xv[cur][s]);
+    }
     // Refill the stage consumed in the PREVIOUS iteration: its registers went through process_chunk, whose warp
     // shuffles order every lane's LDS before this point.  (Refilling the stage just read is a race: the bulk copy
     // runs in the async proxy and can overtake LDS still queued in the LSU - seen as rare wrong rows on B200.)
     __syncwarp();
-    if (lane == 0 && i >= 1 && i - 1 + STAGES < n) {
-      const uint32_t ps = (i - 1) & (STAGES - 1);
-      const uint32_t pbar = smem_u32(&bars[ps]);
-      mbar_expect_tx(pbar, CHUNK_BYTES);
-      bulk_g2s(smem_u32(ring + (size_t)ps * CHUNK_BYTES), stream + chunk_of(i - 1 + STAGES) * 32 * GW, CHUNK_BYTES, pbar);
+    if (lane == 0 && i >= 1 && i - 1 + STAGES < n) issue((i - 1) & (STAGES - 1), ahead(c_cur, i, STAGES - 1));
+    // ---- segmented sums + y updates of chunk i
+    const uint32_t pos = i & (R - 1);
+    const bool sole = (mr[cur].z & kChunkSole) != 0 && !force_red;
+    if (pos == 0) head_red = (mr[cur].z & kChunkStartsMid) != 0;  // stays set until the run's first row end
+    process_chunk<VT, false>(iw[cur], mr[cur], nullptr, prod, rowmap, y, lane, carry, open, next_rank, sole, head_red);
+    if (pos == R - 1 || i + 1 == n) {  // the row left open continues in another warp's run: hand over atomically
+      if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
+      carry = VT(0);
+      open = false;
     }
-    ChunkMeta m;
-    m.rank0 = r.mraw.x; m.block = r.mraw.y; m.valid = r.mraw.z; m.row_first = r.mraw.w;
-    const bool run_start = (i & (R - 1)) == 0;
-    const bool run_end = (i & (R - 1)) == R - 1 || i + 1 == n;
-    if (dbg & 1u) {  // consume the registers without touching y
-      VT t = VT(0);
-#pragma unroll
-      for (int s = 0; s < 8; s++) t = vadd(t, vmul(value_of<VT>(vw, s), r.xv[s]));
-      if (t == VT(123.456) && r.iw.x == 0x12345u) y_add(&y[0], t);
-    } else {
-      const bool sole = (m.valid & kChunkSole) != 0 && !force_red;
-      if (run_start) head_red = (m.valid & kChunkStartsMid) != 0;  // stays set until the run's first row end
-      process_any<VT>(r.iw, vw, m, r.xv, rowmap, y, lane, carry, open, next_rank, sole, head_red);
-      if (run_end) {  // the row left open continues in another warp's run: hand over through an atomic
-        if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
-        carry = VT(0);
-        open = false;
-      }
-    }
+    c_cur = ahead(c_cur, i, 1);
   };
-
-  ChunkRegs<VT> A, B;
-  prefetch(A, 0);
+  // two chunks per trip without a join in between: the compiler then keeps the prefetched x values where the loads
+  // put them (a conditional second half made it copy them right after issue, i.e. wait for them - 30 % slower)
   uint32_t i = 0;
-  for (; i + 1 < n; i += 2) {  // two chunks per trip: the register sets swap roles without moves
-    step(A, B, i);
-    step(B, A, i + 1);
+  for (; i + 1 < n; i += 2) {
+    step(std::integral_constant<int, 0>{}, i);
+    step(std::integral_constant<int, 1>{}, i + 1);
   }
-  if (i < n) step(A, B, i);
+  if (i < n) step(std::integral_constant<int, 0>{}, i);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Variant OCC: the same TMA ring and run-interleaved walk, but no software prefetch of x: two stages per warp and
+// few enough registers for MINB resident CTAs per SM, so that the x gather latency of one warp is covered by the
+// other warps of the SM sub-partition (classic occupancy-based hiding; nothing stays in flight in registers across
+// the row-sum code, so it does not depend on how ptxas assigns scoreboard slots).
+//   step i:  wait stage(i) -> LDS group + meta -> 8 gathers -> products -> segmented sums / y updates
+//            -> refill stage(i) with chunk i+2 (every lane's LDS is ordered before it by process_chunk's shuffles)
+template <typename VT, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+    spmv_occ_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
+                    const VT *__restrict__ x, VT *__restrict__ y, uint32_t n_chunks, uint32_t cdb,
+                    uint32_t run_log2, uint32_t flags) {
+  constexpr int STAGES = 2;
+  constexpr int GW = VTraits<VT>::kGroupWords;
+  constexpr int VW = VTraits<VT>::kValWords;
+  constexpr uint32_t CHUNK_BYTES = GW * 16 * 32;
+  constexpr uint32_t SLOT = CHUNK_BYTES + 16;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t ring = smem_u32(smem) + (uint32_t)warp * STAGES * SLOT;
+  const uint32_t bars = smem_u32(smem) + WARPS * STAGES * SLOT + (uint32_t)warp * STAGES * 8;
+  const uint32_t my = ring + lane * (GW * 16);
+  const uint32_t w = blockIdx.x * WARPS + warp, W = gridDim.x * WARPS;
+  const uint32_t R = 1u << run_log2;
+  const uint32_t total_runs = (n_chunks + R - 1) >> run_log2;
+  if (w >= total_runs) return;
+  const uint32_t my_runs = (total_runs - w + W - 1) / W;
+  uint32_t n = my_runs << run_log2;
+  {
+    const uint32_t over = ((my_runs - 1) * W + w + 1) << run_log2;
+    if (over > n_chunks) n -= over - n_chunks;
+  }
+  const uint32_t jump = (W - 1) << run_log2;
+  auto ahead = [&](uint32_t ci, uint32_t i, uint32_t k) -> uint32_t {
+    return ci + k + ((((i & (R - 1)) + k) >> run_log2) ? jump : 0u);
+  };
+  const bool force_red = (flags & 4u) != 0;
+  auto lds128 = [](uint32_t a) -> uint4 {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+  };
+  auto issue = [&](uint32_t stage, uint32_t chunk) {  // lane 0 only
+    const uint32_t bar = bars + stage * 8;
+    mbar_expect_tx(bar, SLOT);
+    bulk_g2s(ring + stage * SLOT, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar);
+  };
+  uint32_t c_cur = w << run_log2;
+  if (lane == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (lane == 0) {
+    issue(0, c_cur);
+    if (1 < n) issue(1, ahead(c_cur, 0, 1));
+  }
+  VT carry = VT(0);
+  bool open = false, head_red = false;
+  uint32_t next_rank = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t st = i & 1u;
+    mbar_wait(bars + st * 8, (i >> 1) & 1u);
+    const uint32_t base = my + st * SLOT;
+    const uint4 mraw = lds128(ring + st * SLOT + CHUNK_BYTES);
+    const uint4 iw = lds128(base);
+    VT xv[8];
+    gather_x<VT>(iw, x, mraw.y * cdb, xv);
+    uint4 vw[VW];
+#pragma unroll
+    for (int k = 0; k < VW; k++) vw[k] = lds128(base + 16 + k * 16);
+    const uint32_t pos = i & (R - 1);
+    const bool sole = (mraw.z & kChunkSole) != 0 && !force_red;
+    if (pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;
+    process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red);
+    if (pos == R - 1 || i + 1 == n) {
+      if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
+      carry = VT(0);
+      open = false;
+    }
+    __syncwarp();
+    if (lane == 0 && i + 2 < n) issue(st, ahead(c_cur, i, 2));
+    c_cur = ahead(c_cur, i, 1);
+  }
 }
 
 // y[rows[i]] = 0 for the rows that receive atomics or no update at all (Layout::zero_rows)

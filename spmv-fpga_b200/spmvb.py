@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libspmvb.so")
+LIB_PATH = os.environ.get("SPMVB_LIB") or os.path.join(HERE, "lib", "libspmvb.so")  # SPMVB_LIB: A/B builds
 
 _vp = ctypes.c_void_p
 _u32 = ctypes.c_uint32
