@@ -1,0 +1,123 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/spmvb.h declares; matrix-file reader/writer;
+generators; row partition; engine calls fail loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import matgen
+import oracle_api as oa
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "spmvb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(spmvb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(spmvb):
+    L = ctypes.CDLL(spmvb.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 50
+    missing = [n for n in names if not hasattr(L, n)]
+    assert missing == []
+    # and the python binding covers them all
+    assert sorted(spmvb.SYMBOLS) == names
+    assert spmvb.lib().spmvb_version() >= 100
+
+
+def test_engine_fails_loudly_without_gpu(spmvb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rows, cols, rp, ci, va = matgen.band(200)
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va)
+    with pytest.raises(spmvb.SpmvbError) as ei:
+        spmvb.Engine(lay)
+    assert ei.value.code == -3  # SPMVB_E_CUDA: there is no CPU fallback
+
+
+def test_matrix_file_roundtrip_and_reference_reader(spmvb, tmp_path):
+    rows, cols, rp, ci, va = matgen.ragged(300, 500, seed=4)
+    path = str(tmp_path / "m.txt")
+    matgen.write_matrix_file(path, rows, cols, rp, ci, va)
+    A = spmvb.Csr.read(path, True)
+    assert (A.rows, A.cols, A.nnz) == (rows, cols, len(ci))
+    assert np.array_equal(A.row_ptr, rp) and np.array_equal(A.col_ind, ci) and np.array_equal(A.values, va)
+    out = str(tmp_path / "m2.txt")
+    A.write(out)
+    B = spmvb.Csr.read(out, True)
+    assert np.array_equal(B.row_ptr, rp) and np.array_equal(B.col_ind, ci) and np.array_equal(B.values, va)
+    F = spmvb.Csr.read(out, False)
+    assert np.array_equal(F.values, va.astype(np.float32))
+    if oa.have_ref(1, 1, True):  # the reference's own reader parses what we write (csr.cpp:87-136)
+        rc, got = oa.RefLib(1, 1, True).read_matrix_file(out)
+        assert rc == 0
+        r2, c2, n2, blocks, rp2, ci2, va2 = got
+        assert (r2, c2, n2) == (rows, cols, len(ci)) and blocks == 1
+        assert np.array_equal(rp2, rp) and np.array_equal(ci2, ci) and np.array_equal(va2, va)
+
+
+def test_matrix_file_errors(spmvb, tmp_path):
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Csr.read(str(tmp_path / "missing.txt"))
+    p = tmp_path / "bad.txt"
+    p.write_text("3 3 2\n1 1 1.0\nnot a line\n")
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Csr.read(str(p))
+    p.write_text("3 3 2\n2 1 1.0\n1 1 1.0\n")  # rows not sorted
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Csr.read(str(p))
+    p.write_text("3 3 1\n1 1 1.0\n")  # trailing empty rows are fine (the reference leaves them undefined, Q3)
+    A = spmvb.Csr.read(str(p))
+    assert list(A.row_ptr) == [0, 1, 1, 1]
+
+
+def test_generators_match_numpy_twins(spmvb):
+    A = spmvb.Csr.laplacian2d(37, 23)
+    rows, cols, rp, ci, va = matgen.laplacian2d(37, 23)
+    assert np.array_equal(A.row_ptr, rp) and np.array_equal(A.col_ind, ci) and np.array_equal(A.values, va)
+    S = spmvb.Csr.laplacian2d(37, 23, 100, 300)  # a row slice of the same operator (multi-GPU shard)
+    lo, hi = int(rp[100]), int(rp[300])
+    assert np.array_equal(S.col_ind, ci[lo:hi]) and np.array_equal(S.row_ptr, rp[100:301] - rp[100]) and S.cols == cols
+    B = spmvb.Csr.band(1000, 5, 1)
+    r2, c2, rp2, ci2, _ = matgen.band(1000, 5)
+    assert np.array_equal(B.row_ptr, rp2) and np.array_equal(B.col_ind, ci2)
+    assert spmvb.Csr.band(10000, 5, 1).nnz == 109970  # BASELINE config 1 (even: avoids the reference's Q1 defect)
+    assert np.all(np.abs(B.values) <= 1.0) and np.all(B.values != 0.0)
+
+
+def test_uniform_and_rmat_generators(spmvb):
+    U = spmvb.Csr.uniform(5000, 100000, 16, seed=3)
+    assert U.nnz == 5000 * 16
+    c = U.col_ind.reshape(5000, 16).astype(np.int64)
+    assert np.all(np.diff(c, axis=1) > 0) and c.max() < 100000          # distinct, sorted
+    assert abs(c.mean() / 100000 - 0.5) < 0.01
+    U2 = spmvb.Csr.uniform(5000, 100000, 16, seed=3, row_begin=1000, row_end=1500)
+    assert np.array_equal(U2.col_ind, U.col_ind[1000 * 16:1500 * 16]) and np.array_equal(U2.values, U.values[16000:24000])
+    R = spmvb.Csr.rmat(14, 16, seed=1)
+    rp = R.row_ptr.astype(np.int64)
+    assert R.rows == 1 << 14 and rp[-1] == R.nnz and R.nnz <= 16 << 14
+    assert rp[-1] - rp[-2] >= 1                                          # last row non-empty (Q3)
+    empty = float((np.diff(rp) == 0).mean())
+    assert 0.2 < empty < 0.8                                             # the power-law tail leaves many empty rows
+    keys = np.repeat(np.arange(R.rows, dtype=np.int64), np.diff(rp)) * R.cols + R.col_ind
+    assert np.all(np.diff(keys) > 0)                                     # sorted by (row, col), no duplicates
+    R2 = spmvb.Csr.rmat(14, 16, seed=1, row_begin=4096, row_end=8192)
+    assert np.array_equal(R2.col_ind, R.col_ind[rp[4096]:rp[8192]])
+
+
+def test_partition_rows_balances_nonzeros(spmvb):
+    R = spmvb.Csr.rmat(15, 16, seed=2)
+    for parts in (2, 4, 8):
+        b = spmvb.partition_rows(R.rows, R.row_ptr, parts, 2)
+        assert b[0] == 0 and b[-1] == R.rows and np.all(np.diff(b.astype(np.int64)) >= 0)
+        rp = R.row_ptr.astype(np.int64)
+        nnz = np.diff(rp[b])
+        assert nnz.sum() == R.nnz
+        assert nnz[:-1].min() > R.nnz // parts                            # S1: every fired part exceeds the mean
+        assert np.all((b[1:-1] - b[:-2]) % 2 == 0)                        # S3: row counts multiple of RATIO_v

@@ -1,0 +1,105 @@
+"""CPU tests of the product's O(nnz) layout builder (through the C ABI) against the oracle and the golden fixtures:
+bit-exact pieces, metadata and empty_rows_bitmap for every CU / VF / precision."""
+import os
+
+import numpy as np
+import pytest
+
+import matgen
+import oracle_api as oa
+from test_oracle import GOLDEN, load_fixture
+
+
+def product_snapshot(lay, cu, vf, isd):
+    s = oa.Layout(cu, vf, isd, lay.blocks)
+    for b in range(lay.blocks):
+        s.bitmap.append(lay.bitmap_row(b))
+        for k in range(cu):
+            s.info[(k, b)] = lay.piece_info(k, b)
+            s.words[(k, b)] = lay.piece_words(k, b)
+    return s
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_builder_matches_reference_golden(spmvb, path):
+    fx = load_fixture(path)
+    for build in (spmvb.Layout.build, spmvb.Layout.build_u32):
+        lay = build(fx["rows"], fx["cols"], fx["rp"], fx["ci"], fx["va"], fx["cu"], fx["vf"], fx["isd"])
+        assert oa.layouts_equal(fx["layout"], product_snapshot(lay, fx["cu"], fx["vf"], fx["isd"])) == []
+        assert lay.expanded_cols == fx["hw_x_len"]
+        px = lay.pack_x(fx["x"])
+        assert np.array_equal(px[: fx["cols"]], fx["x"]) and not px[fx["cols"]:].any()
+        lay.free()
+
+
+MATS = {
+    "band": lambda: matgen.band(5000, 5, seed=1),
+    "lap": lambda: matgen.laplacian2d(220, 190),
+    "ragged": lambda: matgen.ragged(6000, 120000, seed=21),
+    "uniform": lambda: matgen.uniform(2500, 140000, 16, seed=22),
+    "rmat": lambda: matgen.rmat(12, 8, seed=23),
+    "longrows": lambda: matgen.uniform(30, 70000, 9000, seed=24),
+    "unsorted_cols": lambda: matgen.uniform(3000, 90000, 20, seed=25, sort_cols=False),
+    "tiny": lambda: matgen.uniform(3, 5, 2, seed=26),
+}
+CFGS = [(1, 1, True), (1, 2, False), (2, 1, True), (2, 4, False), (4, 2, True), (8, 4, True), (8, 8, False), (10, 2, True),
+        (12, 8, False), (3, 1, True)]
+
+
+@pytest.mark.parametrize("cfg", CFGS, ids=lambda c: "cu%d_vf%d_%s" % (c[0], c[1], "f64" if c[2] else "f32"))
+@pytest.mark.parametrize("mat", sorted(MATS))
+def test_builder_matches_oracle(spmvb, oracle, mat, cfg):
+    cu, vf, isd = cfg
+    rows, cols, rp, ci, va = MATS[mat]()
+    va = va.astype(oa.vdtype(isd))
+    ho = oracle.build(rows, cols, rp, ci, va, cu, vf, isd)
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, cu, vf, isd)
+    assert oa.layouts_equal(oracle.snapshot(ho, rows, cu, vf, isd), product_snapshot(lay, cu, vf, isd)) == []
+    assert lay.real_nnz == len(ci)
+    assert lay.padded_nnz == sum(lay.piece_info(k, b)[2] for k in range(cu) for b in range(lay.blocks))
+    assert lay.pairs == sum(int((lay.bitmap_row(b) == 0).sum()) for b in range(lay.blocks))
+    oracle.free(ho); lay.free()
+
+
+@pytest.mark.parametrize("cdb", [16384, 4096, 256, 64])
+def test_builder_custom_column_block_width(spmvb, oracle, cdb):
+    rows, cols, rp, ci, va = matgen.ragged(2000, 30000, seed=31)
+    for cu, vf, isd in ((1, 1, True), (4, 2, False)):
+        v = va.astype(oa.vdtype(isd))
+        ho = oracle.build(rows, cols, rp, ci, v, cu, vf, isd, cdb)
+        lay = spmvb.Layout.build(rows, cols, rp, ci, v, cu, vf, isd, cdb)
+        assert lay.blocks == (cols + cdb - 1) // cdb
+        assert oa.layouts_equal(oracle.snapshot(ho, rows, cu, vf, isd), product_snapshot(lay, cu, vf, isd)) == []
+        oracle.free(ho); lay.free()
+
+
+def test_builder_rejects_bad_arguments(spmvb):
+    rows, cols, rp, ci, va = matgen.band(100)
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Layout.build(rows, cols, rp, ci, va, 1, 3, True)          # VF not in {1,2,4,8}
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Layout.build(rows, cols, rp, ci, va, 0, 1, True)          # CU < 1
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True, 65536)   # block wider than a 15-bit index
+    bad = ci.copy(); bad[5] = cols + 7
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Layout.build(rows, cols, rp, bad, va, 1, 1, True)         # column out of range
+
+
+def test_storage_overhead_matches_reference_formula(spmvb):
+    """storage_overhead (csr_hw.cpp:1401-1409): 5 x 32 bit of metadata per block + (nr_ci + nr_val) bus words."""
+    rows, cols, rp, ci, va = matgen.laplacian2d(150, 150)
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, 2, 2, True)
+    for k in range(2):
+        bits = lay.blocks * 5 * 32 + sum((lay.piece_info(k, b)[3] + lay.piece_info(k, b)[4]) * 128 for b in range(lay.blocks))
+        assert abs(lay.storage_mb(k) - bits / (8.0 * 1024 * 1024)) < 1e-12
+
+
+def test_zero_row_list_covers_every_row_not_plainly_stored(spmvb):
+    """Device aux data: rows outside the zero list must be single-block, non-empty rows."""
+    rows, cols, rp, ci, va = matgen.laplacian2d(300, 300)
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True)
+    assert -1 <= lay.zero_rows <= rows
+    rows2, cols2, rp2, ci2, va2 = matgen.uniform(3000, 200000, 16, seed=2)
+    lay2 = spmvb.Layout.build(rows2, cols2, rp2, ci2, va2, 1, 1, True)
+    assert lay2.zero_rows == -1  # every row spans several column blocks: the whole y is cleared
