@@ -133,6 +133,17 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(args, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the main kernel, from the committed ncu --set full
+    capture of this workload (profiles/traffic.json); None when no capture exists for it."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "%s_%s_v%d" % (args.workload, args.dtype, 7 if args.variant == 0 else args.variant)
+        return t.get(key) if world == 1 else None
+    except Exception:
+        return None
+
+
 def cpu_reference_spmv(csr, is_double, budget_s=12.0, min_reps=3, max_reps=50):
     """Times the reference's CPU SpMV (spmv_gold, csr.cpp:184-194) single-threaded, exactly as the reference runs it:
     oracle/_ref (the unmodified reference compiled here) when present, else the oracle port."""
@@ -319,7 +330,8 @@ def main():
                 "what": "spmvb_engine_spmv_host: pinned x -> GPU, kernel, y -> pinned host, y_host += y (spmv_hw semantics)"},
         "gpu_launches": launches_total,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "spmv_ring_kernel" if args.variant in (0, 2) else "variant %d" % args.variant,
+                     "traffic": ncu_traffic(args, world), "peak_source": peak_src, "kernel": {0: "spmv_occ_kernel<3 CTAs/SM>", 7: "spmv_occ_kernel<3 CTAs/SM>", 6: "spmv_occ_kernel<4 CTAs/SM>",
+                                2: "spmv_ring_kernel", 1: "spmv_direct_kernel"}.get(args.variant, "variant %d" % args.variant),
                      "kernel_ms_avg": k_ms, "kernel_ms_min": float(np.min(kernel_ms)),
                      "algorithmic_bytes_per_launch": alg_bytes_local},
         "setup_s": {"generate": t_gen, "layout_build": t_layout, "upload": t_upload},
