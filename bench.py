@@ -33,6 +33,7 @@ def parse_args():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--scale", type=int, default=0, help="log2(rows per GPU) for rmat/uniform (default 24 / 23)")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--cols-div-blocks", type=int, default=0, help="column block width (0 = reference default 32768)")
     ap.add_argument("--flush-l2", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (default min(steps, 20))")
@@ -133,12 +134,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(args, world):
+def ncu_traffic(args, world, variant):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the main kernel, from the committed ncu --set full
     capture of this workload (profiles/traffic.json); None when no capture exists for it."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "%s_%s_v%d" % (args.workload, args.dtype, 7 if args.variant == 0 else args.variant)
+        key = "%s_%s_v%d" % (args.workload, args.dtype, variant)
         return t.get(key) if world == 1 else None
     except Exception:
         return None
@@ -236,7 +237,7 @@ def main():
     csr, rb, re = make_matrix(spmvb, spec, is_double, rank, world)
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
-    lay = spmvb.Layout.from_csr(csr, 1, 1)
+    lay = spmvb.Layout.from_csr(csr, 1, 1, args.cols_div_blocks)
     t_layout = time.perf_counter() - t0
     t0 = time.perf_counter()
     eng = spmvb.Engine(lay, local_rank, args.variant)
@@ -321,7 +322,9 @@ def main():
         "config": {"workload": spec["name"], "rows": spec["rows"], "cols": spec["cols"], "nnz": nnz_total,
                    "layout": "hw_matrix CU=1 VF=1 per GPU (rows sharded over GPUs, x replicated)",
                    "l2": "flushed between steps" if args.flush_l2 else "inputs larger than L2 (no flush)",
-                   "variant": int(args.variant), "step": "zero y + one SpMV kernel launch"},
+                   "variant": int(eng.variant), "variant_requested": int(args.variant), "cols_div_blocks": int(args.cols_div_blocks) or 32768,
+                   "pairs": int(lay.pairs), "zero_rows": int(lay.zero_rows),
+                   "step": "clear listed rows of y + one SpMV kernel launch"},
         "effective_gbs": eff_gbs,
         "roofline_nominal_frac": eff_gbs / (8000.0 * world),
         "clocks": sampler.summary(),
@@ -330,8 +333,8 @@ def main():
                 "what": "spmvb_engine_spmv_host: pinned x -> GPU, kernel, y -> pinned host, y_host += y (spmv_hw semantics)"},
         "gpu_launches": launches_total,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(args, world), "peak_source": peak_src, "kernel": {0: "spmv_occ_kernel<3 CTAs/SM>", 7: "spmv_occ_kernel<3 CTAs/SM>", 6: "spmv_occ_kernel<4 CTAs/SM>",
-                                2: "spmv_ring_kernel", 1: "spmv_direct_kernel"}.get(args.variant, "variant %d" % args.variant),
+                     "traffic": ncu_traffic(args, world, eng.variant), "peak_source": peak_src, "kernel": {7: "spmv_occ_kernel<3 CTAs/SM>", 6: "spmv_occ_kernel<4 CTAs/SM>", 8: "spmv_xs_kernel",
+                                1: "spmv_direct_kernel"}.get(eng.variant, "variant %d" % eng.variant),
                      "kernel_ms_avg": k_ms, "kernel_ms_min": float(np.min(kernel_ms)),
                      "algorithmic_bytes_per_launch": alg_bytes_local},
         "setup_s": {"generate": t_gen, "layout_build": t_layout, "upload": t_upload},

@@ -81,6 +81,16 @@ double spmvb_layout_storage_mb(const spmvb_layout *l, int cu);
 /* write_csr_hw_vector (csr_hw.cpp:1470-1488): x -> expanded_nr_cols zero-padded values. */
 int spmvb_layout_pack_x(const spmvb_layout *l, const void *x, uint32_t n, void *out_expanded);
 
+/* Work plan of the shared-memory-x kernel for a GPU with n_cta SMs (host only; for inspection and tests): items_out
+ * receives up to max_items records of 8 x uint32 {chunk_begin, chunk_count, x_off, x_bytes, col_base, block, 0, 0}
+ * (x_bytes == 0: the item gathers x from global memory), cta_first_out n_cta + 1 item indices.  Returns the number of
+ * items, or a negative error. */
+int64_t spmvb_layout_xs_plan(const spmvb_layout *l, int n_cta, int run_log2, uint32_t *items_out, uint64_t max_items,
+                             uint32_t *cta_first_out);
+/* number of 256-entry chunks of the device image, and the [lo, hi] column-in-block range of chunk c */
+uint64_t spmvb_layout_chunks(const spmvb_layout *l);
+int spmvb_layout_chunk_cols(const spmvb_layout *l, uint64_t c, uint32_t *lo, uint32_t *hi, uint32_t *block);
+
 /* Row partition for multi-GPU (the CU dimension mapped to GPUs, SURVEY 8e mapping A): `parts` contiguous row
  * ranges balanced by non-zero count with the reference's split rule S1/S2/S3 (csr_hw.cpp:459-460) applied
  * to whole rows.  bounds has parts+1 entries. */

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 if [ "$1" = "test" ]; then timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu.log; fi
-for v in 0; do
+for v in 0 8; do
   timeout 120 python bench.py --steps 200 --warmup 5 --variant $v --no-cpu-baseline > gpurun_out/bench_var$v.json 2> gpurun_out/bench_var$v.err; rc=$?
   python - <<PY
 import json
@@ -11,4 +11,4 @@ try:
 except Exception as e: print('variant $v failed rc=$rc', e)
 PY
 done
-bash scripts/gpu_ncu.sh default --variant 0
+bash scripts/gpu_ncu.sh xs --variant 8

@@ -17,16 +17,24 @@
 
 namespace spmvb {
 
-enum Variant { kVariantDefault = 0, kVariantDirect = 1, kVariantRing = 2, kVariantOcc4 = 6, kVariantOcc3 = 7 };
+enum Variant { kVariantDefault = 0, kVariantDirect = 1, kVariantOcc4 = 6, kVariantOcc3 = 7, kVariantXs = 8 };
+
 
 struct Engine {
-  int device = 0, is_double = 1, vb = 8, variant = kVariantRing;
+  int device = 0, is_double = 1, vb = 8, variant = kVariantDefault;
   uint32_t rows = 0, cols = 0, expanded_cols = 0, cdb = 32768;
   int blocks = 0;
   uint64_t real_nnz = 0, n_chunks = 0, n_pairs = 0, stream_bytes = 0, x_len = 0;
   uint8_t *d_stream = nullptr;
   uint32_t *d_rowmap = nullptr;
   uint32_t *d_zero_rows = nullptr;
+  XsItem *d_items = nullptr;  // work items of the XS kernel
+  uint32_t *d_cta_first = nullptr;  // [sms + 1] first item of every CTA
+  uint32_t occ_run_log2 = 3, xs_run_log2 = 1;  // run lengths of the kernels (>= the layout's zero-list granularity)
+  uint32_t n_items = 0;
+  double xs_windowed_frac = 0.0;  // share of the chunks whose x window fits shared memory
+  int auto_variant = kVariantOcc3; // what variant 0 resolves to (autotuned at upload)
+  float tune_ms[2] = {0.f, 0.f};   // autotune timings: OCC, XS
   uint32_t n_zero_rows = 0, run_log2 = 2;
   bool zero_all = true;
   void *d_x = nullptr, *d_y = nullptr;
@@ -39,7 +47,7 @@ struct Engine {
   int sms = 148;
   uint32_t dbg = 0;  // profiling experiments (SPMVB_DEBUG_MODE env), 0 in production
   uint64_t launches = 0;
-  int grid_cache[8][2] = {};  // [variant][is_double] -> grid size
+  int grid_cache[9][2] = {};  // [variant][is_double] -> grid size
   // asynchronous step timing (bench): events of the last enqueue_steps()
   std::vector<cudaEvent_t> ev;
   int ev_steps = 0;
@@ -52,33 +60,15 @@ struct Engine {
       return fail(SPMVB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
   } while (0)
 
-// Kernel variants (spmvb_engine_set_variant): 0 = default (= 7); 1 = DIRECT (ld.global per lane, contiguous chunk
-// ranges, atomics only); 2 = RING (4-stage TMA ring + x prefetched one chunk ahead in registers, 2 CTAs/SM);
-// 5 = RING with 3 CTAs/SM (spills); 6 / 7 = OCC (2-stage TMA ring, no register prefetch, 4 / 3 CTAs per SM).
-template <typename VT, int STAGES, int MINB>
-static int launch_ring(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
-  constexpr int WARPS = 8;
-  const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
-  auto kern = spmv_ring_kernel<VT, WARPS, STAGES, MINB>;
-  const size_t smem = (size_t)WARPS * STAGES * (VTraits<VT>::kGroupWords * 16 * 32 + 16) + (size_t)WARPS * STAGES * 8;
-  int &grid = E->grid_cache[slot][sizeof(VT) == 8];
-  if (grid == 0) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
-    grid = E->sms * std::max(per_sm, 1);
-  }
-  kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_rowmap, x, y, (uint32_t)E->n_chunks, E->cdb, E->run_log2,
-                                       accumulate ? 4u : 0u);
-  return SPMVB_OK;
-}
-
+// Kernel variants (spmvb_engine_set_variant): 0 = auto (the faster of 7 and 8 on this matrix, timed once at upload);
+// 1 = DIRECT (ld.global per lane, contiguous chunk ranges, atomics only: the simple baseline);
+// 6 / 7 = OCC (TMA ring, x gathered from global memory, 4 / 3 CTAs per SM); 8 = XS (x window in shared memory).
 template <typename VT, int MINB>
 static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
   constexpr int WARPS = 8;
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
   auto kern = spmv_occ_kernel<VT, WARPS, MINB>;
-  const size_t smem = (size_t)WARPS * 2 * (VTraits<VT>::kGroupWords * 16 * 32 + 16) + (size_t)WARPS * 2 * 8;
+  const size_t smem = (size_t)WARPS * 2 * (VTraits<VT>::kGroupWords * 16 * 32 + 16) + (size_t)WARPS * 16;
   int &grid = E->grid_cache[slot][sizeof(VT) == 8];
   if (grid == 0) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -86,8 +76,24 @@ static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, 
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     grid = E->sms * std::max(per_sm, 1);
   }
-  kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_rowmap, x, y, (uint32_t)E->n_chunks, E->cdb, E->run_log2,
+  kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_rowmap, x, y, (uint32_t)E->n_chunks, E->cdb, E->occ_run_log2,
                                        accumulate ? 4u : 0u);
+  return SPMVB_OK;
+}
+
+template <typename VT>
+static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
+  const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
+  auto kern = spmv_xs_kernel<VT, kXsWarps, kXsCap>;
+  const size_t smem = (size_t)kXsCap + (size_t)kXsWarps * 2 * (VTraits<VT>::kGroupWords * 16 * 32 + 16) + kXsWarps * 16 + 16;
+  int &grid = E->grid_cache[kVariantXs][sizeof(VT) == 8];
+  if (grid == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    grid = E->sms;
+  }
+  if (E->n_items == 0) return SPMVB_OK;
+  kern<<<grid, kXsWarps * 32, smem, st>>>(stream, E->d_rowmap, x, y, E->d_items, E->d_cta_first, E->cdb, E->xs_run_log2,
+                                          accumulate ? 4u : 0u);
   return SPMVB_OK;
 }
 
@@ -95,7 +101,7 @@ template <typename VT>
 static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
   constexpr int WARPS = 8;
-  int variant = E->variant == kVariantDefault ? kVariantOcc3 : E->variant;
+  int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
   if (E->n_chunks == 0) return SPMVB_OK;
   if (E->n_chunks >= 0x7FFFFFFFull) return fail(SPMVB_E_RANGE, "too many chunks for one engine");
   int rc = SPMVB_OK;
@@ -108,14 +114,14 @@ static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accum
       grid = E->sms * std::max(per_sm, 1);
     }
     kern<<<grid, WARPS * 32, 0, st>>>(stream, E->d_rowmap, x, y, E->n_chunks, E->cdb);
+  } else if (variant == kVariantXs) {
+    rc = launch_xs<VT>(E, x, y, st, accumulate);
   } else if (variant == 6) {
     rc = launch_occ<VT, 4>(E, x, y, st, 6, accumulate);
   } else if (variant == 7) {
     rc = launch_occ<VT, 3>(E, x, y, st, 7, accumulate);
-  } else if (variant == 5) {
-    rc = launch_ring<VT, 4, 3>(E, x, y, st, 5, accumulate);
   } else {
-    rc = launch_ring<VT, 4, 2>(E, x, y, st, 2, accumulate);
+    rc = launch_occ<VT, 3>(E, x, y, st, 7, accumulate);
   }
   if (rc) return rc;
   E->launches++;
@@ -125,7 +131,7 @@ static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accum
 
 // y = A x needs y prepared only where the kernel uses atomics or writes nothing: either the listed rows or all of y
 static int zero_y(Engine *E, void *y, cudaStream_t st) {
-  const int variant = E->variant == kVariantDefault ? kVariantOcc3 : E->variant;
+  const int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
   if (E->zero_all || variant == kVariantDirect) {
     CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)E->rows * E->vb, st));
   } else if (E->n_zero_rows) {
@@ -147,6 +153,40 @@ static int do_spmv(Engine *E, const void *x_dev, void *y_dev, int accumulate, cu
   }
   if (E->is_double) return launch_spmv<double>(E, (const double *)x, (double *)y, st, accumulate);
   return launch_spmv<float>(E, (const float *)x, (float *)y, st, accumulate);
+}
+
+// variant 0: time the two production kernels once on this matrix (x = 0: the access pattern does not depend on the
+// values) and keep the faster one.  Irregular column patterns favour the shared-memory x window, banded ones the
+// global gathers with more resident warps.
+static int autotune(Engine *E) {
+  E->auto_variant = kVariantOcc3;
+  if (getenv("SPMVB_NO_AUTOTUNE") || E->n_chunks == 0 || E->xs_windowed_frac < 0.5) return SPMVB_OK;
+  const int cand[2] = {kVariantOcc3, kVariantXs};
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  const int saved = E->variant;
+  float best = 1e30f;
+  int rc = SPMVB_OK;
+  for (int c = 0; c < 2 && rc == SPMVB_OK; c++) {
+    E->variant = cand[c];
+    for (int rep = 0; rep < 3 && rc == SPMVB_OK; rep++) {
+      cudaEventRecord(a, E->stream);
+      rc = do_spmv(E, nullptr, nullptr, 0, E->stream);  // a whole step: clear listed rows + kernel
+      cudaEventRecord(b, E->stream);
+      if (rc) break;
+      if (cudaEventSynchronize(b) != cudaSuccess) { rc = fail(SPMVB_E_CUDA, "autotune"); break; }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, a, b);
+      if (rep) E->tune_ms[c] = rep == 1 ? ms : std::min(E->tune_ms[c], ms);
+    }
+    if (rc == SPMVB_OK && E->tune_ms[c] < best) { best = E->tune_ms[c]; E->auto_variant = cand[c]; }
+  }
+  E->variant = saved;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  E->launches = 0;
+  return rc;
 }
 
 }  // namespace spmvb
@@ -185,6 +225,11 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   chk(cudaMalloc((void **)&E->d_stream, std::max<uint64_t>(L->n_chunks * slot, 16)));
   chk(cudaMalloc((void **)&E->d_rowmap, (std::max<uint64_t>(L->n_pairs, 1) + 1) * 4));
   E->zero_all = L->zero_all; E->n_zero_rows = (uint32_t)L->zero_rows.size(); E->run_log2 = (uint32_t)L->run_log2;
+  if (const char *v = getenv("SPMVB_OCC_RUN_LOG2")) E->occ_run_log2 = (uint32_t)atoi(v);
+  if (const char *v = getenv("SPMVB_XS_RUN_LOG2")) E->xs_run_log2 = (uint32_t)atoi(v);
+  // rows split across run boundaries are only cleared at the layout's granularity: runs must be multiples of it
+  E->occ_run_log2 = std::min(8u, std::max(E->occ_run_log2, E->run_log2));
+  E->xs_run_log2 = std::min(8u, std::max(E->xs_run_log2, E->run_log2));
   chk(cudaMalloc((void **)&E->d_zero_rows, std::max<size_t>(L->zero_rows.size(), 1) * 4));
   chk(cudaMalloc(&E->d_x, E->x_len * E->vb));
   chk(cudaMalloc(&E->d_y, (size_t)E->rows * E->vb));
@@ -198,6 +243,19 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
     }
     chk(cudaMemcpyAsync(E->d_rowmap, L->rowmap, L->n_pairs * 4, cudaMemcpyHostToDevice, E->stream));
     chk(cudaMemcpyAsync(E->d_zero_rows, L->zero_rows.data(), L->zero_rows.size() * 4, cudaMemcpyHostToDevice, E->stream));
+    {
+      std::vector<XsItem> items;
+      std::vector<uint32_t> cta_first;
+      build_xs_items(L, E->sms, E->xs_run_log2, items, cta_first);
+      E->n_items = (uint32_t)items.size();
+      chk(cudaMalloc((void **)&E->d_items, std::max<size_t>(items.size(), 1) * sizeof(XsItem)));
+      chk(cudaMalloc((void **)&E->d_cta_first, cta_first.size() * 4));
+      if (e == cudaSuccess) chk(cudaMemcpy(E->d_items, items.data(), items.size() * sizeof(XsItem), cudaMemcpyHostToDevice));
+      if (e == cudaSuccess) chk(cudaMemcpy(E->d_cta_first, cta_first.data(), cta_first.size() * 4, cudaMemcpyHostToDevice));
+      uint64_t windowed = 0;
+      for (auto &it : items) windowed += it.x_bytes ? it.chunk_count : 0;
+      E->xs_windowed_frac = L->n_chunks ? (double)windowed / (double)L->n_chunks : 0.0;
+    }
     chk(cudaMemsetAsync(E->d_x, 0, E->x_len * E->vb, E->stream));
     chk(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
     chk(cudaStreamSynchronize(E->stream));
@@ -207,6 +265,12 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
     spmvb_engine_free((spmvb_engine *)E);
     return fail(SPMVB_E_CUDA, msg);
   }
+  if (autotune(E) != SPMVB_OK) {
+    spmvb_engine_free((spmvb_engine *)E);
+    return SPMVB_E_CUDA;
+  }
+  CUDA_TRY(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
+  CUDA_TRY(cudaStreamSynchronize(E->stream));
   *out = (spmvb_engine *)E;
   return SPMVB_OK;
 }
@@ -216,7 +280,7 @@ void spmvb_engine_free(spmvb_engine *e) {
   if (!E) return;
   cudaSetDevice(E->device);
   if (E->stream) cudaStreamSynchronize(E->stream);
-  cudaFree(E->d_stream); cudaFree(E->d_rowmap); cudaFree(E->d_zero_rows);
+  cudaFree(E->d_stream); cudaFree(E->d_rowmap); cudaFree(E->d_zero_rows); cudaFree(E->d_items); cudaFree(E->d_cta_first);
   cudaFree(E->d_x); cudaFree(E->d_y); cudaFree(E->d_scalar); cudaFree(E->d_flush);
   if (E->h_stage) cudaFreeHost(E->h_stage);
   for (auto &x : E->ev) cudaEventDestroy(x);
@@ -225,11 +289,14 @@ void spmvb_engine_free(spmvb_engine *e) {
 }
 
 int spmvb_engine_set_variant(spmvb_engine *e, int variant) {
-  if (!e || variant < 0 || variant > 7) return fail(SPMVB_E_ARG, "variant");
+  if (!e || variant < 0 || variant > 8) return fail(SPMVB_E_ARG, "variant");
   ((Engine *)e)->variant = variant;
   return SPMVB_OK;
 }
-int spmvb_engine_variant(const spmvb_engine *e) { return ((const Engine *)e)->variant; }
+int spmvb_engine_variant(const spmvb_engine *e) {
+  const Engine *E = (const Engine *)e;
+  return E->variant == kVariantDefault ? E->auto_variant : E->variant;
+}
 uint64_t spmvb_engine_launches(const spmvb_engine *e) { return ((const Engine *)e)->launches; }
 uint64_t spmvb_engine_algorithmic_bytes(const spmvb_engine *e) {
   const Engine *E = (const Engine *)e;

@@ -57,6 +57,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   if (rows == 0 || cols == 0 || !row_ptr) return fail(SPMVB_E_ARG, "empty matrix");
   uint32_t cdb = cdb_in ? cdb_in : ((cu == 10 || cu == 12) ? 16384u : 32768u);  // util.h:41-59
   if (cdb > 32768 || cdb % 4 != 0) return fail(SPMVB_E_ARG, "cols_div_blocks must be a multiple of 4 and <= 32768");
+  if ((uint64_t)cols > (uint64_t)cdb * kMetaBlockMask) return fail(SPMVB_E_RANGE, "too many column blocks");
   const uint64_t nnz = (uint64_t)row_ptr[rows];
   if (nnz && (!col_ind || !values)) return fail(SPMVB_E_ARG, "col_ind/values are NULL");
 
@@ -365,7 +366,9 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
       for (uint64_t c = c0; c < c1; c++) {
         const ChunkMeta &m = L->chunks[c];
         if (!(m.valid & 0x3FFu)) continue;
-        if ((m.valid & kChunkStartsMid) && (c % R) == 0) needz[m.row_first] = 1;  // row split across two runs
+        // row split across two runs; runs are aligned globally (OCC/RING kernels) or to the block start (XS kernel)
+        if ((m.valid & kChunkStartsMid) && ((c % R) == 0 || ((c - L->piece_chunk0[(size_t)(bk / cu) * cu]) % R) == 0))
+          needz[m.row_first] = 1;
         if (m.valid & kChunkSole) continue;
         // every row with a segment (or part of one) in an atomics-only chunk
         uint64_t rk = m.rank0;
@@ -387,6 +390,28 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
         if (needz[r]) L->zero_rows.push_back(r);
     }
   }
+
+  // column range of every chunk (real entries only)
+  L->chunk_col_lo.assign((size_t)L->n_chunks, 0xFFFF);
+  L->chunk_col_hi.assign((size_t)L->n_chunks, 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < (int64_t)L->n_chunks; c++) {
+    const uint32_t valid = L->chunks[c].valid & 0x3FFu;
+    const uint8_t *base = L->stream + (uint64_t)c * L->chunk_bytes;
+    uint16_t lo = 0xFFFF, hi = 0;
+    uint32_t row_ends = 0;
+    for (uint32_t e = 0; e < valid; e++) {
+      uint16_t ci;
+      memcpy(&ci, base + (size_t)(e / kRatioCi) * gb + 2 * (e % kRatioCi), 2);
+      row_ends += ci >> 15;
+      ci &= 0x7FFF;
+      lo = std::min(lo, ci); hi = std::max(hi, ci);
+    }
+    L->chunk_col_lo[c] = lo; L->chunk_col_hi[c] = hi;
+    L->chunks[c].block = (L->chunks[c].block & kMetaBlockMask) | (row_ends << kMetaRowsShift);
+  }
+  L->block_chunk0.assign(blocks + 1, L->n_chunks);
+  for (int b = 0; b < blocks; b++) L->block_chunk0[b] = L->piece_chunk0[(size_t)b * cu];
 
   *out = L;
   return SPMVB_OK;
@@ -427,6 +452,15 @@ uint64_t spmvb_layout_real_nnz(const spmvb_layout *l) { return ((const Layout *)
 uint64_t spmvb_layout_padded_nnz(const spmvb_layout *l) { return ((const Layout *)l)->padded_nnz; }
 uint64_t spmvb_layout_pairs(const spmvb_layout *l) { return ((const Layout *)l)->n_pairs; }
 uint64_t spmvb_layout_stream_bytes(const spmvb_layout *l) { return ((const Layout *)l)->stream_bytes; }
+uint64_t spmvb_layout_chunks(const spmvb_layout *l) { return ((const Layout *)l)->n_chunks; }
+int spmvb_layout_chunk_cols(const spmvb_layout *l, uint64_t c, uint32_t *lo, uint32_t *hi, uint32_t *block) {
+  const Layout *L = (const Layout *)l;
+  if (!L || c >= L->n_chunks) return fail(SPMVB_E_ARG, "chunk index");
+  if (lo) *lo = L->chunk_col_lo[c];
+  if (hi) *hi = L->chunk_col_hi[c];
+  if (block) *block = L->chunks[c].block & kMetaBlockMask;
+  return SPMVB_OK;
+}
 int64_t spmvb_layout_zero_rows(const spmvb_layout *l) {
   const Layout *L = (const Layout *)l;
   return L->zero_all ? -1 : (int64_t)L->zero_rows.size();

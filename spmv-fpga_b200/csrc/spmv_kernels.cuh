@@ -62,16 +62,6 @@ __device__ __forceinline__ uint32_t idx16(const uint4 &iw, int s) {
 __device__ __forceinline__ void y_add(double *p, double v) { atomicAdd(p, v); }
 __device__ __forceinline__ void y_add(float *p, float v) { atomicAdd(p, v); }
 
-// predicated variant: the RED is the only instruction under the predicate (no branch, no reconvergence barrier)
-__device__ __forceinline__ void y_add_if(double *p, double v, uint32_t e) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(e)
-               : "memory");
-}
-__device__ __forceinline__ void y_add_if(float *p, float v, uint32_t e) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"(e)
-               : "memory");
-}
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -99,11 +89,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
-}
-// bulk prefetch global -> L2 (no shared memory, no completion tracking): deepens the bytes in flight to DRAM beyond
-// what the shared-memory ring can hold
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -146,6 +131,23 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
   }
   const uint32_t total_eor = (uint32_t)__shfl_sync(FULL, pre, 31);
   const uint32_t rank_t = rank0 + (uint32_t)(pre - n_eor);
+
+  // Row ids of this lane's row ends, all requested now, back to back, so that their latency overlaps the products
+  // and the row sums (fetched one by one inside the update loop below they were 35 % of the XS kernel's stall time
+  // on R-MAT: load -> wait -> RED -> next load ...).
+  uint32_t rows[8];
+  if (!consec) {
+    uint32_t rk = rank_t;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const uint32_t e = (eor >> s) & 1u;
+      rows[s] = 0;
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"
+                   : "+r"(rows[s])
+                   : "l"(rowmap + rk), "r"(e));
+      rk += e;
+    }
+  }
 
   // per-lane running sums of the products that restart after each end-of-row bit (add separately rounded from the
   // multiply, like the HLS cores: spmv.cpp:84-97)
@@ -207,16 +209,14 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
       }
     }
   } else {
-    uint32_t rk = rank_t;
 #pragma unroll
     for (int s = 0; s < 8; s++) {
       if ((eor >> s) & 1u) {
-        const uint32_t row = rowmap[rk];
+        const uint32_t row = rows[s];
         VT v = seg[s];
         if ((first_bit >> s) & 1u) v = vadd(cin, v);
         if ((redm >> s) & 1u) y_add(y + row, v);
         else y[row] = v;
-        rk++;
       }
     }
   }
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 #pragma unroll
     for (int i = 0; i < VW; i++) vw[i] = __ldg(g + 1 + i);
     VT xv[8];
-    gather_x<VT>(iw, x, mraw.y * cdb, xv);
+    gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv);
     bool head_red = false;
     process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, false, head_red);
   }
@@ -281,219 +281,191 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Variant RING: per-warp ring of STAGES chunks filled by cp.async.bulk (one elected lane issues, an mbarrier per
-// stage counts the bytes); lanes read their group with conflict-free LDS.128 (lane stride 80 B / 48 B).
-// Software pipeline per warp, chunk i being summed while chunk i+1's x values are in flight:
-//   iteration i:  wait stage(i+1) -> LDS its index word -> issue its 8 x gathers (not consumed until i+1)
-//                 LDS chunk i's value words -> refill stage(i-1) with chunk i-1+STAGES -> segmented sums of chunk i
-// Chunk assignment: warp w of W walks runs of R = 2^run_log2 consecutive chunks, run q of the warp being global run
-// q*W + w.  All warps therefore sweep one contiguous window of the stream together (DRAM page locality; contiguous
-// per-warp ranges measured ~25 % slower), while inside a run the open row sum stays in registers.
-template <typename VT, int WARPS, int STAGES, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-    spmv_ring_kernel(const uint4 *__restrict__ stream,
-                     const uint32_t *__restrict__ rowmap, const VT *__restrict__ x, VT *__restrict__ y,
-                     uint32_t n_chunks, uint32_t cdb, uint32_t run_log2, uint32_t flags) {
-  // flags bit 2: atomics everywhere (y += A x semantics: plain stores would overwrite the caller's y)
-  static_assert((STAGES & (STAGES - 1)) == 0 && STAGES >= 4,
-                "prefetch one chunk ahead + refill one chunk behind needs >= 3 stages (power of two: 4)");
+// The warp-level chunk walk shared by the OCC and XS kernels: a 2-stage TMA ring per warp, no software prefetch of x.
+//   step i:  wait stage -> LDS group + meta -> 8 x gathers (functor) -> LDS values -> segmented sums / y updates
+//            -> refill the stage with chunk i+2 (every lane's LDS is ordered before it by process_chunk's shuffles)
+// The walk covers the chunk domain [base, base + n_dom): warp w of W takes runs of R = 2^run_log2 consecutive chunks,
+// run q of the warp being run q*W + w of the domain, so that the W warps sweep one contiguous window of the stream
+// together (DRAM page locality) while the open row sum stays in registers inside a run.
+// `t` is the warp's running slot counter: it carries the ring stage / mbarrier phase from one domain to the next.
+template <typename VT, typename Gather>
+__device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
+                                            VT *__restrict__ y, uint32_t ring, uint32_t bars, int lane, uint32_t base,
+                                            uint32_t n_dom, uint32_t w, uint32_t W, uint32_t run_log2, bool force_red,
+                                            uint32_t &t, Gather gather) {
   constexpr int GW = VTraits<VT>::kGroupWords;
   constexpr int VW = VTraits<VT>::kValWords;
   constexpr uint32_t CHUNK_BYTES = GW * 16 * 32;
-  constexpr uint32_t SLOT = CHUNK_BYTES + 16;  // a device slot: the chunk's words followed by its ChunkMeta
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const uint32_t ring = smem_u32(smem) + (uint32_t)warp * STAGES * SLOT;   // shared-window addresses
-  const uint32_t bars = smem_u32(smem) + WARPS * STAGES * SLOT + (uint32_t)warp * STAGES * 8;
-  const uint32_t my = ring + lane * (GW * 16);                                    // this lane's group in stage 0
-  const uint32_t w = blockIdx.x * WARPS + warp, W = gridDim.x * WARPS;
+  constexpr uint32_t SLOT = CHUNK_BYTES + 16;
   const uint32_t R = 1u << run_log2;
-  const uint32_t total_runs = (n_chunks + R - 1) >> run_log2;
+  const uint32_t total_runs = (n_dom + R - 1) >> run_log2;
   if (w >= total_runs) return;
   const uint32_t my_runs = (total_runs - w + W - 1) / W;
   uint32_t n = my_runs << run_log2;  // chunks this warp walks
   {
-    const uint32_t over = ((my_runs - 1) * W + w + 1) << run_log2;  // a partial last run can only be the global last
-    if (over > n_chunks) n -= over - n_chunks;
+    const uint32_t over = ((my_runs - 1) * W + w + 1) << run_log2;  // a partial last run can only be the domain's last
+    if (over > n_dom) n -= over - n_dom;
   }
   const uint32_t jump = (W - 1) << run_log2;  // extra chunk distance when stepping from one run into the next
-  // global chunk index of the warp's (i + k)-th chunk, given ci = index of its i-th, for 0 <= k <= R
-  auto ahead = [&](uint32_t ci, uint32_t i, uint32_t k) -> uint32_t {
+  auto ahead = [&](uint32_t ci, uint32_t i, uint32_t k) -> uint32_t {  // index of chunk i + k given chunk i, k <= R
     return ci + k + ((((i & (R - 1)) + k) >> run_log2) ? jump : 0u);
   };
-  const bool force_red = (flags & 4u) != 0;
   auto lds128 = [](uint32_t a) -> uint4 {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
   };
-  auto issue = [&](uint32_t stage, uint32_t chunk) {  // lane 0 only
-    const uint32_t bar = bars + stage * 8;
+  auto issue = [&](uint32_t slot, uint32_t chunk) {  // lane 0 only
+    const uint32_t bar = bars + (slot & 1u) * 8;
     mbar_expect_tx(bar, SLOT);
-    bulk_g2s(ring + stage * SLOT, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar);
+    bulk_g2s(ring + (slot & 1u) * SLOT, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar);
   };
-
-  uint32_t c_cur = w << run_log2;  // global index of chunk i (i = 0)
+  const uint32_t my = ring + lane * (GW * 16);
+  uint32_t c_cur = base + (w << run_log2);
   if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; s++) mbar_init(bars + s * 8, 1);
-    fence_barrier_init();
+    issue(t, c_cur);
+    if (1 < n) issue(t + 1, ahead(c_cur, 0, 1));
   }
-  __syncwarp();
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; s++)
-      if ((uint32_t)s < n) issue(s, ahead(c_cur, 0, s));
-  }
-
   VT carry = VT(0);
   bool open = false, head_red = false;
   uint32_t next_rank = 0;
-
-  // registers of the chunk being prefetched / processed: [i & 1]
-  uint4 iw[2], mr[2];
-  VT xv[2][8];
-  // prologue: prefetch chunk 0
-  {
-    mbar_wait(bars, 0);
-    mr[0] = lds128(ring + CHUNK_BYTES);
-    iw[0] = lds128(my);
-    gather_x<VT>(iw[0], x, mr[0].y * cdb, xv[0]);
-  }
-  // one pipeline step; CUR is a compile-time 0/1 so that the double-buffered registers are never indexed dynamically
-  auto step = [&](auto CUR, uint32_t i) {
-    constexpr int cur = decltype(CUR)::value, nxt = cur ^ 1;
-    // ---- prefetch chunk i+1: its stage has landed or is about to; leaves the 8 gathers in flight
-    if (i + 1 < n) {
-      const uint32_t st = (i + 1) & (STAGES - 1);
-      mbar_wait(bars + st * 8, ((i + 1) / STAGES) & 1u);
-      mr[nxt] = lds128(ring + st * SLOT + CHUNK_BYTES);  // the chunk's meta travels with it: no separate global load
-      iw[nxt] = lds128(my + st * SLOT);
-      gather_x<VT>(iw[nxt], x, mr[nxt].y * cdb, xv[nxt]);
-    }
-    // ---- values of chunk i and its products with the x values gathered one step ago
-    VT prod[8];
-    {
-      uint4 vw[VW];
-      const uint32_t a = my + (i & (STAGES - 1)) * SLOT + 16;
+  for (uint32_t i = 0; i < n; i++, t++) {
+    const uint32_t st = t & 1u;
+    mbar_wait(bars + st * 8, (t >> 1) & 1u);
+    const uint32_t g = my + st * SLOT;
+    const uint4 mraw = lds128(ring + st * SLOT + CHUNK_BYTES);
+    const uint4 iw = lds128(g);
+    VT xv[8];
+    gather(iw, mraw, xv);
+    uint4 vw[VW];
 #pragma unroll
-      for (int k = 0; k < VW; k++) vw[k] = lds128(a + k * 16);
-#pragma unroll
-      for (int s = 0; s < 8; s++) prod[s] = vmul(value_of<VT>(vw, s), xv[cur][s]);
-    }
-    // Refill the stage consumed in the PREVIOUS iteration: its registers went through process_chunk, whose warp
-    // shuffles order every lane's LDS before this point.  (Refilling the stage just read is a race: the bulk copy
-    // runs in the async proxy and can overtake LDS still queued in the LSU - seen as rare wrong rows on B200.)
-    __syncwarp();
-    if (lane == 0 && i >= 1 && i - 1 + STAGES < n) issue((i - 1) & (STAGES - 1), ahead(c_cur, i, STAGES - 1));
-    // ---- segmented sums + y updates of chunk i
+    for (int k = 0; k < VW; k++) vw[k] = lds128(g + 16 + k * 16);
     const uint32_t pos = i & (R - 1);
-    const bool sole = (mr[cur].z & kChunkSole) != 0 && !force_red;
-    if (pos == 0) head_red = (mr[cur].z & kChunkStartsMid) != 0;  // stays set until the run's first row end
-    process_chunk<VT, false>(iw[cur], mr[cur], nullptr, prod, rowmap, y, lane, carry, open, next_rank, sole, head_red);
+    const bool sole = (mraw.z & kChunkSole) != 0 && !force_red;
+    if (pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;  // stays set until the run's first row end
+    process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red);
     if (pos == R - 1 || i + 1 == n) {  // the row left open continues in another warp's run: hand over atomically
-      if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
+      if (open && lane == 0) {
+        // in a `consecutive` chunk the open row follows from the rank (the flag covers it): no dependent row-map load
+        const uint32_t row = (mraw.z & kChunkRowsConsecutive) ? mraw.w + (next_rank - mraw.x) : rowmap[next_rank];
+        y_add(&y[row], carry);
+      }
       carry = VT(0);
       open = false;
     }
+    __syncwarp();
+    if (lane == 0 && i + 2 < n) issue(t + 2, ahead(c_cur, i, 2));
     c_cur = ahead(c_cur, i, 1);
-  };
-  // two chunks per trip without a join in between: the compiler then keeps the prefetched x values where the loads
-  // put them (a conditional second half made it copy them right after issue, i.e. wait for them - 30 % slower)
-  uint32_t i = 0;
-  for (; i + 1 < n; i += 2) {
-    step(std::integral_constant<int, 0>{}, i);
-    step(std::integral_constant<int, 1>{}, i + 1);
   }
-  if (i < n) step(std::integral_constant<int, 0>{}, i);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Variant OCC: the same TMA ring and run-interleaved walk, but no software prefetch of x: two stages per warp and
-// few enough registers for MINB resident CTAs per SM, so that the x gather latency of one warp is covered by the
-// other warps of the SM sub-partition (classic occupancy-based hiding; nothing stays in flight in registers across
-// the row-sum code, so it does not depend on how ptxas assigns scoreboard slots).
-//   step i:  wait stage(i) -> LDS group + meta -> 8 gathers -> products -> segmented sums / y updates
-//            -> refill stage(i) with chunk i+2 (every lane's LDS is ordered before it by process_chunk's shuffles)
+// Variant OCC: x gathered from global memory (L1/L2); few enough registers for MINB resident CTAs per SM, so that
+// the gather latency of one warp is covered by the other warps of its SM sub-partition.  Nothing stays in flight in
+// registers across the row-sum code, so the kernel does not depend on how ptxas assigns scoreboard slots.
 template <typename VT, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     spmv_occ_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
                     const VT *__restrict__ x, VT *__restrict__ y, uint32_t n_chunks, uint32_t cdb,
                     uint32_t run_log2, uint32_t flags) {
-  constexpr int STAGES = 2;
-  constexpr int GW = VTraits<VT>::kGroupWords;
-  constexpr int VW = VTraits<VT>::kValWords;
-  constexpr uint32_t CHUNK_BYTES = GW * 16 * 32;
-  constexpr uint32_t SLOT = CHUNK_BYTES + 16;
+  constexpr uint32_t SLOT = VTraits<VT>::kGroupWords * 16 * 32 + 16;
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const uint32_t ring = smem_u32(smem) + (uint32_t)warp * STAGES * SLOT;
-  const uint32_t bars = smem_u32(smem) + WARPS * STAGES * SLOT + (uint32_t)warp * STAGES * 8;
-  const uint32_t my = ring + lane * (GW * 16);
-  const uint32_t w = blockIdx.x * WARPS + warp, W = gridDim.x * WARPS;
-  const uint32_t R = 1u << run_log2;
-  const uint32_t total_runs = (n_chunks + R - 1) >> run_log2;
-  if (w >= total_runs) return;
-  const uint32_t my_runs = (total_runs - w + W - 1) / W;
-  uint32_t n = my_runs << run_log2;
-  {
-    const uint32_t over = ((my_runs - 1) * W + w + 1) << run_log2;
-    if (over > n_chunks) n -= over - n_chunks;
-  }
-  const uint32_t jump = (W - 1) << run_log2;
-  auto ahead = [&](uint32_t ci, uint32_t i, uint32_t k) -> uint32_t {
-    return ci + k + ((((i & (R - 1)) + k) >> run_log2) ? jump : 0u);
-  };
-  const bool force_red = (flags & 4u) != 0;
-  auto lds128 = [](uint32_t a) -> uint4 {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-  };
-  auto issue = [&](uint32_t stage, uint32_t chunk) {  // lane 0 only
-    const uint32_t bar = bars + stage * 8;
-    mbar_expect_tx(bar, SLOT);
-    bulk_g2s(ring + stage * SLOT, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar);
-  };
-  uint32_t c_cur = w << run_log2;
+  const uint32_t ring = smem_u32(smem) + (uint32_t)warp * 2 * SLOT;
+  const uint32_t bars = smem_u32(smem) + WARPS * 2 * SLOT + (uint32_t)warp * 16;
   if (lane == 0) {
     mbar_init(bars, 1);
     mbar_init(bars + 8, 1);
     fence_barrier_init();
   }
   __syncwarp();
+  uint32_t t = 0;
+  walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, 0u, n_chunks, blockIdx.x * WARPS + warp, gridDim.x * WARPS,
+                  run_log2, (flags & 4u) != 0, t,
+                  [&](const uint4 &iw, const uint4 &mraw, VT *xv) { gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv); });
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Variant XS: the reference's "x slice in on-chip memory" (spmv.cpp:180-192: every compute unit copies the block's x
+// slice to BRAM before streaming the block).  The stream is cut into work items = a range of chunks of ONE column
+// block whose entries touch a window of at most X_CAP bytes of that block's x slice.  Every CTA (one per SM) owns one
+// contiguous, equally long range of the stream = a few consecutive items; per item one thread TMA-bulk-copies the x window into shared memory (cp.async.bulk, several
+// pieces on one mbarrier) while the warps already fetch their first chunks, then all warps walk the item's chunks and
+// gather x with LDS (2-4 wavefronts per gather instead of 12-32 L1 sectors).  Items whose window does not fit (wide
+// blocks of an irregular matrix in fp64) fall back to global gathers.
+
+__device__ __forceinline__ double lds_x(uint32_t a, double) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_x(uint32_t a, float) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+
+template <typename VT, int WARPS, uint32_t X_CAP>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+    spmv_xs_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap, const VT *__restrict__ x,
+                   VT *__restrict__ y, const XsItem *__restrict__ items, const uint32_t *__restrict__ cta_first,
+                   uint32_t cdb, uint32_t run_log2, uint32_t flags) {
+  constexpr uint32_t SLOT = VTraits<VT>::kGroupWords * 16 * 32 + 16;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t xbuf = smem_u32(smem);
+  const uint32_t ring = xbuf + X_CAP + (uint32_t)warp * 2 * SLOT;
+  const uint32_t bars = xbuf + X_CAP + WARPS * 2 * SLOT + (uint32_t)warp * 16;
+  const uint32_t xbar = xbuf + X_CAP + WARPS * 2 * SLOT + WARPS * 16;
   if (lane == 0) {
-    issue(0, c_cur);
-    if (1 < n) issue(1, ahead(c_cur, 0, 1));
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    if (warp == 0) mbar_init(xbar, 1);
+    fence_barrier_init();
   }
-  VT carry = VT(0);
-  bool open = false, head_red = false;
-  uint32_t next_rank = 0;
-  for (uint32_t i = 0; i < n; i++) {
-    const uint32_t st = i & 1u;
-    mbar_wait(bars + st * 8, (i >> 1) & 1u);
-    const uint32_t base = my + st * SLOT;
-    const uint4 mraw = lds128(ring + st * SLOT + CHUNK_BYTES);
-    const uint4 iw = lds128(base);
-    VT xv[8];
-    gather_x<VT>(iw, x, mraw.y * cdb, xv);
-    uint4 vw[VW];
-#pragma unroll
-    for (int k = 0; k < VW; k++) vw[k] = lds128(base + 16 + k * 16);
-    const uint32_t pos = i & (R - 1);
-    const bool sole = (mraw.z & kChunkSole) != 0 && !force_red;
-    if (pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;
-    process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red);
-    if (pos == R - 1 || i + 1 == n) {
-      if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
-      carry = VT(0);
-      open = false;
+  __syncthreads();
+  uint32_t t = 0, k = 0;  // k counts the windows loaded so far (phase of xbar)
+  const uint32_t it_end = __ldg(cta_first + blockIdx.x + 1);
+  for (uint32_t it = __ldg(cta_first + blockIdx.x); it < it_end; it++) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(items + it));
+    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(items + it) + 1);
+    const uint32_t chunk_begin = a.x, chunk_count = a.y, x_off = a.z, x_bytes = a.w, col_base = b.x;
+    __syncthreads();  // every warp is done gathering from the previous window
+    if (threadIdx.x == 0 && x_bytes) {
+      fence_proxy_async();
+      mbar_expect_tx(xbar, x_bytes);
+      const uint8_t *src = reinterpret_cast<const uint8_t *>(x + x_off);
+      for (uint32_t o = 0; o < x_bytes; o += 16384u) bulk_g2s(xbuf + o, src + o, min(16384u, x_bytes - o), xbar);
     }
-    __syncwarp();
-    if (lane == 0 && i + 2 < n) issue(st, ahead(c_cur, i, 2));
-    c_cur = ahead(c_cur, i, 1);
+    if (x_bytes) {
+      bool waited = false;
+      walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp, (uint32_t)WARPS,
+                      run_log2, (flags & 4u) != 0, t, [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
+                        if (!waited) {  // first chunk of the item: the window must have landed
+                          mbar_wait(xbar, k & 1u);
+                          waited = true;
+                        }
+                        const uint32_t valid = mraw.z & 0x3FFu;
+                        const uint32_t xs = xbuf - col_base * (uint32_t)sizeof(VT);
+                        if (valid == (uint32_t)kChunkEntries) {
+#pragma unroll
+                          for (int s = 0; s < 8; s++) xv[s] = lds_x(xs + (idx16(iw, s) & 0x7FFFu) * (uint32_t)sizeof(VT), VT(0));
+                        } else {  // padding slots carry column 0, which may lie outside the window
+                          const int nv = min(8, max(0, (int)valid - lane * 8));
+#pragma unroll
+                          for (int s = 0; s < 8; s++)
+                            xv[s] = s < nv ? lds_x(xs + (idx16(iw, s) & 0x7FFFu) * (uint32_t)sizeof(VT), VT(0)) : VT(0);
+                        }
+                      });
+      if (!waited) mbar_wait(xbar, k & 1u);  // warps without work still consume the phase
+      k++;
+    } else {
+      walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp, (uint32_t)WARPS,
+                      run_log2, (flags & 4u) != 0, t,
+                      [&](const uint4 &iw, const uint4 &mraw, VT *xv) { gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv); });
+    }
   }
 }
 

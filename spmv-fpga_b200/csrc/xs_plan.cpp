@@ -1,0 +1,86 @@
+// Host-side work plan of the XS kernel (x window in shared memory).  No CUDA here: testable on the CPU.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "../../include/spmvb.h"
+#include "layout.h"
+
+namespace spmvb {
+
+// Work items of the XS kernel.  Every CTA (one per SM) owns ONE contiguous range of chunks of (almost) equal length -
+// static and balanced, no quantisation loss - and the range is cut into items at column-block boundaries and wherever
+// the x window the chunks touch would outgrow the shared-memory budget.  Cut points are block-relative multiples of
+// U = run length x warps per CTA, so that every warp of the CTA gets the same number of whole runs per item.
+void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<XsItem> &items,
+                           std::vector<uint32_t> &cta_first) {
+  const uint64_t U = ((uint64_t)1 << run_log2) * kXsWarps;
+  const uint32_t align = 16u / (uint32_t)L->vb;  // window start in elements: 16-byte aligned for the bulk copy
+  // candidate cut points in global chunk indices: block starts and block-relative multiples of U
+  std::vector<uint64_t> cuts;
+  for (int b = 0; b < L->blocks; b++)
+    for (uint64_t c = L->block_chunk0[b]; c < L->block_chunk0[b + 1]; c += U) cuts.push_back(c);
+  cuts.push_back(L->n_chunks);
+  cta_first.assign(n_cta + 1, 0);
+  size_t ci = 0;  // index into cuts of the current position
+  for (int j = 0; j < n_cta; j++) {
+    cta_first[j] = (uint32_t)items.size();
+    const uint64_t want_end = L->n_chunks * (uint64_t)(j + 1) / (uint64_t)n_cta;
+    size_t ce = ci;  // first cut >= want_end (the last CTA takes everything)
+    while (ce + 1 < cuts.size() && (cuts[ce] < want_end || j == n_cta - 1)) ce++;
+    if (j == n_cta - 1) ce = cuts.size() - 1;
+    // items of [cuts[ci], cuts[ce])
+    while (ci < ce) {
+      const uint64_t c0 = cuts[ci];
+      int b = (int)(std::upper_bound(L->block_chunk0.begin(), L->block_chunk0.end(), c0) - L->block_chunk0.begin()) - 1;
+      const uint64_t b_end = L->block_chunk0[b + 1];
+      uint32_t lo = 0xFFFF, hi = 0;
+      size_t e = ci;
+      bool fits = true;
+      while (e < ce && cuts[e] < b_end) {  // extend by one unit while the window fits
+        uint32_t nlo = lo, nhi = hi;
+        for (uint64_t q = cuts[e]; q < cuts[e + 1]; q++)
+          if (L->chunk_col_lo[q] <= L->chunk_col_hi[q]) {
+            nlo = std::min<uint32_t>(nlo, L->chunk_col_lo[q]);
+            nhi = std::max<uint32_t>(nhi, L->chunk_col_hi[q]);
+          }
+        const uint32_t wlo = nlo == 0xFFFF ? 0 : nlo / align * align;
+        const uint64_t bytes = nlo == 0xFFFF ? 16 : ((uint64_t)(nhi - wlo + 1) * L->vb + 15) / 16 * 16;
+        if (bytes > kXsCap) {
+          if (e == ci) { fits = false; e++; }  // even one unit does not fit: gather from global memory
+          break;
+        }
+        lo = nlo; hi = nhi; e++;
+      }
+      XsItem it{};
+      it.chunk_begin = (uint32_t)c0; it.chunk_count = (uint32_t)(cuts[e] - c0); it.block = (uint32_t)b;
+      if (fits && lo != 0xFFFF) {
+        const uint32_t wlo = lo / align * align;
+        it.col_base = wlo;
+        it.x_off = (uint32_t)((uint64_t)b * L->cdb + wlo);
+        it.x_bytes = (uint32_t)(((uint64_t)(hi - wlo + 1) * L->vb + 15) / 16 * 16);
+      } else if (fits) {
+        it.x_bytes = 16; it.x_off = (uint32_t)((uint64_t)b * L->cdb);  // only padding in there: any window will do
+      }
+      items.push_back(it);
+      ci = e;
+    }
+  }
+  cta_first[n_cta] = (uint32_t)items.size();
+}
+
+}  // namespace spmvb
+
+using namespace spmvb;
+
+extern "C" int64_t spmvb_layout_xs_plan(const spmvb_layout *l, int n_cta, int run_log2, uint32_t *items_out,
+                                        uint64_t max_items, uint32_t *cta_first_out) {
+  const Layout *L = (const Layout *)l;
+  if (!L || n_cta < 1 || run_log2 < L->run_log2 || run_log2 > 8) return fail(SPMVB_E_ARG, "xs_plan");
+  std::vector<XsItem> items;
+  std::vector<uint32_t> cta_first;
+  build_xs_items(L, n_cta, (uint32_t)run_log2, items, cta_first);
+  if (items_out) memcpy(items_out, items.data(), std::min<uint64_t>(items.size(), max_items) * sizeof(XsItem));
+  if (cta_first_out) memcpy(cta_first_out, cta_first.data(), cta_first.size() * 4);
+  return (int64_t)items.size();
+}

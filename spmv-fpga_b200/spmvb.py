@@ -39,6 +39,9 @@ SYMBOLS = {
     "spmvb_layout_bitmap_row": (_int, [_vp, _int, _vp]),
     "spmvb_layout_storage_mb": (ctypes.c_double, [_vp, _int]),
     "spmvb_layout_pack_x": (_int, [_vp, _vp, _u32, _vp]),
+    "spmvb_layout_xs_plan": (ctypes.c_int64, [_vp, _int, _int, _vp, _u64, _vp]),
+    "spmvb_layout_chunks": (_u64, [_vp]),
+    "spmvb_layout_chunk_cols": (_int, [_vp, _u64, _vp, _vp, _vp]),
     "spmvb_partition_rows": (_int, [_u32, _vp, _int, _int, _vp]),
     "spmvb_engine_create": (_int, [_vp, _int, _int, _vp]),
     "spmvb_engine_free": (None, [_vp]),
@@ -266,6 +269,25 @@ class Layout:
         _check(lib().spmvb_layout_pack_x(self.h, _ptr(xx), len(xx), _ptr(out)))
         return out
 
+    def xs_plan(self, n_cta=148, run_log2=1):
+        """Work plan of the shared-memory-x kernel: (items[n, 8] uint32, cta_first[n_cta + 1])."""
+        n = lib().spmvb_layout_xs_plan(self.h, n_cta, run_log2, None, 0, None)
+        if n < 0:
+            _check(int(n))
+        items = np.zeros((max(n, 1), 8), np.uint32)
+        first = np.zeros(n_cta + 1, np.uint32)
+        lib().spmvb_layout_xs_plan(self.h, n_cta, run_log2, _ptr(items), n, _ptr(first))
+        return items[:n], first
+
+    @property
+    def n_chunks(self):
+        return lib().spmvb_layout_chunks(self.h)
+
+    def chunk_cols(self, c):
+        lo, hi, blk = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        _check(lib().spmvb_layout_chunk_cols(self.h, c, ctypes.byref(lo), ctypes.byref(hi), ctypes.byref(blk)))
+        return lo.value, hi.value, blk.value
+
     def free(self):
         if self.h:
             lib().spmvb_layout_free(self.h)
@@ -285,13 +307,13 @@ def partition_rows(rows, row_ptr, parts, ratio_v=2):
     return bounds
 
 
-VARIANT_DEFAULT, VARIANT_DIRECT, VARIANT_RING, VARIANT_XSMEM = 0, 1, 2, 3
+VARIANT_AUTO, VARIANT_DIRECT, VARIANT_OCC4, VARIANT_OCC3, VARIANT_XS = 0, 1, 6, 7, 8
 
 
 class Engine:
     """Device-resident hw_matrix + the SpMV kernels (spmv_hw)."""
 
-    def __init__(self, layout, device=0, variant=VARIANT_DEFAULT):
+    def __init__(self, layout, device=0, variant=VARIANT_AUTO):
         out = _vp()
         _check(lib().spmvb_engine_create(layout.h, device, variant, ctypes.byref(out)))
         self.h = _vp(out.value)
@@ -301,6 +323,11 @@ class Engine:
 
     def set_variant(self, v):
         _check(lib().spmvb_engine_set_variant(self.h, v))
+
+    @property
+    def variant(self):
+        """The kernel variant in use (variant 0 resolves to the autotuned choice)."""
+        return lib().spmvb_engine_variant(self.h)
 
     @property
     def launches(self):

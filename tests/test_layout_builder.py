@@ -103,3 +103,53 @@ def test_zero_row_list_covers_every_row_not_plainly_stored(spmvb):
     rows2, cols2, rp2, ci2, va2 = matgen.uniform(3000, 200000, 16, seed=2)
     lay2 = spmvb.Layout.build(rows2, cols2, rp2, ci2, va2, 1, 1, True)
     assert lay2.zero_rows == -1  # every row spans several column blocks: the whole y is cleared
+
+
+@pytest.mark.parametrize("case", ["lap", "rmat", "uniform16k", "ragged"])
+def test_xs_plan_tiles_the_stream_and_windows_cover_the_columns(spmvb, case):
+    """Work plan of the shared-memory-x kernel (host side of spmv_xs_kernel): items tile the chunk range exactly, each
+    lies in one column block, is cut at block-relative multiples of run x 16 warps, and its x window (<= 128 KB, 16-byte
+    aligned) covers every column its chunks touch."""
+    if case == "lap":
+        rows, cols, rp, ci, va = matgen.laplacian2d(400, 300)
+        cdb = 0
+    elif case == "rmat":
+        rows, cols, rp, ci, va = matgen.rmat(14, 8, seed=2)
+        cdb = 0
+    elif case == "uniform16k":
+        rows, cols, rp, ci, va = matgen.uniform(20000, 60000, 16, seed=3)
+        cdb = 16384
+    else:
+        rows, cols, rp, ci, va = matgen.ragged(30000, 150000, seed=4)
+        cdb = 0
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True, cdb)
+    n_cta, run_log2 = 12, 1
+    items, first = lay.xs_plan(n_cta, run_log2)
+    unit = (1 << run_log2) * 16
+    assert first[0] == 0 and first[-1] == len(items) and np.all(np.diff(first.astype(np.int64)) >= 0)
+    pos = 0
+    block_start = {}
+    for c in range(lay.n_chunks):
+        b = lay.chunk_cols(c)[2]
+        block_start.setdefault(b, c)
+    for it in items:
+        begin, count, x_off, x_bytes, col_base, block = (int(v) for v in it[:6])
+        assert begin == pos and count > 0
+        pos += count
+        assert (begin - block_start[block]) % unit == 0
+        width = cdb or 32768
+        for c in range(begin, begin + count):
+            lo, hi, b = lay.chunk_cols(c)
+            assert b == block
+            if x_bytes and lo <= hi:
+                assert col_base <= lo and (hi - col_base + 1) * 8 <= x_bytes
+        if x_bytes:
+            assert x_bytes <= 128 * 1024 and x_bytes % 16 == 0 and (x_off * 8) % 16 == 0
+            assert x_off == block * width + col_base
+    assert pos == lay.n_chunks
+    per_cta = [int(items[first[j]:first[j + 1], 1].sum()) for j in range(n_cta)]
+    assert max(per_cta) - min(per_cta) <= 2 * unit + max(1, lay.n_chunks // n_cta // 4)
+    if case in ("lap", "uniform16k"):
+        assert np.all(items[:, 3] > 0)      # every window fits shared memory
+    if case == "rmat":
+        assert np.any(items[:, 3] == 0)     # fp64 x slice of a 32768-column block of an irregular matrix: 256 KB
