@@ -114,7 +114,7 @@ def test_xs_plan_tiles_the_stream_and_windows_cover_the_columns(spmvb, case):
         rows, cols, rp, ci, va = matgen.laplacian2d(400, 300)
         cdb = 0
     elif case == "rmat":
-        rows, cols, rp, ci, va = matgen.rmat(14, 8, seed=2)
+        rows, cols, rp, ci, va = matgen.rmat(16, 4, seed=2)  # 65 536 columns: two 32 768-column blocks
         cdb = 0
     elif case == "uniform16k":
         rows, cols, rp, ci, va = matgen.uniform(20000, 60000, 16, seed=3)
