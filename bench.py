@@ -29,10 +29,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="laplacian", choices=["laplacian", "rmat", "uniform", "band"])
+    ap.add_argument("--workload", default="laplacian", choices=["laplacian", "rmat", "uniform", "band", "poweriter"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--scale", type=int, default=0, help="log2(rows per GPU) for rmat/uniform (default 24 / 23)")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--cu", type=int, default=0, help="0 = 1, or enough row tiles that a tile of y is <= 16 MB when y exceeds 256 MB; "
+                    "compute units of the hw_matrix layout per GPU (row tiles: >1 keeps y L2-resident on very tall matrices)")
     ap.add_argument("--cols-div-blocks", type=int, default=0, help="column block width (0 = reference default 32768)")
     ap.add_argument("--flush-l2", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -54,6 +56,9 @@ def workload_spec(args, world):
         s = (args.scale or 23) + int(np.log2(world))
         return dict(kind="uniform", rows=1 << s, cols=1 << s, k=16,
                     name="uniform random %d rows x 16 nnz/row (BASELINE configs[3] shape)" % (1 << s))
+    if args.workload == "poweriter":  # reference arm: one gold SpMV per iteration on the whole matrix
+        s = args.scale or 24
+        return dict(kind="rmat", scale=s, rows=1 << s, cols=1 << s, name="R-MAT scale %d ef16 (power-iteration matrix)" % s)
     return dict(kind="band", rows=10000 * world, cols=10000 * world, name="band 10k rows (BASELINE configs[0])")
 
 
@@ -181,6 +186,108 @@ def cpu_reference_spmv(csr, is_double, budget_s=12.0, min_reps=3, max_reps=50):
     return kind, times, y, x
 
 
+def rmat_row_bounds(scale, world, p_one=0.24):
+    """Row ranges with (almost) equal expected non-zero count for an R-MAT matrix without vertex permutation: every row
+    bit is 1 with probability c + d independently, so the row CDF has a closed form (no need to generate the matrix on
+    every rank just to balance it)."""
+    n = 1 << scale
+
+    def cdf(r):  # P(row < r)
+        acc, pref = 0.0, 1.0
+        for k in range(scale - 1, -1, -1):
+            if (r >> k) & 1:
+                acc += pref * (1.0 - p_one)
+                pref *= p_one
+            else:
+                pref *= (1.0 - p_one)
+        return acc
+
+    bounds = [0]
+    for j in range(1, world):
+        lo, hi = 0, n
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if cdf(mid) < j / world:
+                lo = mid + 1
+            else:
+                hi = mid
+        bounds.append(max(bounds[-1], lo // 4 * 4))
+    bounds.append(n)
+    return bounds
+
+
+def run_poweriter(args, world, rank, local_rank):
+    """BASELINE configs[4]: fp32 power iteration x <- A x / ||A x|| on an R-MAT matrix row-sharded over the GPUs; one
+    step = one iteration = local SpMV + norm all-reduce + all-gather of the y slices into every rank's x (NCCL)."""
+    import torch
+    import host_driver
+    import spmvb
+    spmvb.lib()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    is_double = args.dtype == "f64"
+    tdt = torch.float64 if is_double else torch.float32
+    scale = args.scale or 24
+    n = 1 << scale
+    bounds = rmat_row_bounds(scale, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    t0 = time.perf_counter()
+    csr = spmvb.Csr.rmat(scale, 16, 0.57, 0.19, 0.19, 1, lo, hi, is_double)
+    t_gen = time.perf_counter() - t0
+    lay = spmvb.Layout.from_csr(csr, 1, 1, args.cols_div_blocks)
+    eng = spmvb.Engine(lay, local_rank, args.variant)
+    x_len = lay.blocks * (args.cols_div_blocks or 32768)
+    x = torch.zeros(x_len, dtype=tdt, device="cuda")
+    x[:n] = 1.0 / np.sqrt(n)
+    plan = host_driver.GatherPlan(bounds)
+    y = torch.zeros(plan.max_len, dtype=tdt, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def spmv_local(x_full, y_local):
+        eng.spmv_dev(x_full.data_ptr(), y_local.data_ptr(), accumulate=False, stream=stream)
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    host_driver.power_iteration(spmv_local, x, y, plan, max(args.warmup, 3), dist=dist)
+    sync()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nrm = host_driver.power_iteration(spmv_local, x, y, plan, args.steps, dist=dist)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms, float(csr.nnz), float(eng.launches - l0)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tm = t[:1].clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t[1:].clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms, nnz_total, launches = float(tm.item()), int(ts[0].item()), int(ts[1].item())
+    else:
+        nnz_total, launches = int(csr.nnz), int(eng.launches - l0)
+    if rank == 0:
+        vb = 8 if is_double else 4
+        per = ms / args.steps
+        alg = nnz_total * (2 + vb) + n * vb + world * n * vb
+        print(json.dumps({
+            "metric": "SpMV GFLOP/s (2*nnz/t)", "value": 2.0 * nnz_total / (per * 1e-3) / 1e9, "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": per,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "power iteration on R-MAT scale %d ef16, rows sharded over %d GPU(s), y all-gathered "
+                                   "into x by NCCL every iteration (BASELINE configs[4])" % (scale, world),
+                       "rows": n, "nnz": nnz_total, "variant": int(eng.variant), "row_bounds": bounds,
+                       "step": "clear rows + SpMV kernel + norm (all-reduce) + scale + all-gather"},
+            "effective_gbs": alg / (per * 1e-3) / 1e9, "last_norm": nrm, "gpu_launches": launches,
+            "setup_s": {"generate": t_gen}}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_reference(args, spec, world, rank):
     """--impl reference: the reference's own CPU implementation of the path on the host cores, same config/metric."""
     if rank != 0:
@@ -214,6 +321,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "poweriter" and args.impl != "reference":
+        if args.dtype == "f64" and "--dtype" not in sys.argv:
+            args.dtype = "f32"
+        run_poweriter(args, world, rank, local_rank)
+        return
     spec = workload_spec(args, world)
     if args.impl == "reference":
         run_reference(args, spec, world, rank)
@@ -237,7 +349,10 @@ def main():
     csr, rb, re = make_matrix(spmvb, spec, is_double, rank, world)
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
-    lay = spmvb.Layout.from_csr(csr, 1, 1, args.cols_div_blocks)
+    if args.cu <= 0:  # row tiles (the layout's compute units) so that the y range being updated stays in the L2 cache
+        ybytes = csr.rows * vb
+        args.cu = 1 if ybytes <= (256 << 20) else min(64, 1 << int(np.ceil(np.log2(ybytes / (16 << 20)))))
+    lay = spmvb.Layout.from_csr(csr, args.cu, 1, args.cols_div_blocks)
     t_layout = time.perf_counter() - t0
     t0 = time.perf_counter()
     eng = spmvb.Engine(lay, local_rank, args.variant)
@@ -320,7 +435,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": spec["name"], "rows": spec["rows"], "cols": spec["cols"], "nnz": nnz_total,
-                   "layout": "hw_matrix CU=1 VF=1 per GPU (rows sharded over GPUs, x replicated)",
+                   "layout": "hw_matrix CU=%d VF=1 per GPU (rows sharded over GPUs, x replicated)" % args.cu,
                    "l2": "flushed between steps" if args.flush_l2 else "inputs larger than L2 (no flush)",
                    "variant": int(eng.variant), "variant_requested": int(args.variant), "cols_div_blocks": int(args.cols_div_blocks) or 32768,
                    "pairs": int(lay.pairs), "zero_rows": int(lay.zero_rows),

@@ -33,6 +33,7 @@ struct Engine {
   uint32_t occ_run_log2 = 3, xs_run_log2 = 1;  // run lengths of the kernels (>= the layout's zero-list granularity)
   uint32_t n_items = 0;
   double xs_windowed_frac = 0.0;  // share of the chunks whose x window fits shared memory
+  bool tall = false;               // x and y both exceed the L2 cache: explicit L2 eviction policies
   int auto_variant = kVariantOcc3; // what variant 0 resolves to (autotuned at upload)
   float tune_ms[2] = {0.f, 0.f};   // autotune timings: OCC, XS
   uint32_t n_zero_rows = 0, run_log2 = 2;
@@ -77,7 +78,7 @@ static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, 
     grid = E->sms * std::max(per_sm, 1);
   }
   kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_rowmap, x, y, (uint32_t)E->n_chunks, E->cdb, E->occ_run_log2,
-                                       accumulate ? 4u : 0u);
+                                       (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u));
   return SPMVB_OK;
 }
 
@@ -93,7 +94,7 @@ static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumul
   }
   if (E->n_items == 0) return SPMVB_OK;
   kern<<<grid, kXsWarps * 32, smem, st>>>(stream, E->d_rowmap, x, y, E->d_items, E->d_cta_first, E->cdb, E->xs_run_log2,
-                                          accumulate ? 4u : 0u);
+                                          (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u));
   return SPMVB_OK;
 }
 
@@ -215,6 +216,8 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   E->variant = variant;
   if (const char *dm = getenv("SPMVB_DEBUG_MODE")) E->dbg = (uint32_t)atoi(dm);
   E->sms = prop.multiProcessorCount;
+  E->tall = (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) && (uint64_t)L->cols * L->vb > ((uint64_t)48 << 20);
+  if (const char *v = getenv("SPMVB_TALL")) E->tall = atoi(v) != 0;
   E->x_len = (uint64_t)L->blocks * L->cdb;  // >= expanded_cols: any 15-bit index of any block stays in range
   cudaError_t e = cudaSuccess;
   auto chk = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; };

@@ -37,9 +37,12 @@ struct Layout {
   // [k * blocks + b]
   std::vector<uint32_t> nr_rows, nr_nzeros, nr_ci, nr_val;
   std::vector<uint32_t> nr_cols;         // [b]
-  // [b * cu + k] (device order: block-major so that rows ascend through a block)
+  // [b * cu + k]
   std::vector<uint64_t> piece_off;       // byte offset into stream
   std::vector<uint64_t> piece_chunk0;    // first chunk index
+  std::vector<uint64_t> piece_chunk1;    // one past the last chunk index
+  std::vector<uint32_t> dev_order;       // pieces (b * cu + k) in device order
+  bool cu_major = false;                 // device order: CU-major instead of block-major
   std::vector<uint32_t> piece_real_nnz;  // entries before the padding rows
 
   uint8_t *stream = nullptr;  // all pieces, each zero-padded to whole chunks
@@ -58,7 +61,6 @@ struct Layout {
   bool zero_all = true;
   // smallest / largest column-in-block among the real entries of each chunk (for shared-memory x windows)
   std::vector<uint16_t> chunk_col_lo, chunk_col_hi;
-  std::vector<uint64_t> block_chunk0;  // [blocks + 1] first chunk of every column block
 
   ~Layout();
 };

@@ -208,21 +208,30 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   std::vector<uint32_t>().swap(seglen);
 
   // ---- hw_matrix_alloc (csr_hw.cpp:174-180) + device image offsets (each piece padded to whole chunks)
-  L->piece_off.assign(KB, 0); L->piece_chunk0.assign(KB, 0); L->piece_real_nnz.assign(KB, 0);
+  // Device order of the pieces.  Block-major (rows ascend through a block) is the default; when y does not fit the L2
+  // cache and there are several CUs, CU-major order (all blocks of CU 0's row range, then CU 1, ...) keeps the y
+  // range being updated L2-resident at the price of reading x once per CU - a 1 B-nnz uniform matrix goes from
+  // DRAM-bound scattered read-modify-writes on every update to L2 atomics.
+  L->cu_major = cu > 1 && (uint64_t)rows * vb > ((uint64_t)48 << 20);
+  if (const char *e = getenv("SPMVB_CU_MAJOR")) L->cu_major = cu > 1 && atoi(e) != 0;
+  L->piece_off.assign(KB, 0); L->piece_chunk0.assign(KB, 0); L->piece_chunk1.assign(KB, 0); L->piece_real_nnz.assign(KB, 0);
+  L->dev_order.resize(KB);
   uint64_t off = 0, chunk0 = 0, padded = 0;
-  for (int b = 0; b < blocks; b++)
-    for (int k = 0; k < cu; k++) {
-      const size_t kb = (size_t)k * blocks + b, bk = (size_t)b * cu + k;
-      uint32_t n = L->nr_nzeros[kb];
-      L->nr_ci[kb] = (n + kRatioCi - 1) / kRatioCi;
-      L->nr_val[kb] = n / ratio_v;  // floors like the reference (Q1); ceil(n / ratio_v) words are stored
-      uint64_t nchunks = ((uint64_t)L->nr_ci[kb] + kGroupsPerChunk - 1) / kGroupsPerChunk;
-      L->piece_off[bk] = off; L->piece_chunk0[bk] = chunk0;
-      L->piece_real_nnz[bk] = (uint32_t)(fp[(size_t)b * (cu + 1) + k + 1] - fp[(size_t)b * (cu + 1) + k]);
-      off += nchunks * (uint64_t)L->chunk_bytes;
-      chunk0 += nchunks;
-      padded += n;
-    }
+  for (size_t i = 0; i < KB; i++) {
+    const int b = L->cu_major ? (int)(i % blocks) : (int)(i / cu);
+    const int k = L->cu_major ? (int)(i / blocks) : (int)(i % cu);
+    const size_t kb = (size_t)k * blocks + b, bk = (size_t)b * cu + k;
+    L->dev_order[i] = (uint32_t)bk;
+    uint32_t n = L->nr_nzeros[kb];
+    L->nr_ci[kb] = (n + kRatioCi - 1) / kRatioCi;
+    L->nr_val[kb] = n / ratio_v;  // floors like the reference (Q1); ceil(n / ratio_v) words are stored
+    uint64_t nchunks = ((uint64_t)L->nr_ci[kb] + kGroupsPerChunk - 1) / kGroupsPerChunk;
+    L->piece_off[bk] = off; L->piece_chunk0[bk] = chunk0; L->piece_chunk1[bk] = chunk0 + nchunks;
+    L->piece_real_nnz[bk] = (uint32_t)(fp[(size_t)b * (cu + 1) + k + 1] - fp[(size_t)b * (cu + 1) + k]);
+    off += nchunks * (uint64_t)L->chunk_bytes;
+    chunk0 += nchunks;
+    padded += n;
+  }
   L->stream_bytes = off; L->n_chunks = chunk0; L->padded_nnz = padded;
   L->stream = (uint8_t *)calloc((size_t)std::max<uint64_t>(off, 16), 1);
   L->chunks = (ChunkMeta *)calloc((size_t)std::max<uint64_t>(chunk0, 1), sizeof(ChunkMeta));
@@ -231,7 +240,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   for (int64_t bk = 0; bk < (int64_t)KB; bk++) {
     const int b = (int)(bk / cu);
     uint64_t c0 = L->piece_chunk0[bk];
-    uint64_t c1 = (bk + 1 < (int64_t)KB) ? L->piece_chunk0[bk + 1] : L->n_chunks;
+    uint64_t c1 = L->piece_chunk1[bk];
     uint32_t real = L->piece_real_nnz[bk];
     for (uint64_t c = c0; c < c1; c++) {
       uint64_t first = (c - c0) * kChunkEntries;
@@ -323,7 +332,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   for (int64_t bk = 0; bk < (int64_t)KB; bk++) {
     const int b = (int)(bk / cu);
     uint64_t c0 = L->piece_chunk0[bk];
-    uint64_t c1 = (bk + 1 < (int64_t)KB) ? L->piece_chunk0[bk + 1] : L->n_chunks;
+    uint64_t c1 = L->piece_chunk1[bk];
     // last rank owned by this piece
     uint64_t last_piece_rank = 0;
     bool have = false;
@@ -362,12 +371,12 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
 #pragma omp parallel for schedule(static)
     for (int64_t bk = 0; bk < (int64_t)KB; bk++) {
       uint64_t c0 = L->piece_chunk0[bk];
-      uint64_t c1 = (bk + 1 < (int64_t)KB) ? L->piece_chunk0[bk + 1] : L->n_chunks;
+      uint64_t c1 = L->piece_chunk1[bk];
       for (uint64_t c = c0; c < c1; c++) {
         const ChunkMeta &m = L->chunks[c];
         if (!(m.valid & 0x3FFu)) continue;
-        // row split across two runs; runs are aligned globally (OCC/RING kernels) or to the block start (XS kernel)
-        if ((m.valid & kChunkStartsMid) && ((c % R) == 0 || ((c - L->piece_chunk0[(size_t)(bk / cu) * cu]) % R) == 0))
+        // row split across two runs; runs are aligned globally (OCC kernel) or to the piece start (XS kernel)
+        if ((m.valid & kChunkStartsMid) && ((c % R) == 0 || ((c - c0) % R) == 0))
           needz[m.row_first] = 1;
         if (m.valid & kChunkSole) continue;
         // every row with a segment (or part of one) in an atomics-only chunk
@@ -410,8 +419,6 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     L->chunk_col_lo[c] = lo; L->chunk_col_hi[c] = hi;
     L->chunks[c].block = (L->chunks[c].block & kMetaBlockMask) | (row_ends << kMetaRowsShift);
   }
-  L->block_chunk0.assign(blocks + 1, L->n_chunks);
-  for (int b = 0; b < blocks; b++) L->block_chunk0[b] = L->piece_chunk0[(size_t)b * cu];
 
   *out = L;
   return SPMVB_OK;

@@ -84,6 +84,42 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// L2 eviction policy for data that is read exactly once (the matrix stream): evict first, so that it does not push
+// x and the y range being updated out of the L2 cache
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// y update / x gather with an explicit L2 policy ("tall" matrices: x and y both exceed the L2 cache; the y range in
+// flight must stay resident, x has no reuse left once the pieces are walked CU-major)
+__device__ __forceinline__ void y_add_hint(double *p, double v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void y_add_hint(float *p, float v, uint64_t pol) {
+  asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double ldg_x_hint(const double *p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ldg_x_hint(const float *p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
 // 1-D bulk async copy global -> shared (TMA engine; SASS UBLKCP), completion counted on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -110,7 +146,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <typename VT, bool MUL>
 __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw, const uint4 *vw, const VT *xv,
                                               const uint32_t *__restrict__ rowmap, VT *__restrict__ y, int lane,
-                                              VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red) {
+                                              VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red,
+                                              uint64_t y_policy = 0) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t rank0 = mraw.x, valid = mraw.z & 0x3FFu, row_first = mraw.w;
   const bool consec = (mraw.z & kChunkRowsConsecutive) != 0;
@@ -215,8 +252,12 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
         const uint32_t row = rows[s];
         VT v = seg[s];
         if ((first_bit >> s) & 1u) v = vadd(cin, v);
-        if ((redm >> s) & 1u) y_add(y + row, v);
-        else y[row] = v;
+        if ((redm >> s) & 1u) {
+          if (y_policy) y_add_hint(y + row, v, y_policy);
+          else y_add(y + row, v);
+        } else {
+          y[row] = v;
+        }
       }
     }
   }
@@ -242,9 +283,15 @@ __device__ __forceinline__ float ldg_x(const float *p) {
   return v;
 }
 template <typename VT>
-__device__ __forceinline__ void gather_x(const uint4 &iw, const VT *__restrict__ x, uint32_t xbase, VT *xv) {
+__device__ __forceinline__ void gather_x(const uint4 &iw, const VT *__restrict__ x, uint32_t xbase, VT *xv,
+                                         uint64_t policy = 0) {
+  if (policy) {
 #pragma unroll
-  for (int s = 0; s < 8; s++) xv[s] = ldg_x(x + (xbase + (idx16(iw, s) & 0x7FFFu)));  // 32-bit element index
+    for (int s = 0; s < 8; s++) xv[s] = ldg_x_hint(x + (xbase + (idx16(iw, s) & 0x7FFFu)), policy);
+  } else {
+#pragma unroll
+    for (int s = 0; s < 8; s++) xv[s] = ldg_x(x + (xbase + (idx16(iw, s) & 0x7FFFu)));  // 32-bit element index
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -292,7 +339,7 @@ template <typename VT, typename Gather>
 __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
                                             VT *__restrict__ y, uint32_t ring, uint32_t bars, int lane, uint32_t base,
                                             uint32_t n_dom, uint32_t w, uint32_t W, uint32_t run_log2, bool force_red,
-                                            uint32_t &t, Gather gather) {
+                                            uint32_t &t, uint64_t y_policy, Gather gather) {
   constexpr int GW = VTraits<VT>::kGroupWords;
   constexpr int VW = VTraits<VT>::kValWords;
   constexpr uint32_t CHUNK_BYTES = GW * 16 * 32;
@@ -315,10 +362,11 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
   };
+  const uint64_t stream_policy = l2_policy_evict_first();
   auto issue = [&](uint32_t slot, uint32_t chunk) {  // lane 0 only
     const uint32_t bar = bars + (slot & 1u) * 8;
     mbar_expect_tx(bar, SLOT);
-    bulk_g2s(ring + (slot & 1u) * SLOT, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar);
+    bulk_g2s_hint(ring + (slot & 1u) * SLOT, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar, stream_policy);
   };
   const uint32_t my = ring + lane * (GW * 16);
   uint32_t c_cur = base + (w << run_log2);
@@ -343,7 +391,7 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
     const uint32_t pos = i & (R - 1);
     const bool sole = (mraw.z & kChunkSole) != 0 && !force_red;
     if (pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;  // stays set until the run's first row end
-    process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red);
+    process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red, y_policy);
     if (pos == R - 1 || i + 1 == n) {  // the row left open continues in another warp's run: hand over atomically
       if (open && lane == 0) {
         // in a `consecutive` chunk the open row follows from the rank (the flag covers it): no dependent row-map load
@@ -381,9 +429,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   }
   __syncwarp();
   uint32_t t = 0;
+  // flags bit 3: "tall" matrix (x and y both larger than the L2 cache): y updates evict-last, x gathers evict-first
+  const uint64_t y_policy = (flags & 8u) ? l2_policy_evict_last() : 0ull;
+  const uint64_t x_policy = (flags & 8u) ? l2_policy_evict_first() : 0ull;
   walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, 0u, n_chunks, blockIdx.x * WARPS + warp, gridDim.x * WARPS,
-                  run_log2, (flags & 4u) != 0, t,
-                  [&](const uint4 &iw, const uint4 &mraw, VT *xv) { gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv); });
+                  run_log2, (flags & 4u) != 0, t, y_policy, [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
+                    gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv, x_policy);
+                  });
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -426,6 +478,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     fence_barrier_init();
   }
   __syncthreads();
+  const uint64_t y_policy = (flags & 8u) ? l2_policy_evict_last() : 0ull;  // "tall" matrix: keep the y range in L2
   uint32_t t = 0, k = 0;  // k counts the windows loaded so far (phase of xbar)
   const uint32_t it_end = __ldg(cta_first + blockIdx.x + 1);
   for (uint32_t it = __ldg(cta_first + blockIdx.x); it < it_end; it++) {
@@ -442,7 +495,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     if (x_bytes) {
       bool waited = false;
       walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp, (uint32_t)WARPS,
-                      run_log2, (flags & 4u) != 0, t, [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
+                      run_log2, (flags & 4u) != 0, t, y_policy, [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                         if (!waited) {  // first chunk of the item: the window must have landed
                           mbar_wait(xbar, k & 1u);
                           waited = true;
@@ -463,7 +516,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
       k++;
     } else {
       walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp, (uint32_t)WARPS,
-                      run_log2, (flags & 4u) != 0, t,
+                      run_log2, (flags & 4u) != 0, t, 0ull,
                       [&](const uint4 &iw, const uint4 &mraw, VT *xv) { gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv); });
     }
   }

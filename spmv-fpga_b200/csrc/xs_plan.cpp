@@ -9,8 +9,8 @@
 namespace spmvb {
 
 // Work items of the XS kernel.  Every CTA (one per SM) owns ONE contiguous range of chunks of (almost) equal length -
-// static and balanced, no quantisation loss - and the range is cut into items at column-block boundaries and wherever
-// the x window the chunks touch would outgrow the shared-memory budget.  Cut points are block-relative multiples of
+// static and balanced, no quantisation loss - and the range is cut into items at piece boundaries and wherever
+// the x window the chunks touch would outgrow the shared-memory budget.  Cut points are piece-relative multiples of
 // U = run length x warps per CTA, so that every warp of the CTA gets the same number of whole runs per item.
 void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<XsItem> &items,
                            std::vector<uint32_t> &cta_first) {
@@ -18,8 +18,14 @@ void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<X
   const uint32_t align = 16u / (uint32_t)L->vb;  // window start in elements: 16-byte aligned for the bulk copy
   // candidate cut points in global chunk indices: block starts and block-relative multiples of U
   std::vector<uint64_t> cuts;
-  for (int b = 0; b < L->blocks; b++)
-    for (uint64_t c = L->block_chunk0[b]; c < L->block_chunk0[b + 1]; c += U) cuts.push_back(c);
+  // pieces in device order; an item never spans two pieces (a piece belongs to one column block)
+  std::vector<uint64_t> seg_start, seg_end;
+  std::vector<uint32_t> seg_block;
+  for (uint32_t bk : L->dev_order) {
+    if (L->piece_chunk1[bk] == L->piece_chunk0[bk]) continue;
+    seg_start.push_back(L->piece_chunk0[bk]); seg_end.push_back(L->piece_chunk1[bk]); seg_block.push_back(bk / (uint32_t)L->cu);
+    for (uint64_t c = L->piece_chunk0[bk]; c < L->piece_chunk1[bk]; c += U) cuts.push_back(c);
+  }
   cuts.push_back(L->n_chunks);
   cta_first.assign(n_cta + 1, 0);
   size_t ci = 0;  // index into cuts of the current position
@@ -32,8 +38,9 @@ void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<X
     // items of [cuts[ci], cuts[ce])
     while (ci < ce) {
       const uint64_t c0 = cuts[ci];
-      int b = (int)(std::upper_bound(L->block_chunk0.begin(), L->block_chunk0.end(), c0) - L->block_chunk0.begin()) - 1;
-      const uint64_t b_end = L->block_chunk0[b + 1];
+      const size_t sg = (size_t)(std::upper_bound(seg_start.begin(), seg_start.end(), c0) - seg_start.begin()) - 1;
+      const int b = (int)seg_block[sg];
+      const uint64_t b_end = seg_end[sg];
       uint32_t lo = 0xFFFF, hi = 0;
       size_t e = ci;
       bool fits = true;
@@ -67,6 +74,20 @@ void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<X
     }
   }
   cta_first[n_cta] = (uint32_t)items.size();
+  if (L->cu_major) {
+    // Tall matrices (pieces in CU-major order so that the y range in flight stays L2-resident): deal the items
+    // round-robin instead, so that all CTAs work inside the same CU's row range at any time.
+    std::vector<XsItem> rr;
+    rr.reserve(items.size());
+    std::vector<uint32_t> first(n_cta + 1, 0);
+    for (int j = 0; j < n_cta; j++) {
+      first[j] = (uint32_t)rr.size();
+      for (size_t i = (size_t)j; i < items.size(); i += (size_t)n_cta) rr.push_back(items[i]);
+    }
+    first[n_cta] = (uint32_t)rr.size();
+    items.swap(rr);
+    cta_first.swap(first);
+  }
 }
 
 }  // namespace spmvb

@@ -153,3 +153,21 @@ def test_xs_plan_tiles_the_stream_and_windows_cover_the_columns(spmvb, case):
         assert np.all(items[:, 3] > 0)      # every window fits shared memory
     if case == "rmat":
         assert np.any(items[:, 3] == 0)     # fp64 x slice of a 32768-column block of an irregular matrix: 256 KB
+
+
+def test_cu_major_device_order_keeps_pieces_bit_exact(spmvb, oracle, monkeypatch):
+    """The device order of the pieces (block-major or CU-major) is an engine decision: the pieces themselves do not
+    change, and the work plan still tiles the stream."""
+    rows, cols, rp, ci, va = matgen.uniform(6000, 100000, 12, seed=8)
+    ho = oracle.build(rows, cols, rp, ci, va, 4, 2, True)
+    ref = oracle.snapshot(ho, rows, 4, 2, True)
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SPMVB_CU_MAJOR", flag)
+        lay = spmvb.Layout.build(rows, cols, rp, ci, va, 4, 2, True)
+        assert oa.layouts_equal(ref, product_snapshot(lay, 4, 2, True)) == []
+        items, first = lay.xs_plan(7, 1)
+        assert int(items[:, 1].sum()) == lay.n_chunks
+        blocks_seen = [lay.chunk_cols(int(c))[2] for c in items[:, 0]]
+        assert all(int(b) == int(it[5]) for b, it in zip(blocks_seen, items))
+        lay.free()
+    oracle.free(ho)
