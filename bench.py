@@ -219,6 +219,9 @@ def rmat_row_bounds(scale, world, p_one=0.24):
 def run_poweriter(args, world, rank, local_rank):
     """BASELINE configs[4]: fp32 power iteration x <- A x / ||A x|| on an R-MAT matrix row-sharded over the GPUs; one
     step = one iteration = local SpMV + norm all-reduce + all-gather of the y slices into every rank's x (NCCL)."""
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import host_driver
     import spmvb
@@ -274,6 +277,8 @@ def run_poweriter(args, world, rank, local_rank):
         vb = 8 if is_double else 4
         per = ms / args.steps
         alg = nnz_total * (2 + vb) + n * vb + world * n * vb
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
         print(json.dumps({
             "metric": "SpMV GFLOP/s (2*nnz/t)", "value": 2.0 * nnz_total / (per * 1e-3) / 1e9, "unit": "GFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": per,
@@ -331,6 +336,18 @@ def main():
         run_reference(args, spec, world, rank)
         return
 
+    # Rank 0 must print exactly ONE JSON line on stdout: libraries (NCCL's version banner, ...) write there too, so
+    # stdout is pointed at stderr until the line is ready.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     import torch
     import spmvb
     spmvb.lib()  # fails loudly when the CUDA library is missing: there is no fallback
@@ -350,8 +367,11 @@ def main():
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
     if args.cu <= 0:  # row tiles (the layout's compute units) so that the y range being updated stays in the L2 cache
+        # (uniform columns have no y locality at all: tile as soon as y exceeds half the L2; power-law rows re-touch
+        #  the same heavy rows block after block and prefer one tile up to a few hundred MB)
         ybytes = csr.rows * vb
-        args.cu = 1 if ybytes <= (256 << 20) else min(64, 1 << int(np.ceil(np.log2(ybytes / (16 << 20)))))
+        limit = (64 << 20) if args.workload == "uniform" else (256 << 20)
+        args.cu = 1 if ybytes <= limit else min(64, 1 << int(np.ceil(np.log2(ybytes / (16 << 20)))))
     lay = spmvb.Layout.from_csr(csr, args.cu, 1, args.cols_div_blocks)
     t_layout = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -466,7 +486,7 @@ def main():
         line["cpu_baseline"] = {"value": 2.0 * nnz_local / t / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": kind,
                                 "sample": "whole workload matrix, %d passes of spmv_gold (csr.cpp:184-194), single thread"
                                           % len(times), "ms_per_pass": t * 1e3}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

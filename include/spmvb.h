@@ -106,7 +106,8 @@ int spmvb_engine_set_variant(spmvb_engine *e, int variant);
 int spmvb_engine_variant(const spmvb_engine *e);
 /* number of kernel launches issued by this engine so far (bench.py's gpu_launches) */
 uint64_t spmvb_engine_launches(const spmvb_engine *e);
-/* algorithmic bytes of one SpMV with this engine: nnz*(2+vb) + rows*vb + cols*vb */
+/* algorithmic bytes of one SpMV with this engine: nnz*(2+vb) + rows*vb + x*vb, x = the columns
+ * of the column blocks that hold at least one entry of this shard (= cols for a whole matrix) */
 uint64_t spmvb_engine_algorithmic_bytes(const spmvb_engine *e);
 /* engine-owned device vectors: x has expanded_nr_cols values, y has rows values */
 void *spmvb_engine_x_dev(spmvb_engine *e);

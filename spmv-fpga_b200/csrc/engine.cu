@@ -25,6 +25,7 @@ struct Engine {
   uint32_t rows = 0, cols = 0, expanded_cols = 0, cdb = 32768;
   int blocks = 0;
   uint64_t real_nnz = 0, n_chunks = 0, n_pairs = 0, stream_bytes = 0, x_len = 0;
+  uint64_t x_touched = 0;  // columns of the column blocks that hold at least one entry (what a SpMV must read of x)
   uint8_t *d_stream = nullptr;
   uint32_t *d_rowmap = nullptr;
   uint32_t *d_zero_rows = nullptr;
@@ -218,6 +219,11 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   E->sms = prop.multiProcessorCount;
   E->tall = (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) && (uint64_t)L->cols * L->vb > ((uint64_t)48 << 20);
   if (const char *v = getenv("SPMVB_TALL")) E->tall = atoi(v) != 0;
+  for (int b = 0; b < L->blocks; b++) {
+    uint64_t nz = 0;
+    for (int k = 0; k < L->cu; k++) nz += L->piece_real_nnz[(size_t)b * L->cu + k];
+    if (nz) E->x_touched += std::min<uint64_t>(L->cdb, (uint64_t)L->cols - (uint64_t)b * L->cdb);
+  }
   E->x_len = (uint64_t)L->blocks * L->cdb;  // >= expanded_cols: any 15-bit index of any block stays in range
   cudaError_t e = cudaSuccess;
   auto chk = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; };
@@ -303,7 +309,9 @@ int spmvb_engine_variant(const spmvb_engine *e) {
 uint64_t spmvb_engine_launches(const spmvb_engine *e) { return ((const Engine *)e)->launches; }
 uint64_t spmvb_engine_algorithmic_bytes(const spmvb_engine *e) {
   const Engine *E = (const Engine *)e;
-  return E->real_nnz * (2 + (uint64_t)E->vb) + (uint64_t)E->rows * E->vb + (uint64_t)E->cols * E->vb;
+  // x is credited once, and only the column blocks this shard touches (a row shard of a banded matrix reads a
+  // band of x, not all of it): nnz*(2+vb) + rows*vb + x_touched*vb
+  return E->real_nnz * (2 + (uint64_t)E->vb) + (uint64_t)E->rows * E->vb + E->x_touched * E->vb;
 }
 void *spmvb_engine_x_dev(spmvb_engine *e) { return ((Engine *)e)->d_x; }
 void *spmvb_engine_y_dev(spmvb_engine *e) { return ((Engine *)e)->d_y; }
