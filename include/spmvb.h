@@ -133,7 +133,8 @@ int spmvb_engine_time_spmv(spmvb_engine *e, int iters, int flush_l2, float *ms_o
 /* Asynchronous version for the benchmark: enqueues `steps` x (zero y; SpMV kernel) on the engine stream with
  * CUDA events around the whole region and around every kernel launch, and returns at once so the caller can
  * sample clocks while the GPU works.  collect waits and returns the region time and per-launch kernel times. */
-int spmvb_engine_enqueue_steps(spmvb_engine *e, int steps, int flush_l2);
+int spmvb_engine_enqueue_steps(spmvb_engine *e, int steps, int flags); /* bit 0: flush L2 between steps; bit 1: no
+                                                                          per-launch events (region time only) */
 int spmvb_engine_steps_done(spmvb_engine *e);
 int spmvb_engine_collect_steps(spmvb_engine *e, float *total_ms, float *kernel_ms);
 /* Iterated SpMV on one GPU (square matrices): x <- A x / ||A x||_2, `iters` times, all on device.

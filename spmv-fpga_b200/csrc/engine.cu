@@ -65,6 +65,23 @@ struct Engine {
 // Kernel variants (spmvb_engine_set_variant): 0 = auto (the faster of 7 and 8 on this matrix, timed once at upload);
 // 1 = DIRECT (ld.global per lane, contiguous chunk ranges, atomics only: the simple baseline);
 // 6 / 7 = OCC (TMA ring, x gathered from global memory, 4 / 3 CTAs per SM); 8 = XS (x window in shared memory).
+// Launch with programmatic dependent launch allowed: the kernel may start while the previous kernel of the stream
+// (the row-clearing kernel of the same step) is still draining; it executes griddepcontrol.wait before it touches x/y.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, (KArgs)args...);
+}
+
 template <typename VT, int MINB>
 static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
   constexpr int WARPS = 8;
@@ -78,8 +95,8 @@ static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, 
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     grid = E->sms * std::max(per_sm, 1);
   }
-  kern<<<grid, WARPS * 32, smem, st>>>(stream, E->d_rowmap, x, y, (uint32_t)E->n_chunks, E->cdb, E->occ_run_log2,
-                                       (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u));
+  CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, x, y, (uint32_t)E->n_chunks,
+                      E->cdb, E->occ_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u)));
   return SPMVB_OK;
 }
 
@@ -94,8 +111,9 @@ static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumul
     grid = E->sms;
   }
   if (E->n_items == 0) return SPMVB_OK;
-  kern<<<grid, kXsWarps * 32, smem, st>>>(stream, E->d_rowmap, x, y, E->d_items, E->d_cta_first, E->cdb, E->xs_run_log2,
-                                          (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u));
+  CUDA_TRY(launch_pdl(kern, grid, kXsWarps * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, x, y,
+                      (const XsItem *)E->d_items, (const uint32_t *)E->d_cta_first, E->cdb, E->xs_run_log2,
+                      (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u)));
   return SPMVB_OK;
 }
 
@@ -413,7 +431,8 @@ int spmvb_engine_time_spmv(spmvb_engine *e, int iters, int flush_l2, float *ms_o
   return SPMVB_OK;
 }
 
-int spmvb_engine_enqueue_steps(spmvb_engine *e, int steps, int flush_l2) {
+int spmvb_engine_enqueue_steps(spmvb_engine *e, int steps, int flags) {
+  const int flush_l2 = flags & 1, inner_events = !(flags & 2);
   Engine *E = (Engine *)e;
   if (!E || steps < 1) return fail(SPMVB_E_ARG, "enqueue_steps");
   CUDA_TRY(cudaSetDevice(E->device));
@@ -424,7 +443,7 @@ int spmvb_engine_enqueue_steps(spmvb_engine *e, int steps, int flush_l2) {
   for (auto &x : E->ev) cudaEventDestroy(x);
   E->ev.assign(2 * (size_t)steps + 2, nullptr);
   for (auto &x : E->ev) CUDA_TRY(cudaEventCreate(&x));
-  E->ev_steps = steps;
+  E->ev_steps = inner_events ? steps : 0;
   const void *x = E->d_x;
   void *y = E->d_y;
   CUDA_TRY(cudaEventRecord(E->ev[0], E->stream));
@@ -432,11 +451,11 @@ int spmvb_engine_enqueue_steps(spmvb_engine *e, int steps, int flush_l2) {
     if (flush_l2) l2_flush_kernel<<<E->sms * 4, 256, 0, E->stream>>>(E->d_flush, E->flush_words);
     int rc = zero_y(E, y, E->stream);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(E->ev[2 + 2 * i], E->stream));
+    if (inner_events) CUDA_TRY(cudaEventRecord(E->ev[2 + 2 * i], E->stream));
     rc = E->is_double ? launch_spmv<double>(E, (const double *)x, (double *)y, E->stream, 0)
                       : launch_spmv<float>(E, (const float *)x, (float *)y, E->stream, 0);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(E->ev[3 + 2 * i], E->stream));
+    if (inner_events) CUDA_TRY(cudaEventRecord(E->ev[3 + 2 * i], E->stream));
   }
   CUDA_TRY(cudaEventRecord(E->ev[1], E->stream));
   return SPMVB_OK;

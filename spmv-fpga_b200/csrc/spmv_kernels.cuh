@@ -126,6 +126,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// programmatic dependent launch: wait for the previous kernel of the stream / let the next one start early
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -339,7 +342,7 @@ template <typename VT, typename Gather>
 __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
                                             VT *__restrict__ y, uint32_t ring, uint32_t bars, int lane, uint32_t base,
                                             uint32_t n_dom, uint32_t w, uint32_t W, uint32_t run_log2, bool force_red,
-                                            uint32_t &t, uint64_t y_policy, Gather gather) {
+                                            uint32_t &t, uint64_t y_policy, bool dep_wait, Gather gather) {
   constexpr int GW = VTraits<VT>::kGroupWords;
   constexpr int VW = VTraits<VT>::kValWords;
   constexpr uint32_t CHUNK_BYTES = GW * 16 * 32;
@@ -374,6 +377,9 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
     issue(t, c_cur);
     if (1 < n) issue(t + 1, ahead(c_cur, 0, 1));
   }
+  // the matrix stream never changes, so its first chunks are already in flight; x and y may still be written by
+  // the previous kernel of the stream (row clearing, x <- y / ||y|| of an iterated caller)
+  if (dep_wait) grid_dep_wait();
   VT carry = VT(0);
   bool open = false, head_red = false;
   uint32_t next_rank = 0;
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   const uint64_t y_policy = (flags & 8u) ? l2_policy_evict_last() : 0ull;
   const uint64_t x_policy = (flags & 8u) ? l2_policy_evict_first() : 0ull;
   walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, 0u, n_chunks, blockIdx.x * WARPS + warp, gridDim.x * WARPS,
-                  run_log2, (flags & 4u) != 0, t, y_policy, [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
+                  run_log2, (flags & 4u) != 0, t, y_policy, true, [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                     gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv, x_policy);
                   });
 }
@@ -479,6 +485,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
   }
   __syncthreads();
   const uint64_t y_policy = (flags & 8u) ? l2_policy_evict_last() : 0ull;  // "tall" matrix: keep the y range in L2
+  grid_dep_wait();  // the first thing an item does is copy a window of x, which the previous kernel may have written
   uint32_t t = 0, k = 0;  // k counts the windows loaded so far (phase of xbar)
   const uint32_t it_end = __ldg(cta_first + blockIdx.x + 1);
   for (uint32_t it = __ldg(cta_first + blockIdx.x); it < it_end; it++) {
@@ -495,7 +502,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     if (x_bytes) {
       bool waited = false;
       walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp, (uint32_t)WARPS,
-                      run_log2, (flags & 4u) != 0, t, y_policy, [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
+                      run_log2, (flags & 4u) != 0, t, y_policy, false, [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                         if (!waited) {  // first chunk of the item: the window must have landed
                           mbar_wait(xbar, k & 1u);
                           waited = true;
@@ -516,7 +523,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
       k++;
     } else {
       walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp, (uint32_t)WARPS,
-                      run_log2, (flags & 4u) != 0, t, 0ull,
+                      run_log2, (flags & 4u) != 0, t, 0ull, false,
                       [&](const uint4 &iw, const uint4 &mraw, VT *xv) { gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv); });
     }
   }
@@ -525,6 +532,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
 // y[rows[i]] = 0 for the rows that receive atomics or no update at all (Layout::zero_rows)
 template <typename VT>
 __global__ void zero_rows_kernel(VT *__restrict__ y, const uint32_t *__restrict__ rows, uint32_t n) {
+  grid_dep_launch();  // the SpMV kernel may start its prologue now; it waits for this grid before touching y
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[rows[i]] = VT(0);
 }

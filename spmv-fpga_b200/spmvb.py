@@ -382,9 +382,9 @@ class Engine:
         _check(lib().spmvb_engine_time_spmv(self.h, iters, int(flush_l2), _ptr(ms)))
         return ms
 
-    def enqueue_steps(self, steps, flush_l2=False):
-        self._steps = steps
-        _check(lib().spmvb_engine_enqueue_steps(self.h, steps, int(flush_l2)))
+    def enqueue_steps(self, steps, flush_l2=False, inner_events=True):
+        self._steps = steps if inner_events else 0
+        _check(lib().spmvb_engine_enqueue_steps(self.h, steps, int(bool(flush_l2)) | (0 if inner_events else 2)))
 
     def steps_done(self):
         return bool(lib().spmvb_engine_steps_done(self.h))
