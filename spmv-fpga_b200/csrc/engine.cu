@@ -35,6 +35,7 @@ struct Engine {
   uint32_t n_items = 0;
   double xs_windowed_frac = 0.0;  // share of the chunks whose x window fits shared memory
   bool tall = false;               // x and y both exceed the L2 cache: explicit L2 eviction policies
+  bool cu_major = false;           // pieces in CU-major device order (row tiles)
   int auto_variant = kVariantOcc3; // what variant 0 resolves to (autotuned at upload)
   float tune_ms[2] = {0.f, 0.f};   // autotune timings: OCC, XS
   uint32_t n_zero_rows = 0, run_log2 = 2;
@@ -47,7 +48,6 @@ struct Engine {
   size_t h_stage_bytes = 0;
   cudaStream_t stream = nullptr;
   int sms = 148;
-  uint32_t dbg = 0;  // profiling experiments (SPMVB_DEBUG_MODE env), 0 in production
   uint64_t launches = 0;
   int grid_cache[9][2] = {};  // [variant][is_double] -> grid size
   // asynchronous step timing (bench): events of the last enqueue_steps()
@@ -175,12 +175,18 @@ static int do_spmv(Engine *E, const void *x_dev, void *y_dev, int accumulate, cu
   return launch_spmv<float>(E, (const float *)x, (float *)y, st, accumulate);
 }
 
-// variant 0: time the two production kernels once on this matrix (x = 0: the access pattern does not depend on the
-// values) and keep the faster one.  Irregular column patterns favour the shared-memory x window, banded ones the
-// global gathers with more resident warps.
+// variant 0: pick between the two production kernels from the structure of the layout (deterministic).  The
+// shared-memory x window pays when nearly every entry is its own (row, block) pair with a scattered column - then the
+// global gathers touch one sector per entry - and it is required for tall matrices (CU-major order, x streamed once per
+// row tile).  Banded and power-law matrices keep the global gathers with more resident warps.  Measured on B200:
+// Laplacian 54 vs 69 us, R-MAT 0.28 vs 0.38 ms, uniform 0.55 vs 0.43 ms, 1 B-nnz uniform 27 vs 8.9 ms (OCC vs XS).
+// SPMVB_AUTOTUNE=1 times both kernels on the actual matrix instead (not under a profiler: the timings are noise there).
 static int autotune(Engine *E) {
   E->auto_variant = kVariantOcc3;
-  if (getenv("SPMVB_NO_AUTOTUNE") || E->n_chunks == 0 || E->xs_windowed_frac < 0.5) return SPMVB_OK;
+  if (E->n_chunks == 0 || E->xs_windowed_frac < 0.5) return SPMVB_OK;
+  const double pairs_per_chunk = (double)E->n_pairs / (double)E->n_chunks;
+  if (E->cu_major || pairs_per_chunk > 160.0) E->auto_variant = kVariantXs;
+  if (!getenv("SPMVB_AUTOTUNE")) return SPMVB_OK;
   const int cand[2] = {kVariantOcc3, kVariantXs};
   cudaEvent_t a, b;
   CUDA_TRY(cudaEventCreate(&a));
@@ -233,7 +239,7 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   E->rows = L->rows; E->cols = L->cols; E->expanded_cols = L->expanded_cols; E->cdb = L->cdb; E->blocks = L->blocks;
   E->real_nnz = L->real_nnz; E->n_chunks = L->n_chunks; E->n_pairs = L->n_pairs; E->stream_bytes = L->stream_bytes;
   E->variant = variant;
-  if (const char *dm = getenv("SPMVB_DEBUG_MODE")) E->dbg = (uint32_t)atoi(dm);
+  E->cu_major = L->cu_major;
   E->sms = prop.multiProcessorCount;
   E->tall = (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) && (uint64_t)L->cols * L->vb > ((uint64_t)48 << 20);
   if (const char *v = getenv("SPMVB_TALL")) E->tall = atoi(v) != 0;
