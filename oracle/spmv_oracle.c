@@ -16,6 +16,9 @@
 #include "spmv_oracle.h"
 
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdlib.h>
 #include <string.h>
 
@@ -301,6 +304,36 @@ void orc_spmv_gold(uint32_t rows, const uint64_t *row_ptr, const uint32_t *col_i
       yy[i] = acc;
     }
   }
+}
+
+/* The same loop with the rows split over all host cores (baseline ii): every row is still
+ * summed left to right by one thread, so the result is bit-identical to orc_spmv_gold.  Returns the thread count. */
+int orc_spmv_gold_omp(uint32_t rows, const uint64_t *row_ptr, const uint32_t *col_ind, const void *values,
+                      const void *x, void *y, int is_double) {
+  int threads = 1;
+#ifdef _OPENMP
+  threads = omp_get_max_threads();
+#endif
+  if (is_double) {
+    const double *v = (const double *)values, *xx = (const double *)x;
+    double *yy = (double *)y;
+#pragma omp parallel for schedule(static, 4096)
+    for (int64_t i = 0; i < (int64_t)rows; i++) {
+      double acc = 0.0;
+      for (uint64_t j = row_ptr[i]; j < row_ptr[i + 1]; j++) acc += v[j] * xx[col_ind[j]];
+      yy[i] = acc;
+    }
+  } else {
+    const float *v = (const float *)values, *xx = (const float *)x;
+    float *yy = (float *)y;
+#pragma omp parallel for schedule(static, 4096)
+    for (int64_t i = 0; i < (int64_t)rows; i++) {
+      float acc = 0.0f;
+      for (uint64_t j = row_ptr[i]; j < row_ptr[i + 1]; j++) acc += v[j] * xx[col_ind[j]];
+      yy[i] = acc;
+    }
+  }
+  return threads;
 }
 
 /* per-row sum |a||x| in double: the normaliser of the north-star tolerance */

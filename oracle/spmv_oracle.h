@@ -35,7 +35,9 @@ int orc_spmv_emu(const orc_layout *l, const void *x, uint32_t n, void *y);
 
 void orc_spmv_gold(uint32_t rows, const uint64_t *row_ptr, const uint32_t *col_ind, const void *values,
                    const void *x, void *y, int is_double);
-/* same loop, rows split over OpenMP-free pthreads is NOT provided: single thread like the reference */
+/* same loop, rows split over all host cores with OpenMP (bit-identical result); returns the thread count */
+int orc_spmv_gold_omp(uint32_t rows, const uint64_t *row_ptr, const uint32_t *col_ind, const void *values,
+                      const void *x, void *y, int is_double);
 void orc_abs_ax(uint32_t rows, const uint64_t *row_ptr, const uint32_t *col_ind, const void *values,
                 const void *x, double *out, int is_double);
 int orc_verification(uint32_t n, const void *sw, const void *hw, int is_double);

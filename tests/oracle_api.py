@@ -206,6 +206,7 @@ class OracleLib:
         L.orc_hw_x.argtypes = [_vp, _vp, ctypes.c_uint32, _vp]
         L.orc_spmv_emu.argtypes = [_vp, _vp, ctypes.c_uint32, _vp]
         L.orc_spmv_gold.argtypes = [ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]
+        L.orc_spmv_gold_omp.argtypes = [ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]
         L.orc_abs_ax.argtypes = [ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]
         L.orc_verification.argtypes = [ctypes.c_uint32, _vp, _vp, ctypes.c_int]
         self.L = L
@@ -249,6 +250,15 @@ class OracleLib:
         y = np.zeros(rows, vdtype(is_double))
         self.L.orc_spmv_gold(rows, _ptr(rp), _ptr(ci), _ptr(va), _ptr(xx), _ptr(y), int(is_double))
         return y
+
+    def spmv_gold_omp(self, rows, row_ptr, col_ind, values, x, is_double):
+        rp = np.ascontiguousarray(row_ptr, np.uint64)
+        ci = np.ascontiguousarray(col_ind, np.uint32)
+        va = np.ascontiguousarray(values, vdtype(is_double))
+        xx = np.ascontiguousarray(x, vdtype(is_double))
+        y = np.zeros(rows, vdtype(is_double))
+        threads = self.L.orc_spmv_gold_omp(rows, _ptr(rp), _ptr(ci), _ptr(va), _ptr(xx), _ptr(y), int(is_double))
+        return y, threads
 
     def abs_ax(self, rows, row_ptr, col_ind, values, x, is_double):
         rp = np.ascontiguousarray(row_ptr, np.uint64)

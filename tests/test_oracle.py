@@ -115,3 +115,11 @@ def test_oracle_matches_compiled_reference(oracle, case):
     assert oracle.spmv_emu(ho, x, y_orc, isd) == 0
     assert np.array_equal(y_ref.view(np.uint8), y_orc.view(np.uint8))
     R.free(hr); oracle.free(ho)
+
+
+def test_openmp_gold_is_bit_identical_to_the_single_thread_loop(oracle):
+    rows, cols, rp, ci, va = matgen.ragged(5000, 60000, seed=17)
+    x = np.random.default_rng(1).random(cols)
+    y1 = oracle.spmv_gold(rows, rp, ci, va, x, True)
+    y2, threads = oracle.spmv_gold_omp(rows, rp, ci, va, x, True)
+    assert threads >= 1 and np.array_equal(y1.view(np.uint8), y2.view(np.uint8))
