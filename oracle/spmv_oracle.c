@@ -10,7 +10,7 @@
  *   Q2  compute units whose split never fired get 0 rows / 0 non-zeros
  *   Q4  the bitmap walk in the accumulation is bounded by the row count
  *   Q5  unused 16-bit index slots are zero
- * PARITY PINNED against oracle/_ref (the compiled reference) by tests/test_oracle_vs_ref.py
+ * PARITY PINNED against oracle/_ref (the compiled reference) by tests/test_oracle.py
  * and against tests/golden/ fixtures generated from it.
  */
 #include "spmv_oracle.h"
