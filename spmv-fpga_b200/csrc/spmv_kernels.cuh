@@ -2,21 +2,23 @@
 // fused with the host accumulation accum_results, src/csr_hw.cpp:1531-1565).
 //
 // Mapping of the reference stages:
-//   read_data_submatrix  (spmv.cpp:6-34)    -> chunk fetch: ld.global.v4 per lane (variant DIRECT) or a per-warp
-//                                              cp.async.bulk (TMA 1-D) ring with mbarriers (variant RING / XSMEM)
+//   read_data_submatrix  (spmv.cpp:6-34)    -> chunk fetch: a per-warp ring of slots filled by cp.async.bulk (TMA 1-D,
+//                                              SASS UBLKCP) with an mbarrier per slot and an evict-first L2 policy;
+//                                              lanes read their group with conflict-free LDS.128 (kernels OCC, XS);
+//                                              ld.global.v4 per lane in the DIRECT baseline
 //   stream_data_col_ind  (spmv.cpp:36-49)   -> in-register unpack of 8 x (15-bit column | end-of-row bit)
 //   stream_data_values   (spmv.cpp:51-64)   -> in-register reinterpretation of the value words
 //   compute_results      (spmv.cpp:66-104)  -> per-lane left-to-right multiply/add over its 8 entries (mul and add
 //                                              separately rounded, like the HLS cores) + warp segmented scan keyed on
 //                                              the end-of-row bit
-//   write_back_results + accum_results      -> red.global.add to y[rowmap[rank]] (rank = running count of
+//   write_back_results + accum_results      -> st.global / red.global.add to y[rowmap[rank]] (rank = running count of
 //                                              end-of-row bits), no partial-y buffers, no host pass
-//   x slice copy L0      (spmv.cpp:182-192) -> variant XSMEM: cp.async.bulk of the block's x slice into shared
-//                                              memory; other variants gather x through L1/L2
+//   x slice copy L0      (spmv.cpp:182-192) -> kernel XS: cp.async.bulk of the x window of a work item into shared
+//                                              memory, gathers with LDS; kernel OCC gathers x through L1/L2
 //
-// Work unit: a "chunk" = 32 consecutive 8-entry groups of one piece (one group per lane).  Every warp owns a
-// contiguous range of chunks, carries the open row sum in registers from chunk to chunk, and only the two ends of its
-// range depend on atomics for correctness across warps.
+// Work unit: a "chunk" = 32 consecutive 8-entry groups of one piece (one group per lane).  Warps walk runs of
+// consecutive chunks (walk_chunks), carry the open row sum in registers inside a run, and hand a row that continues
+// into another warp's run over through an atomic.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
