@@ -1,7 +1,11 @@
 // Library-owned CSR matrices: reader/writer for the reference's matrix-file format and the synthetic generators
 // for BASELINE.json's configs.  Reference: read_csr_header / read_csr_matrix, src/csr.cpp:10-46, 87-136 (format
 // "%u %u %u\n" then "%u %u %lf\n" / "%u %u %f\n", 1-based, sorted by row; src/util.h:28-29).
+#include <fcntl.h>
 #include <omp.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cerrno>
@@ -67,69 +71,138 @@ int spmvb_layout_build_csr(const spmvb_csr *m, int n_cu, int vf, uint32_t cols_d
                             A->is_double, cols_div_blocks, out);
 }
 
+// Parallel reader: the file is mapped, cut into one byte range per thread at line boundaries, lines are counted and
+// then parsed in place (strtoul / strtod), so that a 1 B-line file is parsed by all cores instead of one fgets+sscanf
+// loop (the reference: csr.cpp:87-136, minutes per 100 M lines).  Same acceptance rules as the reference reader plus
+// range / order checks.
 int spmvb_csr_read(const char *path, int is_double, spmvb_csr **out) {
   if (!path || !out) return fail(SPMVB_E_ARG, "csr_read");
   *out = nullptr;
-  FILE *fp = fopen(path, "r");
-  if (!fp) return fail(SPMVB_E_IO, std::string("Could not open file ") + path);  // csr.cpp:15-18
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(SPMVB_E_IO, std::string("Could not open file ") + path);  // csr.cpp:15-18
+  struct stat st;
+  if (fstat(fd, &st) != 0 || st.st_size == 0) { close(fd); return fail(SPMVB_E_IO, "unexpected eof found"); }
+  const size_t size = (size_t)st.st_size;
+  const char *buf = (const char *)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (buf == MAP_FAILED) return fail(SPMVB_E_IO, "mmap failed");
+  auto done = [&](int code, const std::string &msg) { munmap((void *)buf, size); return fail(code, msg); };
+  // header line (csr.cpp:21): "%u %u %u\n"
+  const char *eol = (const char *)memchr(buf, '\n', size);
+  const size_t hdr_len = eol ? (size_t)(eol - buf) + 1 : size;
   unsigned rows = 0, cols = 0;
   unsigned long long nnz = 0;
-  char line[1024];
-  if (!fgets(line, sizeof line, fp) || sscanf(line, "%u %u %llu", &rows, &cols, &nnz) != 3) {
-    fclose(fp);
-    return fail(SPMVB_E_IO, "parse error in header");  // csr.cpp:33-36
+  {
+    std::string h(buf, hdr_len);
+    if (sscanf(h.c_str(), "%u %u %llu", &rows, &cols, &nnz) != 3) return done(SPMVB_E_IO, "parse error in header");
   }
+  const int T = std::max(1, omp_get_max_threads());
+  std::vector<size_t> cut(T + 1);
+  cut[0] = hdr_len; cut[T] = size;
+  for (int t = 1; t < T; t++) {
+    size_t p = hdr_len + (size - hdr_len) / T * t;
+    const char *nl = p < size ? (const char *)memchr(buf + p, '\n', size - p) : nullptr;
+    cut[t] = nl ? (size_t)(nl - buf) + 1 : size;
+    if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+  }
+  // pass 1: non-blank lines per range
+  std::vector<uint64_t> first(T + 1, 0);
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    uint64_t n = 0;
+    for (size_t p = cut[t]; p < cut[t + 1];) {
+      const char *nl = (const char *)memchr(buf + p, '\n', cut[t + 1] - p);
+      const size_t e = nl ? (size_t)(nl - buf) : cut[t + 1];
+      size_t q = p;
+      while (q < e && (buf[q] == ' ' || buf[q] == '\t' || buf[q] == '\r')) q++;
+      if (q < e) n++;
+      p = e + 1;
+    }
+    first[t + 1] = n;
+  }
+  for (int t = 0; t < T; t++) first[t + 1] += first[t];
+  if (first[T] != nnz) return done(SPMVB_E_IO, "entry count differs from the header");
   Csr *A = new Csr();
   A->rows = rows; A->cols = cols; A->is_double = is_double ? 1 : 0;
   A->row_ptr.assign((size_t)rows + 1, 0);
   A->col_ind.resize(nnz);
   A->values.resize((size_t)nnz * (is_double ? 8 : 4));
-  uint64_t pos = 0;
-  uint32_t row_pos = 0;  // next row whose row_ptr is not yet written (csr.cpp:115-117)
-  while (fgets(line, sizeof line, fp)) {
-    char *p = line, *q;
-    while (*p == ' ' || *p == '\t') p++;
-    if (*p == '\n' || *p == '\0') continue;
-    errno = 0;
-    unsigned long r = strtoul(p, &q, 10);
-    if (q == p) { fclose(fp); delete A; return fail(SPMVB_E_IO, std::string("parse error: ") + line); }
-    p = q;
-    unsigned long c = strtoul(p, &q, 10);
-    if (q == p) { fclose(fp); delete A; return fail(SPMVB_E_IO, std::string("parse error: ") + line); }
-    p = q;
-    double v = strtod(p, &q);
-    if (q == p) { fclose(fp); delete A; return fail(SPMVB_E_IO, std::string("parse error: ") + line); }
-    if (r < 1 || r > rows || c < 1 || c > cols || pos >= nnz || r < row_pos) {
-      fclose(fp); delete A;
-      return fail(SPMVB_E_IO, std::string("entry out of range or rows not sorted: ") + line);
+  std::vector<uint32_t> row_of(nnz);
+  int bad = 0;
+  // pass 2: parse.  strtoul/strtod stop at the newline; the mapping ends with the file, so the last line is copied
+#pragma omp parallel num_threads(T)
+  {
+    const int t = omp_get_thread_num();
+    uint64_t i = first[t];
+    char tail[256];
+    for (size_t p = cut[t]; p < cut[t + 1] && !bad;) {
+      const char *nl = (const char *)memchr(buf + p, '\n', cut[t + 1] - p);
+      const size_t e = nl ? (size_t)(nl - buf) : cut[t + 1];
+      size_t q = p;
+      while (q < e && (buf[q] == ' ' || buf[q] == '\t' || buf[q] == '\r')) q++;
+      if (q < e) {
+        const char *line = buf + q;
+        if (!nl) {  // last line of the file without a trailing newline: parse a NUL-terminated copy
+          size_t len = std::min(e - q, sizeof tail - 1);
+          memcpy(tail, buf + q, len); tail[len] = 0; line = tail;
+        }
+        char *c1, *c2, *c3;
+        unsigned long r = strtoul(line, &c1, 10);
+        unsigned long c = strtoul(c1, &c2, 10);
+        double v = strtod(c2, &c3);
+        if (c1 == line || c2 == c1 || c3 == c2 || r < 1 || r > rows || c < 1 || c > cols) { bad = 1; break; }
+        row_of[i] = (uint32_t)(r - 1);
+        A->col_ind[i] = (uint32_t)(c - 1);  // mmarket files are not zero-based, csr.cpp:118
+        A->set_value(i, v);
+        i++;
+      }
+      p = e + 1;
     }
-    for (uint32_t i = row_pos; i < r; i++) A->row_ptr[i] = pos;  // empty rows
-    row_pos = (uint32_t)r;
-    A->col_ind[pos] = (uint32_t)(c - 1);
-    A->set_value(pos, v);
-    pos++;
   }
-  fclose(fp);
-  if (pos != nnz) { delete A; return fail(SPMVB_E_IO, "entry count differs from the header"); }
-  for (uint32_t i = row_pos; i <= rows; i++) A->row_ptr[i] = nnz;  // csr.cpp:126 (+ trailing empty rows, Q3)
+  munmap((void *)buf, size);
+  if (bad) { delete A; return fail(SPMVB_E_IO, "parse error: malformed or out-of-range entry"); }
+  // sorted by row? then row_ptr = counts, prefix-summed (empty and trailing rows come out right by construction, Q3)
+#pragma omp parallel for schedule(static) reduction(| : bad)
+  for (int64_t i = 1; i < (int64_t)nnz; i++) bad |= row_of[i] < row_of[i - 1];
+  if (bad) { delete A; return fail(SPMVB_E_IO, "entries are not sorted by row"); }
+  for (uint64_t i = 0; i < nnz; i++) A->row_ptr[(size_t)row_of[i] + 1]++;
+  for (uint32_t r = 0; r < rows; r++) A->row_ptr[r + 1] += A->row_ptr[r];
   *out = (spmvb_csr *)A;
   return SPMVB_OK;
 }
 
+// Writer: every thread formats its own row range, the pieces are written in order.
 int spmvb_csr_write(const spmvb_csr *m, const char *path) {
   const Csr *A = (const Csr *)m;
   if (!A || !path) return fail(SPMVB_E_ARG, "csr_write");
   FILE *fp = fopen(path, "w");
   if (!fp) return fail(SPMVB_E_IO, std::string("cannot create ") + path);
-  std::vector<char> buf(1 << 20);
-  setvbuf(fp, buf.data(), _IOFBF, buf.size());
   fprintf(fp, "%u %u %llu\n", A->rows, A->cols, (unsigned long long)A->nnz());
-  for (uint32_t r = 0; r < A->rows; r++)
-    for (uint64_t j = A->row_ptr[r]; j < A->row_ptr[r + 1]; j++) {
-      if (A->is_double) fprintf(fp, "%u %u %.17g\n", r + 1, A->col_ind[j] + 1, ((const double *)A->values.data())[j]);
-      else fprintf(fp, "%u %u %.9g\n", r + 1, A->col_ind[j] + 1, (double)((const float *)A->values.data())[j]);
+  const int T = std::max(1, omp_get_max_threads());
+  const uint32_t batch = 1u << 20;  // rows per round: bounds the memory of the formatted text
+  int err = 0;
+  for (uint32_t r0 = 0; r0 < A->rows && !err; r0 += batch) {
+    const uint32_t r1 = (uint32_t)std::min<uint64_t>((uint64_t)r0 + batch, A->rows);
+    std::vector<std::string> part(T);
+#pragma omp parallel num_threads(T)
+    {
+      const int t = omp_get_thread_num();
+      const uint32_t a = r0 + (uint32_t)((uint64_t)(r1 - r0) * t / T), b = r0 + (uint32_t)((uint64_t)(r1 - r0) * (t + 1) / T);
+      std::string &s = part[t];
+      char line[96];
+      for (uint32_t r = a; r < b; r++)
+        for (uint64_t j = A->row_ptr[r]; j < A->row_ptr[r + 1]; j++) {
+          int n = A->is_double
+                      ? snprintf(line, sizeof line, "%u %u %.17g\n", r + 1, A->col_ind[j] + 1, ((const double *)A->values.data())[j])
+                      : snprintf(line, sizeof line, "%u %u %.9g\n", r + 1, A->col_ind[j] + 1, (double)((const float *)A->values.data())[j]);
+          s.append(line, (size_t)n);
+        }
     }
-  if (fclose(fp) != 0) return fail(SPMVB_E_IO, "write error");
+    for (int t = 0; t < T && !err; t++)
+      if (!part[t].empty() && fwrite(part[t].data(), 1, part[t].size(), fp) != part[t].size()) err = 1;
+  }
+  if (fclose(fp) != 0 || err) return fail(SPMVB_E_IO, "write error");
   return SPMVB_OK;
 }
 
