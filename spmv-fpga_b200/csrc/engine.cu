@@ -384,18 +384,36 @@ int spmvb_engine_get_y(spmvb_engine *e, void *y_host, uint32_t n, int accumulate
     CUDA_TRY(cudaMallocHost(&E->h_stage, bytes));
     E->h_stage_bytes = bytes;
   }
-  CUDA_TRY(cudaMemcpyAsync(E->h_stage, E->d_y, bytes, cudaMemcpyDeviceToHost, E->stream));
-  CUDA_TRY(cudaStreamSynchronize(E->stream));
-  // y_fpga[row] += partial, csr_hw.cpp:1557 (the per-block partials were already summed on the device)
-  if (E->is_double) {
-    double *dst = (double *)y_host; const double *src = (const double *)E->h_stage;
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < (int64_t)m; i++) dst[i] += src[i];
-  } else {
-    float *dst = (float *)y_host; const float *src = (const float *)E->h_stage;
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < (int64_t)m; i++) dst[i] += src[i];
+  // y_fpga[row] += partial, csr_hw.cpp:1557 (the per-block partials were already summed on the device).  The copy is
+  // cut into pieces so that the host addition of piece i overlaps the transfer of piece i+1.
+  constexpr int kPieces = 8;
+  cudaEvent_t ev[kPieces];
+  uint32_t cutp[kPieces + 1];
+  for (int p = 0; p <= kPieces; p++) cutp[p] = (uint32_t)((uint64_t)m * p / kPieces);
+  for (int p = 0; p < kPieces; p++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&ev[p], cudaEventDisableTiming));
+    const size_t o = (size_t)cutp[p] * E->vb, len = (size_t)(cutp[p + 1] - cutp[p]) * E->vb;
+    if (len) CUDA_TRY(cudaMemcpyAsync((uint8_t *)E->h_stage + o, (const uint8_t *)E->d_y + o, len, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaEventRecord(ev[p], E->stream));
   }
+  cudaError_t werr = cudaSuccess;
+  for (int p = 0; p < kPieces; p++) {
+    cudaError_t r = cudaEventSynchronize(ev[p]);
+    if (r != cudaSuccess) werr = r;
+    cudaEventDestroy(ev[p]);
+    if (werr != cudaSuccess) continue;
+    const int64_t a = cutp[p], b = cutp[p + 1];
+    if (E->is_double) {
+      double *dst = (double *)y_host; const double *src = (const double *)E->h_stage;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = a; i < b; i++) dst[i] += src[i];
+    } else {
+      float *dst = (float *)y_host; const float *src = (const float *)E->h_stage;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = a; i < b; i++) dst[i] += src[i];
+    }
+  }
+  if (werr != cudaSuccess) return fail(SPMVB_E_CUDA, std::string("get_y: ") + cudaGetErrorString(werr));
   return SPMVB_OK;
 }
 
