@@ -78,6 +78,11 @@ constexpr int kXsWarps = 16;             // warps per CTA of the XS kernel (one 
 void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<XsItem> &items,
                     std::vector<uint32_t> &cta_first);
 
+// pieces shared by the host builder (layout_builder.cpp) and the GPU builder (layout_gpu.cuh)
+int layout_init_header(Layout *L, uint32_t rows, uint32_t cols, uint64_t nnz, int cu, int vf, int is_double,
+                       uint32_t cdb_in);
+void layout_finish_pieces(Layout *L, const uint64_t *fp, const uint32_t *pad_rows, std::vector<uint64_t> &piece_last_rank);
+
 void set_error(const std::string &msg);
 int fail(int code, const std::string &msg);
 

@@ -47,21 +47,18 @@ struct BlockOf {  // col -> block, shift when cols_div_blocks is a power of two
   inline uint32_t operator()(uint32_t col) const { return shift >= 0 ? col >> shift : col / cdb; }
 };
 
-template <typename RP>
-int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *col_ind, const void *values, int cu,
-               int vf, int is_double, uint32_t cdb_in, Layout **out) {
-  if (!out) return fail(SPMVB_E_ARG, "out is NULL");
-  *out = nullptr;
+}  // namespace
+
+// Validation + everything that follows from the sizes alone: scan_matrix's block count and expanded_nr_cols
+// (csr_hw.cpp:25-33), thres_h - thres_l + 1 per block (:64-76,167), word geometry (util.h:61-67).
+int layout_init_header(Layout *L, uint32_t rows, uint32_t cols, uint64_t nnz, int cu, int vf, int is_double,
+                       uint32_t cdb_in) {
   if (cu < 1 || cu > 4096) return fail(SPMVB_E_ARG, "n_cu must be >= 1");
   if (!(vf == 1 || vf == 2 || vf == 4 || vf == 8)) return fail(SPMVB_E_ARG, "vf must be 1, 2, 4 or 8");
-  if (rows == 0 || cols == 0 || !row_ptr) return fail(SPMVB_E_ARG, "empty matrix");
+  if (rows == 0 || cols == 0) return fail(SPMVB_E_ARG, "empty matrix");
   uint32_t cdb = cdb_in ? cdb_in : ((cu == 10 || cu == 12) ? 16384u : 32768u);  // util.h:41-59
   if (cdb > 32768 || cdb % 4 != 0) return fail(SPMVB_E_ARG, "cols_div_blocks must be a multiple of 4 and <= 32768");
   if ((uint64_t)cols > (uint64_t)cdb * kMetaBlockMask) return fail(SPMVB_E_RANGE, "too many column blocks");
-  const uint64_t nnz = (uint64_t)row_ptr[rows];
-  if (nnz && (!col_ind || !values)) return fail(SPMVB_E_ARG, "col_ind/values are NULL");
-
-  Layout *L = new Layout();
   L->cu = cu; L->vf = vf; L->is_double = is_double ? 1 : 0;
   L->rows = rows; L->cols = cols; L->cdb = cdb;
   L->ratio_v = is_double ? 2 : 4;
@@ -70,23 +67,85 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   L->group_bytes = L->ratio_col_val * kBusBytes;
   L->chunk_bytes = L->group_bytes * kGroupsPerChunk;
   L->real_nnz = nnz;
-  const int vb = L->vb;
-  const uint32_t ratio_v = (uint32_t)L->ratio_v;
-
-  // scan_matrix, csr_hw.cpp:25-33: blocks and expanded_nr_cols
   int blocks = (int)(cols / cdb) + 1;
   if (cols % cdb == 0) blocks--;
   L->blocks = blocks;
-  {
-    uint64_t N = (uint64_t)ratio_v * (uint64_t)blocks;
-    uint64_t ec = cols;
-    if (ec % N) ec += N - ec % N;
-    if (ec > 0xFFFFFFFFull) { delete L; return fail(SPMVB_E_RANGE, "expanded_nr_cols overflows IndexType"); }
-    L->expanded_cols = (uint32_t)ec;
-  }
+  uint64_t N = (uint64_t)L->ratio_v * (uint64_t)blocks;
+  uint64_t ec = cols;
+  if (ec % N) ec += N - ec % N;
+  if (ec > 0xFFFFFFFFull) return fail(SPMVB_E_RANGE, "expanded_nr_cols overflows IndexType");
+  L->expanded_cols = (uint32_t)ec;
   L->nr_cols.resize(blocks);
-  for (int b = 0; b < blocks; b++)  // thres_h - thres_l + 1, csr_hw.cpp:64-76,167
+  for (int b = 0; b < blocks; b++)
     L->nr_cols[b] = (b == blocks - 1) ? L->expanded_cols - (uint32_t)b * cdb : cdb;
+  if (const char *e = getenv("SPMVB_RUN_LOG2")) L->run_log2 = std::max(0, std::min(8, atoi(e)));
+  return SPMVB_OK;
+}
+
+// hw_matrix_alloc (csr_hw.cpp:174-180) + device image offsets (each piece padded to whole chunks), from the per-piece
+// nr_rows / nr_nzeros and fp[b*(cu+1)+k] = first block position of piece k (real entries only).
+// Device order of the pieces.  Block-major (rows ascend through a block) is the default; when y does not fit the L2
+// cache and there are several CUs, CU-major order (all blocks of CU 0's row range, then CU 1, ...) keeps the y
+// range being updated L2-resident at the price of reading x once per CU - a 1 B-nnz uniform matrix goes from
+// DRAM-bound scattered read-modify-writes on every update to L2 atomics.
+void layout_finish_pieces(Layout *L, const uint64_t *fp, const uint32_t *pad_rows, std::vector<uint64_t> &piece_last_rank) {
+  const int cu = L->cu, blocks = L->blocks;
+  const size_t KB = (size_t)cu * blocks;
+  L->cu_major = cu > 1 && (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20);
+  if (const char *e = getenv("SPMVB_CU_MAJOR")) L->cu_major = cu > 1 && atoi(e) != 0;
+  L->nr_ci.assign(KB, 0); L->nr_val.assign(KB, 0);
+  L->piece_off.assign(KB, 0); L->piece_chunk0.assign(KB, 0); L->piece_chunk1.assign(KB, 0); L->piece_real_nnz.assign(KB, 0);
+  L->dev_order.resize(KB);
+  uint64_t off = 0, chunk0 = 0, padded = 0;
+  for (size_t i = 0; i < KB; i++) {
+    const int b = L->cu_major ? (int)(i % blocks) : (int)(i / cu);
+    const int k = L->cu_major ? (int)(i / blocks) : (int)(i % cu);
+    const size_t kb = (size_t)k * blocks + b, bk = (size_t)b * cu + k;
+    L->dev_order[i] = (uint32_t)bk;
+    uint32_t n = L->nr_nzeros[kb];
+    L->nr_ci[kb] = (n + kRatioCi - 1) / kRatioCi;
+    L->nr_val[kb] = n / (uint32_t)L->ratio_v;  // floors like the reference (Q1); ceil(n / ratio_v) words are stored
+    uint64_t nchunks = ((uint64_t)L->nr_ci[kb] + kGroupsPerChunk - 1) / kGroupsPerChunk;
+    L->piece_off[bk] = off; L->piece_chunk0[bk] = chunk0; L->piece_chunk1[bk] = chunk0 + nchunks;
+    L->piece_real_nnz[bk] = (uint32_t)(fp[(size_t)b * (cu + 1) + k + 1] - fp[(size_t)b * (cu + 1) + k]);
+    off += nchunks * (uint64_t)L->chunk_bytes;
+    chunk0 += nchunks;
+    padded += n;
+  }
+  L->stream_bytes = off; L->n_chunks = chunk0; L->padded_nnz = padded;
+  // last row-map rank owned by each piece: ranks are contiguous per block in CU order
+  piece_last_rank.assign(KB, 0);
+  for (int b = 0; b < blocks; b++) {
+    uint64_t rows_before = 0;
+    for (int k = 0; k < cu; k++) {
+      uint64_t real_rows = L->nr_rows[(size_t)k * blocks + b];
+      if (k == cu - 1) real_rows -= pad_rows[b];
+      if (real_rows) piece_last_rank[(size_t)b * cu + k] = L->rank_base[b] + rows_before + real_rows - 1;
+      rows_before += real_rows;
+    }
+  }
+}
+
+namespace {
+
+template <typename RP>
+int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *col_ind, const void *values, int cu,
+               int vf, int is_double, uint32_t cdb_in, Layout **out) {
+  if (!out) return fail(SPMVB_E_ARG, "out is NULL");
+  *out = nullptr;
+  if (rows == 0 || cols == 0 || !row_ptr) return fail(SPMVB_E_ARG, "empty matrix");
+  const uint64_t nnz = (uint64_t)row_ptr[rows];
+  if (nnz && (!col_ind || !values)) return fail(SPMVB_E_ARG, "col_ind/values are NULL");
+
+  Layout *L = new Layout();
+  {
+    int rc = layout_init_header(L, rows, cols, nnz, cu, vf, is_double, cdb_in);
+    if (rc) { delete L; return rc; }
+  }
+  const uint32_t cdb = L->cdb;
+  const int blocks = L->blocks;
+  const int vb = L->vb;
+  const uint32_t ratio_v = (uint32_t)L->ratio_v;
   const BlockOf block_of(cdb);
 
   // row ranges of (almost) equal non-zero count, one per thread
@@ -207,32 +266,10 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   }
   std::vector<uint32_t>().swap(seglen);
 
-  // ---- hw_matrix_alloc (csr_hw.cpp:174-180) + device image offsets (each piece padded to whole chunks)
-  // Device order of the pieces.  Block-major (rows ascend through a block) is the default; when y does not fit the L2
-  // cache and there are several CUs, CU-major order (all blocks of CU 0's row range, then CU 1, ...) keeps the y
-  // range being updated L2-resident at the price of reading x once per CU - a 1 B-nnz uniform matrix goes from
-  // DRAM-bound scattered read-modify-writes on every update to L2 atomics.
-  L->cu_major = cu > 1 && (uint64_t)rows * vb > ((uint64_t)48 << 20);
-  if (const char *e = getenv("SPMVB_CU_MAJOR")) L->cu_major = cu > 1 && atoi(e) != 0;
-  L->piece_off.assign(KB, 0); L->piece_chunk0.assign(KB, 0); L->piece_chunk1.assign(KB, 0); L->piece_real_nnz.assign(KB, 0);
-  L->dev_order.resize(KB);
-  uint64_t off = 0, chunk0 = 0, padded = 0;
-  for (size_t i = 0; i < KB; i++) {
-    const int b = L->cu_major ? (int)(i % blocks) : (int)(i / cu);
-    const int k = L->cu_major ? (int)(i / blocks) : (int)(i % cu);
-    const size_t kb = (size_t)k * blocks + b, bk = (size_t)b * cu + k;
-    L->dev_order[i] = (uint32_t)bk;
-    uint32_t n = L->nr_nzeros[kb];
-    L->nr_ci[kb] = (n + kRatioCi - 1) / kRatioCi;
-    L->nr_val[kb] = n / ratio_v;  // floors like the reference (Q1); ceil(n / ratio_v) words are stored
-    uint64_t nchunks = ((uint64_t)L->nr_ci[kb] + kGroupsPerChunk - 1) / kGroupsPerChunk;
-    L->piece_off[bk] = off; L->piece_chunk0[bk] = chunk0; L->piece_chunk1[bk] = chunk0 + nchunks;
-    L->piece_real_nnz[bk] = (uint32_t)(fp[(size_t)b * (cu + 1) + k + 1] - fp[(size_t)b * (cu + 1) + k]);
-    off += nchunks * (uint64_t)L->chunk_bytes;
-    chunk0 += nchunks;
-    padded += n;
-  }
-  L->stream_bytes = off; L->n_chunks = chunk0; L->padded_nnz = padded;
+  // ---- hw_matrix_alloc + device image offsets
+  std::vector<uint64_t> piece_last_rank;
+  layout_finish_pieces(L, fp.data(), pad_rows.data(), piece_last_rank);
+  const uint64_t off = L->stream_bytes, chunk0 = L->n_chunks;
   L->stream = (uint8_t *)calloc((size_t)std::max<uint64_t>(off, 16), 1);
   L->chunks = (ChunkMeta *)calloc((size_t)std::max<uint64_t>(chunk0, 1), sizeof(ChunkMeta));
   if (!L->stream || !L->chunks) { delete L; return fail(SPMVB_E_NOMEM, "stream"); }
@@ -327,28 +364,11 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   }
 
   // consecutive-rows fast path: rows of a block ascend, so first/last rank spanning equal row distance <=> consecutive
-  std::vector<uint64_t> piece_last_rank(KB, 0);
 #pragma omp parallel for schedule(static)
   for (int64_t bk = 0; bk < (int64_t)KB; bk++) {
-    const int b = (int)(bk / cu);
     uint64_t c0 = L->piece_chunk0[bk];
     uint64_t c1 = L->piece_chunk1[bk];
-    // last rank owned by this piece
-    uint64_t last_piece_rank = 0;
-    bool have = false;
-    for (uint64_t c = c1; c > c0; c--)
-      if (L->chunks[c - 1].valid & 0x3FFu) { have = true; break; }
-    if (!have) continue;
-    {
-      // rank of the segment holding the last real entry = rank0 of a virtual chunk after the piece - 1:
-      // count pieces' pairs: ranks are contiguous per block in CU order
-      uint64_t rows_before = 0;
-      for (int k = 0; k < (int)(bk % cu); k++) rows_before += L->nr_rows[(size_t)k * blocks + b];
-      uint64_t real_rows = L->nr_rows[(size_t)(bk % cu) * blocks + b];
-      if ((int)(bk % cu) == cu - 1) real_rows -= pad_rows[b];
-      last_piece_rank = L->rank_base[b] + rows_before + real_rows - 1;
-      piece_last_rank[bk] = last_piece_rank;
-    }
+    const uint64_t last_piece_rank = piece_last_rank[bk];
     for (uint64_t c = c0; c < c1; c++) {
       ChunkMeta &m = L->chunks[c];
       if (!(m.valid & 0x3FFu)) continue;
@@ -363,7 +383,6 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
 
   // Rows to clear before every SpMV (see Layout::zero_rows).  Marks are idempotent byte stores.
   {
-    if (const char *e = getenv("SPMVB_RUN_LOG2")) L->run_log2 = std::max(0, std::min(8, atoi(e)));
     const uint64_t R = 1ull << L->run_log2;
     std::vector<uint8_t> needz(rows, 0);
 #pragma omp parallel for schedule(static)
