@@ -91,6 +91,11 @@ int64_t spmvb_layout_xs_plan(const spmvb_layout *l, int n_cta, int run_log2, uin
 uint64_t spmvb_layout_chunks(const spmvb_layout *l);
 int spmvb_layout_chunk_cols(const spmvb_layout *l, uint64_t c, uint32_t *lo, uint32_t *hi, uint32_t *block);
 
+/* 1 if the two layouts are identical in every table and byte (pieces, row map, chunk metadata, rows to clear, column
+ * ranges), 0 if not (why receives the first difference), negative on error.  Used to check the GPU builder against
+ * the host builder. */
+int spmvb_layout_equal(const spmvb_layout *a, const spmvb_layout *b, char *why, size_t why_len);
+
 /* Row partition for multi-GPU (the CU dimension mapped to GPUs, SURVEY 8e mapping A): `parts` contiguous row
  * ranges balanced by non-zero count with the reference's split rule S1/S2/S3 (csr_hw.cpp:459-460) applied
  * to whole rows.  bounds has parts+1 entries. */
@@ -101,6 +106,21 @@ int spmvb_partition_rows(uint32_t rows, const uint64_t *row_ptr, int parts, int 
 /* Uploads the layout to GPU `device` (the analogue of sds_alloc_non_cacheable buffers, csr_hw.cpp:180).
  * variant: 0 = default, otherwise a kernel variant id. */
 int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_engine **out);
+/* create_csr_hw_matrix ON the GPU: same layout, bit for bit, as spmvb_layout_build, built by
+ * CUDA kernels (flag / scan / stable radix sort by column block / scatter) straight into the engine's device image.
+ * row_ptr (rows+1 x uint64), col_ind, values are host pointers (csr_on_device 0; uploaded inside) or device pointers
+ * on `device` (csr_on_device 1).  Inside a row the column blocks must ascend (sorted rows do); fewer than 2^31 rows and
+ * non-zeros.  *layout_out receives every host-side table (piece_info, chunk metadata, rows to clear, XS plan input);
+ * its pieces and row map stay on the device until spmvb_engine_fetch_layout copies them back (piece_words and
+ * bitmap_row fail before that).  There is no host fallback: unsupported input is an error. */
+int spmvb_engine_create_from_csr(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, const uint32_t *col_ind,
+                                 const void *values, int n_cu, int vf, int is_double, uint32_t cols_div_blocks,
+                                 int device, int variant, int csr_on_device, spmvb_layout **layout_out,
+                                 spmvb_engine **engine_out);
+/* device image -> host: hw_matrix[k]->submatrix[b] words and the row map of a GPU-built layout */
+int spmvb_engine_fetch_layout(spmvb_engine *e, spmvb_layout *l);
+/* out3 = milliseconds of {CSR upload, build kernels (CUDA events), whole create_from_csr call (host clock)} */
+int spmvb_engine_build_ms(const spmvb_engine *e, float *out3);
 void spmvb_engine_free(spmvb_engine *e);
 int spmvb_engine_set_variant(spmvb_engine *e, int variant);
 int spmvb_engine_variant(const spmvb_engine *e);

@@ -2,6 +2,7 @@
 // vector traffic.  Replaces the body of spmv_hw (reference src/csr_hw_wrapper.cpp:193-288): the per-block
 // spmv() round trips and the host accum_results loop become ONE kernel launch over all (CU, block) pieces.
 #include <cuda_runtime.h>
+#include <omp.h>
 
 #include <algorithm>
 #include <cmath>
@@ -13,6 +14,7 @@
 
 #include "../../include/spmvb.h"
 #include "layout.h"
+#include "layout_gpu.cuh"
 #include "spmv_kernels.cuh"
 
 namespace spmvb {
@@ -53,6 +55,9 @@ struct Engine {
   // asynchronous step timing (bench): events of the last enqueue_steps()
   std::vector<cudaEvent_t> ev;
   int ev_steps = 0;
+  // GPU-built engines (spmvb_engine_create_from_csr): milliseconds of the CSR upload, of the build kernels (CUDA
+  // events) and of the whole call (host clock)
+  float build_ms[3] = {0.f, 0.f, 0.f};
 };
 
 #define CUDA_TRY(expr)                                                                       \
@@ -221,9 +226,8 @@ using namespace spmvb;
 
 extern "C" {
 
-int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_engine **out) {
-  const Layout *L = (const Layout *)l;
-  if (!L || !out) return fail(SPMVB_E_ARG, "engine_create: NULL");
+// device checks, the Engine object with everything that follows from the layout's tables, stream, x / y
+static int engine_open(int device, int variant, Engine **out) {
   *out = nullptr;
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -235,76 +239,186 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(SPMVB_E_CUDA, "an sm_100-class GPU (B200) is required; there is no fallback path");
   Engine *E = new Engine();
-  E->device = device; E->is_double = L->is_double; E->vb = L->vb;
+  E->device = device; E->variant = variant;
+  E->sms = prop.multiProcessorCount;
+  cudaError_t e = cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&E->d_scalar, 64);
+  if (e != cudaSuccess) {
+    std::string msg = std::string("engine_create: ") + cudaGetErrorString(e);
+    spmvb_engine_free((spmvb_engine *)E);
+    return fail(SPMVB_E_CUDA, msg);
+  }
+  *out = E;
+  return SPMVB_OK;
+}
+
+// everything the engine derives from the layout's host-side tables + the x / y vectors
+static int engine_adopt_layout(Engine *E, const Layout *L) {
+  E->is_double = L->is_double; E->vb = L->vb;
   E->rows = L->rows; E->cols = L->cols; E->expanded_cols = L->expanded_cols; E->cdb = L->cdb; E->blocks = L->blocks;
   E->real_nnz = L->real_nnz; E->n_chunks = L->n_chunks; E->n_pairs = L->n_pairs; E->stream_bytes = L->stream_bytes;
-  E->variant = variant;
   E->cu_major = L->cu_major;
-  E->sms = prop.multiProcessorCount;
   E->tall = (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) && (uint64_t)L->cols * L->vb > ((uint64_t)48 << 20);
   if (const char *v = getenv("SPMVB_TALL")) E->tall = atoi(v) != 0;
+  E->x_touched = 0;
   for (int b = 0; b < L->blocks; b++) {
     uint64_t nz = 0;
     for (int k = 0; k < L->cu; k++) nz += L->piece_real_nnz[(size_t)b * L->cu + k];
     if (nz) E->x_touched += std::min<uint64_t>(L->cdb, (uint64_t)L->cols - (uint64_t)b * L->cdb);
   }
   E->x_len = (uint64_t)L->blocks * L->cdb;  // >= expanded_cols: any 15-bit index of any block stays in range
-  cudaError_t e = cudaSuccess;
-  auto chk = [&](cudaError_t r) { if (e == cudaSuccess && r != cudaSuccess) e = r; };
-  chk(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
-  // device image: one slot per chunk = the chunk's words (bit-exact hw_matrix bytes) followed by its 16-byte ChunkMeta,
-  // so that a single bulk copy brings both into shared memory
-  const size_t slot = (size_t)L->chunk_bytes + sizeof(ChunkMeta);
-  chk(cudaMalloc((void **)&E->d_stream, std::max<uint64_t>(L->n_chunks * slot, 16)));
-  chk(cudaMalloc((void **)&E->d_rowmap, (std::max<uint64_t>(L->n_pairs, 1) + 1) * 4));
   E->zero_all = L->zero_all; E->n_zero_rows = (uint32_t)L->zero_rows.size(); E->run_log2 = (uint32_t)L->run_log2;
   if (const char *v = getenv("SPMVB_OCC_RUN_LOG2")) E->occ_run_log2 = (uint32_t)atoi(v);
   if (const char *v = getenv("SPMVB_XS_RUN_LOG2")) E->xs_run_log2 = (uint32_t)atoi(v);
   // rows split across run boundaries are only cleared at the layout's granularity: runs must be multiples of it
   E->occ_run_log2 = std::min(8u, std::max(E->occ_run_log2, E->run_log2));
   E->xs_run_log2 = std::min(8u, std::max(E->xs_run_log2, E->run_log2));
-  chk(cudaMalloc((void **)&E->d_zero_rows, std::max<size_t>(L->zero_rows.size(), 1) * 4));
-  chk(cudaMalloc(&E->d_x, E->x_len * E->vb));
-  chk(cudaMalloc(&E->d_y, (size_t)E->rows * E->vb));
-  chk(cudaMalloc((void **)&E->d_scalar, 64));
-  if (e == cudaSuccess) {
-    if (L->n_chunks) {
-      chk(cudaMemcpy2DAsync(E->d_stream, slot, L->stream, L->chunk_bytes, L->chunk_bytes, L->n_chunks,
-                            cudaMemcpyHostToDevice, E->stream));
-      chk(cudaMemcpy2DAsync(E->d_stream + L->chunk_bytes, slot, L->chunks, sizeof(ChunkMeta), sizeof(ChunkMeta),
-                            L->n_chunks, cudaMemcpyHostToDevice, E->stream));
-    }
-    chk(cudaMemcpyAsync(E->d_rowmap, L->rowmap, L->n_pairs * 4, cudaMemcpyHostToDevice, E->stream));
-    chk(cudaMemcpyAsync(E->d_zero_rows, L->zero_rows.data(), L->zero_rows.size() * 4, cudaMemcpyHostToDevice, E->stream));
-    {
-      std::vector<XsItem> items;
-      std::vector<uint32_t> cta_first;
-      build_xs_items(L, E->sms, E->xs_run_log2, items, cta_first);
-      E->n_items = (uint32_t)items.size();
-      chk(cudaMalloc((void **)&E->d_items, std::max<size_t>(items.size(), 1) * sizeof(XsItem)));
-      chk(cudaMalloc((void **)&E->d_cta_first, cta_first.size() * 4));
-      if (e == cudaSuccess) chk(cudaMemcpy(E->d_items, items.data(), items.size() * sizeof(XsItem), cudaMemcpyHostToDevice));
-      if (e == cudaSuccess) chk(cudaMemcpy(E->d_cta_first, cta_first.data(), cta_first.size() * 4, cudaMemcpyHostToDevice));
-      uint64_t windowed = 0;
-      for (auto &it : items) windowed += it.x_bytes ? it.chunk_count : 0;
-      E->xs_windowed_frac = L->n_chunks ? (double)windowed / (double)L->n_chunks : 0.0;
-    }
-    chk(cudaMemsetAsync(E->d_x, 0, E->x_len * E->vb, E->stream));
-    chk(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
-    chk(cudaStreamSynchronize(E->stream));
-  }
-  if (e != cudaSuccess) {
-    std::string msg = std::string("engine_create: ") + cudaGetErrorString(e);
-    spmvb_engine_free((spmvb_engine *)E);
-    return fail(SPMVB_E_CUDA, msg);
-  }
-  if (autotune(E) != SPMVB_OK) {
-    spmvb_engine_free((spmvb_engine *)E);
-    return SPMVB_E_CUDA;
-  }
+  CUDA_TRY(cudaMalloc(&E->d_x, E->x_len * E->vb));
+  CUDA_TRY(cudaMalloc(&E->d_y, (size_t)E->rows * E->vb));
+  return SPMVB_OK;
+}
+
+// work plan of the XS kernel, cleared vectors, kernel choice; the image must be on the device (or on its way, on E->stream)
+static int engine_finish(Engine *E, const Layout *L) {
+  std::vector<XsItem> items;
+  std::vector<uint32_t> cta_first;
+  build_xs_items(L, E->sms, E->xs_run_log2, items, cta_first);
+  E->n_items = (uint32_t)items.size();
+  CUDA_TRY(cudaMalloc((void **)&E->d_items, std::max<size_t>(items.size(), 1) * sizeof(XsItem)));
+  CUDA_TRY(cudaMalloc((void **)&E->d_cta_first, cta_first.size() * 4));
+  CUDA_TRY(cudaMemcpy(E->d_items, items.data(), items.size() * sizeof(XsItem), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(E->d_cta_first, cta_first.data(), cta_first.size() * 4, cudaMemcpyHostToDevice));
+  uint64_t windowed = 0;
+  for (auto &it : items) windowed += it.x_bytes ? it.chunk_count : 0;
+  E->xs_windowed_frac = L->n_chunks ? (double)windowed / (double)L->n_chunks : 0.0;
+  CUDA_TRY(cudaMemsetAsync(E->d_x, 0, E->x_len * E->vb, E->stream));
   CUDA_TRY(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
   CUDA_TRY(cudaStreamSynchronize(E->stream));
+  int rc = autotune(E);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
+  CUDA_TRY(cudaStreamSynchronize(E->stream));
+  return SPMVB_OK;
+}
+
+int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_engine **out) {
+  const Layout *L = (const Layout *)l;
+  if (!L || !out) return fail(SPMVB_E_ARG, "engine_create: NULL");
+  *out = nullptr;
+  if (!L->stream || !L->rowmap)
+    return fail(SPMVB_E_ARG, "engine_create: this layout was built on a GPU and lives in its engine; fetch it first");
+  Engine *E = nullptr;
+  int rc = engine_open(device, variant, &E);
+  if (rc) return rc;
+  auto upload = [&]() -> int {
+    int r = engine_adopt_layout(E, L);
+    if (r) return r;
+    // device image: one slot per chunk = the chunk's words (bit-exact hw_matrix bytes) followed by its 16-byte
+    // ChunkMeta, so that a single bulk copy brings both into shared memory
+    const size_t slot = (size_t)L->chunk_bytes + sizeof(ChunkMeta);
+    CUDA_TRY(cudaMalloc((void **)&E->d_stream, std::max<uint64_t>(L->n_chunks * slot, 16)));
+    CUDA_TRY(cudaMalloc((void **)&E->d_rowmap, (std::max<uint64_t>(L->n_pairs, 1) + 1) * 4));
+    CUDA_TRY(cudaMalloc((void **)&E->d_zero_rows, std::max<size_t>(L->zero_rows.size(), 1) * 4));
+    if (L->n_chunks) {
+      CUDA_TRY(cudaMemcpy2DAsync(E->d_stream, slot, L->stream, L->chunk_bytes, L->chunk_bytes, L->n_chunks,
+                                 cudaMemcpyHostToDevice, E->stream));
+      CUDA_TRY(cudaMemcpy2DAsync(E->d_stream + L->chunk_bytes, slot, L->chunks, sizeof(ChunkMeta), sizeof(ChunkMeta),
+                                 L->n_chunks, cudaMemcpyHostToDevice, E->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(E->d_rowmap, L->rowmap, L->n_pairs * 4, cudaMemcpyHostToDevice, E->stream));
+    CUDA_TRY(cudaMemcpyAsync(E->d_zero_rows, L->zero_rows.data(), L->zero_rows.size() * 4, cudaMemcpyHostToDevice, E->stream));
+    return engine_finish(E, L);
+  };
+  rc = upload();
+  if (rc) { spmvb_engine_free((spmvb_engine *)E); return rc; }
   *out = (spmvb_engine *)E;
+  return SPMVB_OK;
+}
+
+// create_csr_hw_matrix on the GPU: the CSR goes to the device (unless it is there already), the layout is built there
+// (layout_gpu_steps.h) straight into the engine's image.  *layout_out gets every host-side table (csr_hw_matrix
+// fields, chunk metadata, rows to clear); its two big arrays - the pieces and the row map - stay on the device until
+// spmvb_engine_fetch_layout asks for them.
+int spmvb_engine_create_from_csr(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, const uint32_t *col_ind,
+                                 const void *values, int n_cu, int vf, int is_double, uint32_t cols_div_blocks,
+                                 int device, int variant, int csr_on_device, spmvb_layout **layout_out,
+                                 spmvb_engine **engine_out) {
+  if (!layout_out || !engine_out || !row_ptr) return fail(SPMVB_E_ARG, "engine_create_from_csr: NULL");
+  *layout_out = nullptr; *engine_out = nullptr;
+  if (rows == 0 || cols == 0) return fail(SPMVB_E_ARG, "empty matrix");
+  const double t0 = omp_get_wtime();
+  Engine *E = nullptr;
+  int rc = engine_open(device, variant, &E);
+  if (rc) return rc;
+  uint64_t *d_rp = nullptr; uint32_t *d_ci = nullptr; void *d_va = nullptr;
+  Layout *L = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  auto run = [&]() -> int {
+    const int vb = is_double ? 8 : 4;
+    uint64_t nnz = 0;
+    for (auto &x : ev) CUDA_TRY(cudaEventCreate(&x));
+    CUDA_TRY(cudaEventRecord(ev[0], E->stream));
+    if (csr_on_device) {
+      CUDA_TRY(cudaMemcpyAsync(&nnz, row_ptr + rows, 8, cudaMemcpyDeviceToHost, E->stream));
+      CUDA_TRY(cudaStreamSynchronize(E->stream));
+    } else {
+      nnz = row_ptr[rows];
+      if (nnz && (!col_ind || !values)) return fail(SPMVB_E_ARG, "col_ind/values are NULL");
+      CUDA_TRY(cudaMallocAsync((void **)&d_rp, ((size_t)rows + 1) * 8, E->stream));
+      CUDA_TRY(cudaMallocAsync((void **)&d_ci, std::max<size_t>(nnz, 1) * 4, E->stream));
+      CUDA_TRY(cudaMallocAsync(&d_va, std::max<size_t>(nnz, 1) * vb, E->stream));
+      CUDA_TRY(cudaMemcpyAsync(d_rp, row_ptr, ((size_t)rows + 1) * 8, cudaMemcpyHostToDevice, E->stream));
+      CUDA_TRY(cudaMemcpyAsync(d_ci, col_ind, (size_t)nnz * 4, cudaMemcpyHostToDevice, E->stream));
+      CUDA_TRY(cudaMemcpyAsync(d_va, values, (size_t)nnz * vb, cudaMemcpyHostToDevice, E->stream));
+    }
+    CUDA_TRY(cudaEventRecord(ev[1], E->stream));
+    CudaBackend be;
+    be.st = E->stream; be.sms = E->sms;
+    LbImage img;
+    int r = lb_build(be, rows, cols, nnz, csr_on_device ? row_ptr : d_rp, csr_on_device ? col_ind : d_ci,
+                     csr_on_device ? values : d_va, n_cu, vf, is_double, cols_div_blocks, &L, &img);
+    if (r) return r;
+    E->d_stream = img.image; E->d_rowmap = img.rowmap; E->d_zero_rows = img.zero_rows;
+    CUDA_TRY(cudaEventRecord(ev[2], E->stream));
+    r = engine_adopt_layout(E, L);
+    if (r) return r;
+    r = engine_finish(E, L);
+    if (r) return r;
+    CUDA_TRY(cudaEventElapsedTime(&E->build_ms[0], ev[0], ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&E->build_ms[1], ev[1], ev[2]));
+    return SPMVB_OK;
+  };
+  rc = run();
+  if (d_rp) cudaFreeAsync(d_rp, E->stream);
+  if (d_ci) cudaFreeAsync(d_ci, E->stream);
+  if (d_va) cudaFreeAsync(d_va, E->stream);
+  for (auto &x : ev) if (x) cudaEventDestroy(x);
+  if (rc) { delete L; spmvb_engine_free((spmvb_engine *)E); return rc; }
+  cudaStreamSynchronize(E->stream);
+  E->build_ms[2] = (float)((omp_get_wtime() - t0) * 1e3);
+  *layout_out = (spmvb_layout *)L;
+  *engine_out = (spmvb_engine *)E;
+  return SPMVB_OK;
+}
+
+int spmvb_engine_fetch_layout(spmvb_engine *e, spmvb_layout *l) {
+  Engine *E = (Engine *)e;
+  Layout *L = (Layout *)l;
+  if (!E || !L) return fail(SPMVB_E_ARG, "fetch_layout: NULL");
+  if (L->n_chunks != E->n_chunks || L->n_pairs != E->n_pairs || L->stream_bytes != E->stream_bytes || L->rows != E->rows)
+    return fail(SPMVB_E_ARG, "fetch_layout: this layout does not belong to this engine");
+  CUDA_TRY(cudaSetDevice(E->device));
+  CudaBackend be;
+  be.st = E->stream; be.sms = E->sms;
+  LbImage img;
+  img.image = E->d_stream; img.rowmap = E->d_rowmap;
+  return lb_fetch_host(be, L, img);
+}
+
+int spmvb_engine_build_ms(const spmvb_engine *e, float *out3) {
+  const Engine *E = (const Engine *)e;
+  if (!E || !out3) return fail(SPMVB_E_ARG, "build_ms");
+  for (int i = 0; i < 3; i++) out3[i] = E->build_ms[i];
   return SPMVB_OK;
 }
 

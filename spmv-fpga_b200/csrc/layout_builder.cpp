@@ -13,6 +13,7 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -504,12 +505,14 @@ int spmvb_layout_piece_info(const spmvb_layout *l, int cu, int block, uint32_t *
 const void *spmvb_layout_piece_words(const spmvb_layout *l, int cu, int block) {
   const Layout *L = (const Layout *)l;
   if (!L || cu < 0 || cu >= L->cu || block < 0 || block >= L->blocks) return nullptr;
+  if (!L->stream) { set_error("piece_words: GPU-built layout, call spmvb_engine_fetch_layout first"); return nullptr; }
   return L->stream + L->piece_off[(size_t)block * L->cu + cu];
 }
 
 int spmvb_layout_bitmap_row(const spmvb_layout *l, int block, uint8_t *out) {
   const Layout *L = (const Layout *)l;
   if (!L || !out || block < 0 || block >= L->blocks) return fail(SPMVB_E_ARG, "block index");
+  if (!L->rowmap) return fail(SPMVB_E_ARG, "bitmap_row: GPU-built layout, call spmvb_engine_fetch_layout first");
   memset(out, 1, L->rows);  // 1 = row has no non-zero in this block (csr_hw.cpp:340-345)
   for (uint64_t i = L->rank_base[block]; i < L->rank_base[block + 1]; i++) out[L->rowmap[i]] = 0;
   return SPMVB_OK;
@@ -534,6 +537,41 @@ int spmvb_layout_pack_x(const spmvb_layout *l, const void *x, uint32_t n, void *
   memcpy(out, x, (size_t)m * L->vb);
   memset((uint8_t *)out + (size_t)m * L->vb, 0, (size_t)(L->expanded_cols - m) * L->vb);
   return SPMVB_OK;
+}
+
+int spmvb_layout_equal(const spmvb_layout *a, const spmvb_layout *b, char *why, size_t why_len) {
+  const Layout *A = (const Layout *)a, *B = (const Layout *)b;
+  auto say = [&](const char *what) { if (why && why_len) snprintf(why, why_len, "%s", what); return 0; };
+  if (!A || !B) return fail(SPMVB_E_ARG, "layout_equal: NULL");
+  if (!A->stream || !B->stream || !A->rowmap || !B->rowmap)
+    return fail(SPMVB_E_ARG, "layout_equal: host image not present (spmvb_engine_fetch_layout)");
+  if (A->cu != B->cu || A->vf != B->vf || A->is_double != B->is_double || A->blocks != B->blocks || A->rows != B->rows ||
+      A->cols != B->cols || A->expanded_cols != B->expanded_cols || A->cdb != B->cdb || A->real_nnz != B->real_nnz ||
+      A->padded_nnz != B->padded_nnz || A->n_pairs != B->n_pairs || A->stream_bytes != B->stream_bytes ||
+      A->n_chunks != B->n_chunks || A->run_log2 != B->run_log2 || A->cu_major != B->cu_major)
+    return say("header");
+  if (A->nr_rows != B->nr_rows) return say("nr_rows");
+  if (A->nr_nzeros != B->nr_nzeros) return say("nr_nzeros");
+  if (A->nr_ci != B->nr_ci || A->nr_val != B->nr_val || A->nr_cols != B->nr_cols) return say("nr_ci/nr_val/nr_cols");
+  if (A->piece_off != B->piece_off || A->piece_chunk0 != B->piece_chunk0 || A->piece_chunk1 != B->piece_chunk1 ||
+      A->dev_order != B->dev_order || A->piece_real_nnz != B->piece_real_nnz)
+    return say("piece tables");
+  if (A->rank_base != B->rank_base) return say("rank_base");
+  if (memcmp(A->rowmap, B->rowmap, (size_t)A->n_pairs * 4) != 0) return say("rowmap");
+  if (memcmp(A->stream, B->stream, (size_t)A->stream_bytes) != 0) return say("stream");
+  for (uint64_t c = 0; c < A->n_chunks; c++)
+    if (memcmp(&A->chunks[c], &B->chunks[c], sizeof(ChunkMeta)) != 0) {
+      if (why && why_len)
+        snprintf(why, why_len, "chunk meta %llu: {%u,%#x,%#x,%u} vs {%u,%#x,%#x,%u}", (unsigned long long)c,
+                 A->chunks[c].rank0, A->chunks[c].block, A->chunks[c].valid, A->chunks[c].row_first,
+                 B->chunks[c].rank0, B->chunks[c].block, B->chunks[c].valid, B->chunks[c].row_first);
+      return 0;
+    }
+  if (A->zero_all != B->zero_all) return say("zero_all");
+  if (A->zero_rows != B->zero_rows) return say("zero_rows");
+  if (A->chunk_col_lo != B->chunk_col_lo || A->chunk_col_hi != B->chunk_col_hi) return say("chunk column ranges");
+  if (why && why_len) why[0] = 0;
+  return 1;
 }
 
 int spmvb_partition_rows(uint32_t rows, const uint64_t *row_ptr, int parts, int ratio_v, uint32_t *bounds) {

@@ -42,8 +42,12 @@ SYMBOLS = {
     "spmvb_layout_xs_plan": (ctypes.c_int64, [_vp, _int, _int, _vp, _u64, _vp]),
     "spmvb_layout_chunks": (_u64, [_vp]),
     "spmvb_layout_chunk_cols": (_int, [_vp, _u64, _vp, _vp, _vp]),
+    "spmvb_layout_equal": (_int, [_vp, _vp, _vp, ctypes.c_size_t]),
     "spmvb_partition_rows": (_int, [_u32, _vp, _int, _int, _vp]),
     "spmvb_engine_create": (_int, [_vp, _int, _int, _vp]),
+    "spmvb_engine_create_from_csr": (_int, [_u32, _u32, _vp, _vp, _vp, _int, _int, _int, _u32, _int, _int, _int, _vp, _vp]),
+    "spmvb_engine_fetch_layout": (_int, [_vp, _vp]),
+    "spmvb_engine_build_ms": (_int, [_vp, _vp]),
     "spmvb_engine_free": (None, [_vp]),
     "spmvb_engine_set_variant": (_int, [_vp, _int]),
     "spmvb_engine_variant": (_int, [_vp]),
@@ -241,6 +245,14 @@ class Layout:
         _check(lib().spmvb_layout_build_csr(csr.h, n_cu, vf, cols_div_blocks, ctypes.byref(out)))
         return Layout(out.value, csr.is_double)
 
+    def difference(self, other):
+        """'' if both layouts are identical in every table and byte, else the first component that differs."""
+        why = ctypes.create_string_buffer(256)
+        rc = lib().spmvb_layout_equal(self.h, other.h, why, 256)
+        if rc < 0:
+            _check(rc)
+        return "" if rc == 1 else (why.value.decode() or "different")
+
     def piece_info(self, cu, block):
         info = (ctypes.c_uint32 * 5)()
         _check(lib().spmvb_layout_piece_info(self.h, cu, block, info))
@@ -251,6 +263,8 @@ class Layout:
         ratio_v = 2 if self.is_double else 4
         nwords = nr_ci + (nnz + ratio_v - 1) // ratio_v
         p = lib().spmvb_layout_piece_words(self.h, cu, block)
+        if not p:
+            raise SpmvbError(-1, lib().spmvb_last_error().decode(errors="replace"))
         if nwords == 0:
             return np.zeros(0, np.uint8)
         return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(nwords * 16,)).copy()
@@ -320,6 +334,40 @@ class Engine:
         self.is_double = layout.is_double
         self.rows, self.cols, self.expanded_cols = layout.rows, layout.cols, layout.expanded_cols
         self.real_nnz = layout.real_nnz
+
+    @staticmethod
+    def from_csr(rows, cols, row_ptr, col_ind, values, n_cu=1, vf=1, is_double=True, cols_div_blocks=0, device=0,
+                 variant=VARIANT_AUTO, on_device=False):
+        """create_csr_hw_matrix on the GPU: returns (layout, engine).  With on_device the three arrays are device
+        pointers (ints); otherwise numpy arrays that are uploaded inside the call."""
+        lay, eng = _vp(), _vp()
+        if on_device:
+            a = (_vp(row_ptr), _vp(col_ind), _vp(values))
+        else:
+            rp = np.ascontiguousarray(row_ptr, np.uint64)
+            ci = np.ascontiguousarray(col_ind, np.uint32)
+            va = np.ascontiguousarray(values, vdtype(is_double))
+            a = (_ptr(rp), _ptr(ci), _ptr(va))
+        _check(lib().spmvb_engine_create_from_csr(rows, cols, a[0], a[1], a[2], n_cu, vf, int(is_double),
+                                                  cols_div_blocks, device, variant, int(on_device),
+                                                  ctypes.byref(lay), ctypes.byref(eng)))
+        layout = Layout(lay.value, is_double)
+        e = Engine.__new__(Engine)
+        e.h = _vp(eng.value)
+        e.layout = layout
+        e.is_double = layout.is_double
+        e.rows, e.cols, e.expanded_cols = layout.rows, layout.cols, layout.expanded_cols
+        e.real_nnz = layout.real_nnz
+        return layout, e
+
+    def fetch_layout(self, layout=None):
+        """Copies the pieces and the row map of a GPU-built layout to the host (piece_words / bitmap_row need them)."""
+        _check(lib().spmvb_engine_fetch_layout(self.h, (layout or self.layout).h))
+
+    def build_ms(self):
+        out = (ctypes.c_float * 3)()
+        _check(lib().spmvb_engine_build_ms(self.h, out))
+        return {"h2d_ms": out[0], "build_ms": out[1], "total_ms": out[2]}
 
     def set_variant(self, v):
         _check(lib().spmvb_engine_set_variant(self.h, v))
