@@ -350,7 +350,7 @@ int spmvb_engine_create_from_csr(uint32_t rows, uint32_t cols, const uint64_t *r
   Engine *E = nullptr;
   int rc = engine_open(device, variant, &E);
   if (rc) return rc;
-  uint64_t *d_rp = nullptr; uint32_t *d_ci = nullptr; void *d_va = nullptr;
+  uint64_t *d_rp = nullptr; uint32_t *d_ci = nullptr; void *d_va = nullptr, *d_csr = nullptr;
   Layout *L = nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   auto run = [&]() -> int {
@@ -364,9 +364,13 @@ int spmvb_engine_create_from_csr(uint32_t rows, uint32_t cols, const uint64_t *r
     } else {
       nnz = row_ptr[rows];
       if (nnz && (!col_ind || !values)) return fail(SPMVB_E_ARG, "col_ind/values are NULL");
-      CUDA_TRY(cudaMallocAsync((void **)&d_rp, ((size_t)rows + 1) * 8, E->stream));
-      CUDA_TRY(cudaMallocAsync((void **)&d_ci, std::max<size_t>(nnz, 1) * 4, E->stream));
-      CUDA_TRY(cudaMallocAsync(&d_va, std::max<size_t>(nnz, 1) * vb, E->stream));
+      // one allocation for the three arrays (values first: 8-byte aligned)
+      const size_t va_bytes = (std::max<size_t>(nnz, 1) * vb + 255) & ~(size_t)255;
+      const size_t rp_bytes = (((size_t)rows + 1) * 8 + 255) & ~(size_t)255;
+      CUDA_TRY(cudaMalloc(&d_csr, va_bytes + rp_bytes + std::max<size_t>(nnz, 1) * 4));
+      d_va = d_csr;
+      d_rp = (uint64_t *)((uint8_t *)d_csr + va_bytes);
+      d_ci = (uint32_t *)((uint8_t *)d_csr + va_bytes + rp_bytes);
       CUDA_TRY(cudaMemcpyAsync(d_rp, row_ptr, ((size_t)rows + 1) * 8, cudaMemcpyHostToDevice, E->stream));
       CUDA_TRY(cudaMemcpyAsync(d_ci, col_ind, (size_t)nnz * 4, cudaMemcpyHostToDevice, E->stream));
       CUDA_TRY(cudaMemcpyAsync(d_va, values, (size_t)nnz * vb, cudaMemcpyHostToDevice, E->stream));
@@ -380,18 +384,19 @@ int spmvb_engine_create_from_csr(uint32_t rows, uint32_t cols, const uint64_t *r
     if (r) return r;
     E->d_stream = img.image; E->d_rowmap = img.rowmap; E->d_zero_rows = img.zero_rows;
     CUDA_TRY(cudaEventRecord(ev[2], E->stream));
+    be.trace("(end of build)");
     r = engine_adopt_layout(E, L);
     if (r) return r;
+    be.trace("x / y allocation");
     r = engine_finish(E, L);
     if (r) return r;
+    be.trace("XS plan + kernel choice");
     CUDA_TRY(cudaEventElapsedTime(&E->build_ms[0], ev[0], ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&E->build_ms[1], ev[1], ev[2]));
     return SPMVB_OK;
   };
   rc = run();
-  if (d_rp) cudaFreeAsync(d_rp, E->stream);
-  if (d_ci) cudaFreeAsync(d_ci, E->stream);
-  if (d_va) cudaFreeAsync(d_va, E->stream);
+  if (d_csr) cudaFree(d_csr);
   for (auto &x : ev) if (x) cudaEventDestroy(x);
   if (rc) { delete L; spmvb_engine_free((spmvb_engine *)E); return rc; }
   cudaStreamSynchronize(E->stream);

@@ -3,9 +3,14 @@
 // Included by engine.cu only.
 #pragma once
 #include <cuda_runtime.h>
+#include <omp.h>
+
+#include <cstdio>
+#include <cstdlib>
 
 #include <cub/cub.cuh>
 #include <string>
+#include <vector>
 
 #include "../../include/spmvb.h"
 #include "layout_gpu_steps.h"
@@ -18,6 +23,9 @@ __global__ void __launch_bounds__(256) lb_kernel(uint64_t n, LbCtx c) {
     Body::run(i, c);
 }
 
+struct LbBit0 {
+  __host__ __device__ __forceinline__ uint32_t operator()(uint8_t v) const { return v & 1u; }
+};
 struct LbCastU32 {
   __host__ __device__ __forceinline__ uint32_t operator()(uint8_t v) const { return v; }
 };
@@ -33,13 +41,17 @@ struct CudaBackend {
   int sms = 148;
   cudaError_t e = cudaSuccess;
   std::string where;
-  void *scratch = nullptr;  // CUB temporary storage, grown on demand
+  void *scratch = nullptr;  // CUB temporary storage (arena memory), grown on demand
   size_t scratch_bytes = 0;
   unsigned long long *d_count = nullptr;
+  // Temporaries are carved out of a few large device allocations (dozens of cudaMalloc / cudaFree calls cost more
+  // than all the build kernels together); they go back in one piece when the backend is destroyed.
+  std::vector<void *> arenas;
+  uint8_t *cur = nullptr;
+  size_t cur_left = 0;
 
   ~CudaBackend() {
-    if (scratch) cudaFreeAsync(scratch, st);
-    if (d_count) cudaFreeAsync(d_count, st);
+    for (void *a : arenas) cudaFree(a);  // cudaFree waits for the work that still uses the memory
   }
   void chk(cudaError_t r, const char *what) {
     if (e == cudaSuccess && r != cudaSuccess) { e = r; where = what; }
@@ -48,12 +60,33 @@ struct CudaBackend {
   int code() const { return SPMVB_E_CUDA; }
   std::string error() const { return "GPU layout build: " + where + ": " + cudaGetErrorString(e); }
 
-  void *alloc(size_t bytes) {
+  // SPMVB_BUILD_TRACE=1: wait for the stream after every stage and print the time it took (diagnostics)
+  bool tracing = getenv("SPMVB_BUILD_TRACE") != nullptr;
+  double t_last = omp_get_wtime();
+  void trace(const char *what) {
+    if (!tracing) return;
+    cudaStreamSynchronize(st);
+    const double t = omp_get_wtime();
+    fprintf(stderr, "[layout build] %-34s %8.3f ms\n", what, (t - t_last) * 1e3);
+    t_last = t;
+  }
+  void reserve(uint64_t bytes) {
+    if (!ok()) return;
     void *p = nullptr;
-    if (ok()) chk(cudaMallocAsync(&p, bytes < 16 ? 16 : bytes, st), "cudaMallocAsync");
+    chk(cudaMalloc(&p, (size_t)bytes), "cudaMalloc (arena)");
+    if (!ok()) return;
+    arenas.push_back(p);
+    cur = (uint8_t *)p; cur_left = (size_t)bytes;
+  }
+  void *alloc(size_t bytes) {
+    bytes = ((bytes < 16 ? 16 : bytes) + 255) & ~(size_t)255;
+    if (bytes > cur_left) reserve(bytes > ((size_t)8 << 20) ? bytes : ((size_t)8 << 20));
+    if (!ok()) return nullptr;
+    void *p = cur;
+    cur += bytes; cur_left -= bytes;
     return p;
   }
-  void release(void *p) { if (p) cudaFreeAsync(p, st); }
+  void release(void *) {}
   void *alloc_output(size_t bytes) {
     void *p = nullptr;
     if (ok()) chk(cudaMalloc(&p, bytes < 16 ? 16 : bytes), "cudaMalloc");
@@ -83,15 +116,13 @@ struct CudaBackend {
   }
   bool temp(size_t bytes) {
     if (bytes <= scratch_bytes) return true;
-    if (scratch) cudaFreeAsync(scratch, st);
-    scratch = nullptr; scratch_bytes = 0;
-    chk(cudaMallocAsync(&scratch, bytes, st), "scratch");
-    if (ok()) scratch_bytes = bytes;
+    scratch = alloc(bytes);
+    scratch_bytes = ok() ? bytes : 0;
     return ok();
   }
-  void inclusive_sum_u8_u32(const uint8_t *in, uint32_t *out, uint64_t n) {
+  void inclusive_sum_bit0_u32(const uint8_t *in, uint32_t *out, uint64_t n) {
     if (!ok() || !n) return;
-    cub::TransformInputIterator<uint32_t, LbCastU32, const uint8_t *> it(in, LbCastU32());
+    cub::TransformInputIterator<uint32_t, LbBit0, const uint8_t *> it(in, LbBit0());
     size_t bytes = 0;
     chk(cub::DeviceScan::InclusiveSum(nullptr, bytes, it, out, (int)n, st), "scan size");
     if (temp(bytes)) chk(cub::DeviceScan::InclusiveSum(scratch, bytes, it, out, (int)n, st), "inclusive scan");
@@ -117,7 +148,7 @@ struct CudaBackend {
     if (temp(bytes)) chk(cub::DeviceRadixSort::SortPairs(scratch, bytes, kin, kout, vin, vout, (int)n, 0, bits, st), "radix sort");
   }
   bool counter() {
-    if (!d_count) chk(cudaMallocAsync((void **)&d_count, 16, st), "counter");
+    if (!d_count) d_count = (unsigned long long *)alloc(16);
     return ok();
   }
   uint64_t count_nonzero_u8(const uint8_t *in, uint64_t n) {

@@ -54,13 +54,14 @@ struct LbCtx {
   int blocks, cu, vf, vb, ratio_v, gb, chunk_bytes, slot, run_log2;
   uint64_t nnz, n_pairs, n_chunks, n_pieces;
   // per entry
-  uint8_t *head;    // [nnz] 1 = first entry of a (row, block) pair
+  uint8_t *head;    // [nnz] bit 0 = first entry of a (row, block) pair, bit 7 = ... but not of its row
   uint32_t *pincl;  // [nnz] inclusive scan of head: pair number + 1 (CSR order)
   // per pair, CSR order
   uint64_t *pj;     // [n_pairs + 1] first entry
   uint32_t *pkey;   // column block
   uint32_t *pval;   // identity, the radix sort's payload
   uint32_t *prow;   // row
+  uint8_t *pmid;    // the pair is not the first of its row
   uint32_t *rank_of;
   // per pair, rank order (= row map order: by block, rows ascending)
   uint32_t *pkey_sorted, *order;
@@ -133,26 +134,39 @@ struct LbEntryHeads {
     const uint32_t prev = c.col_ind[j - 1];
     if (prev >= c.cols) return;
     const uint32_t b = lb_block_of(c, col), bp = lb_block_of(c, prev);
-    if (b != bp) c.head[j] = 1;
+    if (b != bp) c.head[j] = 0x81;
     if (b < bp) lb_flag(c.err, kLbErrBlockOrder);
   }
 };
 
-// per pair (CSR order): first entry, block, row
+// per pair (CSR order): first entry, block
 struct LbPairHeads {
   static SPMVB_HD void run(uint64_t j, const LbCtx &c) {
     if (j == 0) c.pj[c.n_pairs] = c.nnz;
-    if (!c.head[j]) return;
+    const uint8_t h = c.head[j];
+    if (!h) return;
     const uint32_t p = c.pincl[j] - 1;
     c.pj[p] = j;
     c.pkey[p] = lb_block_of(c, c.col_ind[j]);
     c.pval[p] = p;
-    uint64_t lo = 0, hi = c.rows;  // first index with row_ptr[i] > j, in (0, rows]
-    while (lo < hi) {
-      const uint64_t mid = (lo + hi) >> 1;
-      if (c.row_ptr[mid] > j) hi = mid; else lo = mid + 1;
-    }
-    c.prow[p] = (uint32_t)(lo - 1);
+    c.pmid[p] = h >> 7;
+  }
+};
+
+// row of the first pair of every non-empty row ...
+struct LbRowPairs {
+  static SPMVB_HD void run(uint64_t r, const LbCtx &c) {
+    const uint64_t a = c.row_ptr[r];
+    if (a < c.row_ptr[r + 1]) c.prow[c.pincl[a] - 1] = (uint32_t)r;
+  }
+};
+// ... and of the pairs that follow it in the same row (at most one per column block)
+struct LbMidPairs {
+  static SPMVB_HD void run(uint64_t p, const LbCtx &c) {
+    if (!c.pmid[p]) return;
+    uint64_t q = p - 1;
+    while (c.pmid[q]) q--;
+    c.prow[p] = c.prow[q];
   }
 };
 
@@ -357,7 +371,8 @@ inline std::string lb_error_text(uint32_t err) {
 }
 
 // The builder proper.  BE supplies memory (alloc/release: temporaries, alloc_output/release_output: what the engine
-// keeps), launches, scans, the sort and the compaction (CUDA: layout_gpu.cuh).
+// keeps; reserve: a hint of how much alloc() will hand out next), launches, scans, the sort and the compaction
+// (CUDA: layout_gpu.cuh).
 // On success *out is a Layout with every host-side table filled except the two big arrays, stream and rowmap
 // (lb_fetch_host brings them over on demand), and img holds the device buffers.
 template <class BE>
@@ -394,10 +409,14 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   auto bail = [&](int code, const std::string &msg) { cleanup(false); delete L; return fail(code, msg); };
 #define LB_CHECK() do { if (!be.ok()) return bail(be.code(), be.error()); } while (0)
 
+  // temporaries come out of three arenas (per entry, per pair, per chunk): one device allocation each
+  const uint64_t kSlack = (uint64_t)4 << 20;
+  be.reserve((uint64_t)rows + (uint64_t)(blocks + 1) * 8 + nnz * 5 + kSlack);
   c.err = (uint32_t *)T(be.alloc(4)); be.fill(c.err, 0, 4);
   c.needz = (uint8_t *)T(be.alloc(rows)); be.fill(c.needz, 1, rows);
   c.rank_base = (uint64_t *)T(be.alloc((size_t)(blocks + 1) * 8)); be.fill(c.rank_base, 0, (size_t)(blocks + 1) * 8);
   LB_CHECK();
+  be.trace("arena 1");
 
   // ---- 1. pairs
   uint32_t n_pairs32 = 0;
@@ -407,7 +426,7 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
     LB_CHECK();
     be.template launch<LbRowHeads>(rows, c);
     be.template launch<LbEntryHeads>(nnz, c);
-    be.inclusive_sum_u8_u32(c.head, c.pincl, nnz);
+    be.inclusive_sum_bit0_u32(c.head, c.pincl, nnz);
     be.to_host(&n_pairs32, c.pincl + (nnz - 1), 4);
     LB_CHECK();
   } else {
@@ -417,11 +436,13 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   be.to_host(&err, c.err, 4);
   LB_CHECK();
   if (err) return bail(err & kLbErrBlockOverflow ? SPMVB_E_RANGE : SPMVB_E_ARG, "GPU layout build: " + lb_error_text(err));
+  be.trace("pair heads + scan");
   const uint64_t n_pairs = n_pairs32;
   c.n_pairs = n_pairs;
   L->n_pairs = n_pairs;
   if (n_pairs >= 0x7FFFFFF0ull) return bail(SPMVB_E_RANGE, "too many (row, block) pairs for the GPU builder");
 
+  be.reserve((n_pairs + 1) * 64 + (uint64_t)blocks * (cu + 1) * 8 + KB * 48 + kSlack);
   c.rowmap = (uint32_t *)be.alloc_output((n_pairs + 1) * 4);
   img->rowmap = c.rowmap;
   c.plen = (uint32_t *)T(be.alloc((n_pairs + 1) * 4));
@@ -436,17 +457,21 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
     c.pkey = (uint32_t *)T(be.alloc(n_pairs * 4));
     c.pval = (uint32_t *)T(be.alloc(n_pairs * 4));
     c.prow = (uint32_t *)T(be.alloc(n_pairs * 4));
+    c.pmid = (uint8_t *)T(be.alloc(n_pairs));
     c.rank_of = (uint32_t *)T(be.alloc(n_pairs * 4));
     c.pkey_sorted = (uint32_t *)T(be.alloc(n_pairs * 4));
     c.order = (uint32_t *)T(be.alloc(n_pairs * 4));
     LB_CHECK();
     be.template launch<LbPairHeads>(nnz, c);
+    be.template launch<LbRowPairs>(rows, c);
+    be.template launch<LbMidPairs>(n_pairs, c);
     // ---- 2. rank order: stable sort by block
     int bits = 1;
     while ((1ull << bits) < (uint64_t)blocks) bits++;
     be.sort_pairs(c.pkey, c.pkey_sorted, c.pval, c.order, n_pairs, bits);
     be.template launch<LbRanks>(n_pairs, c);
   }
+  be.trace("pairs, sort, ranks");
   be.exclusive_sum_u32_u64(c.plen, c.gpos, n_pairs + 1);
   be.exclusive_sum_u8_u32(c.nonsole, c.nsp, n_pairs + 1);
   LB_CHECK();
@@ -470,6 +495,7 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   be.to_host(&err, c.err, 4);
   LB_CHECK();
   if (err) return bail(err & kLbErrBlockOverflow ? SPMVB_E_RANGE : SPMVB_E_ARG, "GPU layout build: " + lb_error_text(err));
+  be.trace("scans + split + tables to host");
   std::vector<uint64_t> piece_last_rank;
   layout_finish_pieces(L, fp.data(), pad_rows.data(), piece_last_rank);
   if (L->n_chunks >= 0x7FFFFFFFull) return bail(SPMVB_E_RANGE, "too many chunks for one engine");
@@ -490,12 +516,14 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   // ---- 4. the image
   const uint64_t n_chunks = L->n_chunks;
   const size_t image_bytes = (size_t)(n_chunks * (uint64_t)c.slot > 16 ? n_chunks * (uint64_t)c.slot : 16);
+  be.reserve((n_chunks + 1) * 32 + (uint64_t)rows / 2 + kSlack);
   c.image = (uint8_t *)be.alloc_output(image_bytes);
   img->image = c.image;
   c.crank0 = (uint32_t *)T(be.alloc((n_chunks + 1) * 4)); c.cmid = (uint8_t *)T(be.alloc(n_chunks + 1));
   c.metas = (ChunkMeta *)T(be.alloc((n_chunks + 1) * sizeof(ChunkMeta)));
   c.col_lo = (uint16_t *)T(be.alloc((n_chunks + 1) * 2)); c.col_hi = (uint16_t *)T(be.alloc((n_chunks + 1) * 2));
   LB_CHECK();
+  be.trace("piece tables + image alloc");
   be.fill(c.image, 0, image_bytes);
   be.fill(c.crank0, 0, (n_chunks + 1) * 4); be.fill(c.cmid, 0, n_chunks + 1);
   be.template launch<LbScatter>(nnz, c);
@@ -504,6 +532,7 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   be.template launch<LbChunks>(n_chunks, c);
   LB_CHECK();
 
+  be.trace("scatter + chunk metadata");
   // ---- host-side tables of the layout
   L->chunks = (ChunkMeta *)calloc((size_t)(n_chunks ? n_chunks : 1), sizeof(ChunkMeta));
   if (!L->chunks) return bail(SPMVB_E_NOMEM, "chunks");
@@ -527,6 +556,7 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   }
   LB_CHECK();
 #undef LB_CHECK
+  be.trace("metadata to host + zero rows");
   cleanup(true);
   *out = L;
   return SPMVB_OK;

@@ -30,9 +30,11 @@ struct HostBackend {
   void launch(uint64_t n, const LbCtx &c) {
     for (uint64_t i = n; i-- > 0;) Body::run(i, c);
   }
-  void inclusive_sum_u8_u32(const uint8_t *in, uint32_t *out, uint64_t n) {
+  void reserve(uint64_t) {}
+  void trace(const char *) {}
+  void inclusive_sum_bit0_u32(const uint8_t *in, uint32_t *out, uint64_t n) {
     uint32_t s = 0;
-    for (uint64_t i = 0; i < n; i++) { s += in[i]; out[i] = s; }
+    for (uint64_t i = 0; i < n; i++) { s += in[i] & 1; out[i] = s; }
   }
   void exclusive_sum_u32_u64(const uint32_t *in, uint64_t *out, uint64_t n) {
     uint64_t s = 0;
