@@ -249,7 +249,7 @@ def run_poweriter(args, world, rank, local_rank):
     torch.cuda.set_stream(side)
     x = torch.zeros(x_len, dtype=tdt, device="cuda")
     x[:n] = 1.0 / np.sqrt(n)
-    plan = host_driver.GatherPlan(bounds)
+    plan = host_driver.GatherPlan(bounds, mode=os.environ.get("SPMVB_EXCHANGE", "chunks"))
     y = torch.zeros(plan.max_len, dtype=tdt, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -264,12 +264,15 @@ def run_poweriter(args, world, rank, local_rank):
     def sumsq(y_local, n_local, out):
         eng.sumsq(y_local.data_ptr(), n_local, out.data_ptr(), stream=stream)
 
-    host_driver.power_iteration(spmv_local, x, y, plan, max(args.warmup, 3), dist=dist, sumsq=sumsq)
+    def scale(y_local, n_local, ss):
+        eng.scale_rsqrt(y_local.data_ptr(), y_local.data_ptr(), n_local, ss.data_ptr(), stream=stream)
+
+    host_driver.power_iteration(spmv_local, x, y, plan, max(args.warmup, 3), dist=dist, sumsq=sumsq, scale=scale)
     sync()
     l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    nrm = host_driver.power_iteration(spmv_local, x, y, plan, args.steps, dist=dist, sumsq=sumsq)
+    nrm = host_driver.power_iteration(spmv_local, x, y, plan, args.steps, dist=dist, sumsq=sumsq, scale=scale)
     e1.record()
     sync()
     ms = e0.elapsed_time(e1)
@@ -293,7 +296,7 @@ def run_poweriter(args, world, rank, local_rank):
             "config": {"workload": "power iteration on R-MAT scale %d ef16, rows sharded over %d GPU(s), y slices exchanged "
                                    "into x by NCCL every iteration (BASELINE configs[4])" % (scale, world),
                        "rows": n, "nnz": nnz_total, "variant": int(eng.variant), "row_bounds": bounds,
-                       "step": "clear rows + SpMV kernel + norm (all-reduce) + scale + one broadcast per row owner"},
+                       "step": "clear rows + SpMV kernel + sum of squares + all-reduce + scale kernel + exchange (%s)" % ("all-to-all into equal chunks + all-gather" if plan.mode == "chunks" else "one broadcast per row owner")},
             "effective_gbs": alg / (per * 1e-3) / 1e9, "last_norm": nrm, "gpu_launches": launches,
             "setup_s": {"generate": t_gen}}), flush=True)
     if dist is not None:

@@ -163,6 +163,10 @@ int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
 /* x_dev[i] = y_dev[i] * scale for i < n (the normalisation step of the iterated caller) */
 int spmvb_engine_scale_copy(spmvb_engine *e, const void *src_dev, void *dst_dev, uint32_t n, double scale,
                             void *stream);
+/* dst_dev[i] = src_dev[i] / sqrt(*sumsq_dev) for i < n (0 if the sum is 0): the same step with the norm's square
+ * still on the device, e.g. straight after the all-reduce; dst may equal src */
+int spmvb_engine_scale_rsqrt(spmvb_engine *e, const void *src_dev, void *dst_dev, uint32_t n, const double *sumsq_dev,
+                             void *stream);
 /* sum of squares of y_dev[0..n) into a device double (for the norm all-reduce) */
 int spmvb_engine_sumsq(spmvb_engine *e, const void *src_dev, uint32_t n, double *out_dev, void *stream);
 

@@ -638,6 +638,21 @@ int spmvb_engine_scale_copy(spmvb_engine *e, const void *src_dev, void *dst_dev,
   return SPMVB_OK;
 }
 
+int spmvb_engine_scale_rsqrt(spmvb_engine *e, const void *src_dev, void *dst_dev, uint32_t n, const double *sumsq_dev,
+                             void *stream) {
+  Engine *E = (Engine *)e;
+  if (!E || !src_dev || !dst_dev || !sumsq_dev) return fail(SPMVB_E_ARG, "scale_rsqrt");
+  CUDA_TRY(cudaSetDevice(E->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : E->stream;
+  if (E->is_double)
+    scale_rsqrt_kernel<double><<<E->sms * 4, 256, 0, st>>>((const double *)src_dev, (double *)dst_dev, n, sumsq_dev);
+  else
+    scale_rsqrt_kernel<float><<<E->sms * 4, 256, 0, st>>>((const float *)src_dev, (float *)dst_dev, n, sumsq_dev);
+  E->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SPMVB_OK;
+}
+
 int spmvb_engine_sumsq(spmvb_engine *e, const void *src_dev, uint32_t n, double *out_dev, void *stream) {
   Engine *E = (Engine *)e;
   if (!E || !src_dev || !out_dev) return fail(SPMVB_E_ARG, "sumsq");

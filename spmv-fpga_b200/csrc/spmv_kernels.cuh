@@ -547,6 +547,16 @@ __global__ void scale_copy_kernel(const VT *__restrict__ src, VT *__restrict__ d
     dst[i] = src[i] * s;
 }
 
+// dst[i] = src[i] / sqrt(*sumsq): the normalisation of the iterated caller with the norm still on the device
+template <typename VT>
+__global__ void scale_rsqrt_kernel(const VT *__restrict__ src, VT *__restrict__ dst, uint32_t n,
+                                   const double *__restrict__ sumsq) {
+  const double ss = *sumsq;
+  const VT s = (VT)(ss > 0.0 ? 1.0 / sqrt(ss) : 0.0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i] * s;
+}
+
 template <typename VT>
 __global__ void sumsq_kernel(const VT *__restrict__ src, uint32_t n, double *__restrict__ out) {
   double acc = 0.0;

@@ -67,6 +67,7 @@ SYMBOLS = {
     "spmvb_engine_collect_steps": (_int, [_vp, _vp, _vp]),
     "spmvb_engine_power_iter": (_int, [_vp, _int, _vp]),
     "spmvb_engine_scale_copy": (_int, [_vp, _vp, _vp, _u32, ctypes.c_double, _vp]),
+    "spmvb_engine_scale_rsqrt": (_int, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "spmvb_engine_sumsq": (_int, [_vp, _vp, _u32, _vp, _vp]),
     "spmvb_csr_free": (None, [_vp]),
     "spmvb_csr_rows": (_u32, [_vp]),
@@ -450,6 +451,9 @@ class Engine:
 
     def scale_copy(self, src_dev, dst_dev, n, scale, stream=None):
         _check(lib().spmvb_engine_scale_copy(self.h, src_dev, dst_dev, n, scale, stream))
+
+    def scale_rsqrt(self, src_dev, dst_dev, n, sumsq_dev, stream=None):
+        _check(lib().spmvb_engine_scale_rsqrt(self.h, src_dev, dst_dev, n, sumsq_dev, stream))
 
     def sumsq(self, src_dev, n, out_dev, stream=None):
         _check(lib().spmvb_engine_sumsq(self.h, src_dev, n, out_dev, stream))

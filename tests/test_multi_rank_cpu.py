@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, out_dir):
+def _worker(rank, world, port, case, out_dir, mode):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [os.path.join(root, "spmv-fpga_b200"), os.path.join(root, "tests")]
@@ -52,7 +52,7 @@ def _worker(rank, world, port, case, out_dir):
         assert orc.spmv_emu(ho, x_full.numpy()[:cols].copy(), y, True) == 0
         y_local[: hi - lo] = torch.from_numpy(y)
 
-    plan = host_driver.GatherPlan(bounds)
+    plan = host_driver.GatherPlan(bounds, mode=mode)
     x = torch.full((cols,), 1.0 / np.sqrt(cols), dtype=torch.float64)
     y = torch.zeros(plan.max_len, dtype=torch.float64)
     nrm = host_driver.power_iteration(spmv_local, x, y, plan, 12, dist=dist)
@@ -62,10 +62,11 @@ def _worker(rank, world, port, case, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,case", [(2, "rmat"), (2, "lap"), (3, "rmat")])
-def test_power_iteration_over_row_shards_matches_single_process(tmp_path, world, case):
+@pytest.mark.parametrize("world,case,mode", [(2, "rmat", "chunks"), (2, "lap", "chunks"), (3, "rmat", "chunks"),
+                                             (2, "rmat", "broadcast"), (3, "lap", "broadcast")])
+def test_power_iteration_over_row_shards_matches_single_process(tmp_path, world, case, mode):
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, case, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, case, str(tmp_path), mode), nprocs=world, join=True)
     rows, cols, rp, ci, va = matgen.rmat(11, 8, seed=3) if case == "rmat" else matgen.laplacian2d(64, 48)
     va = np.abs(va) + 0.1
     orc = oa.OracleLib()
@@ -90,3 +91,16 @@ def test_row_bounds_fall_back_to_equal_ranges():
     b = host_driver.row_bounds(10, rp, 4, 2, balanced=True, partition_fn=lambda rows, rp, w, rv: [0, 4, 8, 10, 10])
     assert list(b) == [0, 2, 4, 6, 10]  # a split did not fire -> equal ranges
     assert list(host_driver.row_bounds(10, None, 1)) == [0, 10]
+
+
+def test_gather_plan_chunk_splits_tile_the_rows():
+    import host_driver
+    for bounds in ([0, 5, 6, 20], [0, 0, 7, 7, 9], [0, 1000, 1001, 1002, 1003, 2049]):
+        plan = host_driver.GatherPlan(bounds)
+        W = plan.world
+        send = [[plan._overlap(k, c) for c in range(W)] for k in range(W)]
+        for k in range(W):
+            assert sum(send[k]) == plan.lens[k]                      # every owned row is sent exactly once
+        for c in range(W):
+            want = max(0, min((c + 1) * plan.chunk, plan.rows) - c * plan.chunk)
+            assert sum(send[k][c] for k in range(W)) == want         # every chunk is filled exactly
