@@ -249,7 +249,7 @@ def run_poweriter(args, world, rank, local_rank):
     torch.cuda.set_stream(side)
     x = torch.zeros(x_len, dtype=tdt, device="cuda")
     x[:n] = 1.0 / np.sqrt(n)
-    plan = host_driver.GatherPlan(bounds, mode=os.environ.get("SPMVB_EXCHANGE", "chunks"))
+    plan = host_driver.GatherPlan(bounds, mode=os.environ.get("SPMVB_EXCHANGE", "broadcast"))
     y = torch.zeros(plan.max_len, dtype=tdt, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -264,15 +264,15 @@ def run_poweriter(args, world, rank, local_rank):
     def sumsq(y_local, n_local, out):
         eng.sumsq(y_local.data_ptr(), n_local, out.data_ptr(), stream=stream)
 
-    def scale(y_local, n_local, ss):
+    def scale_y(y_local, n_local, ss):
         eng.scale_rsqrt(y_local.data_ptr(), y_local.data_ptr(), n_local, ss.data_ptr(), stream=stream)
 
-    host_driver.power_iteration(spmv_local, x, y, plan, max(args.warmup, 3), dist=dist, sumsq=sumsq, scale=scale)
+    host_driver.power_iteration(spmv_local, x, y, plan, max(args.warmup, 3), dist=dist, sumsq=sumsq, scale=scale_y)
     sync()
     l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    nrm = host_driver.power_iteration(spmv_local, x, y, plan, args.steps, dist=dist, sumsq=sumsq, scale=scale)
+    nrm = host_driver.power_iteration(spmv_local, x, y, plan, args.steps, dist=dist, sumsq=sumsq, scale=scale_y)
     e1.record()
     sync()
     ms = e0.elapsed_time(e1)

@@ -165,9 +165,23 @@ static inline void init_vector_rand(csr_vector *v, ValueType max) {
 /* ---- csr_hw_wrapper.cpp:3-80: builds the layout (bit-exact pieces) and uploads it to the GPU */
 static inline void create_csr_hw_matrix(csr_matrix *matrix, csr_hw_matrix ***hw_matrix, bool ***empty_rows_bitmap) {
   spmvb_layout *L = NULL;
-  if (spmvb_layout_build_u32(matrix->nr_rows, matrix->nr_cols, matrix->row_ptr, matrix->col_ind, matrix->values, CU, VF,
-                             DOUBLE, COLS_DIV_BLOCKS, &L) != SPMVB_OK)
+  spmvb_engine *E = NULL;
+  const char *dev = getenv("SPMVB_DEVICE");
+  const char *gpu_build = getenv("SPMVB_GPU_BUILD");
+  if (gpu_build && atoi(gpu_build)) {
+    /* SPMVB_GPU_BUILD=1: the same layout built by CUDA kernels (needs sorted rows; errors are fatal like any other),
+     * then copied back because this API exposes submatrix[b] and the bitmap on the host */
+    uint64_t *rp64 = (uint64_t *)malloc(((size_t)matrix->nr_rows + 1) * sizeof(uint64_t));
+    for (IndexType i = 0; i <= matrix->nr_rows; i++) rp64[i] = matrix->row_ptr[i];
+    if (spmvb_engine_create_from_csr(matrix->nr_rows, matrix->nr_cols, rp64, matrix->col_ind, matrix->values, CU, VF, DOUBLE,
+                                     COLS_DIV_BLOCKS, dev ? atoi(dev) : 0, 0, 0, &L, &E) != SPMVB_OK ||
+        spmvb_engine_fetch_layout(E, L) != SPMVB_OK)
+      spmvb_compat_die("create_csr_hw_matrix (GPU build)");
+    free(rp64);
+  } else if (spmvb_layout_build_u32(matrix->nr_rows, matrix->nr_cols, matrix->row_ptr, matrix->col_ind, matrix->values, CU,
+                                    VF, DOUBLE, COLS_DIV_BLOCKS, &L) != SPMVB_OK) {
     spmvb_compat_die("create_csr_hw_matrix");
+  }
   const int blocks = spmvb_layout_blocks(L);
   *hw_matrix = (csr_hw_matrix **)malloc(ComputeUnits * sizeof(csr_hw_matrix *));
   for (int k = 0; k < ComputeUnits; k++) {
@@ -209,8 +223,8 @@ static inline void create_csr_hw_matrix(csr_matrix *matrix, csr_hw_matrix ***hw_
     printf("Total non-zeros : %.0f. Total %g MB transferred ( in : %g, out : %g)\n", tot, in + out, in, out);
   }
   spmvb_compat_owner *o = (spmvb_compat_owner *)(*hw_matrix)[0];
-  const char *dev = getenv("SPMVB_DEVICE");
-  if (spmvb_engine_create(L, dev ? atoi(dev) : 0, 0, &o->engine) != SPMVB_OK) spmvb_compat_die("create_csr_hw_matrix (GPU upload)");
+  if (!E && spmvb_engine_create(L, dev ? atoi(dev) : 0, 0, &E) != SPMVB_OK) spmvb_compat_die("create_csr_hw_matrix (GPU upload)");
+  o->engine = E;
 }
 
 /* ---- csr_hw.cpp:1436-1488: per-block packed x slices, zero padded */

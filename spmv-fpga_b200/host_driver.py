@@ -5,8 +5,8 @@ non-zero count with the reference's split rule (csr_hw.cpp:459-460, through spmv
 CU=1 hw_matrix layout of its own rows (bit-exact with the reference run on that row slice), keeps all of x (x is
 replicated per compute unit in the reference too: spmv.cpp:280-294) and owns its slice of y.  A single SpMV therefore
 needs no collective.  Iterated SpMV (power iteration, BASELINE config 4: x <- A x / ||A x||) exchanges the y slices
-into every rank's x once per iteration (NCCL all-to-all into equal chunks + all-gather, see GatherPlan) and
-all-reduces one scalar for the norm.
+into every rank's x once per iteration (NCCL: one broadcast per owner, or all-to-all into equal chunks + all-gather,
+see GatherPlan) and all-reduces one scalar for the norm.
 
 The functions take the local SpMV as a callable so that the same host logic runs on the GPU engine (NCCL) and, in the
 CPU tests, on the oracle (gloo).
@@ -33,13 +33,15 @@ class GatherPlan:
     """Exchange step of the iterated caller: every rank's slice of y becomes the matching slice of every rank's x.
 
     The row slices are balanced by non-zeros, so their lengths differ a lot on skewed matrices (R-MAT scale 24 over 8
-    GPUs: the last rank owns 43 % of the rows).  A padded all-gather would move world x the longest slice, and one
-    broadcast per owner is bound by the biggest owner's link.  Default ("chunks"): the rows are also cut into `world`
-    EQUAL chunks; an all-to-all moves every row once, from its owner to the rank holding its chunk, and a plain
-    all-gather of the equal chunks (ring / NVLS inside NCCL) fills every rank's x.  Rows travel twice, but both
-    collectives are balanced.  mode="broadcast" keeps the one-broadcast-per-owner exchange."""
+    GPUs: the last rank owns 43 % of the rows).  A padded all-gather would move world x the longest slice.
+    mode="broadcast" (default; the one timed on 8 GPUs): one broadcast per owner moves exactly the rows that exist,
+    but is bound by the biggest owner's link.  mode="chunks": the rows are also cut into `world` EQUAL chunks; an
+    all-to-all moves every row once, from its owner to the rank holding its chunk, and a plain all-gather of the equal
+    chunks (ring / NVLS inside NCCL) fills every rank's x - rows travel twice, but both collectives are balanced.
+    Both give the same x (CPU gloo tests; 2 GPUs: norms equal to 8 digits, 0.252 vs 0.241 ms per iteration at
+    scale 22, i.e. no gain without skew across many ranks; not yet timed on 8 GPUs)."""
 
-    def __init__(self, bounds, mode="chunks"):
+    def __init__(self, bounds, mode="broadcast"):
         self.bounds = [int(b) for b in bounds]
         self.world = len(self.bounds) - 1
         self.lens = [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)]

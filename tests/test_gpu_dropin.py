@@ -15,8 +15,8 @@ OURS = os.path.join(ROOT, "spmv-fpga_b200", "lib", "run_cu%d_vf%d_d%d.elf")
 REF = os.path.join(ROOT, "oracle", "_ref", "ref_run_cu%d_vf%d_d%d.elf")
 
 
-def run(exe, path):
-    p = subprocess.run([exe, path], capture_output=True, text=True, timeout=300)
+def run(exe, path, env=None):
+    p = subprocess.run([exe, path], capture_output=True, text=True, timeout=300, env=dict(os.environ, **(env or {})))
     return p.returncode, p.stdout + p.stderr
 
 
@@ -40,6 +40,11 @@ def test_run_elf_verifies_and_reports_like_the_reference(spmvb, tmp_path, cfg):
     rc, out = run(exe, path)
     assert rc == 0, out
     assert "Verification PASSED!" in out
+    # the same run with create_csr_hw_matrix building the layout on the GPU: identical report
+    grc, gout = run(exe, path, {"SPMVB_GPU_BUILD": "1"})
+    assert grc == 0, gout
+    assert "Verification PASSED!" in gout
+    assert last_line(gout) == last_line(out)
     assert re.search(r"Welcome to SpMV \(Compute Units : %d, Vectorization Factor : %d" % cfg[:2], out)
     ref = REF % cfg
     if os.path.exists(ref):  # prebuilt from the unmodified reference (oracle/Makefile ref_elf); travels with the repo

@@ -96,7 +96,7 @@ def test_row_bounds_fall_back_to_equal_ranges():
 def test_gather_plan_chunk_splits_tile_the_rows():
     import host_driver
     for bounds in ([0, 5, 6, 20], [0, 0, 7, 7, 9], [0, 1000, 1001, 1002, 1003, 2049]):
-        plan = host_driver.GatherPlan(bounds)
+        plan = host_driver.GatherPlan(bounds, mode="chunks")
         W = plan.world
         send = [[plan._overlap(k, c) for c in range(W)] for k in range(W)]
         for k in range(W):
