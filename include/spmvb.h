@@ -160,6 +160,13 @@ int spmvb_engine_collect_steps(spmvb_engine *e, float *total_ms, float *kernel_m
 /* Iterated SpMV on one GPU (square matrices): x <- A x / ||A x||_2, `iters` times, all on device.
  * Returns the last norm in *norm_out.  The multi-GPU version lives in the host driver (NCCL all-gather). */
 int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
+/* Conjugate gradients for A x = b on one GPU (A symmetric positive definite, e.g. the Laplacian of BASELINE config 2):
+ * the second iterated caller of SURVEY 8(f) rank 3.  x0 = 0; per iteration one SpMV (the engine's kernel) and three
+ * fused vector kernels (p.q; x += a p, r -= a q, r.r; p = r + b p) with all scalars on the device; the host looks at
+ * ||r|| every 8 iterations and stops when ||r|| <= rel_tol * ||b|| (the recurrence residual) or after max_iters.
+ * b_host / x_host hold rows values of the engine's type.  *relres_out = ||r|| / ||b|| at the last check. */
+int spmvb_engine_cg(spmvb_engine *e, const void *b_host, void *x_host, int max_iters, double rel_tol, int *iters_out,
+                    double *relres_out);
 /* x_dev[i] = y_dev[i] * scale for i < n (the normalisation step of the iterated caller) */
 int spmvb_engine_scale_copy(spmvb_engine *e, const void *src_dev, void *dst_dev, uint32_t n, double scale,
                             void *stream);

@@ -224,6 +224,70 @@ static int autotune(Engine *E) {
 
 using namespace spmvb;
 
+namespace {
+template <typename VT>
+int cg_impl(Engine *E, const VT *b_host, VT *x_host, int max_iters, double rel_tol, int *iters_out, double *relres_out) {
+  const uint32_t n = E->rows;
+  const size_t bytes = (size_t)n * sizeof(VT);
+  VT *d_r = nullptr, *d_xs = nullptr;
+  double *s = nullptr;  // s[0], s[2]: r.r (roles swap every iteration); s[1]: p.q
+  cudaStream_t st = E->stream;
+  const int grid = E->sms * 4;
+  int rc = SPMVB_OK, it = 0;
+  double bnorm2 = 0.0, rr_host = 0.0;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaMalloc((void **)&d_r, bytes));
+    CUDA_TRY(cudaMalloc((void **)&d_xs, bytes));
+    CUDA_TRY(cudaMalloc((void **)&s, 4 * sizeof(double)));
+    VT *p = (VT *)E->d_x, *q = (VT *)E->d_y;
+    // x0 = 0: r = b, p = b (the padding of p beyond n stays zero), rr = b.b
+    CUDA_TRY(cudaMemsetAsync(d_xs, 0, bytes, st));
+    CUDA_TRY(cudaMemcpyAsync(d_r, b_host, bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(E->d_x, 0, E->x_len * sizeof(VT), st));
+    CUDA_TRY(cudaMemcpyAsync(p, d_r, bytes, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(s, 0, 4 * sizeof(double), st));
+    dot_kernel<VT><<<grid, 256, 0, st>>>(d_r, d_r, n, s + 0);
+    E->launches++;
+    CUDA_TRY(cudaMemcpyAsync(&bnorm2, s + 0, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    rr_host = bnorm2;
+    if (bnorm2 == 0.0) return SPMVB_OK;  // b = 0: x = 0
+    const double stop2 = rel_tol * rel_tol * bnorm2;
+    int cur = 0;  // index of the current r.r
+    constexpr int kCheckEvery = 8;
+    while (it < max_iters) {
+      const int nxt = 2 - cur;
+      int r2 = do_spmv(E, p, q, 0, st);  // q = A p
+      if (r2) return r2;
+      CUDA_TRY(cudaMemsetAsync(s + 1, 0, sizeof(double), st));
+      CUDA_TRY(cudaMemsetAsync(s + nxt, 0, sizeof(double), st));
+      dot_kernel<VT><<<grid, 256, 0, st>>>(p, q, n, s + 1);
+      cg_update_kernel<VT><<<grid, 256, 0, st>>>(d_xs, d_r, p, q, n, s + cur, s + 1, s + nxt);
+      cg_direction_kernel<VT><<<grid, 256, 0, st>>>(p, d_r, n, s + cur, s + nxt);
+      E->launches += 3;
+      CUDA_TRY(cudaGetLastError());
+      cur = nxt;
+      it++;
+      if (it % kCheckEvery == 0 || it == max_iters) {
+        CUDA_TRY(cudaMemcpyAsync(&rr_host, s + cur, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (!(rr_host > stop2)) break;  // converged (or NaN: give up)
+      }
+    }
+    CUDA_TRY(cudaMemcpyAsync(x_host, d_xs, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return SPMVB_OK;
+  };
+  rc = body();
+  cudaFree(d_r); cudaFree(d_xs); cudaFree(s);
+  if (rc) return rc;
+  if (bnorm2 == 0.0) memset(x_host, 0, bytes);
+  if (iters_out) *iters_out = it;
+  if (relres_out) *relres_out = bnorm2 > 0.0 ? std::sqrt(rr_host / bnorm2) : 0.0;
+  return SPMVB_OK;
+}
+}  // namespace
+
 extern "C" {
 
 // device checks, the Engine object with everything that follows from the layout's tables, stream, x / y
@@ -689,6 +753,16 @@ int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out) {
   CUDA_TRY(cudaStreamSynchronize(E->stream));
   if (norm_out) *norm_out = nrm;
   return SPMVB_OK;
+}
+
+int spmvb_engine_cg(spmvb_engine *e, const void *b_host, void *x_host, int max_iters, double rel_tol, int *iters_out,
+                    double *relres_out) {
+  Engine *E = (Engine *)e;
+  if (!E || !b_host || !x_host || max_iters < 1 || !(rel_tol >= 0.0)) return fail(SPMVB_E_ARG, "cg");
+  if (E->rows != E->cols) return fail(SPMVB_E_ARG, "cg needs a square matrix");
+  CUDA_TRY(cudaSetDevice(E->device));
+  if (E->is_double) return cg_impl<double>(E, (const double *)b_host, (double *)x_host, max_iters, rel_tol, iters_out, relres_out);
+  return cg_impl<float>(E, (const float *)b_host, (float *)x_host, max_iters, rel_tol, iters_out, relres_out);
 }
 
 }  // extern "C"

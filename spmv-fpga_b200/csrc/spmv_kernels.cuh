@@ -578,6 +578,59 @@ __global__ void sumsq_kernel(const VT *__restrict__ src, uint32_t n, double *__r
   }
 }
 
+// ---- conjugate gradients (the iterated caller on the Laplacian): vector work of one iteration in
+// three kernels around the SpMV.  Scalars stay on the device: s[0], s[2] = r.r of the current / next iteration (the
+// host swaps their roles every iteration), s[1] = p.q.  Sums are accumulated in double.
+__device__ __forceinline__ void block_sum_to(double acc, double *out) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+  __shared__ double part[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    acc = lane < (int)(blockDim.x >> 5) ? part[lane] : 0.0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    if (lane == 0) atomicAdd(out, acc);
+  }
+}
+
+template <typename VT>
+__global__ void dot_kernel(const VT *__restrict__ a, const VT *__restrict__ b, uint32_t n, double *__restrict__ out) {
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    acc += (double)a[i] * (double)b[i];
+  block_sum_to(acc, out);
+}
+
+// x += alpha p; r -= alpha q; *rr_next += r.r   with alpha = *rr / *pq
+template <typename VT>
+__global__ void cg_update_kernel(VT *__restrict__ x, VT *__restrict__ r, const VT *__restrict__ p,
+                                 const VT *__restrict__ q, uint32_t n, const double *__restrict__ rr,
+                                 const double *__restrict__ pq, double *__restrict__ rr_next) {
+  const double d = *pq;
+  const VT alpha = (VT)(d != 0.0 ? *rr / d : 0.0);
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const VT ri = r[i] - alpha * q[i];
+    r[i] = ri;
+    acc += (double)ri * (double)ri;
+  }
+  block_sum_to(acc, rr_next);
+}
+
+// p = r + beta p   with beta = *rr_next / *rr
+template <typename VT>
+__global__ void cg_direction_kernel(VT *__restrict__ p, const VT *__restrict__ r, uint32_t n,
+                                    const double *__restrict__ rr, const double *__restrict__ rr_next) {
+  const double d = *rr;
+  const VT beta = (VT)(d != 0.0 ? *rr_next / d : 0.0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = r[i] + beta * p[i];
+}
+
 __global__ void l2_flush_kernel(uint4 *__restrict__ buf, size_t n_words) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x)
     buf[i] = make_uint4((uint32_t)i, 0, 0, 0);

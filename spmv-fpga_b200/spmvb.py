@@ -66,6 +66,7 @@ SYMBOLS = {
     "spmvb_engine_steps_done": (_int, [_vp]),
     "spmvb_engine_collect_steps": (_int, [_vp, _vp, _vp]),
     "spmvb_engine_power_iter": (_int, [_vp, _int, _vp]),
+    "spmvb_engine_cg": (_int, [_vp, _vp, _vp, _int, ctypes.c_double, _vp, _vp]),
     "spmvb_engine_scale_copy": (_int, [_vp, _vp, _vp, _u32, ctypes.c_double, _vp]),
     "spmvb_engine_scale_rsqrt": (_int, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "spmvb_engine_sumsq": (_int, [_vp, _vp, _u32, _vp, _vp]),
@@ -448,6 +449,14 @@ class Engine:
         nrm = ctypes.c_double()
         _check(lib().spmvb_engine_power_iter(self.h, iters, ctypes.byref(nrm)))
         return nrm.value
+
+    def cg(self, b, max_iters=1000, rel_tol=1e-10):
+        """Conjugate gradients for A x = b (A symmetric positive definite): returns (x, iterations, ||r|| / ||b||)."""
+        bb = np.ascontiguousarray(b, vdtype(self.is_double))
+        x = np.zeros(self.rows, vdtype(self.is_double))
+        it, rel = ctypes.c_int(), ctypes.c_double()
+        _check(lib().spmvb_engine_cg(self.h, _ptr(bb), _ptr(x), max_iters, rel_tol, ctypes.byref(it), ctypes.byref(rel)))
+        return x, it.value, rel.value
 
     def scale_copy(self, src_dev, dst_dev, n, scale, stream=None):
         _check(lib().spmvb_engine_scale_copy(self.h, src_dev, dst_dev, n, scale, stream))
