@@ -109,10 +109,10 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
 /* create_csr_hw_matrix ON the GPU: same layout, bit for bit, as spmvb_layout_build, built by
  * CUDA kernels (flag / scan / stable radix sort by column block / scatter) straight into the engine's device image.
  * row_ptr (rows+1 x uint64), col_ind, values are host pointers (csr_on_device 0; uploaded inside) or device pointers
- * on `device` (csr_on_device 1).  Inside a row the column blocks must ascend (sorted rows do); fewer than 2^31 rows and
- * non-zeros.  *layout_out receives every host-side table (piece_info, chunk metadata, rows to clear, XS plan input);
+ * on `device` (csr_on_device 1).  Fewer than 2^31 rows and non-zeros; rows with unsorted columns cost one extra
+ * sort pass.  *layout_out receives every host-side table (piece_info, chunk metadata, rows to clear, XS plan input);
  * its pieces and row map stay on the device until spmvb_engine_fetch_layout copies them back (piece_words and
- * bitmap_row fail before that).  There is no host fallback: unsupported input is an error. */
+ * bitmap_row fail before that).  There is no host fallback: invalid input is an error. */
 int spmvb_engine_create_from_csr(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, const uint32_t *col_ind,
                                  const void *values, int n_cu, int vf, int is_double, uint32_t cols_div_blocks,
                                  int device, int variant, int csr_on_device, spmvb_layout **layout_out,

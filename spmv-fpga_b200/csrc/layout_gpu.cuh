@@ -147,6 +147,12 @@ struct CudaBackend {
     chk(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, bits, st), "sort size");
     if (temp(bytes)) chk(cub::DeviceRadixSort::SortPairs(scratch, bytes, kin, kout, vin, vout, (int)n, 0, bits, st), "radix sort");
   }
+  void sort_pairs_u64(const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint64_t n, int bits) {
+    if (!ok() || !n) return;
+    size_t bytes = 0;
+    chk(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, bits, st), "sort size");
+    if (temp(bytes)) chk(cub::DeviceRadixSort::SortPairs(scratch, bytes, kin, kout, vin, vout, (int)n, 0, bits, st), "radix sort (entries)");
+  }
   bool counter() {
     if (!d_count) d_count = (unsigned long long *)alloc(16);
     return ok();

@@ -14,8 +14,8 @@
 //   4. Every entry is written straight to its final byte of the device image; per-chunk metadata, the rows to clear
 //      and the column ranges follow from one pass over the chunks.
 //
-// Precondition (checked on the device, error otherwise): inside a row the column blocks ascend - true for sorted rows,
-// the only order the matrix generators and writers of this repo produce.  The host builder has no such restriction.
+// Rows whose column blocks do not ascend (unsorted columns) take one extra pass: a stable radix sort of all entries by
+// (row, block), which keeps the given order inside every pair exactly like the reference's per-block walk of the row.
 //
 // The step bodies are plain functions of (index, context) so that tests can run the very same code on the CPU
 // (tests/emu/layout_emu.cpp: serial loops in reverse order, std::stable_sort, std::partial_sum) and compare it with
@@ -53,6 +53,15 @@ struct LbCtx {
   int cdb_shift;  // >= 0: cols_div_blocks is 1 << cdb_shift
   int blocks, cu, vf, vb, ratio_v, gb, chunk_bytes, slot, run_log2;
   uint64_t nnz, n_pairs, n_chunks, n_pieces;
+  // reorder pass (rows whose column blocks do not ascend)
+  uint64_t *okey;    // [nnz] row << block_bits | block
+  uint32_t *oidx;    // [nnz] identity, the sort's payload
+  uint32_t *perm;    // [nnz] sorted position -> original entry
+  uint32_t *col2;    // [nnz] reordered copies of col_ind / values
+  uint8_t *val2;
+  const uint32_t *col_in;
+  const uint8_t *val_in;
+  int block_bits;
   // per entry
   uint8_t *head;    // [nnz] bit 0 = first entry of a (row, block) pair, bit 7 = ... but not of its row
   uint32_t *pincl;  // [nnz] inclusive scan of head: pair number + 1 (CSR order)
@@ -136,6 +145,27 @@ struct LbEntryHeads {
     const uint32_t b = lb_block_of(c, col), bp = lb_block_of(c, prev);
     if (b != bp) c.head[j] = 0x81;
     if (b < bp) lb_flag(c.err, kLbErrBlockOrder);
+  }
+};
+
+// reorder pass: sort key of every entry = (row, column block); a stable sort keeps the given order inside a pair
+struct LbEntryKeys {
+  static SPMVB_HD void run(uint64_t j, const LbCtx &c) {
+    uint64_t lo = 0, hi = c.rows;  // first index with row_ptr[i] > j, in (0, rows]
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (c.row_ptr[mid] > j) hi = mid; else lo = mid + 1;
+    }
+    c.okey[j] = ((lo - 1) << c.block_bits) | lb_block_of(c, c.col_in[j]);
+    c.oidx[j] = (uint32_t)j;
+  }
+};
+struct LbPermute {
+  static SPMVB_HD void run(uint64_t j, const LbCtx &c) {
+    const uint64_t src = c.perm[j];
+    c.col2[j] = c.col_in[src];
+    if (c.vb == 8) reinterpret_cast<uint64_t *>(c.val2)[j] = reinterpret_cast<const uint64_t *>(c.val_in)[src];
+    else reinterpret_cast<uint32_t *>(c.val2)[j] = reinterpret_cast<const uint32_t *>(c.val_in)[src];
   }
 };
 
@@ -364,7 +394,7 @@ struct LbImage {
 inline std::string lb_error_text(uint32_t err) {
   std::string s;
   if (err & kLbErrColRange) s += "column index out of range; ";
-  if (err & kLbErrBlockOrder) s += "column blocks do not ascend inside a row (sort the rows or use spmvb_layout_build); ";
+  if (err & kLbErrBlockOrder) s += "column blocks do not ascend inside a row; ";
   if (err & kLbErrBlockOverflow) s += "block nnz overflows IndexType; ";
   if (err & kLbErrRowPtr) s += "row_ptr is not monotone; ";
   return s;
@@ -435,6 +465,37 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   uint32_t err = 0;
   be.to_host(&err, c.err, 4);
   LB_CHECK();
+  if (err == kLbErrBlockOrder) {
+    // Some row visits its column blocks out of order (unsorted columns).  The layout keeps, inside every (row, block)
+    // pair, the order the entries were given in (create_block_matrix walks the row once per block,
+    // csr_hw.cpp:212-226), so: stable sort of all entries by (row, block), then the passes above on the reordered copy.
+    int row_bits = 1;
+    while ((1ull << row_bits) < (uint64_t)rows) row_bits++;
+    c.block_bits = 1;
+    while ((1ull << c.block_bits) < (uint64_t)blocks) c.block_bits++;
+    be.reserve(nnz * (uint64_t)(44 + c.vb) + kSlack);
+    c.okey = (uint64_t *)T(be.alloc(nnz * 8));
+    uint64_t *okey_sorted = (uint64_t *)T(be.alloc(nnz * 8));
+    c.oidx = (uint32_t *)T(be.alloc(nnz * 4));
+    c.perm = (uint32_t *)T(be.alloc(nnz * 4));
+    c.col2 = (uint32_t *)T(be.alloc(nnz * 4));
+    c.val2 = (uint8_t *)T(be.alloc(nnz * (uint64_t)c.vb));
+    LB_CHECK();
+    c.col_in = c.col_ind; c.val_in = c.values;
+    be.template launch<LbEntryKeys>(nnz, c);
+    be.sort_pairs_u64(c.okey, okey_sorted, c.oidx, c.perm, nnz, c.block_bits + row_bits);
+    be.template launch<LbPermute>(nnz, c);
+    c.col_ind = c.col2; c.values = c.val2;
+    be.fill(c.head, 0, nnz);
+    be.fill(c.err, 0, 4);
+    be.template launch<LbRowHeads>(rows, c);
+    be.template launch<LbEntryHeads>(nnz, c);
+    be.inclusive_sum_bit0_u32(c.head, c.pincl, nnz);
+    be.to_host(&n_pairs32, c.pincl + (nnz - 1), 4);
+    be.to_host(&err, c.err, 4);
+    LB_CHECK();
+    be.trace("reorder rows by column block");
+  }
   if (err) return bail(err & kLbErrBlockOverflow ? SPMVB_E_RANGE : SPMVB_E_ARG, "GPU layout build: " + lb_error_text(err));
   be.trace("pair heads + scan");
   const uint64_t n_pairs = n_pairs32;

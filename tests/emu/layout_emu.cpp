@@ -51,6 +51,13 @@ struct HostBackend {
     std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return (kin[a] & mask) < (kin[b] & mask); });
     for (uint64_t i = 0; i < n; i++) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
   }
+  void sort_pairs_u64(const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, uint64_t n, int bits) {
+    std::vector<uint32_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0u);
+    const uint64_t mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return (kin[a] & mask) < (kin[b] & mask); });
+    for (uint64_t i = 0; i < n; i++) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
+  }
   uint64_t count_nonzero_u8(const uint8_t *in, uint64_t n) {
     uint64_t s = 0;
     for (uint64_t i = 0; i < n; i++) s += in[i] != 0;
