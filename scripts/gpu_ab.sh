@@ -2,7 +2,7 @@
 # A/B timing of several builds of libspmvb.so: $@ = library names under spmv-fpga_b200/lib
 mkdir -p gpurun_out
 for l in "$@"; do
-  SPMVB_LIB=$PWD/spmv-fpga_b200/lib/$l timeout 120 python bench.py --steps 200 --warmup 5 --variant 2 --no-cpu-baseline > gpurun_out/ab_$l.json 2> gpurun_out/ab_$l.err; rc=$?
+  SPMVB_LIB=$PWD/spmv-fpga_b200/lib/$l timeout 120 python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-gpu-build > gpurun_out/ab_$l.json 2> gpurun_out/ab_$l.err; rc=$?
   python - <<PY
 import json
 try:

@@ -1,10 +1,15 @@
 #!/bin/bash
-# multi-GPU bench check: $1 = N
-N=$1
+# $1 = N GPUs; rest: bench args.  Runs under torchrun and prints a one-line summary.
+N=$1; shift
 mkdir -p gpurun_out
-nvidia-smi -L
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench N=$N exit $?"
-tail -3 gpurun_out/bench_n$N.err
-cat gpurun_out/bench_n$N.json | cut -c1-900
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 5 --warmup 1 --impl reference > gpurun_out/bench_ref_n$N.json 2> gpurun_out/bench_ref_n$N.err; echo "ref N=$N exit $?"
-cat gpurun_out/bench_ref_n$N.json | cut -c1-400
+tag=$(echo "$@" | tr ' /' '__')
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N "$@" > gpurun_out/mg_${N}_$tag.json 2> gpurun_out/mg_${N}_$tag.err; rc=$?
+python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/mg_${N}_$tag.json'))
+    r=d.get('roofline',{})
+    print('N=$N $@: nnz %d ms/step %.4f GF %.1f eff_GBs %.0f kernel_ms %s frac %s e2e %s variant %s'%(d['config']['nnz'],d['ms_per_step'],d['value'],d['effective_gbs'],r.get('kernel_ms_avg'),r.get('frac'),d.get('e2e',{}).get('value'),d['config'].get('variant')))
+except Exception as e:
+    print('N=$N $@ failed rc=$rc', e); import subprocess; print(open('gpurun_out/mg_${N}_$tag.err').read()[-1500:])
+PY
