@@ -328,6 +328,21 @@ def run_reference(args, spec, world, rank):
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:  # for information: the same loop spread over all host cores (oracle port, OpenMP over rows); the reference
+        # itself is single-threaded, so `value` above stays its own number
+        import oracle_api as oa
+        O = oa.OracleLib()
+        x = np.random.default_rng(1).random(csr.cols).astype(np.float64 if is_double else np.float32)
+        O.spmv_gold_omp(csr.rows, csr.row_ptr, csr.col_ind, csr.values, x, is_double)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            _, threads = O.spmv_gold_omp(csr.rows, csr.row_ptr, csr.col_ind, csr.values, x, is_double)
+            ts.append(time.perf_counter() - t0)
+        line["cpu_baseline_all_cores"] = {"value": 2.0 * csr.nnz / min(ts) / 1e9, "unit": "GFLOP/s", "cores": int(threads),
+                                          "kind": "port", "sample": "same matrix, best of 3 passes, OpenMP over rows"}
+    except Exception as exc:
+        line["cpu_baseline_all_cores"] = {"error": str(exc)}
     print(json.dumps(line), flush=True)
 
 
