@@ -106,7 +106,8 @@ int spmvb_partition_rows(uint32_t rows, const uint64_t *row_ptr, int parts, int 
 /* Uploads the layout to GPU `device` (the analogue of sds_alloc_non_cacheable buffers, csr_hw.cpp:180).
  * variant: 0 = default, otherwise a kernel variant id. */
 int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_engine **out);
-/* create_csr_hw_matrix ON the GPU: same layout, bit for bit, as spmvb_layout_build, built by
+/* Replaces create_csr_hw_matrix (csr_hw_wrapper.cpp:3-80 -> csr_hw.cpp:7-429) ON the GPU: same
+ * layout, bit for bit, as spmvb_layout_build, built by
  * CUDA kernels (flag / scan / stable radix sort by column block / scatter) straight into the engine's device image.
  * row_ptr (rows+1 x uint64), col_ind, values are host pointers (csr_on_device 0; uploaded inside) or device pointers
  * on `device` (csr_on_device 1).  Fewer than 2^31 rows and non-zeros; rows with unsorted columns cost one extra
@@ -161,7 +162,8 @@ int spmvb_engine_collect_steps(spmvb_engine *e, float *total_ms, float *kernel_m
  * Returns the last norm in *norm_out.  The multi-GPU version lives in the host driver (NCCL all-gather). */
 int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
 /* Conjugate gradients for A x = b on one GPU (A symmetric positive definite, e.g. the Laplacian of BASELINE config 2):
- * the second iterated caller of SURVEY 8(f) rank 3.  x0 = 0; per iteration one SpMV (the engine's kernel) and three
+ * the second iterated caller of SURVEY 8(f) rank 3 (the reference's caller runs spmv_hw once, main.cpp:68-75; an
+ * iterated caller keeps x / y on the device between the calls).  x0 = 0; per iteration one SpMV (the engine's kernel) and three
  * fused vector kernels (p.q; x += a p, r -= a q, r.r; p = r + b p) with all scalars on the device; the host looks at
  * ||r|| every 8 iterations and stops when ||r|| <= rel_tol * ||b|| (the recurrence residual) or after max_iters.
  * b_host / x_host hold rows values of the engine's type.  *relres_out = ||r|| / ||b|| at the last check. */
