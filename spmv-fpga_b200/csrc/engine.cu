@@ -38,7 +38,7 @@ struct Engine {
   double xs_windowed_frac = 0.0;  // share of the chunks whose x window fits shared memory
   bool tall = false;               // x and y both exceed the L2 cache: explicit L2 eviction policies
   bool cu_major = false;           // pieces in CU-major device order (row tiles)
-  int auto_variant = kVariantOcc3; // what variant 0 resolves to (autotuned at upload)
+  int auto_variant = kVariantOcc3; // what variant 0 resolves to (chosen from the layout at creation)
   float tune_ms[2] = {0.f, 0.f};   // autotune timings: OCC, XS
   uint32_t n_zero_rows = 0, run_log2 = 2;
   bool zero_all = true;
@@ -67,7 +67,7 @@ struct Engine {
       return fail(SPMVB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
   } while (0)
 
-// Kernel variants (spmvb_engine_set_variant): 0 = auto (the faster of 7 and 8 on this matrix, timed once at upload);
+// Kernel variants (spmvb_engine_set_variant): 0 = auto (7 or 8, chosen from the layout's structure, see autotune());
 // 1 = DIRECT (ld.global per lane, contiguous chunk ranges, atomics only: the simple baseline);
 // 6 / 7 = OCC (TMA ring, x gathered from global memory, 4 / 3 CTAs per SM); 8 = XS (x window in shared memory).
 // Launch with programmatic dependent launch allowed: the kernel may start while the previous kernel of the stream

@@ -301,7 +301,7 @@ __device__ __forceinline__ void gather_x(const uint4 &iw, const VT *__restrict__
 
 // ------------------------------------------------------------------------------------------------------------------
 // Variant DIRECT: every lane loads its group straight from global memory (5 / 3 x ld.global.v4); contiguous chunk
-// range per warp, atomics for every row end.  Kept as the simple baseline the RING kernel is measured against.
+// range per warp, atomics for every row end.  Kept as the simple baseline the TMA-ring kernels (OCC, XS) are measured against.
 template <typename VT, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     spmv_direct_kernel(const uint4 *__restrict__ stream,
