@@ -425,6 +425,7 @@ int spmvb_engine_create_from_csr(uint32_t rows, uint32_t cols, const uint64_t *r
     if (csr_on_device) {
       CUDA_TRY(cudaMemcpyAsync(&nnz, row_ptr + rows, 8, cudaMemcpyDeviceToHost, E->stream));
       CUDA_TRY(cudaStreamSynchronize(E->stream));
+      if (nnz && (!col_ind || !values)) return fail(SPMVB_E_ARG, "col_ind/values are NULL");
     } else {
       nnz = row_ptr[rows];
       if (nnz && (!col_ind || !values)) return fail(SPMVB_E_ARG, "col_ind/values are NULL");
