@@ -39,6 +39,9 @@ def test_engine_fails_loudly_without_gpu(spmvb):
     with pytest.raises(spmvb.SpmvbError) as ei:
         spmvb.Engine(lay)
     assert ei.value.code == -3  # SPMVB_E_CUDA: there is no CPU fallback
+    with pytest.raises(spmvb.SpmvbError) as ei:  # the GPU layout builder does not quietly build on the host either
+        spmvb.Engine.from_csr(rows, cols, rp, ci, va)
+    assert ei.value.code == -3
 
 
 def test_matrix_file_roundtrip_and_reference_reader(spmvb, tmp_path):
