@@ -133,7 +133,10 @@ static inline void delete_csr_matrix(csr_matrix *m) {
 /* ---- csr.cpp:87-136 (reads through the library's parser; trailing empty rows get row_ptr = nnz) */
 static inline int read_csr_matrix(csr_matrix *m, char *Filename) {
   spmvb_csr *A = NULL;
-  if (spmvb_csr_read(Filename, DOUBLE, &A) != SPMVB_OK) { printf("parse error: %s\n", spmvb_last_error()); return 1; }
+  /* SPMVB_CSR_CACHE=1: keep the parsed matrix in a binary sidecar next to the file and reuse it while it is current */
+  const char *cache = getenv("SPMVB_CSR_CACHE");
+  const int rc = (cache && atoi(cache)) ? spmvb_csr_read_cached(Filename, DOUBLE, &A) : spmvb_csr_read(Filename, DOUBLE, &A);
+  if (rc != SPMVB_OK) { printf("parse error: %s\n", spmvb_last_error()); return 1; }
   const uint32_t rows = spmvb_csr_rows(A);
   const uint64_t nnz = spmvb_csr_nnz(A);
   if (rows != m->nr_rows || nnz != m->nr_nzeros) { printf("parse error: header mismatch\n"); spmvb_csr_free(A); return 1; }

@@ -199,6 +199,13 @@ int spmvb_layout_build_csr(const spmvb_csr *m, int n_cu, int vf, uint32_t cols_d
  * row_ptr = nnz (the reference leaves them uninitialised). */
 int spmvb_csr_read(const char *path, int is_double, spmvb_csr **out);
 int spmvb_csr_write(const spmvb_csr *m, const char *path);
+/* Binary form of a parsed matrix (header + row_ptr + col_ind + values as they sit in memory) and a reader that keeps
+ * it next to the text file: spmvb_csr_read_cached parses `path` once, writes `path`.f64.spmvb / .f32.spmvb, and loads
+ * that sidecar on later calls as long as it is not older than the text file (csr.cpp:87-136 parses the text with
+ * fgets + sscanf on every run). */
+int spmvb_csr_save(const spmvb_csr *m, const char *path);
+int spmvb_csr_load(const char *path, spmvb_csr **out);
+int spmvb_csr_read_cached(const char *path, int is_double, spmvb_csr **out);
 
 /* Synthetic inputs of BASELINE.json's configs; values are U(-1,1) from a counter-based hash of (seed, row, col)
  * unless stated.  [row_begin,row_end) selects a row slice of the same global matrix (multi-GPU shards);

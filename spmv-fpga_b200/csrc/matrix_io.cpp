@@ -173,6 +173,87 @@ int spmvb_csr_read(const char *path, int is_double, spmvb_csr **out) {
 }
 
 // Writer: every thread formats its own row range, the pieces are written in order.
+// ---- binary sidecar of a matrix file: the parsed CSR as it sits in memory, so that a matrix is
+// parsed from text once.  Layout: 8-byte magic, u32 version, u32 is_double, u32 rows, u32 cols, u64 nnz, then
+// row_ptr[rows + 1] (u64), col_ind[nnz] (u32), values[nnz] (f64 | f32).  Native byte order (little endian here).
+static const char kBinMagic[8] = {'S', 'P', 'M', 'V', 'B', 'C', 'S', 'R'};
+
+int spmvb_csr_save(const spmvb_csr *m, const char *path) {
+  const Csr *A = (const Csr *)m;
+  if (!A || !path) return fail(SPMVB_E_ARG, "csr_save");
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE *fp = fopen(tmp.c_str(), "wb");
+  if (!fp) return fail(SPMVB_E_IO, std::string("cannot create ") + tmp);
+  const uint32_t hdr[4] = {1u, (uint32_t)A->is_double, A->rows, A->cols};
+  const uint64_t nnz = A->nnz();
+  bool ok = fwrite(kBinMagic, 1, 8, fp) == 8 && fwrite(hdr, 4, 4, fp) == 4 && fwrite(&nnz, 8, 1, fp) == 1;
+  ok = ok && fwrite(A->row_ptr.data(), 8, A->row_ptr.size(), fp) == A->row_ptr.size();
+  ok = ok && fwrite(A->col_ind.data(), 4, (size_t)nnz, fp) == (size_t)nnz;
+  ok = ok && fwrite(A->values.data(), 1, A->values.size(), fp) == A->values.size();
+  ok = (fclose(fp) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(SPMVB_E_IO, std::string("write error on ") + path); }
+  return SPMVB_OK;
+}
+
+int spmvb_csr_load(const char *path, spmvb_csr **out) {
+  if (!path || !out) return fail(SPMVB_E_ARG, "csr_load");
+  *out = nullptr;
+  FILE *fp = fopen(path, "rb");
+  if (!fp) return fail(SPMVB_E_IO, std::string("Could not open file ") + path);
+  char magic[8];
+  uint32_t hdr[4];
+  uint64_t nnz = 0;
+  if (fread(magic, 1, 8, fp) != 8 || memcmp(magic, kBinMagic, 8) != 0 || fread(hdr, 4, 4, fp) != 4 ||
+      fread(&nnz, 8, 1, fp) != 1 || hdr[0] != 1u || hdr[1] > 1u || hdr[2] == 0 || hdr[3] == 0) {
+    fclose(fp);
+    return fail(SPMVB_E_IO, std::string("not a spmvb binary matrix: ") + path);
+  }
+  struct stat st;
+  const uint64_t vb = hdr[1] ? 8 : 4;
+  const uint64_t want = 8 + 16 + 8 + ((uint64_t)hdr[2] + 1) * 8 + nnz * 4 + nnz * vb;
+  if (fstat(fileno(fp), &st) != 0 || (uint64_t)st.st_size != want) {
+    fclose(fp);
+    return fail(SPMVB_E_IO, std::string("truncated binary matrix: ") + path);
+  }
+  Csr *A = new Csr();
+  A->is_double = (int)hdr[1]; A->rows = hdr[2]; A->cols = hdr[3];
+  A->row_ptr.resize((size_t)A->rows + 1);
+  A->col_ind.resize((size_t)nnz);
+  A->values.resize((size_t)(nnz * vb));
+  bool ok = fread(A->row_ptr.data(), 8, A->row_ptr.size(), fp) == A->row_ptr.size();
+  ok = ok && fread(A->col_ind.data(), 4, (size_t)nnz, fp) == (size_t)nnz;
+  ok = ok && fread(A->values.data(), 1, A->values.size(), fp) == A->values.size();
+  fclose(fp);
+  // the file is only trusted as far as the builders need: monotone offsets that end at nnz, columns in range
+  ok = ok && A->row_ptr[0] == 0 && A->row_ptr[A->rows] == nnz;
+  for (uint32_t r = 0; ok && r < A->rows; r++) ok = A->row_ptr[r] <= A->row_ptr[r + 1];
+  if (ok) {
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t j = 0; j < (int64_t)nnz; j++) bad |= A->col_ind[j] >= A->cols;
+    ok = !bad;
+  }
+  if (!ok) { delete A; return fail(SPMVB_E_IO, std::string("corrupt binary matrix: ") + path); }
+  *out = (spmvb_csr *)A;
+  return SPMVB_OK;
+}
+
+int spmvb_csr_read_cached(const char *path, int is_double, spmvb_csr **out) {
+  if (!path || !out) return fail(SPMVB_E_ARG, "csr_read_cached");
+  const std::string side = std::string(path) + (is_double ? ".f64.spmvb" : ".f32.spmvb");
+  struct stat ts, bs;
+  if (stat(path, &ts) == 0 && stat(side.c_str(), &bs) == 0 &&
+      (bs.st_mtim.tv_sec > ts.st_mtim.tv_sec ||
+       (bs.st_mtim.tv_sec == ts.st_mtim.tv_sec && bs.st_mtim.tv_nsec >= ts.st_mtim.tv_nsec))) {
+    if (spmvb_csr_load(side.c_str(), out) == SPMVB_OK && spmvb_csr_is_double(*out) == (is_double ? 1 : 0)) return SPMVB_OK;
+    if (*out) { spmvb_csr_free(*out); *out = nullptr; }  // stale or foreign sidecar: parse the text again
+  }
+  int rc = spmvb_csr_read(path, is_double, out);
+  if (rc) return rc;
+  spmvb_csr_save(*out, side.c_str());  // best effort: a read-only directory just means no cache
+  return SPMVB_OK;
+}
+
 int spmvb_csr_write(const spmvb_csr *m, const char *path) {
   const Csr *A = (const Csr *)m;
   if (!A || !path) return fail(SPMVB_E_ARG, "csr_write");

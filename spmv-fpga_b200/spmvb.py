@@ -81,6 +81,9 @@ SYMBOLS = {
     "spmvb_layout_build_csr": (_int, [_vp, _int, _int, _u32, _vp]),
     "spmvb_csr_read": (_int, [ctypes.c_char_p, _int, _vp]),
     "spmvb_csr_write": (_int, [_vp, ctypes.c_char_p]),
+    "spmvb_csr_save": (_int, [_vp, ctypes.c_char_p]),
+    "spmvb_csr_load": (_int, [ctypes.c_char_p, _vp]),
+    "spmvb_csr_read_cached": (_int, [ctypes.c_char_p, _int, _vp]),
     "spmvb_csr_gen_band": (_int, [_u32, _int, _u64, _int, _vp]),
     "spmvb_csr_gen_laplacian2d": (_int, [_u32, _u32, _u32, _u32, _int, _vp]),
     "spmvb_csr_gen_uniform": (_int, [_u32, _u32, _int, _u64, _u32, _u32, _int, _vp]),
@@ -164,6 +167,10 @@ class Csr:
     def write(self, path):
         _check(lib().spmvb_csr_write(self.h, path.encode()))
 
+    def save(self, path):
+        """Binary form (header + the three arrays as they sit in memory)."""
+        _check(lib().spmvb_csr_save(self.h, path.encode()))
+
     def free(self):
         if self.h:
             lib().spmvb_csr_free(self.h)
@@ -185,6 +192,15 @@ class Csr:
     @staticmethod
     def read(path, is_double=True):
         return Csr._new(lib().spmvb_csr_read, path.encode(), int(is_double))
+
+    @staticmethod
+    def load(path):
+        return Csr._new(lib().spmvb_csr_load, path.encode())
+
+    @staticmethod
+    def read_cached(path, is_double=True):
+        """Parses the text file once and keeps a binary sidecar next to it for the following calls."""
+        return Csr._new(lib().spmvb_csr_read_cached, path.encode(), int(is_double))
 
     @staticmethod
     def band(n, half_bw=5, seed=1, is_double=True):

@@ -124,3 +124,40 @@ def test_partition_rows_balances_nonzeros(spmvb):
         assert nnz.sum() == R.nnz
         assert nnz[:-1].min() > R.nnz // parts                            # S1: every fired part exceeds the mean
         assert np.all((b[1:-1] - b[:-2]) % 2 == 0)                        # S3: row counts multiple of RATIO_v
+
+
+def test_binary_sidecar_roundtrip_and_cache(spmvb, tmp_path):
+    """the parsed matrix is kept in binary next to the text file and reused while it is current."""
+    import os
+    import time
+    A = spmvb.Csr.rmat(10, 8, seed=4)
+    txt = str(tmp_path / "m.txt")
+    A.write(txt)
+    for isd in (True, False):
+        B = spmvb.Csr.read_cached(txt, isd)                      # parses, writes the sidecar
+        side = txt + (".f64.spmvb" if isd else ".f32.spmvb")
+        assert os.path.exists(side)
+        C = spmvb.Csr.read_cached(txt, isd)                      # loads the sidecar
+        D = spmvb.Csr.load(side)
+        for M in (B, C, D):
+            assert (M.rows, M.cols, M.nnz, M.is_double) == (A.rows, A.cols, A.nnz, isd)
+            assert np.array_equal(M.row_ptr, A.row_ptr) and np.array_equal(M.col_ind, A.col_ind)
+            assert np.array_equal(M.values, A.values.astype(M.values.dtype))
+    # a sidecar older than the text file is ignored and rewritten
+    side = txt + ".f64.spmvb"
+    A2 = spmvb.Csr.band(300, 2, seed=9)
+    time.sleep(0.02)
+    A2.write(txt)
+    os.utime(side, (os.path.getmtime(txt) - 10, os.path.getmtime(txt) - 10))
+    E = spmvb.Csr.read_cached(txt, True)
+    assert E.rows == 300 and np.array_equal(E.col_ind, A2.col_ind)
+    assert spmvb.Csr.load(side).rows == 300
+    # corrupt / truncated / foreign files are errors, not garbage matrices
+    raw = open(side, "rb").read()
+    bad = str(tmp_path / "bad.spmvb")
+    for blob in (raw[:-5], b"NOTSPMVB" + raw[8:], raw[:40] + b"\xff" * 8 + raw[48:]):
+        open(bad, "wb").write(blob)
+        with pytest.raises(spmvb.SpmvbError):
+            spmvb.Csr.load(bad)
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Csr.load(str(tmp_path / "missing.spmvb"))
