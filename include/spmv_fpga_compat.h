@@ -312,6 +312,29 @@ static inline void delete_empty_rows_bitmap(bool **bitmap, int blocks) {
   for (int b = 0; b < blocks; b++) free(bitmap[b]);
   free(bitmap);
 }
+/* ---- csr_hw.cpp:1493-1521: debug print of bus words, flag 0 = as RATIO_v values, otherwise as 8 x (15-bit column
+ * index <end-of-row bit>); same text as the reference's std::cout << std::setprecision(14) */
+static inline void print_wide(BusDataType *values, IndexType nr_values, int flag) {
+  for (IndexType j = 0; j < nr_values; j++) {
+    const unsigned char *w = (const unsigned char *)&values[j];
+    if (flag == 0) {
+      for (int k = 0; k < RATIO_v; k++) {
+        ValueType v;
+        memcpy(&v, w + k * sizeof(ValueType), sizeof(ValueType));
+        printf("| (%d : %d) = %.14g ", VALUE_TYPE_BIT_WIDTH * (k + 1) - 1, VALUE_TYPE_BIT_WIDTH * k, (double)v);
+      }
+    } else {
+      for (int k = 0; k < RATIO_ci; k++) {
+        uint16_t ci;
+        memcpy(&ci, w + 2 * k, 2);
+        printf("| (%d : %d) = %u <%u>\t", COMPRESSED_INDEX_TYPE_BIT_WIDTH * (k + 1) - 1, COMPRESSED_INDEX_TYPE_BIT_WIDTH * k,
+               (unsigned)(ci & 0x7FFFu), (unsigned)(ci >> 15));
+      }
+    }
+    printf("|\n");
+  }
+}
+
 /* ---- csr_hw.cpp:1401-1409 */
 static inline ValueType storage_overhead(csr_hw_matrix *matrix) {
   double bits = (double)matrix->blocks * 5 * INDEX_TYPE_BIT_WIDTH;

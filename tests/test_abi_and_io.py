@@ -161,3 +161,35 @@ def test_binary_sidecar_roundtrip_and_cache(spmvb, tmp_path):
             spmvb.Csr.load(bad)
     with pytest.raises(spmvb.SpmvbError):
         spmvb.Csr.load(str(tmp_path / "missing.spmvb"))
+
+
+def test_print_wide_of_the_drop_in_header(tmp_path):
+    """print_wide (csr_hw.cpp:1493-1521): bus words as values / as 8 x (15-bit index <end-of-row>), the reference's text."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "pw.cpp"
+    src.write_text('''#include "spmv_fpga_compat.h"
+int main() {
+  BusDataType w[2];
+  ValueType v[RATIO_v];
+  for (int k = 0; k < RATIO_v; k++) v[k] = (ValueType)(1.5 - k);
+  memcpy(&w[0], v, 16);
+  uint16_t ci[8] = {5, 0x8000 | 7, 0, 32767, 0x8000, 1, 2, 3};
+  memcpy(&w[1], ci, 16);
+  print_wide(&w[0], 1, 0);
+  print_wide(&w[1], 1, 1);
+  return 0;
+}
+''')
+    lib = os.path.join(root, "spmv-fpga_b200", "lib")
+    for isd, want0 in ((1, "| (63 : 0) = 1.5 | (127 : 64) = 0.5 |"),
+                       (0, "| (31 : 0) = 1.5 | (63 : 32) = 0.5 | (95 : 64) = -0.5 | (127 : 96) = -1.5 |")):
+        exe = str(tmp_path / ("pw%d" % isd))
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-DCU=1", "-DVF=1", "-DDOUBLE=%d" % isd,
+                               "-I" + os.path.join(root, "include"), "-o", exe, str(src), "-L" + lib, "-lspmvb",
+                               "-Wl,-rpath," + lib])
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines()
+        assert out[0] == want0
+        assert out[1] == ("| (15 : 0) = 5 <0>\t| (31 : 16) = 7 <1>\t| (47 : 32) = 0 <0>\t| (63 : 48) = 32767 <0>\t"
+                          "| (79 : 64) = 0 <1>\t| (95 : 80) = 1 <0>\t| (111 : 96) = 2 <0>\t| (127 : 112) = 3 <0>\t|")
