@@ -20,6 +20,7 @@
 #ifndef SPMV_FPGA_COMPAT_H
 #define SPMV_FPGA_COMPAT_H
 
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -163,6 +164,33 @@ static inline void delete_csr_vector(csr_vector *v) {
 static inline void init_vector_rand(csr_vector *v, ValueType max) {
   if (!v) return;
   for (IndexType i = 0; i < v->nr_values; i++) v->values[i] = max * (rand() / (ValueType)RAND_MAX);
+}
+
+/* ---- csr.cpp:184-194 and csr_hw.cpp:1571-1590: the CALLER's CPU self-check (main.cpp:61, :76).  They are here so that
+ * a main() written against the reference compiles unchanged; spmv_hw never calls them and nothing in libspmvb.so does. */
+static inline void spmv_gold(csr_matrix *matrix, ValueType *x, ValueType *y) {
+  for (IndexType row = 0; row < matrix->nr_rows; row++) {
+    ValueType acc = 0.0;
+    for (IndexType j = matrix->row_ptr[row]; j < matrix->row_ptr[row + 1]; j++) acc += matrix->values[j] * x[matrix->col_ind[j]];
+    y[row] = acc;
+  }
+}
+/* verbose: 0 = nothing, 1 = only errors, 2 = every value; returns 1 if any |sw - hw| >= 1e-5 (or NaN) */
+static inline int verification(IndexType nr_values, ValueType *sw_values, ValueType *hw_values, int verbose) {
+  const ValueType limit = (ValueType)1e-5;
+  IndexType bad = 0;
+  for (IndexType i = 0; i < nr_values; i++) {
+    const ValueType d = (ValueType)fabs((double)(sw_values[i] - hw_values[i]));
+    if (verbose == 2) printf("%u : y_gold = %.14g\ty_hw = %.14g\n", (unsigned)i, (double)sw_values[i], (double)hw_values[i]);
+    if (d >= limit || d != d) {
+      bad++;
+      if (verbose == 1 || verbose == 2)
+        printf("\tError occurs at %u : y_gold = %.14g, y_hw = %.14g. Relative difference is %.14g\n", (unsigned)i,
+               (double)sw_values[i], (double)hw_values[i], fabs((double)(d / sw_values[i])));
+    }
+  }
+  if (bad) printf("Total errors : %u\n", (unsigned)bad);
+  return bad != 0;
 }
 
 /* ---- csr_hw_wrapper.cpp:3-80: builds the layout (bit-exact pieces) and uploads it to the GPU */

@@ -1,33 +1,14 @@
 // run.elf analogue: the call sequence of the reference's src/main.cpp:16-99 against the B200 engine, through the
 // reference's own host API (include/spmv_fpga_compat.h).  Build with the reference's macros: -DCU= -DVF= -DDOUBLE=.
 //   run_cu<C>_vf<V>_d<D>.elf <matrix-file>
-// The gold SpMV and the verification below are this driver's self-check (the reference's main() does the same with
-// csr.cpp:184-194 and csr_hw.cpp:1571-1590); spmv_hw itself never touches them.
+// spmv_gold and verification are the caller's self-check from the drop-in header (the reference's main() does the same
+// with csr.cpp:184-194 and csr_hw.cpp:1571-1590); spmv_hw itself never touches them.
 #include <math.h>
 
 #include <iostream>
 #include <string>
 
 #include "spmv_fpga_compat.h"
-
-static void spmv_gold_check(csr_matrix *m, ValueType *x, ValueType *y) {
-  for (IndexType i = 0; i < m->nr_rows; i++) {
-    ValueType acc = 0.0;
-    for (IndexType j = m->row_ptr[i]; j < m->row_ptr[i + 1]; j++) acc += m->values[j] * x[m->col_ind[j]];
-    y[i] = acc;
-  }
-}
-
-static int verification_check(IndexType n, ValueType *sw, ValueType *hw) {
-  const ValueType thres = 1e-5;  // csr_hw.cpp:1573
-  IndexType errs = 0;
-  for (IndexType i = 0; i < n; i++) {
-    ValueType d = fabs(sw[i] - hw[i]);
-    if (d >= thres || d != d) errs++;
-  }
-  if (errs) std::cout << "Total errors : " << errs << "\n";
-  return errs != 0;
-}
 
 int main(int argc, char **argv) {
   std::cout << "Welcome to SpMV (Compute Units : " << ComputeUnits << ", Vectorization Factor : " << VectFactor << ", "
@@ -44,7 +25,7 @@ int main(int argc, char **argv) {
   init_vector_rand(x, 1);
   csr_vector *y = create_csr_vector(hdr.nr_rows);
   double t0 = getTimestamp();
-  spmv_gold_check(matrix, x->values, y->values);
+  spmv_gold(matrix, x->values, y->values);
   printf("Software execution time : %.6f ms elapsed\n", (getTimestamp() - t0) / 1000);
 
   bool **empty_rows_bitmap;
@@ -57,7 +38,7 @@ int main(int argc, char **argv) {
 
   csr_vector *y_fpga = create_csr_vector(hdr.nr_rows);
   spmv_hw(hw_matrix, hw_x, y_fpga, empty_rows_bitmap);
-  int status = verification_check(y->nr_values, y->values, y_fpga->values);
+  int status = verification(y->nr_values, y->values, y_fpga->values, 0);
   std::cout << (status == 0 ? "Verification PASSED!\n" : "Verification FAILED!\n");
 
   double csr_mem = (((double)matrix->nr_rows + 1) * INDEX_TYPE_BIT_WIDTH +

@@ -193,3 +193,20 @@ int main() {
         assert out[0] == want0
         assert out[1] == ("| (15 : 0) = 5 <0>\t| (31 : 16) = 7 <1>\t| (47 : 32) = 0 <0>\t| (63 : 48) = 32767 <0>\t"
                           "| (79 : 64) = 0 <1>\t| (95 : 80) = 1 <0>\t| (111 : 96) = 2 <0>\t| (127 : 112) = 3 <0>\t|")
+
+
+def test_reference_main_on_the_engine_fails_loudly_without_gpu(spmvb, tmp_path):
+    """oracle/_ref/refmain_on_b200_*.elf = the reference's unmodified main.cpp on the drop-in API: no GPU, no result."""
+    import os
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "refmain_on_b200_cu1_vf1_d1.elf")
+    if not os.path.exists(exe):
+        pytest.skip("not built (needs /root/reference)")
+    path = str(tmp_path / "b.txt")
+    spmvb.Csr.band(500, 2, 1).write(path)
+    p = subprocess.run([exe, path], capture_output=True, text=True)
+    assert p.returncode != 0 and "no CUDA device" in p.stderr and "Verification" not in p.stdout

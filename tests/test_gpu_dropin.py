@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OURS = os.path.join(ROOT, "spmv-fpga_b200", "lib", "run_cu%d_vf%d_d%d.elf")
 REF = os.path.join(ROOT, "oracle", "_ref", "ref_run_cu%d_vf%d_d%d.elf")
+REFMAIN = os.path.join(ROOT, "oracle", "_ref", "refmain_on_b200_cu%d_vf%d_d%d.elf")
 
 
 def run(exe, path, env=None):
@@ -59,3 +60,24 @@ def test_missing_file_is_reported_like_the_reference(tmp_path):
     exe = OURS % (1, 1, 1)
     rc, out = run(exe, str(tmp_path / "nope.txt"))
     assert rc == 1 and "Could not open file" in out and "Error reading matrix header" in out
+
+
+@pytest.mark.parametrize("cfg", [(1, 1, 1), (8, 4, 1), (8, 4, 0)], ids=lambda c: "cu%d_vf%d_d%d" % c)
+def test_unmodified_reference_main_runs_on_the_b200_engine(spmvb, tmp_path, cfg):
+    """The reference's own src/main.cpp, unmodified, compiled against include/refnames/ + libspmvb.so (oracle/Makefile
+    dropin_elf, built where /root/reference exists): it must verify its result and print the reference's report."""
+    exe = REFMAIN % cfg
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/refmain_on_b200_*.elf not built (needs /root/reference at build time)")
+    rows, cols, rp, ci, va = matgen.laplacian2d(250, 250)
+    path = str(tmp_path / "lap.txt")
+    matgen.write_matrix_file(path, rows, cols, rp, ci, va, fmt="%.17g" if cfg[2] else "%.9g")
+    rc, out = run(exe, path)
+    assert rc == 0, out
+    assert "Verification PASSED!" in out
+    assert re.search(r"Welcome to SpMV \(Compute Units : %d, Vectorization Factor : %d" % cfg[:2], out)
+    ref = REF % cfg
+    if os.path.exists(ref):
+        rrc, rout = run(ref, path)
+        assert rrc == 0 and "Verification PASSED!" in rout
+        assert last_line(out) == last_line(rout)
