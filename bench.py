@@ -328,6 +328,32 @@ def run_reference(args, spec, world, rank):
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if spec.get("kind") == "band" and world == 1:
+        # BASELINE configs[0] IS the CPU emulation run (make TARGET=emu CU=1 VF=1 DOUBLE=1 ./run.elf): time the
+        # unmodified reference's create_csr_hw_matrix + spmv_hw (HLS functions compiled for the CPU) as well
+        try:
+            import oracle_api as oa
+            if oa.have_ref(1, 1, is_double):
+                R = oa.RefLib(1, 1, is_double)
+                t0 = time.perf_counter()
+                h = R.build(csr.rows, csr.cols, csr.row_ptr, csr.col_ind, csr.values)
+                t_build = time.perf_counter() - t0
+                xx = np.random.default_rng(1).random(csr.cols).astype(np.float64 if is_double else np.float32)
+                ts = []
+                for _ in range(max(args.steps, 1)):
+                    yy = np.zeros(csr.rows, xx.dtype)
+                    t0 = time.perf_counter()
+                    rc = R.spmv_hw(h, xx, yy)
+                    ts.append(time.perf_counter() - t0)
+                    if rc:
+                        raise RuntimeError("reference spmv_hw: FIFO under-run (SURVEY Q1)")
+                R.free(h)
+                line["emu_spmv_hw"] = {"value": 2.0 * csr.nnz / float(np.mean(ts)) / 1e9, "unit": "GFLOP/s", "cores": 1,
+                                       "kind": "reference", "ms_per_call": float(np.mean(ts)) * 1e3,
+                                       "create_csr_hw_matrix_ms": t_build * 1e3,
+                                       "sample": "TARGET=emu path: create_csr_hw_matrix + spmv_hw of the unmodified reference"}
+        except Exception as exc:
+            line["emu_spmv_hw"] = {"error": str(exc)}
     try:  # for information: the same loop spread over all host cores (oracle port, OpenMP over rows); the reference
         # itself is single-threaded, so `value` above stays its own number
         import oracle_api as oa
