@@ -430,6 +430,7 @@ def main():
     t_upload = time.perf_counter() - t0
     nnz_local = int(csr.nnz)
     alg_bytes_local = int(eng.algorithmic_bytes)
+    x_upload_local = int(eng.x_upload_bytes)  # set_x copies only the column blocks this rank's rows touch
 
     # x replicated on every rank (pinned host copy for the e2e leg), y sharded by rows
     x_host = torch.empty(csr.cols, dtype=torch.float64 if is_double else torch.float32).pin_memory()
@@ -472,11 +473,12 @@ def main():
         t = torch.tensor([t_job_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_job_ms = float(t.item())
-        n = torch.tensor([nnz_local, alg_bytes_local, launches], dtype=torch.float64, device="cuda")
+        n = torch.tensor([nnz_local, alg_bytes_local, launches, x_upload_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
         nnz_total, alg_total, launches_total = int(n[0].item()), int(n[1].item()), int(n[2].item())
+        x_upload_total = int(n[3].item())
     else:
-        alg_total, launches_total = alg_bytes_local, launches
+        alg_total, launches_total, x_upload_total = alg_bytes_local, launches, x_upload_local
     ms_per_step = t_job_ms / args.steps
     gflops = 2.0 * nnz_total / (ms_per_step * 1e-3) / 1e9
     eff_gbs = alg_total / (ms_per_step * 1e-3) / 1e9
@@ -520,7 +522,7 @@ def main():
         "effective_gbs": eff_gbs,
         "roofline_nominal_frac": eff_gbs / (8000.0 * world),
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": int(csr.cols * vb) * world,
+        "e2e": {"value": e2e_gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": x_upload_total,
                 "d2h_bytes_per_step": int(spec["rows"] * vb), "steps": e2e_steps,
                 "what": "spmvb_engine_spmv_host: pinned x -> GPU, kernel, y -> pinned host, y_host += y (spmv_hw semantics)"},
         "gpu_launches": launches_total,

@@ -87,6 +87,11 @@ int spmvb_layout_pack_x(const spmvb_layout *l, const void *x, uint32_t n, void *
  * items, or a negative error. */
 int64_t spmvb_layout_xs_plan(const spmvb_layout *l, int n_cta, int run_log2, uint32_t *items_out, uint64_t max_items,
                              uint32_t *cta_first_out);
+/* Column ranges of x a SpMV with this layout can read: maximal runs of column blocks that hold at least one entry,
+ * as [first, end) pairs in out_pairs (2 x uint64 each, at most max_ranges of them; NULL just counts).  Returns the
+ * number of ranges.  spmvb_engine_set_x / spmv_host upload only these (a row shard of a banded matrix reads a band of
+ * x, not all of it - the reference copies every block's slice to every compute unit, spmv.cpp:180-192). */
+int64_t spmvb_layout_x_ranges(const spmvb_layout *l, uint64_t *out_pairs, uint64_t max_ranges);
 /* number of 256-entry chunks of the device image, and the [lo, hi] column-in-block range of chunk c */
 uint64_t spmvb_layout_chunks(const spmvb_layout *l);
 int spmvb_layout_chunk_cols(const spmvb_layout *l, uint64_t c, uint32_t *lo, uint32_t *hi, uint32_t *block);
@@ -135,8 +140,12 @@ void *spmvb_engine_x_dev(spmvb_engine *e);
 void *spmvb_engine_y_dev(spmvb_engine *e);
 void *spmvb_engine_stream(spmvb_engine *e); /* cudaStream_t */
 
-/* Replaces create_csr_hw_x_vector (csr_hw_wrapper.cpp:187-191): host x[n] -> device hw_x (zero padded). */
+/* Replaces create_csr_hw_x_vector (csr_hw_wrapper.cpp:187-191): host x[n] -> device hw_x (zero padded).  Only the
+ * column ranges the matrix can read (spmvb_layout_x_ranges) are copied; the rest of the device vector keeps its old
+ * contents, which no kernel of this engine reads. */
 int spmvb_engine_set_x(spmvb_engine *e, const void *x_host, uint32_t n);
+/* bytes one spmvb_engine_set_x of a full-length x moves to the device */
+uint64_t spmvb_engine_x_upload_bytes(const spmvb_engine *e);
 /* Replaces the per-block spmv() loop (csr_hw_wrapper.cpp:202-271; spmv.cpp:6-205) fused with accum_results
  * (csr_hw.cpp:1531-1565): y_dev (+)= A * x_dev on `stream` (NULL = engine stream).  x_dev must hold
  * expanded_nr_cols values (or NULL = engine x), y_dev rows values (or NULL = engine y).  accumulate 1 keeps

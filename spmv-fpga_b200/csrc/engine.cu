@@ -28,6 +28,7 @@ struct Engine {
   int blocks = 0;
   uint64_t real_nnz = 0, n_chunks = 0, n_pairs = 0, stream_bytes = 0, x_len = 0;
   uint64_t x_touched = 0;  // columns of the column blocks that hold at least one entry (what a SpMV must read of x)
+  std::vector<uint64_t> x_ranges;  // [first, end) pairs of those blocks, merged: what set_x uploads
   uint8_t *d_stream = nullptr;
   uint32_t *d_rowmap = nullptr;
   uint32_t *d_zero_rows = nullptr;
@@ -331,6 +332,11 @@ static int engine_adopt_layout(Engine *E, const Layout *L) {
     if (nz) E->x_touched += std::min<uint64_t>(L->cdb, (uint64_t)L->cols - (uint64_t)b * L->cdb);
   }
   E->x_len = (uint64_t)L->blocks * L->cdb;  // >= expanded_cols: any 15-bit index of any block stays in range
+  {
+    const int64_t nr = spmvb_layout_x_ranges((const spmvb_layout *)L, nullptr, 0);
+    E->x_ranges.assign((size_t)(nr > 0 ? 2 * nr : 0), 0);
+    if (nr > 0) spmvb_layout_x_ranges((const spmvb_layout *)L, E->x_ranges.data(), (uint64_t)nr);
+  }
   E->zero_all = L->zero_all; E->n_zero_rows = (uint32_t)L->zero_rows.size(); E->run_log2 = (uint32_t)L->run_log2;
   if (const char *v = getenv("SPMVB_OCC_RUN_LOG2")) E->occ_run_log2 = (uint32_t)atoi(v);
   if (const char *v = getenv("SPMVB_XS_RUN_LOG2")) E->xs_run_log2 = (uint32_t)atoi(v);
@@ -521,6 +527,15 @@ uint64_t spmvb_engine_algorithmic_bytes(const spmvb_engine *e) {
   // band of x, not all of it): nnz*(2+vb) + rows*vb + x_touched*vb
   return E->real_nnz * (2 + (uint64_t)E->vb) + (uint64_t)E->rows * E->vb + E->x_touched * E->vb;
 }
+uint64_t spmvb_engine_x_upload_bytes(const spmvb_engine *e) {
+  const Engine *E = (const Engine *)e;
+  uint64_t cols = 0;
+  for (size_t i = 0; i + 1 < E->x_ranges.size(); i += 2) {
+    const uint64_t end = std::min<uint64_t>(E->x_ranges[i + 1], E->expanded_cols);
+    if (end > E->x_ranges[i]) cols += end - E->x_ranges[i];
+  }
+  return cols * E->vb;
+}
 void *spmvb_engine_x_dev(spmvb_engine *e) { return ((Engine *)e)->d_x; }
 void *spmvb_engine_y_dev(spmvb_engine *e) { return ((Engine *)e)->d_y; }
 void *spmvb_engine_stream(spmvb_engine *e) { return (void *)((Engine *)e)->stream; }
@@ -529,8 +544,13 @@ int spmvb_engine_set_x(spmvb_engine *e, const void *x_host, uint32_t n) {
   Engine *E = (Engine *)e;
   if (!E || !x_host) return fail(SPMVB_E_ARG, "set_x");
   CUDA_TRY(cudaSetDevice(E->device));
-  const uint32_t m = std::min<uint32_t>(n, E->expanded_cols);
-  CUDA_TRY(cudaMemcpyAsync(E->d_x, x_host, (size_t)m * E->vb, cudaMemcpyHostToDevice, E->stream));
+  const uint64_t m = std::min<uint32_t>(n, E->expanded_cols);
+  for (size_t i = 0; i + 1 < E->x_ranges.size(); i += 2) {  // only what the matrix can read
+    const uint64_t first = E->x_ranges[i], end = std::min<uint64_t>(E->x_ranges[i + 1], m);
+    if (first >= end) continue;
+    CUDA_TRY(cudaMemcpyAsync((uint8_t *)E->d_x + first * E->vb, (const uint8_t *)x_host + first * E->vb,
+                             (size_t)(end - first) * E->vb, cudaMemcpyHostToDevice, E->stream));
+  }
   if (m < E->x_len)  // zero-pad the remaining columns (csr_hw.cpp:1478-1481)
     CUDA_TRY(cudaMemsetAsync((uint8_t *)E->d_x + (size_t)m * E->vb, 0, (E->x_len - m) * E->vb, E->stream));
   return SPMVB_OK;

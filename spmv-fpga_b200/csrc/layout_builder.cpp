@@ -530,6 +530,28 @@ double spmvb_layout_storage_mb(const spmvb_layout *l, int cu) {
   return bits / (8.0 * 1024 * 1024);
 }
 
+// Column ranges [first, end) that a SpMV with this layout can read from x: maximal runs of column blocks that hold at
+// least one entry, in units of whole blocks (the last block ends at blocks * cols_div_blocks).  A row shard of a banded
+// matrix touches only its band; a whole matrix normally gives the single range [0, blocks * cols_div_blocks).
+int64_t spmvb_layout_x_ranges(const spmvb_layout *l, uint64_t *out_pairs, uint64_t max_ranges) {
+  const Layout *L = (const Layout *)l;
+  if (!L) return fail(SPMVB_E_ARG, "x_ranges");
+  uint64_t n = 0, open_first = 0;
+  bool open = false;
+  for (int b = 0; b <= L->blocks; b++) {
+    bool touched = false;
+    if (b < L->blocks)
+      for (int k = 0; k < L->cu && !touched; k++) touched = L->piece_real_nnz[(size_t)b * L->cu + k] != 0;
+    if (touched && !open) { open = true; open_first = (uint64_t)b * L->cdb; }
+    if (!touched && open) {
+      if (out_pairs && n < max_ranges) { out_pairs[2 * n] = open_first; out_pairs[2 * n + 1] = (uint64_t)b * L->cdb; }
+      n++;
+      open = false;
+    }
+  }
+  return (int64_t)n;
+}
+
 int spmvb_layout_pack_x(const spmvb_layout *l, const void *x, uint32_t n, void *out) {
   const Layout *L = (const Layout *)l;
   if (!L || !x || !out) return fail(SPMVB_E_ARG, "pack_x");

@@ -40,6 +40,7 @@ SYMBOLS = {
     "spmvb_layout_storage_mb": (ctypes.c_double, [_vp, _int]),
     "spmvb_layout_pack_x": (_int, [_vp, _vp, _u32, _vp]),
     "spmvb_layout_xs_plan": (ctypes.c_int64, [_vp, _int, _int, _vp, _u64, _vp]),
+    "spmvb_layout_x_ranges": (ctypes.c_int64, [_vp, _vp, _u64]),
     "spmvb_layout_chunks": (_u64, [_vp]),
     "spmvb_layout_chunk_cols": (_int, [_vp, _u64, _vp, _vp, _vp]),
     "spmvb_layout_equal": (_int, [_vp, _vp, _vp, ctypes.c_size_t]),
@@ -53,6 +54,7 @@ SYMBOLS = {
     "spmvb_engine_variant": (_int, [_vp]),
     "spmvb_engine_launches": (_u64, [_vp]),
     "spmvb_engine_algorithmic_bytes": (_u64, [_vp]),
+    "spmvb_engine_x_upload_bytes": (_u64, [_vp]),
     "spmvb_engine_x_dev": (_vp, [_vp]),
     "spmvb_engine_y_dev": (_vp, [_vp]),
     "spmvb_engine_stream": (_vp, [_vp]),
@@ -311,6 +313,16 @@ class Layout:
         lib().spmvb_layout_xs_plan(self.h, n_cta, run_log2, _ptr(items), n, _ptr(first))
         return items[:n], first
 
+    def x_ranges(self):
+        """[first, end) column ranges of x that a SpMV with this layout can read (whole column blocks)."""
+        n = lib().spmvb_layout_x_ranges(self.h, None, 0)
+        if n < 0:
+            _check(int(n))
+        out = np.zeros((int(n), 2), np.uint64)
+        if n:
+            lib().spmvb_layout_x_ranges(self.h, _ptr(out), int(n))
+        return out
+
     @property
     def n_chunks(self):
         return lib().spmvb_layout_chunks(self.h)
@@ -402,6 +414,11 @@ class Engine:
     @property
     def algorithmic_bytes(self):
         return lib().spmvb_engine_algorithmic_bytes(self.h)
+
+    @property
+    def x_upload_bytes(self):
+        """Bytes one set_x of a full-length x moves to the device (only the column blocks the matrix touches)."""
+        return lib().spmvb_engine_x_upload_bytes(self.h)
 
     @property
     def x_dev(self):

@@ -154,3 +154,36 @@ def test_cu_major_device_order(spmvb, oracle, monkeypatch, variant):
     _check(spmvb, oracle, matgen.uniform(6000, 100000, 12, seed=8), 4, 1, True, variant)
     _check(spmvb, oracle, matgen.ragged(5000, 100000, seed=7), 8, 4, False, variant)
     _check(spmvb, oracle, matgen.laplacian2d(256, 256), 2, 2, True, variant, cdb=16384)
+
+
+@pytest.mark.parametrize("variant", [7, 8])
+def test_x_upload_skips_untouched_column_blocks(spmvb, oracle, variant):
+    """set_x / spmv_host copy only the column ranges the matrix can read (two ranges here, block 1 and 4 untouched):
+    same result, fewer bytes; a second x replaces the first everywhere it matters."""
+    rng = np.random.default_rng(3)
+    cdb, rows, cols = 4096, 3000, 5 * 4096
+    rp, ci = [0], []
+    for _ in range(rows):
+        c = np.concatenate([rng.integers(0, cdb, 2), rng.integers(2 * cdb, 4 * cdb, 3)])
+        ci.extend(sorted(int(v) for v in set(c.tolist())))
+        rp.append(len(ci))
+    rp = np.array(rp, np.uint64); ci = np.array(ci, np.uint32)
+    va = rng.uniform(-1, 1, len(ci))
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True, cdb)
+    eng = spmvb.Engine(lay, 0, variant)
+    assert eng.x_upload_bytes == 3 * cdb * 8
+    for seed in (1, 2):
+        x = np.random.default_rng(seed).random(cols)
+        y = np.zeros(rows)
+        eng.spmv_host(x, y, accumulate=False)
+        gold = oracle.spmv_gold(rows, rp, ci, va, x, True)
+        scale = oracle.abs_ax(rows, rp, ci, va, x, True)
+        assert np.all(np.abs(y - gold) <= 1e-12 * scale + 1e-300)
+    # a short x (fewer values than columns) is zero padded: entries beyond it contribute nothing
+    xs = np.random.default_rng(5).random(3 * cdb - 100)
+    y = np.zeros(rows)
+    eng.spmv_host(xs, y, accumulate=False)
+    xfull = np.zeros(cols); xfull[: len(xs)] = xs
+    gold = oracle.spmv_gold(rows, rp, ci, va, xfull, True)
+    scale = oracle.abs_ax(rows, rp, ci, va, np.abs(xfull) + 1e-3, True)
+    assert np.all(np.abs(y - gold) <= 1e-12 * scale + 1e-300)

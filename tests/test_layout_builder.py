@@ -171,3 +171,34 @@ def test_cu_major_device_order_keeps_pieces_bit_exact(spmvb, oracle, monkeypatch
         assert all(int(b) == int(it[5]) for b, it in zip(blocks_seen, items))
         lay.free()
     oracle.free(ho)
+
+
+def test_x_ranges_cover_exactly_the_touched_column_blocks(spmvb):
+    """What set_x uploads: maximal runs of column blocks with at least one entry."""
+    # whole matrix: one range over all blocks
+    rows, cols, rp, ci, va = matgen.laplacian2d(300, 300)
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, 2, 1, True)
+    assert lay.x_ranges().tolist() == [[0, lay.blocks * 32768]]
+    # a row shard of a banded matrix reads a band of x
+    A = spmvb.Csr.laplacian2d(512, 2048, 300000, 500000)
+    shard = spmvb.Layout.from_csr(A, 1, 1, 16384)
+    r = shard.x_ranges()
+    assert len(r) == 1
+    lo, hi = (300000 - 512) // 16384 * 16384, -(-(500000 + 512) // 16384) * 16384
+    assert r.tolist() == [[lo, hi]]
+    # columns only in blocks 0, 2 and 3 of 5; every column index lies inside a range
+    rng = np.random.default_rng(3)
+    cdb, rows, cols = 4096, 200, 5 * 4096
+    rp, ci = [0], []
+    for _ in range(rows):
+        c = np.concatenate([rng.integers(0, cdb, 2), rng.integers(2 * cdb, 4 * cdb, 3)])
+        ci.extend(sorted(int(v) for v in set(c.tolist())))
+        rp.append(len(ci))
+    ci = np.array(ci, np.uint32)
+    lay2 = spmvb.Layout.build(rows, cols, np.array(rp, np.uint64), ci, rng.random(len(ci)), 1, 1, True, cdb)
+    r2 = lay2.x_ranges()
+    assert r2.tolist() == [[0, cdb], [2 * cdb, 4 * cdb]]
+    assert all(any(a <= c < b for a, b in r2.tolist()) for c in ci.tolist())
+    # a matrix without entries reads nothing
+    lay3 = spmvb.Layout.build(3, 10, np.zeros(4, np.uint64), np.zeros(0, np.uint32), np.zeros(0), 1, 1, True)
+    assert lay3.x_ranges().shape == (0, 2)
