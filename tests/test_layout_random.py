@@ -59,4 +59,16 @@ def test_oracle_host_builder_and_gpu_builder_steps_agree(spmvb, oracle, emu, cas
     assert oa.layouts_equal(oracle.snapshot(ho, rows, cu, vf, isd), product_snapshot(host, cu, vf, isd)) == []
     dev = emu(rows, cols, rp, ci, va, cu, vf, isd, cdb)
     assert host.difference(dev) == ""
+    # what set_x uploads: block-aligned, ascending, disjoint ranges that contain every column index of the matrix
+    width = cdb or (16384 if cu in (10, 12) else 32768)
+    r = host.x_ranges().astype(np.int64)
+    assert np.array_equal(r, dev.x_ranges().astype(np.int64))
+    assert np.all(r % width == 0) and np.all(r[:, 0] < r[:, 1]) and np.all(r[1:, 0] > r[:-1, 1])
+    if len(ci):
+        idx = np.searchsorted(r[:, 0], ci.astype(np.int64), side="right") - 1
+        assert np.all(idx >= 0) and np.all(ci.astype(np.int64) < r[idx, 1])
+        blocks_touched = np.unique(ci.astype(np.int64) // width)
+        assert int((r[:, 1] - r[:, 0]).sum()) == len(blocks_touched) * width
+    else:
+        assert len(r) == 0
     oracle.free(ho); host.free(); dev.free()
