@@ -16,6 +16,13 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 when it is unset.  The host side of the path is OpenMP (layout build, y_host += y
+# in spmv_hw, the all-cores CPU baseline): give every rank its share of the cores instead - before anything loads an
+# OpenMP runtime.  The reference arm works on rank 0 alone and may use them all.
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+    _share = 1 if "reference" in sys.argv else int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _share))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
