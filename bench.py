@@ -508,6 +508,30 @@ def main():
         e2e_s = float(t.item())
     e2e_gflops = 2.0 * nnz_total * e2e_steps / e2e_s / 1e9
 
+    # ---- every rank checks the first and last rows of its shard against the CPU SpMV of the same rows (the oracle as
+    #      the checker): at N > 1 these are the rows that read x across the neighbouring ranks' column ranges.  A wrong
+    #      result is an error, not a number.
+    shard_err = 0.0
+    if world > 1:
+        import oracle_api as oa
+        O = oa.OracleLib()
+        eng.set_x(x_np)
+        eng.spmv_dev()
+        y_gpu = eng.get_y()
+        rp_all = csr.row_ptr
+        for lo_r, hi_r in ((0, min(csr.rows, 4096)), (max(0, csr.rows - 4096), csr.rows)):
+            j0 = int(rp_all[lo_r])
+            rp_s = (rp_all[lo_r:hi_r + 1] - rp_all[lo_r]).astype(np.uint64)
+            ci_s, va_s = csr.col_ind[j0:int(rp_all[hi_r])], csr.values[j0:int(rp_all[hi_r])]
+            gold = O.spmv_gold(hi_r - lo_r, rp_s, ci_s, va_s, x_np, is_double).astype(np.float64)
+            bound = O.abs_ax(hi_r - lo_r, rp_s, ci_s, va_s, x_np, is_double) * (1e-12 if is_double else 1e-5) + 1e-300
+            shard_err = max(shard_err, float(np.max(np.abs(y_gpu[lo_r:hi_r].astype(np.float64) - gold) / bound)))
+        t = torch.tensor([shard_err], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        shard_err = float(t.item())
+        if not shard_err <= 1.0:
+            raise RuntimeError("multi-GPU result check failed: error = %g x the tolerance" % shard_err)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -540,6 +564,8 @@ def main():
                      "algorithmic_bytes_per_launch": alg_bytes_local},
         "setup_s": {"generate": t_gen, "layout_build": t_layout, "upload": t_upload},
     }
+    if world > 1:
+        line["check_shard_edges_max_err_over_tolerance"] = shard_err
     if world == 1 and not args.no_gpu_build and nnz_local < (1 << 29):
         # the same layout built by CUDA kernels straight into a second engine's image; reported next
         # to the host builder's time.  The first call pays the one-time kernel loading, the second is the steady state.

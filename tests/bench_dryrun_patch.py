@@ -74,7 +74,7 @@ class FakeEngine:
 
     def fetch_layout(self, layout=None): pass
     def build_ms(self): return {"h2d_ms": 1.0, "build_ms": 1.0, "total_ms": 3.0}
-    def set_x(self, x): pass
+    def set_x(self, x): self._x = np.array(x, copy=True)
     def sync(self): pass
     def free(self): pass
 
@@ -108,7 +108,27 @@ class FakeEngine:
         self.launches += 1
         ss = ctypes.c_double.from_address(sumsq_dev).value
         self._view(dst_dev, n)[:] = self._view(src_dev, n) / np.sqrt(ss)
-    def get_y(self, out=None, accumulate=False): return np.zeros(self.rows, np.float64 if self.is_double else np.float32)
+    def get_y(self, out=None, accumulate=False):
+        dt = np.float64 if self.is_double else np.float32
+        csr = getattr(self.layout, "_csr", None)
+        if csr is None or getattr(self, "_x", None) is None:
+            return np.zeros(self.rows, dt)
+        import scipy.sparse as sp
+        A = sp.csr_matrix((csr.values, csr.col_ind.astype(np.int64), csr.row_ptr.astype(np.int64)), shape=(csr.rows, csr.cols))
+        y = (A @ self._x[: csr.cols]).astype(dt)
+        if os.environ.get("DRYRUN_BREAK_RANK") == os.environ.get("RANK", "0"):
+            y[-1] += 1e-3  # a wrong last row on one rank: bench.py must refuse to print a number
+        return y
 
 
+_real_from_csr = spmvb.Layout.from_csr
+
+
+def _from_csr(csr, *a, **k):  # remember the matrix so that the stand-in can produce A x where bench.py checks it
+    lay = _real_from_csr(csr, *a, **k)
+    lay._csr = csr
+    return lay
+
+
+spmvb.Layout.from_csr = staticmethod(_from_csr)
 spmvb.Engine = FakeEngine

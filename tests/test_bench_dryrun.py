@@ -75,3 +75,14 @@ def test_power_iteration_line_over_gloo(mode):
     # the stand-in engine returns y = 1 on every rank: after normalisation ||x|| = 1 and the last norm is sqrt(rows)
     assert abs(d["last_norm"] - 128.0) < 1e-3
     assert ("broadcast" in d["config"]["step"]) == (mode == "broadcast")
+
+
+def test_two_rank_run_refuses_a_wrong_result():
+    port = _free_port()
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), "--no-python", sys.executable, "-c", CODE,
+                        "--gpus", "2", "--steps", "3", "--warmup", "3"], cwd=ROOT, capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, DRYRUN_BREAK_RANK="1"))
+    assert p.returncode != 0
+    assert "multi-GPU result check failed" in p.stderr
+    assert not [l for l in p.stdout.splitlines() if l.strip().startswith("{")]   # no JSON line
