@@ -514,6 +514,9 @@ def main():
     shard_err = 0.0
     if world > 1:
         import oracle_api as oa
+        if rank == 0:
+            oa.build_port()  # (re)compiles the checker if it is missing or stale: once, not by every rank at a time
+        dist.barrier()
         O = oa.OracleLib()
         eng.set_x(x_np)
         eng.spmv_dev()
