@@ -384,9 +384,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "poweriter" and args.dtype == "f64" and "--dtype" not in sys.argv:
+        args.dtype = "f32"  # BASELINE configs[4] is the DOUBLE=0 run, in both arms
     if args.workload == "poweriter" and args.impl != "reference":
-        if args.dtype == "f64" and "--dtype" not in sys.argv:
-            args.dtype = "f32"
         run_poweriter(args, world, rank, local_rank)
         return
     spec = workload_spec(args, world)
