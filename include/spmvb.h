@@ -38,6 +38,20 @@ typedef struct spmvb_engine spmvb_engine; /* device-resident copy of a layout + 
 const char *spmvb_last_error(void);
 int spmvb_version(void);
 
+/* Process-wide tuning options for A/B experiments and tests; every one has a default chosen by the library (-1) and
+ * applies to the layouts built / engines created after the call.  The library itself never reads the environment.
+ *   run_log2, occ_run_log2, xs_run_log2  run lengths (log2 chunks) of the zero list / the two kernels, 1..8
+ *   cu_major 0/1      device order of the pieces        zero_all 1   clear all of y before every SpMV
+ *   tall 0/1          explicit L2 eviction policies     autotune 1   time both kernels at engine creation
+ *   dev_tiles, dev_cdb, tile_mb, xs_pairs               the engine-private device layout
+ *   xs_rowids 0       per-lane global loads of the row ids in the x-window kernel instead of the staged copy
+ *   build_trace 1     print the time of every stage of the GPU layout builder
+ * spmvb_options_from_env() applies SPMVB_<NAME>=<integer> for every option and returns how many it found: for
+ * executables with no other means of configuration (the reference's run.elf is configured by -D macros only). */
+int spmvb_set_option(const char *name, int64_t value);
+int64_t spmvb_get_option(const char *name); /* INT64_MIN for an unknown name */
+int spmvb_options_from_env(void);
+
 /* ------------------------------------------------------------------ layout (host) */
 
 /* Replaces create_csr_hw_matrix (csr_hw_wrapper.cpp:3-80 -> csr_hw.cpp:377-429, 496-554, ... 1277-1395):
@@ -95,6 +109,11 @@ int64_t spmvb_layout_x_ranges(const spmvb_layout *l, uint64_t *out_pairs, uint64
 /* number of 256-entry chunks of the device image, and the [lo, hi] column-in-block range of chunk c */
 uint64_t spmvb_layout_chunks(const spmvb_layout *l);
 int spmvb_layout_chunk_cols(const spmvb_layout *l, uint64_t c, uint32_t *lo, uint32_t *hi, uint32_t *block);
+
+/* What the GPU streams for this layout: out[9] = {compute units (row tiles), VF, column-block width, 1 = CU-major
+ * order, 1 = an engine-private device layout exists next to the API pieces, (row, block) pairs, chunks, rows cleared
+ * per SpMV (UINT64_MAX = all), image bytes}.  The API-visible pieces (piece_info / piece_words) never change with it. */
+int spmvb_layout_device_params(const spmvb_layout *l, uint64_t *out);
 
 /* 1 if the two layouts are identical in every table and byte (pieces, row map, chunk metadata, rows to clear, column
  * ranges), 0 if not (why receives the first difference), negative on error.  Used to check the GPU builder against
@@ -170,6 +189,11 @@ int spmvb_engine_collect_steps(spmvb_engine *e, float *total_ms, float *kernel_m
 /* Iterated SpMV on one GPU (square matrices): x <- A x / ||A x||_2, `iters` times, all on device.
  * Returns the last norm in *norm_out.  The multi-GPU version lives in the host driver (NCCL all-gather). */
 int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
+/* device time per iteration (CUDA events around the loop) of the last spmvb_engine_power_iter / spmvb_engine_cg call */
+float spmvb_engine_last_iter_ms(const spmvb_engine *e);
+/* out[10] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per
+ * SpMV (UINT64_MAX = all), image bytes, 1 = row ids staged by the x-window kernel, 1 = explicit L2 policies} */
+int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out);
 /* Conjugate gradients for A x = b on one GPU (A symmetric positive definite, e.g. the Laplacian of BASELINE config 2):
  * the second iterated caller of SURVEY 8(f) rank 3 (the reference's caller runs spmv_hw once, main.cpp:68-75; an
  * iterated caller keeps x / y on the device between the calls).  x0 = 0; per iteration one SpMV (the engine's kernel) and three

@@ -34,11 +34,18 @@ struct Engine {
   uint32_t *d_zero_rows = nullptr;
   XsItem *d_items = nullptr;  // work items of the XS kernel
   uint32_t *d_cta_first = nullptr;  // [sms + 1] first item of every CTA
+  uint2 *d_rowaux = nullptr;  // [n_chunks] slice of the row map every chunk needs (XS kernel stages it with the chunk)
+  bool xs_rowids = false;     // the XS kernel stages row ids (the image has chunks whose rows are not consecutive)
+  // API image of a GPU-built layout whose device layout differs from it (kept for spmvb_engine_fetch_layout)
+  uint8_t *d_api_stream = nullptr;
+  uint32_t *d_api_rowmap = nullptr;
+  int dev_cu = 1, dev_vf = 1;  // parameters of the layout the device streams (may differ from the API layout's)
   uint32_t occ_run_log2 = 3, xs_run_log2 = 1;  // run lengths of the kernels (>= the layout's zero-list granularity)
   uint32_t n_items = 0;
   double xs_windowed_frac = 0.0;  // share of the chunks whose x window fits shared memory
   bool tall = false;               // x and y both exceed the L2 cache: explicit L2 eviction policies
   bool cu_major = false;           // pieces in CU-major device order (row tiles)
+  bool irregular = false;          // layout_is_irregular(): x gathers are scattered, the x-window kernel pays
   int auto_variant = kVariantOcc3; // what variant 0 resolves to (chosen from the layout at creation)
   float tune_ms[2] = {0.f, 0.f};   // autotune timings: OCC, XS
   uint32_t n_zero_rows = 0, run_log2 = 2;
@@ -49,6 +56,13 @@ struct Engine {
   size_t flush_words = 0;
   void *h_stage = nullptr;  // pinned staging for get_y(accumulate)
   size_t h_stage_bytes = 0;
+  static constexpr int kPieces = 8;  // get_y(accumulate) overlaps the host addition of piece i with the copy of i+1
+  cudaEvent_t ev_piece[kPieces] = {};
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // device time of the last iterated call
+  float last_iter_ms = 0.f;                      // ... per iteration
+  double *h_scalar = nullptr;                    // pinned: scalar read-backs of the iterated callers
+  void *d_cg = nullptr;                          // conjugate gradients: r, x (rows values each) + 4 scalars
+  size_t d_cg_bytes = 0;
   cudaStream_t stream = nullptr;
   int sms = 148;
   uint64_t launches = 0;
@@ -106,21 +120,27 @@ static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, 
   return SPMVB_OK;
 }
 
-template <typename VT>
-static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
+template <typename VT, bool ROWIDS>
+static int launch_xs_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
+  constexpr int WARPS = sizeof(VT) == 8 ? kXsWarpsF64 : kXsWarpsF32;
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
-  auto kern = spmv_xs_kernel<VT, kXsWarps, kXsCap>;
-  const size_t smem = (size_t)kXsCap + (size_t)kXsWarps * 2 * (VTraits<VT>::kGroupWords * 16 * 32 + 16) + kXsWarps * 16 + 16;
+  auto kern = spmv_xs_kernel<VT, WARPS, kXsCap, ROWIDS>;
+  const size_t stage = (size_t)VTraits<VT>::kGroupWords * 16 * 32 + 16 + (ROWIDS ? kXsRowIdBytes : 0);
+  const size_t smem = (size_t)kXsCap + (size_t)WARPS * 2 * stage + WARPS * 16 + 16;
   int &grid = E->grid_cache[kVariantXs][sizeof(VT) == 8];
   if (grid == 0) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     grid = E->sms;
   }
   if (E->n_items == 0) return SPMVB_OK;
-  CUDA_TRY(launch_pdl(kern, grid, kXsWarps * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, x, y,
-                      (const XsItem *)E->d_items, (const uint32_t *)E->d_cta_first, E->cdb, E->xs_run_log2,
+  CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, (const uint2 *)E->d_rowaux,
+                      x, y, (const XsItem *)E->d_items, (const uint32_t *)E->d_cta_first, E->cdb, E->xs_run_log2,
                       (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u)));
   return SPMVB_OK;
+}
+template <typename VT>
+static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
+  return E->xs_rowids ? launch_xs_impl<VT, true>(E, x, y, st, accumulate) : launch_xs_impl<VT, false>(E, x, y, st, accumulate);
 }
 
 template <typename VT>
@@ -182,17 +202,17 @@ static int do_spmv(Engine *E, const void *x_dev, void *y_dev, int accumulate, cu
 }
 
 // variant 0: pick between the two production kernels from the structure of the layout (deterministic).  The
-// shared-memory x window pays when nearly every entry is its own (row, block) pair with a scattered column - then the
-// global gathers touch one sector per entry - and it is required for tall matrices (CU-major order, x streamed once per
-// row tile).  Banded and power-law matrices keep the global gathers with more resident warps.  Measured on B200:
-// Laplacian 54 vs 69 us, R-MAT 0.28 vs 0.38 ms, uniform 0.55 vs 0.43 ms, 1 B-nnz uniform 27 vs 8.9 ms (OCC vs XS).
-// SPMVB_AUTOTUNE=1 times both kernels on the actual matrix instead (not under a profiler: the timings are noise there).
+// shared-memory x window pays when the (row, block) pairs are short and their columns scattered - then the global
+// gathers touch one 128-byte line per entry, 2 cycles of L1 tag time each - and it is required for tall matrices
+// (CU-major order, x streamed once per row tile).  Banded matrices keep the global gathers with more resident warps.
+// The same criterion (layout_is_irregular: distinct x lines per chunk) decides the engine-private device layout (plan_device_params), so that the
+// windows of the chosen kernel fit.  Option autotune = 1 times both kernels on the actual matrix instead (not under a
+// profiler: the timings are noise there).
 static int autotune(Engine *E) {
   E->auto_variant = kVariantOcc3;
   if (E->n_chunks == 0 || E->xs_windowed_frac < 0.5) return SPMVB_OK;
-  const double pairs_per_chunk = (double)E->n_pairs / (double)E->n_chunks;
-  if (E->cu_major || pairs_per_chunk > 160.0) E->auto_variant = kVariantXs;
-  if (!getenv("SPMVB_AUTOTUNE")) return SPMVB_OK;
+  if (E->cu_major || E->irregular) E->auto_variant = kVariantXs;
+  if (options().autotune <= 0) return SPMVB_OK;
   const int cand[2] = {kVariantOcc3, kVariantXs};
   cudaEvent_t a, b;
   CUDA_TRY(cudaEventCreate(&a));
@@ -226,65 +246,77 @@ static int autotune(Engine *E) {
 using namespace spmvb;
 
 namespace {
+// Conjugate gradients (spmvb_engine_cg).  The work vectors r, x and the four scalars live in one engine-owned
+// allocation that is made on the first call and reused; the scalar read-backs go through pinned memory.  The device
+// time of the iteration loop is taken with two events (spmvb_engine_last_iter_ms).
 template <typename VT>
 int cg_impl(Engine *E, const VT *b_host, VT *x_host, int max_iters, double rel_tol, int *iters_out, double *relres_out) {
   const uint32_t n = E->rows;
-  const size_t bytes = (size_t)n * sizeof(VT);
-  VT *d_r = nullptr, *d_xs = nullptr;
-  double *s = nullptr;  // s[0], s[2]: r.r (roles swap every iteration); s[1]: p.q
+  const size_t bytes = ((size_t)n * sizeof(VT) + 255) & ~(size_t)255;
+  if (E->d_cg_bytes < 2 * bytes + 64) {
+    cudaFree(E->d_cg);
+    E->d_cg = nullptr; E->d_cg_bytes = 0;
+    CUDA_TRY(cudaMalloc(&E->d_cg, 2 * bytes + 64));
+    E->d_cg_bytes = 2 * bytes + 64;
+  }
+  VT *d_r = (VT *)E->d_cg, *d_xs = (VT *)((uint8_t *)E->d_cg + bytes);
+  double *s = (double *)((uint8_t *)E->d_cg + 2 * bytes);  // s[0], s[2]: r.r (roles swap every iteration); s[1]: p.q
   cudaStream_t st = E->stream;
   const int grid = E->sms * 4;
-  int rc = SPMVB_OK, it = 0;
-  double bnorm2 = 0.0, rr_host = 0.0;
-  auto body = [&]() -> int {
-    CUDA_TRY(cudaMalloc((void **)&d_r, bytes));
-    CUDA_TRY(cudaMalloc((void **)&d_xs, bytes));
-    CUDA_TRY(cudaMalloc((void **)&s, 4 * sizeof(double)));
-    VT *p = (VT *)E->d_x, *q = (VT *)E->d_y;
-    // x0 = 0: r = b, p = b (the padding of p beyond n stays zero), rr = b.b
-    CUDA_TRY(cudaMemsetAsync(d_xs, 0, bytes, st));
-    CUDA_TRY(cudaMemcpyAsync(d_r, b_host, bytes, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(E->d_x, 0, E->x_len * sizeof(VT), st));
-    CUDA_TRY(cudaMemcpyAsync(p, d_r, bytes, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(s, 0, 4 * sizeof(double), st));
-    dot_kernel<VT><<<grid, 256, 0, st>>>(d_r, d_r, n, s + 0);
-    E->launches++;
-    CUDA_TRY(cudaMemcpyAsync(&bnorm2, s + 0, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    rr_host = bnorm2;
-    if (bnorm2 == 0.0) return SPMVB_OK;  // b = 0: x = 0
-    const double stop2 = rel_tol * rel_tol * bnorm2;
-    int cur = 0;  // index of the current r.r
-    constexpr int kCheckEvery = 8;
-    while (it < max_iters) {
-      const int nxt = 2 - cur;
-      int r2 = do_spmv(E, p, q, 0, st);  // q = A p
-      if (r2) return r2;
-      CUDA_TRY(cudaMemsetAsync(s + 1, 0, sizeof(double), st));
-      CUDA_TRY(cudaMemsetAsync(s + nxt, 0, sizeof(double), st));
-      dot_kernel<VT><<<grid, 256, 0, st>>>(p, q, n, s + 1);
-      cg_update_kernel<VT><<<grid, 256, 0, st>>>(d_xs, d_r, p, q, n, s + cur, s + 1, s + nxt);
-      cg_direction_kernel<VT><<<grid, 256, 0, st>>>(p, d_r, n, s + cur, s + nxt);
-      E->launches += 3;
-      CUDA_TRY(cudaGetLastError());
-      cur = nxt;
-      it++;
-      if (it % kCheckEvery == 0 || it == max_iters) {
-        CUDA_TRY(cudaMemcpyAsync(&rr_host, s + cur, sizeof(double), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        if (!(rr_host > stop2)) break;  // converged (or NaN: give up)
-      }
-    }
-    CUDA_TRY(cudaMemcpyAsync(x_host, d_xs, bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+  int it = 0;
+  VT *p = (VT *)E->d_x, *q = (VT *)E->d_y;
+  // x0 = 0: r = b, p = b (the padding of p beyond n stays zero), rr = b.b
+  CUDA_TRY(cudaMemsetAsync(d_xs, 0, (size_t)n * sizeof(VT), st));
+  CUDA_TRY(cudaMemcpyAsync(d_r, b_host, (size_t)n * sizeof(VT), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(E->d_x, 0, E->x_len * sizeof(VT), st));
+  CUDA_TRY(cudaMemcpyAsync(p, d_r, (size_t)n * sizeof(VT), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(s, 0, 4 * sizeof(double), st));
+  dot_kernel<VT><<<grid, 256, 0, st>>>(d_r, d_r, n, s + 0);
+  E->launches++;
+  CUDA_TRY(cudaMemcpyAsync(E->h_scalar, s + 0, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const double bnorm2 = E->h_scalar[0];
+  double rr_host = bnorm2;
+  E->last_iter_ms = 0.f;
+  if (bnorm2 == 0.0) {  // b = 0: x = 0
+    memset(x_host, 0, (size_t)n * sizeof(VT));
+    if (iters_out) *iters_out = 0;
+    if (relres_out) *relres_out = 0.0;
     return SPMVB_OK;
-  };
-  rc = body();
-  cudaFree(d_r); cudaFree(d_xs); cudaFree(s);
-  if (rc) return rc;
-  if (bnorm2 == 0.0) memset(x_host, 0, bytes);
+  }
+  const double stop2 = rel_tol * rel_tol * bnorm2;
+  int cur = 0;  // index of the current r.r
+  constexpr int kCheckEvery = 8;
+  CUDA_TRY(cudaEventRecord(E->ev_t0, st));
+  while (it < max_iters) {
+    const int nxt = 2 - cur;
+    int r2 = do_spmv(E, p, q, 0, st);  // q = A p
+    if (r2) return r2;
+    CUDA_TRY(cudaMemsetAsync(s + 1, 0, sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(s + nxt, 0, sizeof(double), st));
+    dot_kernel<VT><<<grid, 256, 0, st>>>(p, q, n, s + 1);
+    cg_update_kernel<VT><<<grid, 256, 0, st>>>(d_xs, d_r, p, q, n, s + cur, s + 1, s + nxt);
+    cg_direction_kernel<VT><<<grid, 256, 0, st>>>(p, d_r, n, s + cur, s + nxt);
+    E->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    cur = nxt;
+    it++;
+    if (it % kCheckEvery == 0 || it == max_iters) {
+      CUDA_TRY(cudaMemcpyAsync(E->h_scalar, s + cur, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      rr_host = E->h_scalar[0];
+      if (!(rr_host > stop2)) break;  // converged (or NaN: give up)
+    }
+  }
+  CUDA_TRY(cudaEventRecord(E->ev_t1, st));
+  CUDA_TRY(cudaMemcpyAsync(x_host, d_xs, (size_t)n * sizeof(VT), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (it > 0) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, E->ev_t0, E->ev_t1) == cudaSuccess) E->last_iter_ms = ms / (float)it;
+  }
   if (iters_out) *iters_out = it;
-  if (relres_out) *relres_out = bnorm2 > 0.0 ? std::sqrt(rr_host / bnorm2) : 0.0;
+  if (relres_out) *relres_out = std::sqrt(rr_host / bnorm2);
   return SPMVB_OK;
 }
 }  // namespace
@@ -308,6 +340,10 @@ static int engine_open(int device, int variant, Engine **out) {
   E->sms = prop.multiProcessorCount;
   cudaError_t e = cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc((void **)&E->d_scalar, 64);
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&E->h_scalar, 64);
+  for (int p = 0; p < Engine::kPieces && e == cudaSuccess; p++) e = cudaEventCreateWithFlags(&E->ev_piece[p], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreate(&E->ev_t0);
+  if (e == cudaSuccess) e = cudaEventCreate(&E->ev_t1);
   if (e != cudaSuccess) {
     std::string msg = std::string("engine_create: ") + cudaGetErrorString(e);
     spmvb_engine_free((spmvb_engine *)E);
@@ -322,9 +358,10 @@ static int engine_adopt_layout(Engine *E, const Layout *L) {
   E->is_double = L->is_double; E->vb = L->vb;
   E->rows = L->rows; E->cols = L->cols; E->expanded_cols = L->expanded_cols; E->cdb = L->cdb; E->blocks = L->blocks;
   E->real_nnz = L->real_nnz; E->n_chunks = L->n_chunks; E->n_pairs = L->n_pairs; E->stream_bytes = L->stream_bytes;
-  E->cu_major = L->cu_major;
+  E->cu_major = L->cu_major; E->dev_cu = L->cu; E->dev_vf = L->vf;
+  E->irregular = layout_is_irregular(L);
   E->tall = (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) && (uint64_t)L->cols * L->vb > ((uint64_t)48 << 20);
-  if (const char *v = getenv("SPMVB_TALL")) E->tall = atoi(v) != 0;
+  if (options().tall >= 0) E->tall = options().tall != 0;
   E->x_touched = 0;
   for (int b = 0; b < L->blocks; b++) {
     uint64_t nz = 0;
@@ -338,11 +375,12 @@ static int engine_adopt_layout(Engine *E, const Layout *L) {
     if (nr > 0) spmvb_layout_x_ranges((const spmvb_layout *)L, E->x_ranges.data(), (uint64_t)nr);
   }
   E->zero_all = L->zero_all; E->n_zero_rows = (uint32_t)L->zero_rows.size(); E->run_log2 = (uint32_t)L->run_log2;
-  if (const char *v = getenv("SPMVB_OCC_RUN_LOG2")) E->occ_run_log2 = (uint32_t)atoi(v);
-  if (const char *v = getenv("SPMVB_XS_RUN_LOG2")) E->xs_run_log2 = (uint32_t)atoi(v);
-  // rows split across run boundaries are only cleared at the layout's granularity: runs must be multiples of it
-  E->occ_run_log2 = std::min(8u, std::max(E->occ_run_log2, E->run_log2));
-  E->xs_run_log2 = std::min(8u, std::max(E->xs_run_log2, E->run_log2));
+  if (options().occ_run_log2 >= 0) E->occ_run_log2 = (uint32_t)options().occ_run_log2;
+  if (options().xs_run_log2 >= 0) E->xs_run_log2 = (uint32_t)options().xs_run_log2;
+  // rows split across run boundaries are only cleared at the layout's granularity: runs must be multiples of it;
+  // and a run is at least two chunks (the walk refills two chunks ahead)
+  E->occ_run_log2 = std::min(8u, std::max(1u, std::max(E->occ_run_log2, E->run_log2)));
+  E->xs_run_log2 = std::min(8u, std::max(1u, std::max(E->xs_run_log2, E->run_log2)));
   CUDA_TRY(cudaMalloc(&E->d_x, E->x_len * E->vb));
   CUDA_TRY(cudaMalloc(&E->d_y, (size_t)E->rows * E->vb));
   return SPMVB_OK;
@@ -361,6 +399,26 @@ static int engine_finish(Engine *E, const Layout *L) {
   uint64_t windowed = 0;
   for (auto &it : items) windowed += it.x_bytes ? it.chunk_count : 0;
   E->xs_windowed_frac = L->n_chunks ? (double)windowed / (double)L->n_chunks : 0.0;
+  // row-map slice of every chunk, for the XS kernel's staging copy: entries [rank0 & ~3, ...) so that the source is
+  // 16-byte aligned, one entry beyond the chunk's last row end (the row a run may leave open)
+  {
+    std::vector<uint2> aux((size_t)std::max<uint64_t>(L->n_chunks, 1), make_uint2(0u, 0u));
+    bool any = false;
+#pragma omp parallel for schedule(static) reduction(| : any)
+    for (int64_t c = 0; c < (int64_t)L->n_chunks; c++) {
+      const ChunkMeta &m = L->chunks[c];
+      if (!(m.valid & 0x3FFu) || (m.valid & kChunkRowsConsecutive)) continue;
+      const uint32_t n_eor = (m.block >> kMetaRowsShift) & 0x1FFu;
+      aux[c].x = m.rank0 & ~3u;
+      aux[c].y = (((m.rank0 & 3u) + n_eor + 1u + 3u) & ~3u) * 4u;
+      any = true;
+    }
+    E->xs_rowids = any && options().xs_rowids != 0;
+    if (E->xs_rowids) {
+      CUDA_TRY(cudaMalloc((void **)&E->d_rowaux, aux.size() * sizeof(uint2)));
+      CUDA_TRY(cudaMemcpy(E->d_rowaux, aux.data(), aux.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
+  }
   CUDA_TRY(cudaMemsetAsync(E->d_x, 0, E->x_len * E->vb, E->stream));
   CUDA_TRY(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
   CUDA_TRY(cudaStreamSynchronize(E->stream));
@@ -372,9 +430,10 @@ static int engine_finish(Engine *E, const Layout *L) {
 }
 
 int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_engine **out) {
-  const Layout *L = (const Layout *)l;
-  if (!L || !out) return fail(SPMVB_E_ARG, "engine_create: NULL");
+  const Layout *A = (const Layout *)l;
+  if (!A || !out) return fail(SPMVB_E_ARG, "engine_create: NULL");
   *out = nullptr;
+  const Layout *L = A->dev ? A->dev : A;  // what the GPU streams: the engine-private device layout when there is one
   if (!L->stream || !L->rowmap)
     return fail(SPMVB_E_ARG, "engine_create: this layout was built on a GPU and lives in its engine; fetch it first");
   Engine *E = nullptr;
@@ -387,7 +446,7 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
     // ChunkMeta, so that a single bulk copy brings both into shared memory
     const size_t slot = (size_t)L->chunk_bytes + sizeof(ChunkMeta);
     CUDA_TRY(cudaMalloc((void **)&E->d_stream, std::max<uint64_t>(L->n_chunks * slot, 16)));
-    CUDA_TRY(cudaMalloc((void **)&E->d_rowmap, (std::max<uint64_t>(L->n_pairs, 1) + 1) * 4));
+    CUDA_TRY(cudaMalloc((void **)&E->d_rowmap, (L->n_pairs + 8) * 4));  // slack: 16-byte aligned slices are copied
     CUDA_TRY(cudaMalloc((void **)&E->d_zero_rows, std::max<size_t>(L->zero_rows.size(), 1) * 4));
     if (L->n_chunks) {
       CUDA_TRY(cudaMemcpy2DAsync(E->d_stream, slot, L->stream, L->chunk_bytes, L->chunk_bytes, L->n_chunks,
@@ -395,6 +454,7 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
       CUDA_TRY(cudaMemcpy2DAsync(E->d_stream + L->chunk_bytes, slot, L->chunks, sizeof(ChunkMeta), sizeof(ChunkMeta),
                                  L->n_chunks, cudaMemcpyHostToDevice, E->stream));
     }
+    CUDA_TRY(cudaMemsetAsync(E->d_rowmap + L->n_pairs, 0, 8 * 4, E->stream));
     CUDA_TRY(cudaMemcpyAsync(E->d_rowmap, L->rowmap, L->n_pairs * 4, cudaMemcpyHostToDevice, E->stream));
     CUDA_TRY(cudaMemcpyAsync(E->d_zero_rows, L->zero_rows.data(), L->zero_rows.size() * 4, cudaMemcpyHostToDevice, E->stream));
     return engine_finish(E, L);
@@ -408,7 +468,9 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
 // create_csr_hw_matrix on the GPU: the CSR goes to the device (unless it is there already), the layout is built there
 // (layout_gpu_steps.h) straight into the engine's image.  *layout_out gets every host-side table (csr_hw_matrix
 // fields, chunk metadata, rows to clear); its two big arrays - the pieces and the row map - stay on the device until
-// spmvb_engine_fetch_layout asks for them.
+// spmvb_engine_fetch_layout asks for them.  When the engine wants to stream the matrix under other parameters than the
+// API layout's (plan_device_params), the builder runs a second time with those: the first image then only serves
+// spmvb_engine_fetch_layout.
 int spmvb_engine_create_from_csr(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, const uint32_t *col_ind,
                                  const void *values, int n_cu, int vf, int is_double, uint32_t cols_div_blocks,
                                  int device, int variant, int csr_on_device, spmvb_layout **layout_out,
@@ -447,21 +509,33 @@ int spmvb_engine_create_from_csr(uint32_t rows, uint32_t cols, const uint64_t *r
       CUDA_TRY(cudaMemcpyAsync(d_va, values, (size_t)nnz * vb, cudaMemcpyHostToDevice, E->stream));
     }
     CUDA_TRY(cudaEventRecord(ev[1], E->stream));
-    CudaBackend be;
-    be.st = E->stream; be.sms = E->sms;
-    LbImage img;
-    int r = lb_build(be, rows, cols, nnz, csr_on_device ? row_ptr : d_rp, csr_on_device ? col_ind : d_ci,
-                     csr_on_device ? values : d_va, n_cu, vf, is_double, cols_div_blocks, &L, &img);
-    if (r) return r;
-    E->d_stream = img.image; E->d_rowmap = img.rowmap; E->d_zero_rows = img.zero_rows;
+    const uint64_t *rp = csr_on_device ? row_ptr : d_rp;
+    const uint32_t *ci = csr_on_device ? col_ind : d_ci;
+    const void *va = csr_on_device ? values : d_va;
+    const Layout *D = nullptr;
+    {
+      CudaBackend be_api, be_dev;
+      be_api.st = be_dev.st = E->stream; be_api.sms = be_dev.sms = E->sms;
+      LbImage api, dev;
+      int r = lb_build_pair(be_api, be_dev, rows, cols, nnz, rp, ci, va, n_cu, vf, is_double, cols_div_blocks, &L, &api, &dev);
+      if (r) return r;
+      if (L->dev) {
+        // the API image keeps the pieces and the row map for fetch_layout; its rows-to-clear list is of no use
+        E->d_api_stream = api.image; E->d_api_rowmap = api.rowmap;
+        cudaFree(api.zero_rows);
+        E->d_stream = dev.image; E->d_rowmap = dev.rowmap; E->d_zero_rows = dev.zero_rows;
+        D = L->dev;
+      } else {
+        E->d_stream = api.image; E->d_rowmap = api.rowmap; E->d_zero_rows = api.zero_rows;
+        D = L;
+      }
+      be_dev.trace("(end of build)");
+    }
     CUDA_TRY(cudaEventRecord(ev[2], E->stream));
-    be.trace("(end of build)");
-    r = engine_adopt_layout(E, L);
+    int r = engine_adopt_layout(E, D);
     if (r) return r;
-    be.trace("x / y allocation");
-    r = engine_finish(E, L);
+    r = engine_finish(E, D);
     if (r) return r;
-    be.trace("XS plan + kernel choice");
     CUDA_TRY(cudaEventElapsedTime(&E->build_ms[0], ev[0], ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&E->build_ms[1], ev[1], ev[2]));
     return SPMVB_OK;
@@ -481,14 +555,23 @@ int spmvb_engine_fetch_layout(spmvb_engine *e, spmvb_layout *l) {
   Engine *E = (Engine *)e;
   Layout *L = (Layout *)l;
   if (!E || !L) return fail(SPMVB_E_ARG, "fetch_layout: NULL");
-  if (L->n_chunks != E->n_chunks || L->n_pairs != E->n_pairs || L->stream_bytes != E->stream_bytes || L->rows != E->rows)
+  const Layout *D = L->dev ? L->dev : L;
+  if (D->n_chunks != E->n_chunks || D->n_pairs != E->n_pairs || D->stream_bytes != E->stream_bytes || L->rows != E->rows)
     return fail(SPMVB_E_ARG, "fetch_layout: this layout does not belong to this engine");
+  if (L->stream && L->rowmap) return SPMVB_OK;
+  if (L->dev && !E->d_api_stream) return fail(SPMVB_E_ARG, "fetch_layout: the API image was already released");
   CUDA_TRY(cudaSetDevice(E->device));
   CudaBackend be;
   be.st = E->stream; be.sms = E->sms;
   LbImage img;
-  img.image = E->d_stream; img.rowmap = E->d_rowmap;
-  return lb_fetch_host(be, L, img);
+  img.image = L->dev ? E->d_api_stream : E->d_stream;
+  img.rowmap = L->dev ? E->d_api_rowmap : E->d_rowmap;
+  int rc = lb_fetch_host(be, L, img);
+  if (rc == SPMVB_OK && L->dev) {  // the pieces are on the host now: the device copy of the API image can go
+    cudaFree(E->d_api_stream); cudaFree(E->d_api_rowmap);
+    E->d_api_stream = nullptr; E->d_api_rowmap = nullptr;
+  }
+  return rc;
 }
 
 int spmvb_engine_build_ms(const spmvb_engine *e, float *out3) {
@@ -505,7 +588,12 @@ void spmvb_engine_free(spmvb_engine *e) {
   if (E->stream) cudaStreamSynchronize(E->stream);
   cudaFree(E->d_stream); cudaFree(E->d_rowmap); cudaFree(E->d_zero_rows); cudaFree(E->d_items); cudaFree(E->d_cta_first);
   cudaFree(E->d_x); cudaFree(E->d_y); cudaFree(E->d_scalar); cudaFree(E->d_flush);
+  cudaFree(E->d_rowaux); cudaFree(E->d_api_stream); cudaFree(E->d_api_rowmap); cudaFree(E->d_cg);
   if (E->h_stage) cudaFreeHost(E->h_stage);
+  if (E->h_scalar) cudaFreeHost(E->h_scalar);
+  for (auto &x : E->ev_piece) if (x) cudaEventDestroy(x);
+  if (E->ev_t0) cudaEventDestroy(E->ev_t0);
+  if (E->ev_t1) cudaEventDestroy(E->ev_t1);
   for (auto &x : E->ev) cudaEventDestroy(x);
   if (E->stream) cudaStreamDestroy(E->stream);
   delete E;
@@ -590,21 +678,20 @@ int spmvb_engine_get_y(spmvb_engine *e, void *y_host, uint32_t n, int accumulate
   }
   // y_fpga[row] += partial, csr_hw.cpp:1557 (the per-block partials were already summed on the device).  The copy is
   // cut into pieces so that the host addition of piece i overlaps the transfer of piece i+1.
-  constexpr int kPieces = 8;
-  cudaEvent_t ev[kPieces];
+  constexpr int kPieces = Engine::kPieces;
   uint32_t cutp[kPieces + 1];
   for (int p = 0; p <= kPieces; p++) cutp[p] = (uint32_t)((uint64_t)m * p / kPieces);
-  for (int p = 0; p < kPieces; p++) {
-    CUDA_TRY(cudaEventCreateWithFlags(&ev[p], cudaEventDisableTiming));
-    const size_t o = (size_t)cutp[p] * E->vb, len = (size_t)(cutp[p + 1] - cutp[p]) * E->vb;
-    if (len) CUDA_TRY(cudaMemcpyAsync((uint8_t *)E->h_stage + o, (const uint8_t *)E->d_y + o, len, cudaMemcpyDeviceToHost, E->stream));
-    CUDA_TRY(cudaEventRecord(ev[p], E->stream));
-  }
   cudaError_t werr = cudaSuccess;
-  for (int p = 0; p < kPieces; p++) {
-    cudaError_t r = cudaEventSynchronize(ev[p]);
+  int queued = 0;  // pieces whose copy + event made it into the stream (on an error the rest is not waited for)
+  for (int p = 0; p < kPieces && werr == cudaSuccess; p++) {
+    const size_t o = (size_t)cutp[p] * E->vb, len = (size_t)(cutp[p + 1] - cutp[p]) * E->vb;
+    if (len) werr = cudaMemcpyAsync((uint8_t *)E->h_stage + o, (const uint8_t *)E->d_y + o, len, cudaMemcpyDeviceToHost, E->stream);
+    if (werr == cudaSuccess) werr = cudaEventRecord(E->ev_piece[p], E->stream);
+    if (werr == cudaSuccess) queued++;
+  }
+  for (int p = 0; p < queued; p++) {
+    cudaError_t r = cudaEventSynchronize(E->ev_piece[p]);
     if (r != cudaSuccess) werr = r;
-    cudaEventDestroy(ev[p]);
     if (werr != cudaSuccess) continue;
     const int64_t a = cutp[p], b = cutp[p + 1];
     if (E->is_double) {
@@ -758,21 +845,34 @@ int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out) {
   if (!E || iters < 1) return fail(SPMVB_E_ARG, "power_iter");
   if (E->rows != E->cols) return fail(SPMVB_E_ARG, "power_iter needs a square matrix");
   CUDA_TRY(cudaSetDevice(E->device));
-  double nrm = 0.0;
+  // everything stays on the device: the norm's square is consumed by the scale kernel where it was summed, and only
+  // the last one comes back
+  CUDA_TRY(cudaEventRecord(E->ev_t0, E->stream));
   for (int it = 0; it < iters; it++) {
     int rc = do_spmv(E, nullptr, nullptr, 0, E->stream);
     if (rc) return rc;
     rc = spmvb_engine_sumsq(e, E->d_y, E->rows, E->d_scalar, E->stream);
     if (rc) return rc;
-    double ss = 0.0;
-    CUDA_TRY(cudaMemcpyAsync(&ss, E->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, E->stream));
-    CUDA_TRY(cudaStreamSynchronize(E->stream));
-    nrm = std::sqrt(ss);
-    rc = spmvb_engine_scale_copy(e, E->d_y, E->d_x, E->rows, nrm > 0 ? 1.0 / nrm : 0.0, E->stream);
+    rc = spmvb_engine_scale_rsqrt(e, E->d_y, E->d_x, E->rows, E->d_scalar, E->stream);
     if (rc) return rc;
   }
+  CUDA_TRY(cudaEventRecord(E->ev_t1, E->stream));
+  CUDA_TRY(cudaMemcpyAsync(E->h_scalar, E->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, E->stream));
   CUDA_TRY(cudaStreamSynchronize(E->stream));
-  if (norm_out) *norm_out = nrm;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, E->ev_t0, E->ev_t1) == cudaSuccess) E->last_iter_ms = ms / (float)iters;
+  if (norm_out) *norm_out = std::sqrt(E->h_scalar[0]);
+  return SPMVB_OK;
+}
+
+float spmvb_engine_last_iter_ms(const spmvb_engine *e) { return e ? ((const Engine *)e)->last_iter_ms : 0.f; }
+
+int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out) {
+  const Engine *E = (const Engine *)e;
+  if (!E || !out) return fail(SPMVB_E_ARG, "device_layout");
+  out[0] = (uint64_t)E->dev_cu; out[1] = (uint64_t)E->dev_vf; out[2] = E->cdb; out[3] = E->cu_major ? 1u : 0u;
+  out[4] = E->n_pairs; out[5] = E->n_chunks; out[6] = E->zero_all ? UINT64_MAX : (uint64_t)E->n_zero_rows;
+  out[7] = E->stream_bytes; out[8] = E->xs_rowids ? 1u : 0u; out[9] = E->tall ? 1u : 0u;
   return SPMVB_OK;
 }
 

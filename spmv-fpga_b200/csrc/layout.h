@@ -61,9 +61,23 @@ struct Layout {
   bool zero_all = true;
   // smallest / largest column-in-block among the real entries of each chunk (for shared-memory x windows)
   std::vector<uint16_t> chunk_col_lo, chunk_col_hi;
+  // distinct 128-byte lines of x the real entries of each chunk touch: what a gather from global memory costs in L1
+  // tag lookups, and the measure of "irregular" that picks the kernel and the device layout (plan_device_params)
+  std::vector<uint16_t> chunk_x_lines;
+
+  // Engine-private device layout (owned; nullptr = the device image is this layout itself).  The API-visible pieces
+  // above are fixed by the caller's CU / VF / COLS_DIV_BLOCKS; what the GPU streams is the same matrix in the same
+  // hw_matrix format under parameters the engine picks for the device (plan_device_params): column blocks whose x
+  // slice fits the kernel's shared-memory window, row tiles whose y range stays in the L2 cache, no VF padding.
+  Layout *dev = nullptr;
 
   ~Layout();
 };
+
+// Parameters of the engine-private device layout for the API layout L; false when the API layout is what should be
+// streamed as it is.
+bool plan_device_params(const Layout *L, int *cu_dev, int *vf_dev, uint32_t *cdb_dev);
+bool layout_is_irregular(const Layout *L);
 
 // Work item of the XS kernel (x window in shared memory): a range of chunks of one column block.
 struct XsItem {
@@ -74,7 +88,11 @@ struct XsItem {
   uint32_t block, pad0, pad1;
 };
 constexpr uint32_t kXsCap = 128 * 1024;  // bytes of shared memory for the x window of an XS work item
-constexpr int kXsWarps = 16;             // warps per CTA of the XS kernel (one CTA per SM)
+// warps per CTA of the XS kernel (one CTA per SM): what fits next to the x window - every warp owns two ring stages of
+// one chunk slot + the chunk's row ids (257 + alignment slack, 4 bytes each)
+constexpr int kXsWarpsF64 = 12, kXsWarpsF32 = 16;
+constexpr uint32_t kXsRowIdBytes = 1040;
+inline int xs_warps(int is_double) { return is_double ? kXsWarpsF64 : kXsWarpsF32; }
 void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<XsItem> &items,
                     std::vector<uint32_t> &cta_first);
 
@@ -82,6 +100,25 @@ void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<X
 int layout_init_header(Layout *L, uint32_t rows, uint32_t cols, uint64_t nnz, int cu, int vf, int is_double,
                        uint32_t cdb_in);
 void layout_finish_pieces(Layout *L, const uint64_t *fp, const uint32_t *pad_rows, std::vector<uint64_t> &piece_last_rank);
+
+// Process-wide tuning options (include/spmvb.h: spmvb_set_option).  -1 = let the library decide.  Nothing in the
+// library reads the environment: a caller that wants SPMVB_* variables honoured calls spmvb_options_from_env() itself.
+struct Options {
+  int64_t run_log2 = -1;      // zero-list granularity of new layouts (1..8)
+  int64_t cu_major = -1;      // device order of the pieces: 0 block-major, 1 CU-major
+  int64_t zero_all = -1;      // 1: clear all of y before every SpMV instead of the listed rows
+  int64_t tall = -1;          // explicit L2 eviction policies (x evict-first, y evict-last)
+  int64_t occ_run_log2 = -1;  // run length of the OCC kernel
+  int64_t xs_run_log2 = -1;   // run length of the XS kernel
+  int64_t autotune = -1;      // 1: time the candidate kernels on the actual matrix at engine creation
+  int64_t build_trace = 0;    // 1: print the time of every stage of the GPU layout builder
+  int64_t dev_tiles = -1;     // row tiles of the engine-private device layout (0/1 = none)
+  int64_t dev_cdb = -1;       // column-block width of the engine-private device layout (0 = same as the API layout)
+  int64_t xs_pairs = -1;      // distinct x lines per 256-entry chunk above which the x-window kernel is preferred
+  int64_t tile_mb = -1;       // target size of a row tile's y range in MB
+  int64_t xs_rowids = -1;     // 0: XS kernel reads row ids with per-lane global loads instead of staging them
+};
+Options &options();
 
 void set_error(const std::string &msg);
 int fail(int code, const std::string &msg);

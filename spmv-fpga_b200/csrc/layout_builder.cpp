@@ -13,6 +13,8 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <cctype>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,6 +35,69 @@ Layout::~Layout() {
   free(stream);
   free(rowmap);
   free(chunks);
+  delete dev;
+}
+
+Options &options() {
+  static Options o;
+  return o;
+}
+
+namespace {
+struct OptionName { const char *name; int64_t Options::*field; };
+const OptionName kOptionNames[] = {
+    {"run_log2", &Options::run_log2},         {"cu_major", &Options::cu_major},       {"zero_all", &Options::zero_all},
+    {"tall", &Options::tall},                 {"occ_run_log2", &Options::occ_run_log2}, {"xs_run_log2", &Options::xs_run_log2},
+    {"autotune", &Options::autotune},         {"build_trace", &Options::build_trace}, {"dev_tiles", &Options::dev_tiles},
+    {"dev_cdb", &Options::dev_cdb},           {"xs_pairs", &Options::xs_pairs},       {"tile_mb", &Options::tile_mb},
+    {"xs_rowids", &Options::xs_rowids},
+};
+}  // namespace
+
+// The engine-private device layout (see Layout::dev).  Two questions, both answered from the API layout's own tables:
+//  1. Is the matrix irregular (layout_is_irregular), so that the kernel with the x window in shared memory is the one
+//     to run?
+//     Then the window of a column block must fit the kernel's 128 KB: fp64 blocks wider than 16 384 columns are cut
+//     in two (the reference's own CU 10/12 block width, util.h:53-58), which is the split on index bit 14.
+//  2. Is y larger than the L2 cache can hold next to the stream?  An irregular matrix updates y at random, one
+//     red.global per pair: rows are cut into tiles (compute units of the device layout, walked CU-major) so that the
+//     y range being updated stays L2-resident, at the price of streaming x once per tile.
+// "Irregular": the chunks' entries are scattered over x - on average more than xs_pairs (default 64) distinct 128-byte
+// lines per 256-entry chunk (a 5-point Laplacian touches 12, a band 3-4, R-MAT and uniform matrices 150-256).  Gathers
+// from global memory then cost ~2 cycles of L1 tag time per entry, and the x window in shared memory is what pays.
+bool layout_is_irregular(const Layout *L) {
+  const uint64_t thr = options().xs_pairs >= 0 ? (uint64_t)options().xs_pairs : 64;
+  uint64_t lines = 0, used = 0;
+  for (uint64_t c = 0; c < L->n_chunks; c++)
+    if (L->chunk_x_lines[c]) { lines += L->chunk_x_lines[c]; used++; }
+  return used > 0 && lines > thr * used;
+}
+
+bool plan_device_params(const Layout *L, int *cu_dev, int *vf_dev, uint32_t *cdb_dev) {
+  const Options &o = options();
+  int cu = L->cu, vf = L->vf;
+  uint32_t cdb = L->cdb;
+  const bool irregular = layout_is_irregular(L);
+  if (irregular) {
+    if (L->is_double && cdb > 16384) {
+      uint64_t wide = 0, used = 0;
+      for (uint64_t c = 0; c < L->n_chunks; c++)
+        if (L->chunk_col_lo[c] <= L->chunk_col_hi[c]) {
+          used++;
+          wide += (uint64_t)(L->chunk_col_hi[c] - L->chunk_col_lo[c] + 1) * L->vb > kXsCap;
+        }
+      if (2 * wide > used) cdb = 16384;
+    }
+    const uint64_t ybytes = (uint64_t)L->rows * L->vb;
+    const uint64_t tile = (uint64_t)(o.tile_mb > 0 ? o.tile_mb : 32) << 20;
+    if (ybytes > 2 * tile) cu = (int)std::min<uint64_t>(4096, (ybytes + tile - 1) / tile);
+  }
+  if (o.dev_cdb > 0) cdb = (uint32_t)o.dev_cdb;
+  if (o.dev_tiles > 0) cu = (int)o.dev_tiles;
+  if (cu == L->cu && cdb == L->cdb) return false;
+  vf = 1;  // VF only pads (csr_hw.cpp:108-112); the SIMT kernel has no use for it
+  *cu_dev = cu; *vf_dev = vf; *cdb_dev = cdb;
+  return true;
 }
 
 static inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
@@ -79,7 +144,8 @@ int layout_init_header(Layout *L, uint32_t rows, uint32_t cols, uint64_t nnz, in
   L->nr_cols.resize(blocks);
   for (int b = 0; b < blocks; b++)
     L->nr_cols[b] = (b == blocks - 1) ? L->expanded_cols - (uint32_t)b * cdb : cdb;
-  if (const char *e = getenv("SPMVB_RUN_LOG2")) L->run_log2 = std::max(0, std::min(8, atoi(e)));
+  // >= 1: the chunk walk prefetches two chunks ahead and a run must cover that distance (spmv_kernels.cuh)
+  if (options().run_log2 >= 0) L->run_log2 = (int)std::max<int64_t>(1, std::min<int64_t>(8, options().run_log2));
   return SPMVB_OK;
 }
 
@@ -93,7 +159,7 @@ void layout_finish_pieces(Layout *L, const uint64_t *fp, const uint32_t *pad_row
   const int cu = L->cu, blocks = L->blocks;
   const size_t KB = (size_t)cu * blocks;
   L->cu_major = cu > 1 && (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20);
-  if (const char *e = getenv("SPMVB_CU_MAJOR")) L->cu_major = cu > 1 && atoi(e) != 0;
+  if (options().cu_major >= 0) L->cu_major = cu > 1 && options().cu_major != 0;
   L->nr_ci.assign(KB, 0); L->nr_val.assign(KB, 0);
   L->piece_off.assign(KB, 0); L->piece_chunk0.assign(KB, 0); L->piece_chunk1.assign(KB, 0); L->piece_real_nnz.assign(KB, 0);
   L->dev_order.resize(KB);
@@ -131,12 +197,18 @@ namespace {
 
 template <typename RP>
 int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *col_ind, const void *values, int cu,
-               int vf, int is_double, uint32_t cdb_in, Layout **out) {
+               int vf, int is_double, uint32_t cdb_in, Layout **out, bool plan_device = true) {
   if (!out) return fail(SPMVB_E_ARG, "out is NULL");
   *out = nullptr;
   if (rows == 0 || cols == 0 || !row_ptr) return fail(SPMVB_E_ARG, "empty matrix");
   const uint64_t nnz = (uint64_t)row_ptr[rows];
   if (nnz && (!col_ind || !values)) return fail(SPMVB_E_ARG, "col_ind/values are NULL");
+  {  // row_ptr must start at 0 and never decrease (the GPU builder rejects the same input, LbRowHeads)
+    int bad = row_ptr[0] != 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t r = 0; r < (int64_t)rows; r++) bad |= row_ptr[r + 1] < row_ptr[r];
+    if (bad) return fail(SPMVB_E_ARG, "row_ptr must start at 0 and be non-decreasing");
+  }
 
   Layout *L = new Layout();
   {
@@ -412,7 +484,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     uint64_t nz = 0;
     for (uint32_t r = 0; r < rows; r++) nz += needz[r];
     L->zero_all = nz > (uint64_t)rows / 3;
-    if (getenv("SPMVB_ZERO_ALL")) L->zero_all = true;
+    if (options().zero_all > 0) L->zero_all = true;
     if (!L->zero_all) {
       L->zero_rows.reserve(nz);
       for (uint32_t r = 0; r < rows; r++)
@@ -423,21 +495,35 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   // column range of every chunk (real entries only)
   L->chunk_col_lo.assign((size_t)L->n_chunks, 0xFFFF);
   L->chunk_col_hi.assign((size_t)L->n_chunks, 0);
+  L->chunk_x_lines.assign((size_t)L->n_chunks, 0);
+  const int line_shift = vb == 8 ? 4 : 5;  // columns per 128-byte line of x: 16 (fp64) / 32 (fp32)
 #pragma omp parallel for schedule(static)
   for (int64_t c = 0; c < (int64_t)L->n_chunks; c++) {
     const uint32_t valid = L->chunks[c].valid & 0x3FFu;
     const uint8_t *base = L->stream + (uint64_t)c * L->chunk_bytes;
     uint16_t lo = 0xFFFF, hi = 0;
-    uint32_t row_ends = 0;
+    uint32_t row_ends = 0, lines = 0;
+    uint32_t seen[64] = {0};  // 32768 columns >> 4 = 2048 lines at most
     for (uint32_t e = 0; e < valid; e++) {
       uint16_t ci;
       memcpy(&ci, base + (size_t)(e / kRatioCi) * gb + 2 * (e % kRatioCi), 2);
       row_ends += ci >> 15;
       ci &= 0x7FFF;
       lo = std::min(lo, ci); hi = std::max(hi, ci);
+      const uint32_t ln = (uint32_t)ci >> line_shift, bit = 1u << (ln & 31);
+      lines += !(seen[ln >> 5] & bit);
+      seen[ln >> 5] |= bit;
     }
-    L->chunk_col_lo[c] = lo; L->chunk_col_hi[c] = hi;
+    L->chunk_col_lo[c] = lo; L->chunk_col_hi[c] = hi; L->chunk_x_lines[c] = (uint16_t)lines;
     L->chunks[c].block = (L->chunks[c].block & kMetaBlockMask) | (row_ends << kMetaRowsShift);
+  }
+
+  // the engine-private device layout, when the API parameters are not what the GPU should stream
+  int cu_dev = cu, vf_dev = vf;
+  uint32_t cdb_dev = cdb;
+  if (plan_device && plan_device_params(L, &cu_dev, &vf_dev, &cdb_dev)) {
+    int rc = build_impl<RP>(rows, cols, row_ptr, col_ind, values, cu_dev, vf_dev, is_double, cdb_dev, &L->dev, false);
+    if (rc) { delete L; return rc; }
   }
 
   *out = L;
@@ -452,7 +538,31 @@ using namespace spmvb;
 extern "C" {
 
 const char *spmvb_last_error(void) { return last_error_cstr(); }
-int spmvb_version(void) { return 100; }
+int spmvb_version(void) { return 200; }
+
+int spmvb_set_option(const char *name, int64_t value) {
+  if (!name) return fail(SPMVB_E_ARG, "set_option: NULL");
+  for (const OptionName &n : kOptionNames)
+    if (strcmp(n.name, name) == 0) { options().*(n.field) = value; return SPMVB_OK; }
+  return fail(SPMVB_E_ARG, std::string("set_option: unknown option ") + name);
+}
+int64_t spmvb_get_option(const char *name) {
+  if (name)
+    for (const OptionName &n : kOptionNames)
+      if (strcmp(n.name, name) == 0) return options().*(n.field);
+  return INT64_MIN;
+}
+// SPMVB_<NAME>=<integer> for every option; meant for executables that have no other way to be configured (the
+// reference's run.elf takes compile-time macros only).  Returns the number of variables applied.
+int spmvb_options_from_env(void) {
+  int n = 0;
+  for (const OptionName &nm : kOptionNames) {
+    std::string var = "SPMVB_";
+    for (const char *p = nm.name; *p; p++) var += (char)toupper((unsigned char)*p);
+    if (const char *v = getenv(var.c_str())) { options().*(nm.field) = atoll(v); n++; }
+  }
+  return n;
+}
 
 int spmvb_layout_build(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, const uint32_t *col_ind,
                        const void *values, int n_cu, int vf, int is_double, uint32_t cols_div_blocks,
@@ -479,9 +589,14 @@ uint64_t spmvb_layout_real_nnz(const spmvb_layout *l) { return ((const Layout *)
 uint64_t spmvb_layout_padded_nnz(const spmvb_layout *l) { return ((const Layout *)l)->padded_nnz; }
 uint64_t spmvb_layout_pairs(const spmvb_layout *l) { return ((const Layout *)l)->n_pairs; }
 uint64_t spmvb_layout_stream_bytes(const spmvb_layout *l) { return ((const Layout *)l)->stream_bytes; }
-uint64_t spmvb_layout_chunks(const spmvb_layout *l) { return ((const Layout *)l)->n_chunks; }
+// chunks are units of the device image: these two describe the engine-private device layout when there is one
+uint64_t spmvb_layout_chunks(const spmvb_layout *l) {
+  const Layout *L = (const Layout *)l;
+  return (L->dev ? L->dev : L)->n_chunks;
+}
 int spmvb_layout_chunk_cols(const spmvb_layout *l, uint64_t c, uint32_t *lo, uint32_t *hi, uint32_t *block) {
   const Layout *L = (const Layout *)l;
+  if (L && L->dev) L = L->dev;
   if (!L || c >= L->n_chunks) return fail(SPMVB_E_ARG, "chunk index");
   if (lo) *lo = L->chunk_col_lo[c];
   if (hi) *hi = L->chunk_col_hi[c];
@@ -561,11 +676,11 @@ int spmvb_layout_pack_x(const spmvb_layout *l, const void *x, uint32_t n, void *
   return SPMVB_OK;
 }
 
-int spmvb_layout_equal(const spmvb_layout *a, const spmvb_layout *b, char *why, size_t why_len) {
-  const Layout *A = (const Layout *)a, *B = (const Layout *)b;
+static int layout_equal_impl(const Layout *A, const Layout *B, char *why, size_t why_len, bool need_image) {
   auto say = [&](const char *what) { if (why && why_len) snprintf(why, why_len, "%s", what); return 0; };
   if (!A || !B) return fail(SPMVB_E_ARG, "layout_equal: NULL");
-  if (!A->stream || !B->stream || !A->rowmap || !B->rowmap)
+  const bool images = A->stream && B->stream && A->rowmap && B->rowmap;
+  if (need_image && !images)
     return fail(SPMVB_E_ARG, "layout_equal: host image not present (spmvb_engine_fetch_layout)");
   if (A->cu != B->cu || A->vf != B->vf || A->is_double != B->is_double || A->blocks != B->blocks || A->rows != B->rows ||
       A->cols != B->cols || A->expanded_cols != B->expanded_cols || A->cdb != B->cdb || A->real_nnz != B->real_nnz ||
@@ -579,8 +694,8 @@ int spmvb_layout_equal(const spmvb_layout *a, const spmvb_layout *b, char *why, 
       A->dev_order != B->dev_order || A->piece_real_nnz != B->piece_real_nnz)
     return say("piece tables");
   if (A->rank_base != B->rank_base) return say("rank_base");
-  if (memcmp(A->rowmap, B->rowmap, (size_t)A->n_pairs * 4) != 0) return say("rowmap");
-  if (memcmp(A->stream, B->stream, (size_t)A->stream_bytes) != 0) return say("stream");
+  if (images && memcmp(A->rowmap, B->rowmap, (size_t)A->n_pairs * 4) != 0) return say("rowmap");
+  if (images && memcmp(A->stream, B->stream, (size_t)A->stream_bytes) != 0) return say("stream");
   for (uint64_t c = 0; c < A->n_chunks; c++)
     if (memcmp(&A->chunks[c], &B->chunks[c], sizeof(ChunkMeta)) != 0) {
       if (why && why_len)
@@ -592,8 +707,32 @@ int spmvb_layout_equal(const spmvb_layout *a, const spmvb_layout *b, char *why, 
   if (A->zero_all != B->zero_all) return say("zero_all");
   if (A->zero_rows != B->zero_rows) return say("zero_rows");
   if (A->chunk_col_lo != B->chunk_col_lo || A->chunk_col_hi != B->chunk_col_hi) return say("chunk column ranges");
+  if (A->chunk_x_lines != B->chunk_x_lines) return say("chunk x lines");
+  if ((A->dev != nullptr) != (B->dev != nullptr)) return say("device layout present in one only");
+  if (A->dev) {  // the engine-private device layout: its image stays on the GPU when it was built there
+    char sub[200] = "";
+    const int r = layout_equal_impl(A->dev, B->dev, sub, sizeof sub, false);
+    if (r != 1) {
+      if (why && why_len) snprintf(why, why_len, "device layout: %s", sub);
+      return r;
+    }
+  }
   if (why && why_len) why[0] = 0;
   return 1;
+}
+
+int spmvb_layout_equal(const spmvb_layout *a, const spmvb_layout *b, char *why, size_t why_len) {
+  return layout_equal_impl((const Layout *)a, (const Layout *)b, why, why_len, true);
+}
+
+int spmvb_layout_device_params(const spmvb_layout *l, uint64_t *out) {
+  const Layout *L = (const Layout *)l;
+  if (!L || !out) return fail(SPMVB_E_ARG, "device_params");
+  const Layout *D = L->dev ? L->dev : L;
+  out[0] = (uint64_t)D->cu; out[1] = (uint64_t)D->vf; out[2] = D->cdb; out[3] = D->cu_major ? 1u : 0u;
+  out[4] = L->dev ? 1u : 0u; out[5] = D->n_pairs; out[6] = D->n_chunks;
+  out[7] = D->zero_all ? UINT64_MAX : (uint64_t)D->zero_rows.size(); out[8] = D->stream_bytes;
+  return SPMVB_OK;
 }
 
 int spmvb_partition_rows(uint32_t rows, const uint64_t *row_ptr, int parts, int ratio_v, uint32_t *bounds) {

@@ -60,8 +60,8 @@ struct CudaBackend {
   int code() const { return SPMVB_E_CUDA; }
   std::string error() const { return "GPU layout build: " + where + ": " + cudaGetErrorString(e); }
 
-  // SPMVB_BUILD_TRACE=1: wait for the stream after every stage and print the time it took (diagnostics)
-  bool tracing = getenv("SPMVB_BUILD_TRACE") != nullptr;
+  // option build_trace = 1: wait for the stream after every stage and print the time it took (diagnostics)
+  bool tracing = options().build_trace > 0;
   double t_last = omp_get_wtime();
   void trace(const char *what) {
     if (!tracing) return;

@@ -94,6 +94,7 @@ struct LbCtx {
   uint8_t *image;    // OUTPUT n_chunks slots of chunk_bytes + 16
   ChunkMeta *metas;  // OUTPUT compact copy of the slot metadata
   uint16_t *col_lo, *col_hi;  // OUTPUT
+  uint16_t *x_lines;          // OUTPUT distinct 128-byte lines of x per chunk
   uint8_t *needz;    // [rows] OUTPUT row must be cleared before y = A x
   uint32_t *err;     // OR of LbError
 };
@@ -129,7 +130,7 @@ SPMVB_HD void lb_write_ci(const LbCtx &c, uint64_t bk, uint64_t e, uint16_t ci) 
 struct LbRowHeads {
   static SPMVB_HD void run(uint64_t r, const LbCtx &c) {
     const uint64_t a = c.row_ptr[r], b = c.row_ptr[r + 1];
-    if (b < a || b > c.nnz) { lb_flag(c.err, kLbErrRowPtr); return; }
+    if (b < a || b > c.nnz || (r == 0 && a != 0)) { lb_flag(c.err, kLbErrRowPtr); return; }
     if (a < b) c.head[a] = 1;
   }
 };
@@ -348,6 +349,7 @@ struct LbChunks {
     m.valid = valid;
     m.row_first = 0;
     uint16_t clo = 0xFFFF, chi = 0;
+    uint32_t lines = 0;
     if (valid) {
       if (c.cmid[ch]) m.valid |= kChunkStartsMid;
       m.row_first = c.rowmap[m.rank0];
@@ -364,6 +366,9 @@ struct LbChunks {
         for (uint64_t rk = m.rank0; rk <= last_rank; rk++) c.needz[c.rowmap[rk]] = 1;
       const uint8_t *base = c.image + ch * (uint64_t)c.slot;
       uint32_t row_ends = 0;
+      uint32_t seen[64];
+      for (int i = 0; i < 64; i++) seen[i] = 0;
+      const int line_shift = c.vb == 8 ? 4 : 5;
       for (uint32_t g = 0; g * kRatioCi < valid; g++) {
         const uint16_t *w = reinterpret_cast<const uint16_t *>(base + (uint64_t)g * c.gb);
         const uint32_t n = valid - g * kRatioCi < (uint32_t)kRatioCi ? valid - g * kRatioCi : (uint32_t)kRatioCi;
@@ -373,11 +378,14 @@ struct LbChunks {
           ci &= 0x7FFF;
           if (ci < clo) clo = ci;
           if (ci > chi) chi = ci;
+          const uint32_t ln = (uint32_t)ci >> line_shift, bit = 1u << (ln & 31);
+          lines += !(seen[ln >> 5] & bit);
+          seen[ln >> 5] |= bit;
         }
       }
       m.block |= row_ends << kMetaRowsShift;
     }
-    c.col_lo[ch] = clo; c.col_hi[ch] = chi;
+    c.col_lo[ch] = clo; c.col_hi[ch] = chi; c.x_lines[ch] = (uint16_t)lines;
     c.metas[ch] = m;
     *reinterpret_cast<ChunkMeta *>(c.image + ch * (uint64_t)c.slot + c.chunk_bytes) = m;
   }
@@ -396,7 +404,7 @@ inline std::string lb_error_text(uint32_t err) {
   if (err & kLbErrColRange) s += "column index out of range; ";
   if (err & kLbErrBlockOrder) s += "column blocks do not ascend inside a row; ";
   if (err & kLbErrBlockOverflow) s += "block nnz overflows IndexType; ";
-  if (err & kLbErrRowPtr) s += "row_ptr is not monotone; ";
+  if (err & kLbErrRowPtr) s += "row_ptr must start at 0 and be non-decreasing; ";
   return s;
 }
 
@@ -504,7 +512,7 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   if (n_pairs >= 0x7FFFFFF0ull) return bail(SPMVB_E_RANGE, "too many (row, block) pairs for the GPU builder");
 
   be.reserve((n_pairs + 1) * 64 + (uint64_t)blocks * (cu + 1) * 8 + KB * 48 + kSlack);
-  c.rowmap = (uint32_t *)be.alloc_output((n_pairs + 1) * 4);
+  c.rowmap = (uint32_t *)be.alloc_output((n_pairs + 8) * 4);  // slack: the kernels copy 16-byte aligned slices
   img->rowmap = c.rowmap;
   c.plen = (uint32_t *)T(be.alloc((n_pairs + 1) * 4));
   c.gpos = (uint64_t *)T(be.alloc((n_pairs + 1) * 8));
@@ -577,12 +585,13 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   // ---- 4. the image
   const uint64_t n_chunks = L->n_chunks;
   const size_t image_bytes = (size_t)(n_chunks * (uint64_t)c.slot > 16 ? n_chunks * (uint64_t)c.slot : 16);
-  be.reserve((n_chunks + 1) * 32 + (uint64_t)rows / 2 + kSlack);
+  be.reserve((n_chunks + 1) * 36 + (uint64_t)rows / 2 + kSlack);
   c.image = (uint8_t *)be.alloc_output(image_bytes);
   img->image = c.image;
   c.crank0 = (uint32_t *)T(be.alloc((n_chunks + 1) * 4)); c.cmid = (uint8_t *)T(be.alloc(n_chunks + 1));
   c.metas = (ChunkMeta *)T(be.alloc((n_chunks + 1) * sizeof(ChunkMeta)));
   c.col_lo = (uint16_t *)T(be.alloc((n_chunks + 1) * 2)); c.col_hi = (uint16_t *)T(be.alloc((n_chunks + 1) * 2));
+  c.x_lines = (uint16_t *)T(be.alloc((n_chunks + 1) * 2));
   LB_CHECK();
   be.trace("piece tables + image alloc");
   be.fill(c.image, 0, image_bytes);
@@ -601,10 +610,12 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   be.to_host(L->chunks, c.metas, n_chunks * sizeof(ChunkMeta));
   be.to_host(L->chunk_col_lo.data(), c.col_lo, n_chunks * 2);
   be.to_host(L->chunk_col_hi.data(), c.col_hi, n_chunks * 2);
+  L->chunk_x_lines.assign((size_t)n_chunks, 0);
+  be.to_host(L->chunk_x_lines.data(), c.x_lines, n_chunks * 2);
   const uint64_t nz = be.count_nonzero_u8(c.needz, rows);
   LB_CHECK();
   L->zero_all = nz > (uint64_t)rows / 3;
-  if (getenv("SPMVB_ZERO_ALL")) L->zero_all = true;
+  if (options().zero_all > 0) L->zero_all = true;
   if (!L->zero_all && nz) {
     img->zero_rows = (uint32_t *)be.alloc_output(nz * 4);
     LB_CHECK();
@@ -621,6 +632,29 @@ int lb_build(BE &be, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t 
   cleanup(true);
   *out = L;
   return SPMVB_OK;
+}
+
+// The API layout and - when plan_device_params asks for one - the engine-private device layout (Layout::dev), each
+// built by lb_build with a backend of its own (their temporaries never live at the same time).  *dev_img stays empty
+// when the API image is what the device streams.
+template <class BE>
+int lb_build_pair(BE &be_api, BE &be_dev, uint32_t rows, uint32_t cols, uint64_t nnz, const uint64_t *d_row_ptr,
+                  const uint32_t *d_col_ind, const void *d_values, int cu, int vf, int is_double, uint32_t cdb_in,
+                  Layout **out, LbImage *api_img, LbImage *dev_img) {
+  int rc = lb_build(be_api, rows, cols, nnz, d_row_ptr, d_col_ind, d_values, cu, vf, is_double, cdb_in, out, api_img);
+  if (rc) return rc;
+  Layout *L = *out;
+  int cu_dev = cu, vf_dev = vf;
+  uint32_t cdb_dev = L->cdb;
+  if (!plan_device_params(L, &cu_dev, &vf_dev, &cdb_dev)) return SPMVB_OK;
+  rc = lb_build(be_dev, rows, cols, nnz, d_row_ptr, d_col_ind, d_values, cu_dev, vf_dev, is_double, cdb_dev, &L->dev, dev_img);
+  if (rc) {
+    be_api.release_output(api_img->image); be_api.release_output(api_img->rowmap); be_api.release_output(api_img->zero_rows);
+    *api_img = LbImage();
+    delete L;
+    *out = nullptr;
+  }
+  return rc;
 }
 
 // Brings the two big arrays of a GPU-built layout to the host: the pieces (slots stripped of their metadata, i.e.

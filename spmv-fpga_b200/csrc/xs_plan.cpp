@@ -14,7 +14,7 @@ namespace spmvb {
 // U = run length x warps per CTA, so that every warp of the CTA gets the same number of whole runs per item.
 void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<XsItem> &items,
                            std::vector<uint32_t> &cta_first) {
-  const uint64_t U = ((uint64_t)1 << run_log2) * kXsWarps;
+  const uint64_t U = ((uint64_t)1 << run_log2) * (uint64_t)xs_warps(L->is_double);
   const uint32_t align = 16u / (uint32_t)L->vb;  // window start in elements: 16-byte aligned for the bulk copy
   // candidate cut points in global chunk indices: block starts and block-relative multiples of U
   std::vector<uint64_t> cuts;
@@ -97,7 +97,8 @@ using namespace spmvb;
 extern "C" int64_t spmvb_layout_xs_plan(const spmvb_layout *l, int n_cta, int run_log2, uint32_t *items_out,
                                         uint64_t max_items, uint32_t *cta_first_out) {
   const Layout *L = (const Layout *)l;
-  if (!L || n_cta < 1 || run_log2 < L->run_log2 || run_log2 > 8) return fail(SPMVB_E_ARG, "xs_plan");
+  if (!L || n_cta < 1 || run_log2 < 1 || run_log2 < L->run_log2 || run_log2 > 8) return fail(SPMVB_E_ARG, "xs_plan");
+  if (L->dev) L = L->dev;  // the plan is made for what the GPU streams
   std::vector<XsItem> items;
   std::vector<uint32_t> cta_first;
   build_xs_items(L, n_cta, (uint32_t)run_log2, items, cta_first);

@@ -21,6 +21,12 @@ _int = ctypes.c_int
 SYMBOLS = {
     "spmvb_last_error": (ctypes.c_char_p, []),
     "spmvb_version": (_int, []),
+    "spmvb_set_option": (_int, [ctypes.c_char_p, ctypes.c_int64]),
+    "spmvb_get_option": (ctypes.c_int64, [ctypes.c_char_p]),
+    "spmvb_options_from_env": (_int, []),
+    "spmvb_layout_device_params": (_int, [_vp, _vp]),
+    "spmvb_engine_last_iter_ms": (ctypes.c_float, [_vp]),
+    "spmvb_engine_device_layout": (_int, [_vp, _vp]),
     "spmvb_layout_build": (_int, [_u32, _u32, _vp, _vp, _vp, _int, _int, _int, _u32, _vp]),
     "spmvb_layout_build_u32": (_int, [_u32, _u32, _vp, _vp, _vp, _int, _int, _int, _u32, _vp]),
     "spmvb_layout_free": (None, [_vp]),
@@ -127,6 +133,32 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise SpmvbError(rc, lib().spmvb_last_error().decode(errors="replace"))
+
+
+def set_option(name, value):
+    """Process-wide tuning option (include/spmvb.h: spmvb_set_option); -1 restores the library's own choice."""
+    _check(lib().spmvb_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    return int(lib().spmvb_get_option(name.encode()))
+
+
+class options:
+    """with spmvb.options(cu_major=1, tall=1): ...  - sets the options and restores the previous values on exit."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        self.old = {k: get_option(k) for k in self.kw}
+        for k, v in self.kw.items():
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
 
 
 def _ptr(a):
@@ -265,6 +297,15 @@ class Layout:
         _check(lib().spmvb_layout_build_csr(csr.h, n_cu, vf, cols_div_blocks, ctypes.byref(out)))
         return Layout(out.value, csr.is_double)
 
+    @property
+    def device_params(self):
+        """What the GPU streams: dict(cu, vf, cdb, cu_major, private, pairs, chunks, zero_rows (-1 = all), bytes)."""
+        out = (ctypes.c_uint64 * 9)()
+        _check(lib().spmvb_layout_device_params(self.h, out))
+        v = [int(x) for x in out]
+        return dict(cu=v[0], vf=v[1], cdb=v[2], cu_major=bool(v[3]), private=bool(v[4]), pairs=v[5], chunks=v[6],
+                    zero_rows=-1 if v[7] == 2 ** 64 - 1 else v[7], bytes=v[8])
+
     def difference(self, other):
         """'' if both layouts are identical in every table and byte, else the first component that differs."""
         why = ctypes.create_string_buffer(256)
@@ -398,6 +439,19 @@ class Engine:
         out = (ctypes.c_float * 3)()
         _check(lib().spmvb_engine_build_ms(self.h, out))
         return {"h2d_ms": out[0], "build_ms": out[1], "total_ms": out[2]}
+
+    @property
+    def last_iter_ms(self):
+        """Device time per iteration of the last power_iter / cg call (CUDA events)."""
+        return float(lib().spmvb_engine_last_iter_ms(self.h))
+
+    @property
+    def device_layout(self):
+        out = (ctypes.c_uint64 * 10)()
+        _check(lib().spmvb_engine_device_layout(self.h, out))
+        v = [int(x) for x in out]
+        return dict(cu=v[0], vf=v[1], cdb=v[2], cu_major=bool(v[3]), pairs=v[4], chunks=v[5],
+                    zero_rows=-1 if v[6] == 2 ** 64 - 1 else v[6], bytes=v[7], xs_rowids=bool(v[8]), tall=bool(v[9]))
 
     def set_variant(self, v):
         _check(lib().spmvb_engine_set_variant(self.h, v))

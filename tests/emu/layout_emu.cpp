@@ -76,17 +76,26 @@ extern "C" int emu_layout_build(uint32_t rows, uint32_t cols, const uint64_t *ro
                                 const void *values, int n_cu, int vf, int is_double, uint32_t cols_div_blocks,
                                 spmvb_layout **out) {
   if (!out || !row_ptr) return SPMVB_E_ARG;
-  HostBackend be;
+  HostBackend be, be_dev;
   Layout *L = nullptr;
-  LbImage img;
-  int rc = lb_build(be, rows, cols, row_ptr[rows], row_ptr, col_ind, values, n_cu, vf, is_double, cols_div_blocks, &L, &img);
+  LbImage img, img_dev;
+  // the same two-step build as spmvb_engine_create_from_csr: API layout, then the engine-private device layout
+  int rc = lb_build_pair(be, be_dev, rows, cols, row_ptr[rows], row_ptr, col_ind, values, n_cu, vf, is_double,
+                         cols_div_blocks, &L, &img, &img_dev);
   if (rc) return rc;
   rc = lb_fetch_host(be, L, img);
+  if (rc == SPMVB_OK && L->dev) rc = lb_fetch_host(be_dev, L->dev, img_dev);
   // the slot metadata inside the image must equal the compact copy
-  const size_t slot = (size_t)L->chunk_bytes + sizeof(ChunkMeta);
-  for (uint64_t c = 0; c < L->n_chunks && rc == SPMVB_OK; c++)
-    if (memcmp(img.image + c * slot + L->chunk_bytes, &L->chunks[c], sizeof(ChunkMeta)) != 0) rc = fail(SPMVB_E_ARG, "slot meta");
+  for (int which = 0; which < 2 && rc == SPMVB_OK; which++) {
+    const Layout *X = which ? L->dev : L;
+    const LbImage &xi = which ? img_dev : img;
+    if (!X) continue;
+    const size_t slot = (size_t)X->chunk_bytes + sizeof(ChunkMeta);
+    for (uint64_t c = 0; c < X->n_chunks && rc == SPMVB_OK; c++)
+      if (memcmp(xi.image + c * slot + X->chunk_bytes, &X->chunks[c], sizeof(ChunkMeta)) != 0) rc = fail(SPMVB_E_ARG, "slot meta");
+  }
   be.release_output(img.image); be.release_output(img.rowmap); be.release_output(img.zero_rows);
+  be.release_output(img_dev.image); be.release_output(img_dev.rowmap); be.release_output(img_dev.zero_rows);
   if (rc) { delete L; return rc; }
   *out = (spmvb_layout *)L;
   return SPMVB_OK;

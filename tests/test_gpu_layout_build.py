@@ -60,12 +60,12 @@ def test_gpu_built_image_equals_host_built(spmvb, oracle, case, cfg):
 
 
 @pytest.mark.parametrize("cdb", [16384, 256, 12])
-def test_gpu_builder_custom_block_width_cu_major(spmvb, oracle, cdb, monkeypatch):
+def test_gpu_builder_custom_block_width_cu_major(spmvb, oracle, cdb):
     M = matgen.uniform(3000, 40000, 9, seed=4, empty_frac=0.3)
     rows, cols, rp, ci, va = M
-    monkeypatch.setenv("SPMVB_CU_MAJOR", "1")
-    host = spmvb.Layout.build(rows, cols, rp, ci, va, 4, 2, True, cdb)
-    lay, eng = spmvb.Engine.from_csr(rows, cols, rp, ci, va, 4, 2, True, cdb)
+    with spmvb.options(cu_major=1):
+        host = spmvb.Layout.build(rows, cols, rp, ci, va, 4, 2, True, cdb)
+        lay, eng = spmvb.Engine.from_csr(rows, cols, rp, ci, va, 4, 2, True, cdb)
     eng.fetch_layout()
     assert host.difference(lay) == ""
     _parity(oracle, eng, M, True)

@@ -147,13 +147,13 @@ def test_config2_scale_every_variant_repeated(spmvb, oracle, variant):
 
 
 @pytest.mark.parametrize("variant", [7, 8])
-def test_cu_major_device_order(spmvb, oracle, monkeypatch, variant):
+def test_cu_major_device_order(spmvb, oracle, variant):
     """CU-major order of the pieces on the device (used when y does not fit the L2 cache): same results."""
-    monkeypatch.setenv("SPMVB_CU_MAJOR", "1")
-    monkeypatch.setenv("SPMVB_TALL", "1")  # and the explicit L2 eviction policies of the tall-matrix path
-    _check(spmvb, oracle, matgen.uniform(6000, 100000, 12, seed=8), 4, 1, True, variant)
-    _check(spmvb, oracle, matgen.ragged(5000, 100000, seed=7), 8, 4, False, variant)
-    _check(spmvb, oracle, matgen.laplacian2d(256, 256), 2, 2, True, variant, cdb=16384)
+    # cu_major + the explicit L2 eviction policies of the tall-matrix path
+    with spmvb.options(cu_major=1, tall=1):
+        _check(spmvb, oracle, matgen.uniform(6000, 100000, 12, seed=8), 4, 1, True, variant)
+        _check(spmvb, oracle, matgen.ragged(5000, 100000, seed=7), 8, 4, False, variant)
+        _check(spmvb, oracle, matgen.laplacian2d(256, 256), 2, 2, True, variant, cdb=16384)
 
 
 @pytest.mark.parametrize("variant", [7, 8])

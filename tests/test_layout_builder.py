@@ -108,8 +108,10 @@ def test_zero_row_list_covers_every_row_not_plainly_stored(spmvb):
 @pytest.mark.parametrize("case", ["lap", "rmat", "uniform16k", "ragged"])
 def test_xs_plan_tiles_the_stream_and_windows_cover_the_columns(spmvb, case):
     """Work plan of the shared-memory-x kernel (host side of spmv_xs_kernel): items tile the chunk range exactly, each
-    lies in one column block, is cut at block-relative multiples of run x 16 warps, and its x window (<= 128 KB, 16-byte
-    aligned) covers every column its chunks touch."""
+    lies in one column block, is cut at block-relative multiples of run x 12 warps (fp64), and its x window (<= 128 KB,
+    16-byte aligned) covers every column its chunks touch.  The plan is made for what the GPU streams: an irregular fp64
+    matrix with 32 768-column API blocks gets an engine-private device layout with 16 384-column blocks (x slice of a
+    block = 128 KB = the kernel's window, the split on index bit 14), so every window fits."""
     if case == "lap":
         rows, cols, rp, ci, va = matgen.laplacian2d(400, 300)
         cdb = 0
@@ -125,7 +127,8 @@ def test_xs_plan_tiles_the_stream_and_windows_cover_the_columns(spmvb, case):
     lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True, cdb)
     n_cta, run_log2 = 12, 1
     items, first = lay.xs_plan(n_cta, run_log2)
-    unit = (1 << run_log2) * 16
+    unit = (1 << run_log2) * 12
+    dp = lay.device_params
     assert first[0] == 0 and first[-1] == len(items) and np.all(np.diff(first.astype(np.int64)) >= 0)
     pos = 0
     block_start = {}
@@ -137,7 +140,7 @@ def test_xs_plan_tiles_the_stream_and_windows_cover_the_columns(spmvb, case):
         assert begin == pos and count > 0
         pos += count
         assert (begin - block_start[block]) % unit == 0
-        width = cdb or 32768
+        width = dp["cdb"]
         for c in range(begin, begin + count):
             lo, hi, b = lay.chunk_cols(c)
             assert b == block
@@ -149,21 +152,22 @@ def test_xs_plan_tiles_the_stream_and_windows_cover_the_columns(spmvb, case):
     assert pos == lay.n_chunks
     per_cta = [int(items[first[j]:first[j + 1], 1].sum()) for j in range(n_cta)]
     assert max(per_cta) - min(per_cta) <= 2 * unit + max(1, lay.n_chunks // n_cta // 4)
-    if case in ("lap", "uniform16k"):
-        assert np.all(items[:, 3] > 0)      # every window fits shared memory
-    if case == "rmat":
-        assert np.any(items[:, 3] == 0)     # fp64 x slice of a 32768-column block of an irregular matrix: 256 KB
+    assert np.all(items[:, 3] > 0)          # every window fits shared memory
+    if case in ("rmat", "ragged"):          # fp64 x slice of a 32768-column block of an irregular matrix: 256 KB
+        assert dp["private"] and dp["cdb"] == 16384 and lay.blocks == -(-cols // 32768)
+    else:
+        assert not dp["private"] and dp["cdb"] == (cdb or 32768)
 
 
-def test_cu_major_device_order_keeps_pieces_bit_exact(spmvb, oracle, monkeypatch):
+def test_cu_major_device_order_keeps_pieces_bit_exact(spmvb, oracle):
     """The device order of the pieces (block-major or CU-major) is an engine decision: the pieces themselves do not
     change, and the work plan still tiles the stream."""
     rows, cols, rp, ci, va = matgen.uniform(6000, 100000, 12, seed=8)
     ho = oracle.build(rows, cols, rp, ci, va, 4, 2, True)
     ref = oracle.snapshot(ho, rows, 4, 2, True)
-    for flag in ("0", "1"):
-        monkeypatch.setenv("SPMVB_CU_MAJOR", flag)
-        lay = spmvb.Layout.build(rows, cols, rp, ci, va, 4, 2, True)
+    for flag in (0, 1):
+        with spmvb.options(cu_major=flag, dev_tiles=4, dev_cdb=32768):  # the device layout = the API layout
+            lay = spmvb.Layout.build(rows, cols, rp, ci, va, 4, 2, True)
         assert oa.layouts_equal(ref, product_snapshot(lay, 4, 2, True)) == []
         items, first = lay.xs_plan(7, 1)
         assert int(items[:, 1].sum()) == lay.n_chunks

@@ -69,17 +69,17 @@ def test_gpu_builder_steps_custom_block_width_and_empty_rows(spmvb, emu, cdb):
         host.free(); dev.free()
 
 
-def test_gpu_builder_steps_cu_major_and_run_granularity(spmvb, emu, monkeypatch):
+def test_gpu_builder_steps_cu_major_and_run_granularity(spmvb, emu):
     rows, cols, rp, ci, va = matgen.uniform(3000, 100000, 12, seed=5)
-    for env in ({"SPMVB_CU_MAJOR": "1"}, {"SPMVB_RUN_LOG2": "3"}, {"SPMVB_ZERO_ALL": "1"}):
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        host = spmvb.Layout.build(rows, cols, rp, ci, va, 4, 1, True, 16384)
-        dev = emu(rows, cols, rp, ci, va, 4, 1, True, 16384)
-        assert host.difference(dev) == ""
-        host.free(); dev.free()
-        for k in env:
-            monkeypatch.delenv(k)
+    for opt in ({"cu_major": 1}, {"run_log2": 3}, {"zero_all": 1}, {"dev_tiles": 3, "dev_cdb": 8192}):
+        with spmvb.options(**opt):
+            host = spmvb.Layout.build(rows, cols, rp, ci, va, 4, 1, True, 16384)
+            dev = emu(rows, cols, rp, ci, va, 4, 1, True, 16384)
+            assert host.difference(dev) == ""
+            if "dev_tiles" in opt:  # an engine-private device layout next to untouched API pieces
+                assert host.device_params["private"] and host.device_params["cu"] == 3 and host.device_params["cdb"] == 8192
+                assert host.n_cu == 4
+            host.free(); dev.free()
 
 
 def test_gpu_builder_steps_degenerate_inputs(spmvb, emu):
