@@ -307,11 +307,17 @@ static inline void spmv_hw(csr_hw_matrix **hw_matrix, csr_hw_vector *hw_x, csr_v
   (void)empty_rows_bitmap; /* the device keeps the bitmap in its compact row-map form */
   spmvb_compat_owner *o = (spmvb_compat_owner *)hw_matrix[0];
   if (o->magic != SPMVB_COMPAT_MAGIC) { fprintf(stderr, "spmv_hw: hw_matrix was not made by create_csr_hw_matrix\n"); abort(); }
-  /* hw_x is x in block order: concatenate the slices again */
+  /* hw_x is x in block order: concatenate the slices again.  It must be the vector create_csr_hw_x_vector made for
+   * THIS matrix (same blocks, nr_values[b] = nr_cols[b], a whole number of bus words each): anything else would overrun
+   * x_scratch, which holds expanded_nr_cols values */
+  const uint32_t cap = spmvb_layout_expanded_cols(o->layout);
   uint32_t n = 0;
+  if (hw_x->blocks != hw_matrix[0]->blocks) { fprintf(stderr, "spmv_hw: hw_x has %d blocks, the matrix %d\n", hw_x->blocks, hw_matrix[0]->blocks); abort(); }
   for (int b = 0; b < hw_x->blocks; b++) {
-    memcpy(o->x_scratch + n, hw_x->values[b], (size_t)hw_x->nr_values[b] * sizeof(ValueType));
-    n += hw_x->nr_values[b];
+    const uint32_t nv = hw_x->nr_values[b];
+    if (nv % RATIO_v != 0 || nv > cap - n) { fprintf(stderr, "spmv_hw: hw_x block %d does not belong to this matrix\n", b); abort(); }
+    memcpy(o->x_scratch + n, hw_x->values[b], (size_t)nv * sizeof(ValueType));
+    n += nv;
   }
   double t0 = getTimestamp();
   if (spmvb_engine_spmv_host(o->engine, o->x_scratch, n, y_fpga->values, 1) != SPMVB_OK) spmvb_compat_die("spmv_hw");

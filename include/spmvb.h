@@ -212,6 +212,44 @@ int spmvb_engine_scale_rsqrt(spmvb_engine *e, const void *src_dev, void *dst_dev
 /* sum of squares of y_dev[0..n) into a device double (for the norm all-reduce) */
 int spmvb_engine_sumsq(spmvb_engine *e, const void *src_dev, uint32_t n, double *out_dev, void *stream);
 
+/* ------------------------------------------------------------------ multi-GPU (the CU dimension mapped to GPUs) */
+
+/* A group of engines over one matrix: every GPU owns a contiguous row range balanced by non-zero count
+ * (spmvb_partition_rows), the hw_matrix layout of its own rows, all of x and its slice of y.  Replaces the reference's
+ * CU > 1 dispatch, where all compute units run inside one spmv() call with a private x each
+ * (spmv.cpp:249-294; csr_hw_wrapper.cpp:3-80, 202-271).  A single SpMV needs no collective; the iterated caller
+ * exchanges the y slices into every GPU's x over NVLink (NCCL, loaded on first use). */
+typedef struct spmvb_group spmvb_group;
+/* One process drives n_devices GPUs (devices NULL = 0 .. n_devices-1): what a -DCU=n program of the reference becomes. */
+int spmvb_group_create(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, const uint32_t *col_ind,
+                       const void *values, int is_double, int n_devices, const int *devices, int variant,
+                       spmvb_group **out);
+/* This process is rank `rank` of `world` (one process per GPU, e.g. under torchrun).  bounds[world + 1] = the row
+ * ownership of ALL ranks, the CSR holds this rank's rows only (row_ptr_local rebased to 0, global column indices).
+ * unique_id128 = the 128 bytes of spmvb_group_unique_id() made on one rank and handed to all by the launcher. */
+int spmvb_group_unique_id(uint8_t *out128);
+int spmvb_group_create_rank(uint32_t global_rows, uint32_t cols, const uint32_t *bounds, const uint64_t *row_ptr_local,
+                            const uint32_t *col_ind, const void *values, int is_double, int device, int variant,
+                            const uint8_t *unique_id128, int rank, int world, spmvb_group **out);
+void spmvb_group_free(spmvb_group *g);
+int spmvb_group_world(const spmvb_group *g);
+int spmvb_group_local_count(const spmvb_group *g);            /* GPUs driven by this process */
+int spmvb_group_bounds(const spmvb_group *g, uint32_t *out);  /* world + 1 */
+spmvb_engine *spmvb_group_engine(spmvb_group *g, int local_index);
+int spmvb_group_rank(const spmvb_group *g, int local_index);
+/* spmv_hw (csr_hw_wrapper.cpp:193-288) over the group with HOST buffers: x (n values) to every GPU, all kernels
+ * concurrently, every local GPU's rows of y into their place of y_host (global row index; accumulate like spmv_hw). */
+int spmvb_group_spmv_host(spmvb_group *g, const void *x_host, uint32_t n, void *y_host, int accumulate);
+int spmvb_group_set_x(spmvb_group *g, const void *x_host, uint32_t n);
+int spmvb_group_get_x(spmvb_group *g, void *x_host, uint32_t n); /* from the first local GPU */
+int spmvb_group_get_y(spmvb_group *g, void *y_host);             /* local GPUs' rows into their place of y_host */
+/* x <- A x / ||A x||_2, `iters` times (square matrices), x replicated on every GPU, nothing leaves the devices.  Per
+ * iteration: SpMV, sum of squares, all-reduce of one double, scale kernel writing the normalised slice into its place of
+ * x, ONE grouped NCCL exchange (a broadcast per row owner, in place).  Collective across the ranks of a multi-process
+ * group.  *norm_out = the last norm. */
+int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out);
+float spmvb_group_last_iter_ms(const spmvb_group *g); /* device time per iteration of the last call, max over local GPUs */
+
 /* ------------------------------------------------------------------ matrix files and synthetic inputs */
 
 /* A CSR matrix owned by the library (csr.h:15-24 csr_matrix with 64-bit row offsets). */

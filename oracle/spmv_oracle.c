@@ -339,7 +339,8 @@ int orc_spmv_gold_omp(uint32_t rows, const uint64_t *row_ptr, const uint32_t *co
 /* per-row sum |a||x| in double: the normaliser of the north-star tolerance */
 void orc_abs_ax(uint32_t rows, const uint64_t *row_ptr, const uint32_t *col_ind, const void *values,
                 const void *x, double *out, int is_double) {
-  for (uint32_t i = 0; i < rows; i++) {
+#pragma omp parallel for schedule(static, 4096)
+  for (int64_t i = 0; i < (int64_t)rows; i++) {
     double acc = 0.0;
     for (uint64_t j = row_ptr[i]; j < row_ptr[i + 1]; j++) {
       double a = is_double ? ((const double *)values)[j] : (double)((const float *)values)[j];

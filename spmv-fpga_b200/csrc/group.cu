@@ -1,0 +1,393 @@
+// Multi-GPU behind the C ABI (include/spmvb.h, spmvb_group_*): the reference's compute-unit dimension mapped to the
+// GPUs of one box.  The reference runs all CUs inside one spmv() call, every CU with a private copy of x
+// (src/spmv.cpp:249-294; dispatch src/csr_hw_wrapper.cpp:3-80, 202-271); here every GPU owns a contiguous range of
+// rows balanced by non-zero count (the S1/S2/S3 rule of csr_hw.cpp:459-468 applied to whole rows: SURVEY 8e mapping
+// A), builds the hw_matrix layout of its own rows, keeps all of x and produces its slice of y.  A single SpMV needs no
+// collective.  The iterated caller (power iteration, BASELINE configs[4]) exchanges the y slices into every GPU's x
+// once per iteration: ONE grouped NCCL call (a broadcast per row owner inside ncclGroupStart/End - the slices are
+// balanced by non-zeros, so their lengths differ and an all-gather would have to pad) plus a one-scalar all-reduce
+// for the norm; the scale kernel writes the normalised slice straight into the owner's place in x, so the exchange is
+// in place.
+//
+// Two ways to form a group, same code underneath: spmvb_group_create drives n GPUs from ONE process (what a -DCU=8
+// program of the reference becomes: include/spmv_fpga_compat.h with SPMVB_DEVICES), spmvb_group_create_rank makes this
+// process one rank of a multi-process group (one process per GPU, e.g. under torchrun; the NCCL unique id travels
+// through the launcher).  NCCL is loaded with dlopen on first use: libspmvb.so itself does not depend on it.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <omp.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/spmvb.h"
+#include "errors.h"
+
+namespace spmvb {
+
+namespace {
+
+struct Nccl {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+};
+
+Nccl *nccl() {
+  static Nccl n;
+  static bool tried = false;
+  if (tried) return &n;
+  tried = true;
+  // a process that already holds NCCL (torch brings its own) gets that copy back: same soname
+  for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+    n.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (n.handle) break;
+  }
+  if (!n.handle) { n.error = std::string("NCCL is not available: ") + dlerror(); return &n; }
+  auto sym = [&](const char *s) -> void * {
+    void *p = dlsym(n.handle, s);
+    if (!p && n.error.empty()) n.error = std::string("NCCL symbol missing: ") + s;
+    return p;
+  };
+  n.GetUniqueId = (decltype(n.GetUniqueId))sym("ncclGetUniqueId");
+  n.CommInitRank = (decltype(n.CommInitRank))sym("ncclCommInitRank");
+  n.CommInitAll = (decltype(n.CommInitAll))sym("ncclCommInitAll");
+  n.CommDestroy = (decltype(n.CommDestroy))sym("ncclCommDestroy");
+  n.GroupStart = (decltype(n.GroupStart))sym("ncclGroupStart");
+  n.GroupEnd = (decltype(n.GroupEnd))sym("ncclGroupEnd");
+  n.AllReduce = (decltype(n.AllReduce))sym("ncclAllReduce");
+  n.Broadcast = (decltype(n.Broadcast))sym("ncclBroadcast");
+  n.GetErrorString = (decltype(n.GetErrorString))sym("ncclGetErrorString");
+  return &n;
+}
+
+struct Member {  // one GPU of this process
+  int rank = 0, device = 0;
+  spmvb_layout *layout = nullptr;
+  spmvb_engine *engine = nullptr;
+  ncclComm_t comm = nullptr;
+  double *d_scalar = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+}  // namespace
+
+struct Group {
+  int world = 1, is_double = 1, vb = 8;
+  uint32_t rows = 0, cols = 0;           // of the whole matrix
+  std::vector<uint32_t> bounds;          // [world + 1] row ownership
+  std::vector<Member> local;             // the members this process drives
+  double *h_scalar = nullptr;            // pinned
+  float last_iter_ms = 0.f;
+  uint64_t nnz_local = 0;
+};
+
+#define G_CUDA(expr)                                                                       \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) return fail(SPMVB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+#define G_NCCL(expr)                                                                       \
+  do {                                                                                     \
+    ncclResult_t _r = (expr);                                                              \
+    if (_r != ncclSuccess) return fail(SPMVB_E_CUDA, std::string(#expr) + ": " + nccl()->GetErrorString(_r)); \
+  } while (0)
+
+static int need_nccl() {
+  Nccl *n = nccl();
+  if (!n->handle || !n->error.empty()) return fail(SPMVB_E_CUDA, n->error.empty() ? "NCCL is not available" : n->error);
+  return SPMVB_OK;
+}
+
+// layout + engine of one member from its row slice (row_ptr rebased to 0)
+static int member_build(Group *G, Member &m, uint32_t n_rows, const uint64_t *row_ptr, const uint32_t *col_ind,
+                        const void *values, int variant) {
+  int rc = spmvb_layout_build(n_rows, G->cols, row_ptr, col_ind, values, 1, 1, G->is_double, 0, &m.layout);
+  if (rc) return rc;
+  rc = spmvb_engine_create(m.layout, m.device, variant, &m.engine);
+  if (rc) return rc;
+  G_CUDA(cudaSetDevice(m.device));
+  G_CUDA(cudaMalloc((void **)&m.d_scalar, 64));
+  G_CUDA(cudaEventCreate(&m.ev0));
+  G_CUDA(cudaEventCreate(&m.ev1));
+  return SPMVB_OK;
+}
+
+static void group_destroy(Group *G) {
+  if (!G) return;
+  for (Member &m : G->local) {
+    cudaSetDevice(m.device);
+    if (m.comm && nccl()->CommDestroy) nccl()->CommDestroy(m.comm);
+    if (m.engine) spmvb_engine_free(m.engine);
+    if (m.layout) spmvb_layout_free(m.layout);
+    cudaFree(m.d_scalar);
+    if (m.ev0) cudaEventDestroy(m.ev0);
+    if (m.ev1) cudaEventDestroy(m.ev1);
+  }
+  if (G->h_scalar) cudaFreeHost(G->h_scalar);
+  delete G;
+}
+
+}  // namespace spmvb
+
+using namespace spmvb;
+
+extern "C" {
+
+int spmvb_group_unique_id(uint8_t *out128) {
+  if (!out128) return fail(SPMVB_E_ARG, "group_unique_id");
+  int rc = need_nccl();
+  if (rc) return rc;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  G_NCCL(nccl()->GetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  return SPMVB_OK;
+}
+
+int spmvb_group_create(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, const uint32_t *col_ind,
+                       const void *values, int is_double, int n_devices, const int *devices, int variant,
+                       spmvb_group **out) {
+  if (!out || !row_ptr || n_devices < 1 || rows == 0 || cols == 0) return fail(SPMVB_E_ARG, "group_create");
+  *out = nullptr;
+  Group *G = new Group();
+  G->world = n_devices; G->is_double = is_double ? 1 : 0; G->vb = is_double ? 8 : 4;
+  G->rows = rows; G->cols = cols;
+  G->bounds.assign((size_t)n_devices + 1, 0);
+  int rc = spmvb_partition_rows(rows, row_ptr, n_devices, is_double ? 2 : 4, G->bounds.data());
+  // a split that did not fire leaves an owner without rows: fall back to equal row counts
+  bool all = rc == SPMVB_OK;
+  for (int k = 0; k < n_devices && all; k++) all = G->bounds[k + 1] > G->bounds[k];
+  if (!all)
+    for (int k = 0; k <= n_devices; k++) G->bounds[k] = (uint32_t)((uint64_t)rows * k / n_devices);
+  G->local.resize(n_devices);
+  auto build = [&]() -> int {
+    for (int k = 0; k < n_devices; k++) {
+      Member &m = G->local[k];
+      m.rank = k; m.device = devices ? devices[k] : k;
+      const uint32_t r0 = G->bounds[k], r1 = G->bounds[k + 1];
+      std::vector<uint64_t> rp((size_t)(r1 - r0) + 1);
+      for (uint32_t r = r0; r <= r1; r++) rp[r - r0] = row_ptr[r] - row_ptr[r0];
+      const size_t j0 = (size_t)row_ptr[r0];
+      int r = member_build(G, m, r1 - r0, rp.data(), col_ind ? col_ind + j0 : nullptr,
+                           values ? (const uint8_t *)values + j0 * G->vb : nullptr, variant);
+      if (r) return r;
+      G->nnz_local += row_ptr[r1] - row_ptr[r0];
+    }
+    G_CUDA(cudaMallocHost((void **)&G->h_scalar, 64));
+    if (n_devices > 1) {
+      int r = need_nccl();
+      if (r) return r;
+      std::vector<ncclComm_t> comms(n_devices);
+      std::vector<int> devs(n_devices);
+      for (int k = 0; k < n_devices; k++) devs[k] = G->local[k].device;
+      G_NCCL(nccl()->CommInitAll(comms.data(), n_devices, devs.data()));
+      for (int k = 0; k < n_devices; k++) G->local[k].comm = comms[k];
+    }
+    return SPMVB_OK;
+  };
+  rc = build();
+  if (rc) { group_destroy(G); return rc; }
+  *out = (spmvb_group *)G;
+  return SPMVB_OK;
+}
+
+int spmvb_group_create_rank(uint32_t global_rows, uint32_t cols, const uint32_t *bounds, const uint64_t *row_ptr_local,
+                            const uint32_t *col_ind, const void *values, int is_double, int device, int variant,
+                            const uint8_t *unique_id128, int rank, int world, spmvb_group **out) {
+  if (!out || !bounds || !row_ptr_local || world < 1 || rank < 0 || rank >= world || (world > 1 && !unique_id128))
+    return fail(SPMVB_E_ARG, "group_create_rank");
+  *out = nullptr;
+  if (bounds[0] != 0 || bounds[world] != global_rows) return fail(SPMVB_E_ARG, "group_create_rank: bounds must cover the rows");
+  for (int k = 0; k < world; k++)
+    if (bounds[k + 1] < bounds[k]) return fail(SPMVB_E_ARG, "group_create_rank: bounds must ascend");
+  if (bounds[rank + 1] == bounds[rank]) return fail(SPMVB_E_ARG, "group_create_rank: this rank owns no rows");
+  Group *G = new Group();
+  G->world = world; G->is_double = is_double ? 1 : 0; G->vb = is_double ? 8 : 4;
+  G->rows = global_rows; G->cols = cols;
+  G->bounds.assign(bounds, bounds + world + 1);
+  G->local.resize(1);
+  Member &m = G->local[0];
+  m.rank = rank; m.device = device;
+  auto build = [&]() -> int {
+    const uint32_t n_rows = bounds[rank + 1] - bounds[rank];
+    int r = member_build(G, m, n_rows, row_ptr_local, col_ind, values, variant);
+    if (r) return r;
+    G->nnz_local = row_ptr_local[n_rows];
+    G_CUDA(cudaMallocHost((void **)&G->h_scalar, 64));
+    if (world > 1) {
+      r = need_nccl();
+      if (r) return r;
+      ncclUniqueId id;
+      memcpy(&id, unique_id128, 128);
+      G_CUDA(cudaSetDevice(device));
+      G_NCCL(nccl()->CommInitRank(&m.comm, world, id, rank));
+    }
+    return SPMVB_OK;
+  };
+  int rc = build();
+  if (rc) { group_destroy(G); return rc; }
+  *out = (spmvb_group *)G;
+  return SPMVB_OK;
+}
+
+void spmvb_group_free(spmvb_group *g) { group_destroy((Group *)g); }
+
+int spmvb_group_world(const spmvb_group *g) { return g ? ((const Group *)g)->world : 0; }
+int spmvb_group_local_count(const spmvb_group *g) { return g ? (int)((const Group *)g)->local.size() : 0; }
+int spmvb_group_bounds(const spmvb_group *g, uint32_t *out) {
+  const Group *G = (const Group *)g;
+  if (!G || !out) return fail(SPMVB_E_ARG, "group_bounds");
+  memcpy(out, G->bounds.data(), G->bounds.size() * 4);
+  return SPMVB_OK;
+}
+spmvb_engine *spmvb_group_engine(spmvb_group *g, int local_index) {
+  Group *G = (Group *)g;
+  if (!G || local_index < 0 || local_index >= (int)G->local.size()) return nullptr;
+  return G->local[local_index].engine;
+}
+int spmvb_group_rank(const spmvb_group *g, int local_index) {
+  const Group *G = (const Group *)g;
+  if (!G || local_index < 0 || local_index >= (int)G->local.size()) return -1;
+  return G->local[local_index].rank;
+}
+float spmvb_group_last_iter_ms(const spmvb_group *g) { return g ? ((const Group *)g)->last_iter_ms : 0.f; }
+
+int spmvb_group_set_x(spmvb_group *g, const void *x_host, uint32_t n) {
+  Group *G = (Group *)g;
+  if (!G || !x_host) return fail(SPMVB_E_ARG, "group_set_x");
+  for (Member &m : G->local) {  // replicated: every GPU gets what its rows can read of x
+    int rc = spmvb_engine_set_x(m.engine, x_host, n);
+    if (rc) return rc;
+  }
+  for (Member &m : G->local) {
+    int rc = spmvb_engine_sync(m.engine);
+    if (rc) return rc;
+  }
+  return SPMVB_OK;
+}
+
+int spmvb_group_get_x(spmvb_group *g, void *x_host, uint32_t n) {
+  Group *G = (Group *)g;
+  if (!G || !x_host) return fail(SPMVB_E_ARG, "group_get_x");
+  Member &m = G->local[0];
+  G_CUDA(cudaSetDevice(m.device));
+  const uint32_t k = std::min(n, G->cols);
+  G_CUDA(cudaMemcpyAsync(x_host, spmvb_engine_x_dev(m.engine), (size_t)k * G->vb, cudaMemcpyDeviceToHost,
+                         (cudaStream_t)spmvb_engine_stream(m.engine)));
+  return spmvb_engine_sync(m.engine);
+}
+
+// spmv_hw over the group: x goes to every GPU, all kernels run concurrently (one stream per GPU), every GPU's slice of
+// y comes back into its place of y_host.  The local members' rows only: in a multi-process group every rank fills its
+// own slice of its own y_host.
+int spmvb_group_spmv_host(spmvb_group *g, const void *x_host, uint32_t n, void *y_host, int accumulate) {
+  Group *G = (Group *)g;
+  if (!G || !x_host || !y_host) return fail(SPMVB_E_ARG, "group_spmv_host");
+  for (Member &m : G->local) {  // uploads and kernels of all GPUs are queued before anything is waited for
+    int rc = spmvb_engine_set_x(m.engine, x_host, n);
+    if (rc) return rc;
+    rc = spmvb_engine_spmv_dev(m.engine, nullptr, nullptr, 0, nullptr);
+    if (rc) return rc;
+  }
+  for (Member &m : G->local) {
+    const uint32_t r0 = G->bounds[m.rank], r1 = G->bounds[m.rank + 1];
+    int rc = spmvb_engine_get_y(m.engine, (uint8_t *)y_host + (size_t)r0 * G->vb, r1 - r0, accumulate);
+    if (rc) return rc;
+  }
+  return SPMVB_OK;
+}
+
+// y slices of the local members after the last SpMV / iteration, into their places of y_host (diagnostics, tests)
+int spmvb_group_get_y(spmvb_group *g, void *y_host) {
+  Group *G = (Group *)g;
+  if (!G || !y_host) return fail(SPMVB_E_ARG, "group_get_y");
+  for (Member &m : G->local) {
+    const uint32_t r0 = G->bounds[m.rank], r1 = G->bounds[m.rank + 1];
+    int rc = spmvb_engine_get_y(m.engine, (uint8_t *)y_host + (size_t)r0 * G->vb, r1 - r0, 0);
+    if (rc) return rc;
+  }
+  return SPMVB_OK;
+}
+
+// x <- A x / ||A x||_2, `iters` times, x replicated on every GPU.  Collective: every rank of a multi-process group
+// calls it with the same `iters`.  Per iteration and GPU: clear rows + SpMV kernel, sum of squares, [all-reduce of
+// one double], scale kernel that writes the normalised slice into its place of x, [one grouped NCCL exchange].
+int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out) {
+  Group *G = (Group *)g;
+  if (!G || iters < 1) return fail(SPMVB_E_ARG, "group_power_iter");
+  if (G->rows != G->cols) return fail(SPMVB_E_ARG, "power_iter needs a square matrix");
+  Nccl *N = nccl();
+  const bool multi = G->world > 1;
+  const ncclDataType_t dt = G->is_double ? ncclDouble : ncclFloat;
+  for (Member &m : G->local) {
+    G_CUDA(cudaSetDevice(m.device));
+    G_CUDA(cudaEventRecord(m.ev0, (cudaStream_t)spmvb_engine_stream(m.engine)));
+  }
+  for (int it = 0; it < iters; it++) {
+    for (Member &m : G->local) {
+      const uint32_t n_local = G->bounds[m.rank + 1] - G->bounds[m.rank];
+      int rc = spmvb_engine_spmv_dev(m.engine, nullptr, nullptr, 0, nullptr);
+      if (rc) return rc;
+      rc = spmvb_engine_sumsq(m.engine, spmvb_engine_y_dev(m.engine), n_local, m.d_scalar, nullptr);
+      if (rc) return rc;
+    }
+    if (multi) {
+      G_NCCL(N->GroupStart());
+      for (Member &m : G->local)
+        G_NCCL(N->AllReduce(m.d_scalar, m.d_scalar, 1, ncclDouble, ncclSum, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
+      G_NCCL(N->GroupEnd());
+    }
+    for (Member &m : G->local) {
+      const uint32_t r0 = G->bounds[m.rank], n_local = G->bounds[m.rank + 1] - r0;
+      uint8_t *x = (uint8_t *)spmvb_engine_x_dev(m.engine);
+      int rc = spmvb_engine_scale_rsqrt(m.engine, spmvb_engine_y_dev(m.engine), x + (size_t)r0 * G->vb, n_local, m.d_scalar, nullptr);
+      if (rc) return rc;
+    }
+    if (multi) {  // every owner's slice into every GPU's x, in place: one NCCL launch per GPU
+      G_NCCL(N->GroupStart());
+      for (Member &m : G->local) {
+        uint8_t *x = (uint8_t *)spmvb_engine_x_dev(m.engine);
+        for (int r = 0; r < G->world; r++) {
+          const uint32_t b0 = G->bounds[r], len = G->bounds[r + 1] - b0;
+          if (!len) continue;
+          void *p = x + (size_t)b0 * G->vb;
+          G_NCCL(N->Broadcast(p, p, len, dt, r, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
+        }
+      }
+      G_NCCL(N->GroupEnd());
+    }
+  }
+  for (Member &m : G->local) {
+    G_CUDA(cudaSetDevice(m.device));
+    G_CUDA(cudaEventRecord(m.ev1, (cudaStream_t)spmvb_engine_stream(m.engine)));
+  }
+  Member &m0 = G->local[0];
+  G_CUDA(cudaSetDevice(m0.device));
+  G_CUDA(cudaMemcpyAsync(G->h_scalar, m0.d_scalar, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)spmvb_engine_stream(m0.engine)));
+  float worst = 0.f;
+  for (Member &m : G->local) {
+    int rc = spmvb_engine_sync(m.engine);
+    if (rc) return rc;
+    float ms = 0.f;
+    G_CUDA(cudaSetDevice(m.device));
+    if (cudaEventElapsedTime(&ms, m.ev0, m.ev1) == cudaSuccess) worst = std::max(worst, ms);
+  }
+  G->last_iter_ms = worst / (float)iters;
+  if (norm_out) *norm_out = std::sqrt(G->h_scalar[0]);
+  return SPMVB_OK;
+}
+
+}  // extern "C"

@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+#include "errors.h"
+
 namespace spmvb {
 
 constexpr int kBusBytes = 16;        // BUS_BIT_WIDTH / 8, reference src/util.h:61
@@ -120,7 +122,5 @@ struct Options {
 };
 Options &options();
 
-void set_error(const std::string &msg);
-int fail(int code, const std::string &msg);
 
 }  // namespace spmvb

@@ -26,11 +26,6 @@
 
 namespace spmvb {
 
-static thread_local std::string g_err;
-void set_error(const std::string &msg) { g_err = msg; }
-int fail(int code, const std::string &msg) { g_err = msg; return code; }
-const char *last_error_cstr() { return g_err.c_str(); }
-
 Layout::~Layout() {
   free(stream);
   free(rowmap);
@@ -215,6 +210,13 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     int rc = layout_init_header(L, rows, cols, nnz, cu, vf, is_double, cdb_in);
     if (rc) { delete L; return rc; }
   }
+  double t_phase = omp_get_wtime();
+  auto phase = [&](const char *what) {  // option build_trace: time of every phase of the host builder
+    if (options().build_trace <= 0) return;
+    const double t = omp_get_wtime();
+    fprintf(stderr, "[host layout build cu=%d cdb=%u] %-28s %8.1f ms\n", cu, L->cdb, what, (t - t_phase) * 1e3);
+    t_phase = t;
+  };
   const uint32_t cdb = L->cdb;
   const int blocks = L->blocks;
   const int vb = L->vb;
@@ -259,6 +261,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   }
   if (bad_col) { delete L; return fail(SPMVB_E_ARG, "column index out of range"); }
 
+  phase("pass 1 (count)");
   // exclusive scan over threads per block -> per-thread starting rank / position inside each block
   std::vector<uint64_t> P(blocks), Z(blocks);
   for (int b = 0; b < blocks; b++) {
@@ -302,6 +305,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     }
   }
 
+  phase("scan + pass 2");
   // ---- prepare_balanced_hw_matrix: S1 && S2 && S3 split per block (csr_hw.cpp:459-468), leftovers + row padding to
   //      the last CU (:474-482).  fp[b*(cu+1)+k] = first block position of piece k (real entries only).
   const size_t KB = (size_t)cu * blocks;
@@ -339,6 +343,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   }
   std::vector<uint32_t>().swap(seglen);
 
+  phase("split");
   // ---- hw_matrix_alloc + device image offsets
   std::vector<uint64_t> piece_last_rank;
   layout_finish_pieces(L, fp.data(), pad_rows.data(), piece_last_rank);
@@ -359,6 +364,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     }
   }
 
+  phase("alloc + chunk init");
   // ---- pass 3: scatter every entry to its final byte (create_block_matrix + generate_balanced_hw_submatrix)
   const uint8_t *vals = (const uint8_t *)values;
   const int gb = L->group_bytes;
@@ -424,6 +430,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     }
   }
 
+  phase("pass 3 (scatter)");
   // padding rows of the last CU: VF x (col 0, val 0) with the end-of-row bit on the last (csr_hw.cpp:246-255)
   for (int b = 0; b < blocks; b++) {
     const size_t bk = (size_t)b * cu + (cu - 1);
@@ -454,6 +461,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     }
   }
 
+  phase("consecutive / sole flags");
   // Rows to clear before every SpMV (see Layout::zero_rows).  Marks are idempotent byte stores.
   {
     const uint64_t R = 1ull << L->run_log2;
@@ -492,6 +500,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     }
   }
 
+  phase("rows to clear");
   // column range of every chunk (real entries only)
   L->chunk_col_lo.assign((size_t)L->n_chunks, 0xFFFF);
   L->chunk_col_hi.assign((size_t)L->n_chunks, 0);
@@ -518,6 +527,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     L->chunks[c].block = (L->chunks[c].block & kMetaBlockMask) | (row_ends << kMetaRowsShift);
   }
 
+  phase("chunk column ranges");
   // the engine-private device layout, when the API parameters are not what the GPU should stream
   int cu_dev = cu, vf_dev = vf;
   uint32_t cdb_dev = cdb;
@@ -537,7 +547,6 @@ using namespace spmvb;
 
 extern "C" {
 
-const char *spmvb_last_error(void) { return last_error_cstr(); }
 int spmvb_version(void) { return 200; }
 
 int spmvb_set_option(const char *name, int64_t value) {

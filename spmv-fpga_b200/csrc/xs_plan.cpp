@@ -8,9 +8,10 @@
 
 namespace spmvb {
 
-// Work items of the XS kernel.  Every CTA (one per SM) owns ONE contiguous range of chunks of (almost) equal length -
-// static and balanced, no quantisation loss - and the range is cut into items at piece boundaries and wherever
-// the x window the chunks touch would outgrow the shared-memory budget.  Cut points are piece-relative multiples of
+// Work items of the XS kernel.  Block-major layouts: every CTA (one per SM) owns ONE contiguous range of chunks of
+// (almost) equal length - static and balanced, no quantisation loss - and the range is cut into items at piece
+// boundaries and wherever the x window the chunks touch would outgrow the shared-memory budget.  CU-major layouts
+// (row tiles): see below.  Cut points are piece-relative multiples of
 // U = run length x warps per CTA, so that every warp of the CTA gets the same number of whole runs per item.
 void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<XsItem> &items,
                            std::vector<uint32_t> &cta_first) {
@@ -28,14 +29,9 @@ void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<X
   }
   cuts.push_back(L->n_chunks);
   cta_first.assign(n_cta + 1, 0);
-  size_t ci = 0;  // index into cuts of the current position
-  for (int j = 0; j < n_cta; j++) {
-    cta_first[j] = (uint32_t)items.size();
-    const uint64_t want_end = L->n_chunks * (uint64_t)(j + 1) / (uint64_t)n_cta;
-    size_t ce = ci;  // first cut >= want_end (the last CTA takes everything)
-    while (ce + 1 < cuts.size() && (cuts[ce] < want_end || j == n_cta - 1)) ce++;
-    if (j == n_cta - 1) ce = cuts.size() - 1;
-    // items of [cuts[ci], cuts[ce])
+  // items of the cut range [ci, ce): each extends unit by unit inside its piece while the window fits (and, with a
+  // cap, while it holds fewer than `cap` chunks)
+  auto emit = [&](size_t ci, size_t ce, uint64_t cap) {
     while (ci < ce) {
       const uint64_t c0 = cuts[ci];
       const size_t sg = (size_t)(std::upper_bound(seg_start.begin(), seg_start.end(), c0) - seg_start.begin()) - 1;
@@ -44,7 +40,7 @@ void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<X
       uint32_t lo = 0xFFFF, hi = 0;
       size_t e = ci;
       bool fits = true;
-      while (e < ce && cuts[e] < b_end) {  // extend by one unit while the window fits
+      while (e < ce && cuts[e] < b_end && (cap == 0 || cuts[e] - c0 < cap)) {  // extend by one unit while the window fits
         uint32_t nlo = lo, nhi = hi;
         for (uint64_t q = cuts[e]; q < cuts[e + 1]; q++)
           if (L->chunk_col_lo[q] <= L->chunk_col_hi[q]) {
@@ -72,21 +68,34 @@ void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<X
       items.push_back(it);
       ci = e;
     }
-  }
-  cta_first[n_cta] = (uint32_t)items.size();
-  if (L->cu_major) {
-    // Tall matrices (pieces in CU-major order so that the y range in flight stays L2-resident): deal the items
-    // round-robin instead, so that all CTAs work inside the same CU's row range at any time.
+  };
+  if (!L->cu_major) {
+    size_t ci = 0;  // index into cuts of the current position
+    for (int j = 0; j < n_cta; j++) {
+      cta_first[j] = (uint32_t)items.size();
+      const uint64_t want_end = L->n_chunks * (uint64_t)(j + 1) / (uint64_t)n_cta;
+      size_t ce = ci;  // first cut >= want_end (the last CTA takes everything)
+      while (ce + 1 < cuts.size() && (cuts[ce] < want_end || j == n_cta - 1)) ce++;
+      if (j == n_cta - 1) ce = cuts.size() - 1;
+      emit(ci, ce, 0);
+      ci = ce;
+    }
+    cta_first[n_cta] = (uint32_t)items.size();
+  } else {
+    // Tall matrices (pieces in CU-major order so that the y range in flight stays L2-resident).  A piece here is one
+    // column block of one row tile: short (the tile's share of the block) but with a full-width x window, so a window
+    // must serve as many chunks as it can - an item is a WHOLE piece (up to ~256 chunks) - and the items are dealt
+    // round-robin, so that all CTAs work on neighbouring column blocks of the same row tile at any time.
+    const uint64_t cap = std::max<uint64_t>(U, 256 / U * U);
+    emit(0, cuts.size() - 1, cap);
     std::vector<XsItem> rr;
     rr.reserve(items.size());
-    std::vector<uint32_t> first(n_cta + 1, 0);
     for (int j = 0; j < n_cta; j++) {
-      first[j] = (uint32_t)rr.size();
+      cta_first[j] = (uint32_t)rr.size();
       for (size_t i = (size_t)j; i < items.size(); i += (size_t)n_cta) rr.push_back(items[i]);
     }
-    first[n_cta] = (uint32_t)rr.size();
+    cta_first[n_cta] = (uint32_t)rr.size();
     items.swap(rr);
-    cta_first.swap(first);
   }
 }
 

@@ -78,6 +78,21 @@ SYMBOLS = {
     "spmvb_engine_scale_copy": (_int, [_vp, _vp, _vp, _u32, ctypes.c_double, _vp]),
     "spmvb_engine_scale_rsqrt": (_int, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "spmvb_engine_sumsq": (_int, [_vp, _vp, _u32, _vp, _vp]),
+    "spmvb_group_create": (_int, [_u32, _u32, _vp, _vp, _vp, _int, _int, _vp, _int, _vp]),
+    "spmvb_group_unique_id": (_int, [_vp]),
+    "spmvb_group_create_rank": (_int, [_u32, _u32, _vp, _vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _vp]),
+    "spmvb_group_free": (None, [_vp]),
+    "spmvb_group_world": (_int, [_vp]),
+    "spmvb_group_local_count": (_int, [_vp]),
+    "spmvb_group_bounds": (_int, [_vp, _vp]),
+    "spmvb_group_engine": (_vp, [_vp, _int]),
+    "spmvb_group_rank": (_int, [_vp, _int]),
+    "spmvb_group_spmv_host": (_int, [_vp, _vp, _u32, _vp, _int]),
+    "spmvb_group_set_x": (_int, [_vp, _vp, _u32]),
+    "spmvb_group_get_x": (_int, [_vp, _vp, _u32]),
+    "spmvb_group_get_y": (_int, [_vp, _vp]),
+    "spmvb_group_power_iter": (_int, [_vp, _int, _vp]),
+    "spmvb_group_last_iter_ms": (ctypes.c_float, [_vp]),
     "spmvb_csr_free": (None, [_vp]),
     "spmvb_csr_rows": (_u32, [_vp]),
     "spmvb_csr_cols": (_u32, [_vp]),
@@ -130,9 +145,32 @@ def lib():
     return _lib
 
 
-def _check(rc):
+GEN_LIB_PATH = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libmatgen.so")
+_GEN_SYMBOLS = [n for n in SYMBOLS if n.startswith("spmvb_csr_gen_") or n in (
+    "spmvb_last_error", "spmvb_csr_free", "spmvb_csr_rows", "spmvb_csr_cols", "spmvb_csr_nnz", "spmvb_csr_is_double",
+    "spmvb_csr_row_ptr", "spmvb_csr_col_ind", "spmvb_csr_values")]
+_gen_lib = None
+
+
+def gen_lib():
+    """The synthetic-matrix generators alone (oracle/_ref/libmatgen.so: matrix_gen.cpp built without the engine).  The
+    reference arm of bench.py generates its workload through this handle, so that it never loads libspmvb.so."""
+    global _gen_lib
+    if _gen_lib is None:
+        if not os.path.exists(GEN_LIB_PATH):
+            subprocess.check_call(["make", "-C", os.path.dirname(os.path.dirname(GEN_LIB_PATH)), "gen"],
+                                  stdout=subprocess.DEVNULL)
+        L = ctypes.CDLL(GEN_LIB_PATH)
+        for name in _GEN_SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = SYMBOLS[name]
+        _gen_lib = L
+    return _gen_lib
+
+
+def _check(rc, L=None):
     if rc != 0:
-        raise SpmvbError(rc, lib().spmvb_last_error().decode(errors="replace"))
+        raise SpmvbError(rc, (L or lib()).spmvb_last_error().decode(errors="replace"))
 
 
 def set_option(name, value):
@@ -170,11 +208,12 @@ def vdtype(is_double):
 
 
 class Csr:
-    """Library-owned CSR matrix (numpy views are zero-copy and valid while the object lives)."""
+    """Library-owned CSR matrix (numpy views are zero-copy and valid while the object lives).  L = the ctypes library
+    that owns it: libspmvb.so by default, gen_lib() for matrices generated without the engine."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, L=None):
         self.h = _vp(handle)
-        L = lib()
+        self.L = L = L or lib()
         self.rows = L.spmvb_csr_rows(self.h)
         self.cols = L.spmvb_csr_cols(self.h)
         self.nnz = L.spmvb_csr_nnz(self.h)
@@ -188,15 +227,15 @@ class Csr:
 
     @property
     def row_ptr(self):
-        return self._view(lib().spmvb_csr_row_ptr(self.h), self.rows + 1, np.uint64)
+        return self._view(self.L.spmvb_csr_row_ptr(self.h), self.rows + 1, np.uint64)
 
     @property
     def col_ind(self):
-        return self._view(lib().spmvb_csr_col_ind(self.h), self.nnz, np.uint32)
+        return self._view(self.L.spmvb_csr_col_ind(self.h), self.nnz, np.uint32)
 
     @property
     def values(self):
-        return self._view(lib().spmvb_csr_values(self.h), self.nnz, vdtype(self.is_double))
+        return self._view(self.L.spmvb_csr_values(self.h), self.nnz, vdtype(self.is_double))
 
     def write(self, path):
         _check(lib().spmvb_csr_write(self.h, path.encode()))
@@ -207,7 +246,7 @@ class Csr:
 
     def free(self):
         if self.h:
-            lib().spmvb_csr_free(self.h)
+            self.L.spmvb_csr_free(self.h)
             self.h = None
 
     def __del__(self):
@@ -218,39 +257,40 @@ class Csr:
 
     # ---- constructors
     @staticmethod
-    def _new(fn, *args):
+    def _new(L, name, *args):
+        L = L or lib()
         out = _vp()
-        _check(fn(*args, ctypes.byref(out)))
-        return Csr(out.value)
+        _check(getattr(L, name)(*args, ctypes.byref(out)), L)
+        return Csr(out.value, L)
 
     @staticmethod
     def read(path, is_double=True):
-        return Csr._new(lib().spmvb_csr_read, path.encode(), int(is_double))
+        return Csr._new(None, "spmvb_csr_read", path.encode(), int(is_double))
 
     @staticmethod
     def load(path):
-        return Csr._new(lib().spmvb_csr_load, path.encode())
+        return Csr._new(None, "spmvb_csr_load", path.encode())
 
     @staticmethod
     def read_cached(path, is_double=True):
         """Parses the text file once and keeps a binary sidecar next to it for the following calls."""
-        return Csr._new(lib().spmvb_csr_read_cached, path.encode(), int(is_double))
+        return Csr._new(None, "spmvb_csr_read_cached", path.encode(), int(is_double))
 
     @staticmethod
-    def band(n, half_bw=5, seed=1, is_double=True):
-        return Csr._new(lib().spmvb_csr_gen_band, n, half_bw, seed, int(is_double))
+    def band(n, half_bw=5, seed=1, is_double=True, L=None):
+        return Csr._new(L, "spmvb_csr_gen_band", n, half_bw, seed, int(is_double))
 
     @staticmethod
-    def laplacian2d(nx, ny, row_begin=0, row_end=0, is_double=True):
-        return Csr._new(lib().spmvb_csr_gen_laplacian2d, nx, ny, row_begin, row_end, int(is_double))
+    def laplacian2d(nx, ny, row_begin=0, row_end=0, is_double=True, L=None):
+        return Csr._new(L, "spmvb_csr_gen_laplacian2d", nx, ny, row_begin, row_end, int(is_double))
 
     @staticmethod
-    def uniform(rows, cols, nnz_per_row, seed=1, row_begin=0, row_end=0, is_double=True):
-        return Csr._new(lib().spmvb_csr_gen_uniform, rows, cols, nnz_per_row, seed, row_begin, row_end, int(is_double))
+    def uniform(rows, cols, nnz_per_row, seed=1, row_begin=0, row_end=0, is_double=True, L=None):
+        return Csr._new(L, "spmvb_csr_gen_uniform", rows, cols, nnz_per_row, seed, row_begin, row_end, int(is_double))
 
     @staticmethod
-    def rmat(scale, edge_factor=16, a=0.57, b=0.19, c=0.19, seed=1, row_begin=0, row_end=0, is_double=True):
-        return Csr._new(lib().spmvb_csr_gen_rmat, scale, edge_factor, a, b, c, seed, row_begin, row_end, int(is_double))
+    def rmat(scale, edge_factor=16, a=0.57, b=0.19, c=0.19, seed=1, row_begin=0, row_end=0, is_double=True, L=None):
+        return Csr._new(L, "spmvb_csr_gen_rmat", scale, edge_factor, a, b, c, seed, row_begin, row_end, int(is_double))
 
 
 class Layout:
@@ -557,6 +597,99 @@ class Engine:
     def free(self):
         if self.h:
             lib().spmvb_engine_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Group:
+    """Engines over one matrix on several GPUs (include/spmvb.h: spmvb_group_*): rows owned in contiguous ranges
+    balanced by non-zeros, x replicated.  Group.create drives n GPUs from this process; Group.create_rank makes this
+    process one rank of a multi-process group (the NCCL unique id comes from Group.unique_id() on one rank)."""
+
+    def __init__(self, handle, is_double, rows, cols):
+        self.h = _vp(handle)
+        self.is_double, self.rows, self.cols = bool(is_double), rows, cols
+        L = lib()
+        self.world = L.spmvb_group_world(self.h)
+        self.local_count = L.spmvb_group_local_count(self.h)
+        b = np.zeros(self.world + 1, np.uint32)
+        _check(L.spmvb_group_bounds(self.h, _ptr(b)))
+        self.bounds = b
+        self.ranks = [L.spmvb_group_rank(self.h, i) for i in range(self.local_count)]
+
+    @staticmethod
+    def create(rows, cols, row_ptr, col_ind, values, is_double=True, devices=(0,), variant=VARIANT_AUTO):
+        rp = np.ascontiguousarray(row_ptr, np.uint64)
+        ci = np.ascontiguousarray(col_ind, np.uint32)
+        va = np.ascontiguousarray(values, vdtype(is_double))
+        dv = np.ascontiguousarray(list(devices), np.int32)
+        out = _vp()
+        _check(lib().spmvb_group_create(rows, cols, _ptr(rp), _ptr(ci), _ptr(va), int(is_double), len(dv), _ptr(dv), variant,
+                                        ctypes.byref(out)))
+        return Group(out.value, is_double, rows, cols)
+
+    @staticmethod
+    def unique_id():
+        out = np.zeros(128, np.uint8)
+        _check(lib().spmvb_group_unique_id(_ptr(out)))
+        return out
+
+    @staticmethod
+    def create_rank(global_rows, cols, bounds, row_ptr_local, col_ind, values, is_double, device, unique_id, rank, world,
+                    variant=VARIANT_AUTO):
+        b = np.ascontiguousarray(bounds, np.uint32)
+        rp = np.ascontiguousarray(row_ptr_local, np.uint64)
+        ci = np.ascontiguousarray(col_ind, np.uint32)
+        va = np.ascontiguousarray(values, vdtype(is_double))
+        uid = np.ascontiguousarray(unique_id, np.uint8) if unique_id is not None else None
+        out = _vp()
+        _check(lib().spmvb_group_create_rank(global_rows, cols, _ptr(b), _ptr(rp), _ptr(ci), _ptr(va), int(is_double), device,
+                                             variant, _ptr(uid), rank, world, ctypes.byref(out)))
+        return Group(out.value, is_double, global_rows, cols)
+
+    def engine_handle(self, i=0):
+        return lib().spmvb_group_engine(self.h, i)
+
+    def launches(self):
+        return sum(int(lib().spmvb_engine_launches(_vp(self.engine_handle(i)))) for i in range(self.local_count))
+
+    def set_x(self, x):
+        xx = np.ascontiguousarray(x, vdtype(self.is_double))
+        _check(lib().spmvb_group_set_x(self.h, _ptr(xx), len(xx)))
+
+    def get_x(self):
+        out = np.zeros(self.cols, vdtype(self.is_double))
+        _check(lib().spmvb_group_get_x(self.h, _ptr(out), len(out)))
+        return out
+
+    def get_y(self):
+        """Full-length y with the rows of this process's GPUs filled in (the other rows stay 0)."""
+        out = np.zeros(self.rows, vdtype(self.is_double))
+        _check(lib().spmvb_group_get_y(self.h, _ptr(out)))
+        return out
+
+    def spmv_host(self, x, y, accumulate=True):
+        assert x.dtype == vdtype(self.is_double) and y.dtype == x.dtype and len(y) == self.rows
+        _check(lib().spmvb_group_spmv_host(self.h, _ptr(x), len(x), _ptr(y), int(accumulate)))
+        return y
+
+    def power_iter(self, iters):
+        nrm = ctypes.c_double()
+        _check(lib().spmvb_group_power_iter(self.h, iters, ctypes.byref(nrm)))
+        return nrm.value
+
+    @property
+    def last_iter_ms(self):
+        return float(lib().spmvb_group_last_iter_ms(self.h))
+
+    def free(self):
+        if self.h:
+            lib().spmvb_group_free(self.h)
             self.h = None
 
     def __del__(self):

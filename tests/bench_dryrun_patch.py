@@ -56,6 +56,14 @@ def _init(backend=None, **k):
 dist.init_process_group = _init
 
 
+torch.Tensor.cuda = lambda self, *_a, **_k: self
+
+
+def _scipy(csr):
+    import scipy.sparse as sp
+    return sp.csr_matrix((csr.values, csr.col_ind.astype(np.int64), csr.row_ptr.astype(np.int64)), shape=(csr.rows, csr.cols))
+
+
 class FakeEngine:
     def __init__(self, layout, device=0, variant=0):
         self.layout, self.rows, self.cols, self.is_double = layout, layout.rows, layout.cols, layout.is_double
@@ -65,6 +73,9 @@ class FakeEngine:
         self.algorithmic_bytes = layout.real_nnz * (10 if layout.is_double else 6) + layout.rows * 8 + layout.cols * 8
         r = layout.x_ranges()
         self.x_upload_bytes = int((np.minimum(r[:, 1], layout.expanded_cols) - r[:, 0]).sum()) * (8 if layout.is_double else 4)
+        self.device_layout = dict(layout.device_params)
+        self._A = _scipy(layout._csr) if getattr(layout, "_csr", None) is not None else None
+        self._x = None
 
     @staticmethod
     def from_csr(rows, cols, row_ptr, col_ind, values, n_cu=1, vf=1, is_double=True, cols_div_blocks=0, device=0,
@@ -85,40 +96,85 @@ class FakeEngine:
     def collect_steps(self):
         return 0.05 * self._steps, np.full(self._steps if self._inner else 0, 0.05, np.float32)
 
-    def spmv_host(self, x, y, accumulate=True): return y
-
     def _view(self, ptr, n):
         import ctypes
         dt = np.float64 if self.is_double else np.float32
         return np.frombuffer((ctypes.c_uint8 * (n * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt, count=n)
 
-    def spmv_dev(self, x_dev=None, y_dev=None, accumulate=False, stream=None):
-        self.launches += 2
-        if y_dev:  # "device" pointers are host pointers in a dry run: y = 1
-            self._view(y_dev, self.rows)[:] = 1.0
-
-    def sumsq(self, src_dev, n, out_dev, stream=None):
-        import ctypes
-        self.launches += 1
-        v = self._view(src_dev, n).astype(np.float64)
-        ctypes.c_double.from_address(out_dev).value = float(v @ v)
-
-    def scale_rsqrt(self, src_dev, dst_dev, n, sumsq_dev, stream=None):
-        import ctypes
-        self.launches += 1
-        ss = ctypes.c_double.from_address(sumsq_dev).value
-        self._view(dst_dev, n)[:] = self._view(src_dev, n) / np.sqrt(ss)
-    def get_y(self, out=None, accumulate=False):
+    def _ax(self, x):
         dt = np.float64 if self.is_double else np.float32
-        csr = getattr(self.layout, "_csr", None)
-        if csr is None or getattr(self, "_x", None) is None:
-            return np.zeros(self.rows, dt)
-        import scipy.sparse as sp
-        A = sp.csr_matrix((csr.values, csr.col_ind.astype(np.int64), csr.row_ptr.astype(np.int64)), shape=(csr.rows, csr.cols))
-        y = (A @ self._x[: csr.cols]).astype(dt)
+        y = (self._A @ x[: self.cols]).astype(dt) if self._A is not None else np.zeros(self.rows, dt)
         if os.environ.get("DRYRUN_BREAK_RANK") == os.environ.get("RANK", "0"):
             y[-1] += 1e-3  # a wrong last row on one rank: bench.py must refuse to print a number
         return y
+
+    def spmv_host(self, x, y, accumulate=True):
+        xv = self._view(x[0], x[1]) if isinstance(x, tuple) else x
+        yv = self._view(y, self.rows) if isinstance(y, int) else y
+        r = self._ax(xv)
+        yv[:] = yv + r if accumulate else r
+        return y
+
+    def spmv_dev(self, x_dev=None, y_dev=None, accumulate=False, stream=None):
+        self.launches += 2
+
+    def get_y(self, out=None, accumulate=False):
+        return self._ax(self._x)
+
+
+class FakeGroup:
+    """Stand-in for spmvb.Group (one rank of a multi-process group): the arithmetic is scipy, the exchange gloo."""
+
+    def __init__(self, n, bounds, csr_arrays, is_double, rank, world):
+        import scipy.sparse as sp
+        rp, ci, va = csr_arrays
+        self.rows = self.cols = n
+        self.bounds, self.rank, self.world, self.is_double = [int(b) for b in bounds], rank, world, is_double
+        self.A = sp.csr_matrix((va, ci.astype(np.int64), rp.astype(np.int64)), shape=(self.bounds[rank + 1] - self.bounds[rank], n))
+        self.dt = np.float64 if is_double else np.float32
+        self.x = np.zeros(n, self.dt)
+        self.y = np.zeros(self.A.shape[0], self.dt)
+        self._launches = 0
+        self.last_iter_ms = 0.25
+
+    @staticmethod
+    def unique_id():
+        return np.arange(128, dtype=np.uint8)
+
+    @staticmethod
+    def create_rank(global_rows, cols, bounds, row_ptr_local, col_ind, values, is_double, device, unique_id, rank, world,
+                    variant=0):
+        assert world == 1 or (unique_id is not None and np.array_equal(np.asarray(unique_id), np.arange(128, dtype=np.uint8)))
+        return FakeGroup(global_rows, bounds, (np.array(row_ptr_local), np.array(col_ind), np.array(values)), is_double, rank, world)
+
+    def set_x(self, x): self.x = np.array(x, dtype=self.dt, copy=True)
+    def get_x(self): return self.x.copy()
+
+    def get_y(self):
+        out = np.zeros(self.rows, self.dt)
+        out[self.bounds[self.rank]:self.bounds[self.rank + 1]] = self.y
+        return out
+
+    def launches(self): return self._launches
+    def free(self): pass
+
+    def power_iter(self, iters):
+        nrm = 0.0
+        for _ in range(iters):
+            self.y = (self.A @ self.x).astype(self.dt)
+            ss = _real_tensor([float(np.sum(self.y.astype(np.float64) ** 2))], dtype=torch.float64)
+            if self.world > 1:
+                dist.all_reduce(ss)
+            nrm = float(np.sqrt(ss.item()))
+            mine = (self.y / self.dt(nrm)).astype(self.dt)
+            if self.world > 1:
+                parts = [None] * self.world
+                dist.all_gather_object(parts, mine)
+                self.x = np.concatenate(parts).astype(self.dt)
+            else:
+                self.x = mine
+            self._launches += 4
+        return nrm
 
 
 _real_from_csr = spmvb.Layout.from_csr
@@ -132,3 +188,4 @@ def _from_csr(csr, *a, **k):  # remember the matrix so that the stand-in can pro
 
 spmvb.Layout.from_csr = staticmethod(_from_csr)
 spmvb.Engine = FakeEngine
+spmvb.Group = FakeGroup

@@ -41,47 +41,85 @@ def test_single_rank_line():
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     d = _check_line(p.stdout, 1, 4)
-    assert "cpu_baseline" in d and d["cpu_baseline"]["cores"] == 1
-    assert d["setup_s"]["gpu_layout_build"]["identical_to_host_build"] is True
+    assert "cpu_baseline" in d and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["check"]["max_err_over_tolerance"] <= 1.0 and d["scaling"] == "weak"
+    assert set(d["config"]) == {"workload", "rows", "cols", "nnz"}
+
+
+def test_default_workload_is_the_target_matrix_strong_scaling_with_also_block():
+    """The default run at reduced scale: uniform 16 nnz/row, strong scaling, and the `also` block with the Laplacian and
+    the R-MAT workload (reduced through --also at a small scale is not possible: the block is checked for presence on the
+    band-size run below instead)."""
+    p = subprocess.run([sys.executable, "-c", CODE, "--scale", "14", "--steps", "3", "--warmup", "3", "--also", "band"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = _check_line(p.stdout, 1, 3)
+    assert d["scaling"] == "strong" and d["config"]["nnz"] == 16 << 14 and d["dtype"] == "f64"
+    assert "band" in d["also"] and d["also"]["band"]["check"]["max_err_over_tolerance"] <= 1.0
+    assert d["engine"]["device_layout"]["cdb"] in (16384, 32768)
+
+
+def test_reference_arm_prints_the_same_config_without_loading_the_engine():
+    env = dict(os.environ)
+    code = ("import sys, json; sys.argv = ['bench.py', '--impl', 'reference', '--scale', '14', '--steps', '2', '--warmup', '1'];"
+            "sys.path.insert(0, %r); import bench; bench.main();"
+            "maps = open('/proc/self/maps').read(); assert 'libspmvb.so' not in maps, 'engine library loaded'; "
+            "assert 'libmatgen.so' in maps") % ROOT
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.strip()][0])
+    assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["value"] == d["value"]
+    g = subprocess.run([sys.executable, "-c", CODE, "--scale", "14", "--steps", "3", "--warmup", "3", "--also", ""], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert g.returncode == 0, g.stderr[-2000:]
+    assert json.loads(g.stdout.strip())["config"] == d["config"]      # both arms: the identical config dict
 
 
 def test_two_rank_line_over_gloo():
     port = _free_port()
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), "--no-python", sys.executable, "-c", CODE,
-                        "--gpus", "2", "--steps", "4", "--warmup", "3"], cwd=ROOT,
+                        "--gpus", "2", "--workload", "laplacian", "--steps", "4", "--warmup", "3"], cwd=ROOT,
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-3000:]
     d = _check_line(p.stdout, 2, 4)
     assert d["config"]["rows"] == 2 * 4194304            # weak scaling: the config-2 Laplacian per rank
     # every rank uploads only the band of x its rows read, not the whole replicated vector
     assert d["e2e"]["h2d_bytes_per_step"] < 1.2 * d["config"]["cols"] * 8
-    assert "cpu_baseline" not in d                       # N = 1 only
+    assert "cpu_baseline" not in d and "also" not in d   # N = 1 only
 
 
-@pytest.mark.parametrize("mode", ["broadcast", "chunks"])
-def test_power_iteration_line_over_gloo(mode):
+def test_two_rank_strong_scaling_of_the_default_workload_over_gloo():
     port = _free_port()
-    env = dict(os.environ, SPMVB_EXCHANGE=mode)
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), "--no-python", sys.executable, "-c", CODE,
+                        "--gpus", "2", "--scale", "14", "--steps", "3", "--warmup", "3"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    d = _check_line(p.stdout, 2, 3)
+    assert d["scaling"] == "strong" and d["config"]["rows"] == 1 << 14 and d["config"]["nnz"] == 16 << 14
+    assert d["engine"]["rows_per_gpu"] == [1 << 13, 1 << 13]
+    assert d["e2e"]["h2d_bytes_per_step"] == 2 * (1 << 14) * 8   # x replicated: every rank uploads all of it
+
+
+def test_power_iteration_line_over_gloo():
+    port = _free_port()
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), "--no-python", sys.executable, "-c", CODE,
                         "--gpus", "2", "--workload", "poweriter", "--scale", "14", "--steps", "3", "--warmup", "3"], cwd=ROOT,
-                       capture_output=True, text=True, timeout=900, env=env)
+                       capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-3000:]
-    lines = [l for l in p.stdout.splitlines() if l.strip()]
-    assert len(lines) == 1, p.stdout
-    d = json.loads(lines[0])
-    assert d["n_gpus"] == 2 and d["steps"] == 3 and d["dtype"] == "f32" and d["config"]["rows"] == 1 << 14
-    # the stand-in engine returns y = 1 on every rank: after normalisation ||x|| = 1 and the last norm is sqrt(rows)
-    assert abs(d["last_norm"] - 128.0) < 1e-3
-    assert ("broadcast" in d["config"]["step"]) == (mode == "broadcast")
+    d = _check_line(p.stdout, 2, 3)
+    assert d["dtype"] == "f32" and d["config"]["rows"] == 1 << 14 and d["scaling"] == "strong"
+    assert d["check"]["x_identical_on_all_ranks"] is True and d["check"]["rows_max_err_over_tolerance"] <= 1.0
+    assert d["last_norm"] > 0
 
 
 def test_two_rank_run_refuses_a_wrong_result():
     port = _free_port()
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), "--no-python", sys.executable, "-c", CODE,
-                        "--gpus", "2", "--steps", "3", "--warmup", "3"], cwd=ROOT, capture_output=True, text=True,
+                        "--gpus", "2", "--scale", "14", "--steps", "3", "--warmup", "3"], cwd=ROOT, capture_output=True, text=True,
                        timeout=900, env=dict(os.environ, DRYRUN_BREAK_RANK="1"))
     assert p.returncode != 0
     assert "multi-GPU result check failed" in p.stderr

