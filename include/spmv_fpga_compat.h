@@ -93,7 +93,8 @@ typedef struct spmvb_compat_owner {
   csr_hw_matrix pub;
   uint32_t magic;
   spmvb_layout *layout;
-  spmvb_engine *engine;
+  spmvb_engine *engine; /* one GPU ... */
+  spmvb_group *group;   /* ... or several (SPMVB_DEVICES): the compute units mapped to GPUs */
   IndexType rows, cols;
   ValueType *x_scratch; /* expanded_nr_cols values */
 } spmvb_compat_owner;
@@ -194,12 +195,46 @@ static inline int verification(IndexType nr_values, ValueType *sw_values, ValueT
 }
 
 /* ---- csr_hw_wrapper.cpp:3-80: builds the layout (bit-exact pieces) and uploads it to the GPU */
+/* Run-time configuration of a drop-in executable (the reference has compile-time macros only, Makefile:71):
+ *   SPMVB_DEVICE=i        the GPU to use (default 0)
+ *   SPMVB_DEVICES=a,b,..  several GPUs of this box: the CU dimension mapped to GPUs (spmvb_group_create) - rows are
+ *                         split over them by non-zero count, x goes to every GPU, all kernels run concurrently
+ *   SPMVB_GPU_BUILD=1     build the hw_matrix layout on the GPU; SPMVB_CSR_CACHE=1 binary sidecar of the matrix file
+ *   SPMVB_<OPTION>=n      any spmvb_set_option name (spmvb_options_from_env) */
+static inline int spmvb_compat_devices(int *devs, int max) {
+  const char *list = getenv("SPMVB_DEVICES");
+  int n = 0;
+  if (!list) return 0;
+  while (*list && n < max) {
+    char *end;
+    long v = strtol(list, &end, 10);
+    if (end == list) break;
+    devs[n++] = (int)v;
+    list = (*end == ',') ? end + 1 : end;
+  }
+  return n;
+}
+
 static inline void create_csr_hw_matrix(csr_matrix *matrix, csr_hw_matrix ***hw_matrix, bool ***empty_rows_bitmap) {
   spmvb_layout *L = NULL;
   spmvb_engine *E = NULL;
+  spmvb_group *G = NULL;
+  spmvb_options_from_env();
   const char *dev = getenv("SPMVB_DEVICE");
   const char *gpu_build = getenv("SPMVB_GPU_BUILD");
-  if (gpu_build && atoi(gpu_build)) {
+  int devs[64];
+  const int n_devs = spmvb_compat_devices(devs, 64);
+  if (n_devs > 1) {
+    /* hw_matrix[k] keeps the reference's per-block CU pieces on the host (below); the GPUs get contiguous row ranges of
+     * their own, balanced by non-zero count with the same split rule applied to whole rows (SURVEY 8e mapping A) */
+    uint64_t *rp64 = (uint64_t *)malloc(((size_t)matrix->nr_rows + 1) * sizeof(uint64_t));
+    for (IndexType i = 0; i <= matrix->nr_rows; i++) rp64[i] = matrix->row_ptr[i];
+    if (spmvb_group_create(matrix->nr_rows, matrix->nr_cols, rp64, matrix->col_ind, matrix->values, DOUBLE, n_devs, devs, 0,
+                           &G) != SPMVB_OK)
+      spmvb_compat_die("create_csr_hw_matrix (multi-GPU)");
+    free(rp64);
+  }
+  if (!G && gpu_build && atoi(gpu_build)) {
     /* SPMVB_GPU_BUILD=1: the same layout built by CUDA kernels (needs sorted rows; errors are fatal like any other),
      * then copied back because this API exposes submatrix[b] and the bitmap on the host */
     uint64_t *rp64 = (uint64_t *)malloc(((size_t)matrix->nr_rows + 1) * sizeof(uint64_t));
@@ -254,8 +289,9 @@ static inline void create_csr_hw_matrix(csr_matrix *matrix, csr_hw_matrix ***hw_
     printf("Total non-zeros : %.0f. Total %g MB transferred ( in : %g, out : %g)\n", tot, in + out, in, out);
   }
   spmvb_compat_owner *o = (spmvb_compat_owner *)(*hw_matrix)[0];
-  if (!E && spmvb_engine_create(L, dev ? atoi(dev) : 0, 0, &E) != SPMVB_OK) spmvb_compat_die("create_csr_hw_matrix (GPU upload)");
+  if (!E && !G && spmvb_engine_create(L, dev ? atoi(dev) : 0, 0, &E) != SPMVB_OK) spmvb_compat_die("create_csr_hw_matrix (GPU upload)");
   o->engine = E;
+  o->group = G;
 }
 
 /* ---- csr_hw.cpp:1436-1488: per-block packed x slices, zero padded */
@@ -320,7 +356,9 @@ static inline void spmv_hw(csr_hw_matrix **hw_matrix, csr_hw_vector *hw_x, csr_v
     n += nv;
   }
   double t0 = getTimestamp();
-  if (spmvb_engine_spmv_host(o->engine, o->x_scratch, n, y_fpga->values, 1) != SPMVB_OK) spmvb_compat_die("spmv_hw");
+  const int rc = o->group ? spmvb_group_spmv_host(o->group, o->x_scratch, n, y_fpga->values, 1)
+                          : spmvb_engine_spmv_host(o->engine, o->x_scratch, n, y_fpga->values, 1);
+  if (rc != SPMVB_OK) spmvb_compat_die("spmv_hw");
   double t1 = getTimestamp();
   printf("Hardware execution time : %.6f ms elapsed\n", (t1 - t0) / 1000);
   printf("Result accumulation time : %.6f ms elapsed\n", 0.0); /* fused on the device */
@@ -330,7 +368,8 @@ static inline void spmv_hw(csr_hw_matrix **hw_matrix, csr_hw_vector *hw_x, csr_v
 /* ---- csr_hw_wrapper.cpp:291-296 */
 static inline void delete_csr_hw_matrix(csr_hw_matrix **hw_matrix) {
   spmvb_compat_owner *o = (spmvb_compat_owner *)hw_matrix[0];
-  spmvb_engine_free(o->engine);
+  if (o->engine) spmvb_engine_free(o->engine);
+  if (o->group) spmvb_group_free(o->group);
   spmvb_layout *L = o->layout;
   for (int k = 0; k < ComputeUnits; k++) {
     csr_hw_matrix *p = hw_matrix[k];

@@ -2,6 +2,9 @@
 # round 2, GPU session 1: the GPU suite, the default bench + reference arm, option A/Bs, first ncu captures
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/s1_box.txt; nproc >> gpurun_out/s1_box.txt; free -g >> gpurun_out/s1_box.txt
+# the new kernel paths on small cases first, with a short leash: a hang here must not take the box down with it
+timeout 300 python scripts/sanitize_case.py > gpurun_out/s1_smallcases.log 2>&1; rc=$?; echo "small cases exit $rc"; tail -4 gpurun_out/s1_smallcases.log
+if [ $rc -ne 0 ]; then echo "ABORT: small cases failed"; exit 1; fi
 ( time timeout 1500 python -m pytest tests -x -q -m gpu --durations=12 ) > gpurun_out/s1_pytest_gpu.log 2>&1; echo "gpu suite exit $?"; tail -25 gpurun_out/s1_pytest_gpu.log
 ( time timeout 900 python bench.py ) > gpurun_out/s1_bench_default.json 2> gpurun_out/s1_bench_default.err; echo "bench exit $?"; tail -3 gpurun_out/s1_bench_default.err; head -c 3000 gpurun_out/s1_bench_default.json
 ( time timeout 600 python bench.py --impl reference --steps 10 --warmup 2 ) > gpurun_out/s1_bench_ref.json 2> gpurun_out/s1_bench_ref.err; echo "ref exit $?"; head -c 1500 gpurun_out/s1_bench_ref.json

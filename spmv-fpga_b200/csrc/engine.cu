@@ -34,6 +34,14 @@ struct Engine {
   uint32_t *d_zero_rows = nullptr;
   XsItem *d_items = nullptr;  // work items of the XS kernel
   uint32_t *d_cta_first = nullptr;  // [sms + 1] first item of every CTA
+  // CU-major layouts: the XS work dealt tile by tile as well (spmv_host launches one kernel per row tile and sends the
+  // tile's rows of y to the host while the next tile is computed)
+  int n_tiles = 0;
+  XsItem *d_items_t = nullptr;
+  uint32_t *d_cta_first_t = nullptr;   // [n_tiles * (sms + 1)]
+  std::vector<uint32_t> tile_rows_end; // rows [0, tile_rows_end[k]) are final once tiles 0..k are done
+  std::vector<cudaEvent_t> ev_tile;    // [2 * n_tiles] kernel done / copy done
+  cudaStream_t copy_stream = nullptr;
   uint2 *d_rowaux = nullptr;  // [n_chunks] slice of the row map every chunk needs (XS kernel stages it with the chunk)
   bool xs_rowids = false;     // the XS kernel stages row ids (the image has chunks whose rows are not consecutive)
   // API image of a GPU-built layout whose device layout differs from it (kept for spmvb_engine_fetch_layout)
@@ -120,8 +128,9 @@ static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, 
   return SPMVB_OK;
 }
 
+// tile < 0: the whole matrix in one launch; otherwise row tile `tile` only (per-tile plan)
 template <typename VT, bool ROWIDS>
-static int launch_xs_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
+static int launch_xs_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
   constexpr int WARPS = sizeof(VT) == 8 ? kXsWarpsF64 : kXsWarpsF32;
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
   auto kern = spmv_xs_kernel<VT, WARPS, kXsCap, ROWIDS>;
@@ -133,14 +142,16 @@ static int launch_xs_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int ac
     grid = E->sms;
   }
   if (E->n_items == 0) return SPMVB_OK;
+  const XsItem *items = tile < 0 ? E->d_items : E->d_items_t;
+  const uint32_t *first = tile < 0 ? E->d_cta_first : E->d_cta_first_t + (size_t)tile * (E->sms + 1);
   CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, (const uint2 *)E->d_rowaux,
-                      x, y, (const XsItem *)E->d_items, (const uint32_t *)E->d_cta_first, E->cdb, E->xs_run_log2,
-                      (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u)));
+                      x, y, items, first, E->cdb, E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u)));
   return SPMVB_OK;
 }
 template <typename VT>
-static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
-  return E->xs_rowids ? launch_xs_impl<VT, true>(E, x, y, st, accumulate) : launch_xs_impl<VT, false>(E, x, y, st, accumulate);
+static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile = -1) {
+  return E->xs_rowids ? launch_xs_impl<VT, true>(E, x, y, st, accumulate, tile)
+                      : launch_xs_impl<VT, false>(E, x, y, st, accumulate, tile);
 }
 
 template <typename VT>
@@ -239,6 +250,61 @@ static int autotune(Engine *E) {
   cudaEventDestroy(b);
   E->launches = 0;
   return rc;
+}
+
+// host y (+)= device y for rows [a, b): the addition of spmv_hw (csr_hw.cpp:1557) on all host cores
+static void host_accumulate(Engine *E, void *y_host, int64_t a, int64_t b) {
+  if (E->is_double) {
+    double *dst = (double *)y_host; const double *src = (const double *)E->h_stage;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = a; i < b; i++) dst[i] += src[i];
+  } else {
+    float *dst = (float *)y_host; const float *src = (const float *)E->h_stage;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = a; i < b; i++) dst[i] += src[i];
+  }
+}
+
+// spmv_hw end to end for a row-tiled (CU-major) layout: x up, then one kernel launch per row tile; as soon as a tile
+// is done its final rows of y travel to the host on a second stream while the next tiles are computed, and the host adds
+// them into y_host while later rows are still on their way.
+template <typename VT>
+static int spmv_host_tiled(Engine *E, void *y_host, int accumulate) {
+  const size_t bytes = (size_t)E->rows * E->vb;
+  if (accumulate && E->h_stage_bytes < bytes) {
+    if (E->h_stage) cudaFreeHost(E->h_stage);
+    E->h_stage = nullptr; E->h_stage_bytes = 0;
+    CUDA_TRY(cudaMallocHost(&E->h_stage, bytes));
+    E->h_stage_bytes = bytes;
+  }
+  int rc = zero_y(E, E->d_y, E->stream);
+  if (rc) return rc;
+  uint8_t *dst = accumulate ? (uint8_t *)E->h_stage : (uint8_t *)y_host;
+  uint32_t prev = 0;
+  for (int k = 0; k < E->n_tiles; k++) {
+    rc = launch_xs<VT>(E, (const VT *)E->d_x, (VT *)E->d_y, E->stream, 0, k);
+    if (rc) return rc;
+    E->launches++;
+    CUDA_TRY(cudaEventRecord(E->ev_tile[2 * k], E->stream));
+    CUDA_TRY(cudaStreamWaitEvent(E->copy_stream, E->ev_tile[2 * k], 0));
+    const uint32_t end = k + 1 == E->n_tiles ? E->rows : E->tile_rows_end[k];
+    if (end > prev)
+      CUDA_TRY(cudaMemcpyAsync(dst + (size_t)prev * E->vb, (const uint8_t *)E->d_y + (size_t)prev * E->vb,
+                               (size_t)(end - prev) * E->vb, cudaMemcpyDeviceToHost, E->copy_stream));
+    CUDA_TRY(cudaEventRecord(E->ev_tile[2 * k + 1], E->copy_stream));
+    prev = std::max(prev, end);
+  }
+  cudaError_t werr = cudaSuccess;
+  prev = 0;
+  for (int k = 0; k < E->n_tiles; k++) {
+    cudaError_t r = cudaEventSynchronize(E->ev_tile[2 * k + 1]);
+    if (r != cudaSuccess) werr = r;
+    const uint32_t end = k + 1 == E->n_tiles ? E->rows : E->tile_rows_end[k];
+    if (werr == cudaSuccess && accumulate && end > prev) host_accumulate(E, y_host, prev, end);
+    prev = std::max(prev, end);
+  }
+  if (werr != cudaSuccess) return fail(SPMVB_E_CUDA, std::string("spmv_host: ") + cudaGetErrorString(werr));
+  return SPMVB_OK;
 }
 
 }  // namespace spmvb
@@ -390,8 +456,20 @@ static int engine_adopt_layout(Engine *E, const Layout *L) {
 static int engine_finish(Engine *E, const Layout *L) {
   std::vector<XsItem> items;
   std::vector<uint32_t> cta_first;
-  build_xs_items(L, E->sms, E->xs_run_log2, items, cta_first);
+  XsTilePlan tiles;
+  build_xs_items(L, E->sms, E->xs_run_log2, items, cta_first, L->cu_major ? &tiles : nullptr);
   E->n_items = (uint32_t)items.size();
+  if (tiles.n_tiles > 1 && tiles.n_tiles <= 1024 && !tiles.items.empty()) {
+    E->n_tiles = tiles.n_tiles;
+    E->tile_rows_end = tiles.rows_end;
+    CUDA_TRY(cudaMalloc((void **)&E->d_items_t, tiles.items.size() * sizeof(XsItem)));
+    CUDA_TRY(cudaMalloc((void **)&E->d_cta_first_t, tiles.cta_first.size() * 4));
+    CUDA_TRY(cudaMemcpy(E->d_items_t, tiles.items.data(), tiles.items.size() * sizeof(XsItem), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(E->d_cta_first_t, tiles.cta_first.data(), tiles.cta_first.size() * 4, cudaMemcpyHostToDevice));
+    E->ev_tile.assign(2 * (size_t)E->n_tiles, nullptr);
+    for (auto &e : E->ev_tile) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
+  }
   CUDA_TRY(cudaMalloc((void **)&E->d_items, std::max<size_t>(items.size(), 1) * sizeof(XsItem)));
   CUDA_TRY(cudaMalloc((void **)&E->d_cta_first, cta_first.size() * 4));
   CUDA_TRY(cudaMemcpy(E->d_items, items.data(), items.size() * sizeof(XsItem), cudaMemcpyHostToDevice));
@@ -588,6 +666,9 @@ void spmvb_engine_free(spmvb_engine *e) {
   if (E->stream) cudaStreamSynchronize(E->stream);
   cudaFree(E->d_stream); cudaFree(E->d_rowmap); cudaFree(E->d_zero_rows); cudaFree(E->d_items); cudaFree(E->d_cta_first);
   cudaFree(E->d_x); cudaFree(E->d_y); cudaFree(E->d_scalar); cudaFree(E->d_flush);
+  cudaFree(E->d_items_t); cudaFree(E->d_cta_first_t);
+  for (auto &x : E->ev_tile) if (x) cudaEventDestroy(x);
+  if (E->copy_stream) cudaStreamDestroy(E->copy_stream);
   cudaFree(E->d_rowaux); cudaFree(E->d_api_stream); cudaFree(E->d_api_rowmap); cudaFree(E->d_cg);
   if (E->h_stage) cudaFreeHost(E->h_stage);
   if (E->h_scalar) cudaFreeHost(E->h_scalar);
@@ -693,16 +774,7 @@ int spmvb_engine_get_y(spmvb_engine *e, void *y_host, uint32_t n, int accumulate
     cudaError_t r = cudaEventSynchronize(E->ev_piece[p]);
     if (r != cudaSuccess) werr = r;
     if (werr != cudaSuccess) continue;
-    const int64_t a = cutp[p], b = cutp[p + 1];
-    if (E->is_double) {
-      double *dst = (double *)y_host; const double *src = (const double *)E->h_stage;
-#pragma omp parallel for schedule(static)
-      for (int64_t i = a; i < b; i++) dst[i] += src[i];
-    } else {
-      float *dst = (float *)y_host; const float *src = (const float *)E->h_stage;
-#pragma omp parallel for schedule(static)
-      for (int64_t i = a; i < b; i++) dst[i] += src[i];
-    }
+    host_accumulate(E, y_host, cutp[p], cutp[p + 1]);
   }
   if (werr != cudaSuccess) return fail(SPMVB_E_CUDA, std::string("get_y: ") + cudaGetErrorString(werr));
   return SPMVB_OK;
@@ -713,6 +785,9 @@ int spmvb_engine_spmv_host(spmvb_engine *e, const void *x_host, uint32_t n, void
   if (!E) return fail(SPMVB_E_ARG, "spmv_host");
   int rc = spmvb_engine_set_x(e, x_host, n);
   if (rc) return rc;
+  const int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
+  if (variant == kVariantXs && E->n_tiles > 1 && y_host && options().e2e_tiles != 0)
+    return E->is_double ? spmv_host_tiled<double>(E, y_host, accumulate) : spmv_host_tiled<float>(E, y_host, accumulate);
   rc = do_spmv(E, nullptr, nullptr, 0, E->stream);
   if (rc) return rc;
   return spmvb_engine_get_y(e, y_host, E->rows, accumulate);

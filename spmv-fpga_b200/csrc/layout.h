@@ -95,8 +95,15 @@ constexpr uint32_t kXsCap = 128 * 1024;  // bytes of shared memory for the x win
 constexpr int kXsWarpsF64 = 12, kXsWarpsF32 = 16;
 constexpr uint32_t kXsRowIdBytes = 1040;
 inline int xs_warps(int is_double) { return is_double ? kXsWarpsF64 : kXsWarpsF32; }
+// CU-major layouts only: the same work dealt tile by tile (one kernel launch per row tile)
+struct XsTilePlan {
+  int n_tiles = 0;
+  std::vector<XsItem> items;
+  std::vector<uint32_t> cta_first;  // [n_tiles * (n_cta + 1)]
+  std::vector<uint32_t> rows_end;   // [n_tiles] rows [0, rows_end[k]) are final once tiles 0..k are done
+};
 void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<XsItem> &items,
-                    std::vector<uint32_t> &cta_first);
+                    std::vector<uint32_t> &cta_first, XsTilePlan *tiles);
 
 // pieces shared by the host builder (layout_builder.cpp) and the GPU builder (layout_gpu.cuh)
 int layout_init_header(Layout *L, uint32_t rows, uint32_t cols, uint64_t nnz, int cu, int vf, int is_double,
@@ -118,6 +125,7 @@ struct Options {
   int64_t dev_cdb = -1;       // column-block width of the engine-private device layout (0 = same as the API layout)
   int64_t xs_pairs = -1;      // distinct x lines per 256-entry chunk above which the x-window kernel is preferred
   int64_t tile_mb = -1;       // target size of a row tile's y range in MB
+  int64_t e2e_tiles = -1;     // 0: spmv_host does not pipeline row tiles (one launch, then the copy of y)
   int64_t xs_rowids = -1;     // 0: XS kernel reads row ids with per-lane global loads instead of staging them
 };
 Options &options();

@@ -14,7 +14,7 @@ namespace spmvb {
 // (row tiles): see below.  Cut points are piece-relative multiples of
 // U = run length x warps per CTA, so that every warp of the CTA gets the same number of whole runs per item.
 void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<XsItem> &items,
-                           std::vector<uint32_t> &cta_first) {
+                    std::vector<uint32_t> &cta_first, XsTilePlan *tiles) {
   const uint64_t U = ((uint64_t)1 << run_log2) * (uint64_t)xs_warps(L->is_double);
   const uint32_t align = 16u / (uint32_t)L->vb;  // window start in elements: 16-byte aligned for the bulk copy
   // candidate cut points in global chunk indices: block starts and block-relative multiples of U
@@ -88,6 +88,46 @@ void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<X
     // round-robin, so that all CTAs work on neighbouring column blocks of the same row tile at any time.
     const uint64_t cap = std::max<uint64_t>(U, 256 / U * U);
     emit(0, cuts.size() - 1, cap);
+    if (tiles) {
+      // The same items dealt tile by tile (one launch per row tile: spmv_host sends a tile's rows of y to the host
+      // while the next tile is computed).  In CU-major order tile k's pieces are contiguous: chunks
+      // [piece_chunk0 of its first piece, ... of tile k+1's first piece).
+      const int T = L->cu, B = L->blocks;
+      tiles->n_tiles = T;
+      tiles->items.clear();
+      tiles->cta_first.assign((size_t)T * (n_cta + 1), 0);
+      tiles->rows_end.assign(T, L->rows);
+      std::vector<uint64_t> tile_chunk0(T + 1, L->n_chunks);
+      for (int k = T - 1; k >= 0; k--) tile_chunk0[k] = L->piece_chunk0[(size_t)0 * T + k];  // piece (block 0, CU k) opens tile k
+      size_t i0 = 0;
+      for (int k = 0; k < T; k++) {
+        size_t i1 = i0;
+        while (i1 < items.size() && items[i1].chunk_begin < tile_chunk0[k + 1]) i1++;
+        uint32_t *first = &tiles->cta_first[(size_t)k * (n_cta + 1)];
+        for (int j = 0; j < n_cta; j++) {
+          first[j] = (uint32_t)tiles->items.size();
+          for (size_t i = i0 + (size_t)j; i < i1; i += (size_t)n_cta) tiles->items.push_back(items[i]);
+        }
+        first[n_cta] = (uint32_t)tiles->items.size();
+        i0 = i1;
+      }
+      // rows that are final once tile k is done: everything below the first row of any later tile's piece (the CU
+      // split is made per column block, csr_hw.cpp:459-468, so the tiles' row ranges differ a little from block to block)
+      std::vector<uint32_t> first_row(T, L->rows);
+      for (int b = 0; b < B; b++)
+        for (int k = 0; k < T; k++) {
+          const size_t bk = (size_t)b * T + k;
+          if (L->piece_chunk1[bk] == L->piece_chunk0[bk]) continue;
+          const ChunkMeta &m = L->chunks[L->piece_chunk0[bk]];
+          if (m.valid & 0x3FFu) first_row[k] = std::min(first_row[k], m.row_first);
+        }
+      uint32_t later = L->rows;
+      for (int k = T - 1; k >= 0; k--) {
+        tiles->rows_end[k] = later;          // min first row over the tiles after k
+        later = std::min(later, first_row[k]);
+      }
+      for (int k = 1; k < T; k++) tiles->rows_end[k] = std::max(tiles->rows_end[k], tiles->rows_end[k - 1]);
+    }
     std::vector<XsItem> rr;
     rr.reserve(items.size());
     for (int j = 0; j < n_cta; j++) {
@@ -110,7 +150,7 @@ extern "C" int64_t spmvb_layout_xs_plan(const spmvb_layout *l, int n_cta, int ru
   if (L->dev) L = L->dev;  // the plan is made for what the GPU streams
   std::vector<XsItem> items;
   std::vector<uint32_t> cta_first;
-  build_xs_items(L, n_cta, (uint32_t)run_log2, items, cta_first);
+  build_xs_items(L, n_cta, (uint32_t)run_log2, items, cta_first, nullptr);
   if (items_out) memcpy(items_out, items.data(), std::min<uint64_t>(items.size(), max_items) * sizeof(XsItem));
   if (cta_first_out) memcpy(cta_first_out, cta_first.data(), cta_first.size() * 4);
   return (int64_t)items.size();
