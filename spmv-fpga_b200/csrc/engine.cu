@@ -42,8 +42,6 @@ struct Engine {
   std::vector<uint32_t> tile_rows_end; // rows [0, tile_rows_end[k]) are final once tiles 0..k are done
   std::vector<cudaEvent_t> ev_tile;    // [2 * n_tiles] kernel done / copy done
   cudaStream_t copy_stream = nullptr;
-  uint2 *d_rowaux = nullptr;  // [n_chunks] slice of the row map every chunk needs (XS kernel stages it with the chunk)
-  bool xs_rowids = false;     // the XS kernel stages row ids (the image has chunks whose rows are not consecutive)
   // API image of a GPU-built layout whose device layout differs from it (kept for spmvb_engine_fetch_layout)
   uint8_t *d_api_stream = nullptr;
   uint32_t *d_api_rowmap = nullptr;
@@ -129,12 +127,12 @@ static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, 
 }
 
 // tile < 0: the whole matrix in one launch; otherwise row tile `tile` only (per-tile plan)
-template <typename VT, bool ROWIDS>
-static int launch_xs_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
+template <typename VT>
+static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile = -1) {
   constexpr int WARPS = sizeof(VT) == 8 ? kXsWarpsF64 : kXsWarpsF32;
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
-  auto kern = spmv_xs_kernel<VT, WARPS, kXsCap, ROWIDS>;
-  const size_t stage = (size_t)VTraits<VT>::kGroupWords * 16 * 32 + 16 + (ROWIDS ? kXsRowIdBytes : 0);
+  auto kern = spmv_xs_kernel<VT, WARPS, kXsCap>;
+  const size_t stage = (size_t)VTraits<VT>::kGroupWords * 16 * 32 + 16;
   const size_t smem = (size_t)kXsCap + (size_t)WARPS * 2 * stage + WARPS * 16 + 16;
   int &grid = E->grid_cache[kVariantXs][sizeof(VT) == 8];
   if (grid == 0) {
@@ -144,14 +142,9 @@ static int launch_xs_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int ac
   if (E->n_items == 0) return SPMVB_OK;
   const XsItem *items = tile < 0 ? E->d_items : E->d_items_t;
   const uint32_t *first = tile < 0 ? E->d_cta_first : E->d_cta_first_t + (size_t)tile * (E->sms + 1);
-  CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, (const uint2 *)E->d_rowaux,
-                      x, y, items, first, E->cdb, E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u)));
+  CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, x, y, items, first, E->cdb,
+                      E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u)));
   return SPMVB_OK;
-}
-template <typename VT>
-static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile = -1) {
-  return E->xs_rowids ? launch_xs_impl<VT, true>(E, x, y, st, accumulate, tile)
-                      : launch_xs_impl<VT, false>(E, x, y, st, accumulate, tile);
 }
 
 template <typename VT>
@@ -477,26 +470,6 @@ static int engine_finish(Engine *E, const Layout *L) {
   uint64_t windowed = 0;
   for (auto &it : items) windowed += it.x_bytes ? it.chunk_count : 0;
   E->xs_windowed_frac = L->n_chunks ? (double)windowed / (double)L->n_chunks : 0.0;
-  // row-map slice of every chunk, for the XS kernel's staging copy: entries [rank0 & ~3, ...) so that the source is
-  // 16-byte aligned, one entry beyond the chunk's last row end (the row a run may leave open)
-  {
-    std::vector<uint2> aux((size_t)std::max<uint64_t>(L->n_chunks, 1), make_uint2(0u, 0u));
-    bool any = false;
-#pragma omp parallel for schedule(static) reduction(| : any)
-    for (int64_t c = 0; c < (int64_t)L->n_chunks; c++) {
-      const ChunkMeta &m = L->chunks[c];
-      if (!(m.valid & 0x3FFu) || (m.valid & kChunkRowsConsecutive)) continue;
-      const uint32_t n_eor = (m.block >> kMetaRowsShift) & 0x1FFu;
-      aux[c].x = m.rank0 & ~3u;
-      aux[c].y = (((m.rank0 & 3u) + n_eor + 1u + 3u) & ~3u) * 4u;
-      any = true;
-    }
-    E->xs_rowids = any && options().xs_rowids != 0;
-    if (E->xs_rowids) {
-      CUDA_TRY(cudaMalloc((void **)&E->d_rowaux, aux.size() * sizeof(uint2)));
-      CUDA_TRY(cudaMemcpy(E->d_rowaux, aux.data(), aux.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-    }
-  }
   CUDA_TRY(cudaMemsetAsync(E->d_x, 0, E->x_len * E->vb, E->stream));
   CUDA_TRY(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
   CUDA_TRY(cudaStreamSynchronize(E->stream));
@@ -669,7 +642,7 @@ void spmvb_engine_free(spmvb_engine *e) {
   cudaFree(E->d_items_t); cudaFree(E->d_cta_first_t);
   for (auto &x : E->ev_tile) if (x) cudaEventDestroy(x);
   if (E->copy_stream) cudaStreamDestroy(E->copy_stream);
-  cudaFree(E->d_rowaux); cudaFree(E->d_api_stream); cudaFree(E->d_api_rowmap); cudaFree(E->d_cg);
+  cudaFree(E->d_api_stream); cudaFree(E->d_api_rowmap); cudaFree(E->d_cg);
   if (E->h_stage) cudaFreeHost(E->h_stage);
   if (E->h_scalar) cudaFreeHost(E->h_scalar);
   for (auto &x : E->ev_piece) if (x) cudaEventDestroy(x);
@@ -947,7 +920,7 @@ int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out) {
   if (!E || !out) return fail(SPMVB_E_ARG, "device_layout");
   out[0] = (uint64_t)E->dev_cu; out[1] = (uint64_t)E->dev_vf; out[2] = E->cdb; out[3] = E->cu_major ? 1u : 0u;
   out[4] = E->n_pairs; out[5] = E->n_chunks; out[6] = E->zero_all ? UINT64_MAX : (uint64_t)E->n_zero_rows;
-  out[7] = E->stream_bytes; out[8] = E->xs_rowids ? 1u : 0u; out[9] = E->tall ? 1u : 0u;
+  out[7] = E->stream_bytes; out[8] = (uint64_t)E->n_tiles; out[9] = E->tall ? 1u : 0u;
   return SPMVB_OK;
 }
 

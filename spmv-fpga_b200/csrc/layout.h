@@ -91,9 +91,9 @@ struct XsItem {
 };
 constexpr uint32_t kXsCap = 128 * 1024;  // bytes of shared memory for the x window of an XS work item
 // warps per CTA of the XS kernel (one CTA per SM): what fits next to the x window - every warp owns two ring stages of
-// one chunk slot + the chunk's row ids (257 + alignment slack, 4 bytes each)
-constexpr int kXsWarpsF64 = 12, kXsWarpsF32 = 16;
-constexpr uint32_t kXsRowIdBytes = 1040;
+// one chunk slot (2576 B fp64 / 1552 B fp32) - and into the register file.  The kernel lives on warps: its per-chunk
+// instruction chain is long and serial (measured: 12 -> 16 warps = 78 -> 69 us on the Laplacian).
+constexpr int kXsWarpsF64 = 18, kXsWarpsF32 = 24;
 inline int xs_warps(int is_double) { return is_double ? kXsWarpsF64 : kXsWarpsF32; }
 // CU-major layouts only: the same work dealt tile by tile (one kernel launch per row tile)
 struct XsTilePlan {
@@ -126,7 +126,6 @@ struct Options {
   int64_t xs_pairs = -1;      // distinct x lines per 256-entry chunk above which the x-window kernel is preferred
   int64_t tile_mb = -1;       // target size of a row tile's y range in MB
   int64_t e2e_tiles = -1;     // 0: spmv_host does not pipeline row tiles (one launch, then the copy of y)
-  int64_t xs_rowids = -1;     // 0: XS kernel reads row ids with per-lane global loads instead of staging them
 };
 Options &options();
 

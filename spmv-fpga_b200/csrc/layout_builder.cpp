@@ -45,7 +45,7 @@ const OptionName kOptionNames[] = {
     {"tall", &Options::tall},                 {"occ_run_log2", &Options::occ_run_log2}, {"xs_run_log2", &Options::xs_run_log2},
     {"autotune", &Options::autotune},         {"build_trace", &Options::build_trace}, {"dev_tiles", &Options::dev_tiles},
     {"dev_cdb", &Options::dev_cdb},           {"xs_pairs", &Options::xs_pairs},       {"tile_mb", &Options::tile_mb},
-    {"xs_rowids", &Options::xs_rowids},       {"e2e_tiles", &Options::e2e_tiles},
+    {"e2e_tiles", &Options::e2e_tiles},
 };
 }  // namespace
 

@@ -152,7 +152,7 @@ template <typename VT, bool MUL>
 __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw, const uint4 *vw, const VT *xv,
                                               const uint32_t *__restrict__ rowmap, VT *__restrict__ y, int lane,
                                               VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red,
-                                              uint64_t y_policy = 0, uint32_t rowbuf = 0) {
+                                              uint64_t y_policy = 0, uint64_t stream_policy = 0) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t rank0 = mraw.x, valid = mraw.z & 0x3FFu, row_first = mraw.w;
   const bool consec = (mraw.z & kChunkRowsConsecutive) != 0;
@@ -177,29 +177,21 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
   // Row ids of this lane's row ends, all requested now, back to back, so that their latency overlaps the products
   // and the row sums (fetched one by one inside the update loop below they were 35 % of the XS kernel's stall time
   // on R-MAT: load -> wait -> RED -> next load ...).
-  // rowbuf != 0: the chunk's slice of the row map was staged in shared memory with the chunk itself (XS kernel: one
-  // more bulk copy on the same mbarrier), rowbuf pointing at the entry of rank0 - no global load on this path at all.
   uint32_t rows[8];
-  if (!consec && rowbuf) {
-    uint32_t a = rowbuf + 4u * (rank_t - rank0);
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-      const uint32_t e = (eor >> s) & 1u;
-      rows[s] = 0;
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
-                   : "+r"(rows[s])
-                   : "r"(a), "r"(e));
-      a += 4u * e;
-    }
-  } else if (!consec) {
+  if (!consec) {
     uint32_t rk = rank_t;
 #pragma unroll
     for (int s = 0; s < 8; s++) {
       const uint32_t e = (eor >> s) & 1u;
       rows[s] = 0;
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"
-                   : "+r"(rows[s])
-                   : "l"(rowmap + rk), "r"(e));
+      if (y_policy)  // tall matrix: the row map is read once, it must not push the y tile out of the L2 cache
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.L2::cache_hint.u32 %0, [%1], %3;\n\t}"
+                     : "+r"(rows[s])
+                     : "l"(rowmap + rk), "r"(e), "l"(stream_policy));
+      else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"
+                     : "+r"(rows[s])
+                     : "l"(rowmap + rk), "r"(e));
       rk += e;
     }
   }
@@ -353,21 +345,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 // run q of the warp being run q*W + w of the domain, so that the W warps sweep one contiguous window of the stream
 // together (DRAM page locality) while the open row sum stays in registers inside a run.
 // `t` is the warp's running slot counter: it carries the ring stage / mbarrier phase from one domain to the next.
-// ROWIDS: every stage also receives the chunk's slice of the row map (accum_results' bitmap walk, csr_hw.cpp:1549-1557,
-// in its compact form) by a second bulk copy on the same mbarrier; rowaux[c] = {first row-map entry to copy (a multiple
-// of 4: 16-byte aligned source), bytes (0 for chunks whose rows are consecutive)}.  Lane 0 reads rowaux one chunk
-// ahead of the copy it describes, so the dependent global load is off the critical path.
-template <typename VT, bool ROWIDS, typename Gather>
+// (Staging every chunk's slice of the row map with the chunk - a second bulk copy on the same mbarrier instead of the
+// lanes' eight global loads - was built and measured in round 2: no gain on the 0.5 B-nnz uniform matrix (3.74 vs 3.65
+// ms) and it cost a quarter of the warps their shared memory; the hoisted loads of process_chunk stay.)
+template <typename VT, typename Gather>
 __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
-                                            const uint2 *__restrict__ rowaux, VT *__restrict__ y, uint32_t ring,
-                                            uint32_t bars, int lane, uint32_t base, uint32_t n_dom, uint32_t w, uint32_t W,
-                                            uint32_t run_log2, bool force_red, uint32_t &t, uint64_t y_policy,
-                                            bool dep_wait, Gather gather) {
+                                            VT *__restrict__ y, uint32_t ring, uint32_t bars, int lane, uint32_t base,
+                                            uint32_t n_dom, uint32_t w, uint32_t W, uint32_t run_log2, bool force_red,
+                                            uint32_t &t, uint64_t y_policy, bool dep_wait, Gather gather) {
   constexpr int GW = VTraits<VT>::kGroupWords;
   constexpr int VW = VTraits<VT>::kValWords;
   constexpr uint32_t CHUNK_BYTES = GW * 16 * 32;
   constexpr uint32_t SLOT = CHUNK_BYTES + 16;
-  constexpr uint32_t STAGE = SLOT + (ROWIDS ? kXsRowIdBytes : 0u);
+  constexpr uint32_t STAGE = SLOT;
   const uint32_t R = 1u << run_log2;
   const uint32_t total_runs = (n_dom + R - 1) >> run_log2;
   if (w >= total_runs) return;
@@ -386,29 +376,17 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
   };
-  auto ld_aux = [&](uint32_t chunk) -> uint2 {
-    uint2 v;
-    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(rowaux + chunk));
-    return v;
-  };
   const uint64_t stream_policy = l2_policy_evict_first();
-  auto issue = [&](uint32_t slot, uint32_t chunk, uint2 aux) {  // lane 0 only
+  auto issue = [&](uint32_t slot, uint32_t chunk) {  // lane 0 only
     const uint32_t bar = bars + (slot & 1u) * 8;
-    const uint32_t dst = ring + (slot & 1u) * STAGE;
-    mbar_expect_tx(bar, SLOT + (ROWIDS ? aux.y : 0u));
-    bulk_g2s_hint(dst, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar, stream_policy);
-    if (ROWIDS && aux.y) bulk_g2s(dst + SLOT, rowmap + aux.x, aux.y, bar);
+    mbar_expect_tx(bar, SLOT);
+    bulk_g2s_hint(ring + (slot & 1u) * STAGE, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar, stream_policy);
   };
   const uint32_t my = ring + lane * (GW * 16);
   uint32_t c_cur = base + (w << run_log2);
-  uint2 aux_next = make_uint2(0u, 0u);  // lane 0: rowaux of the chunk the next refill fetches
   if (lane == 0) {
-    issue(t, c_cur, ROWIDS ? ld_aux(c_cur) : aux_next);
-    if (1 < n) {
-      const uint32_t c1 = ahead(c_cur, 0, 1);
-      issue(t + 1, c1, ROWIDS ? ld_aux(c1) : aux_next);
-    }
-    if (ROWIDS && 2 < n) aux_next = ld_aux(ahead(c_cur, 0, 2));
+    issue(t, c_cur);
+    if (1 < n) issue(t + 1, ahead(c_cur, 0, 1));
   }
   // the matrix stream never changes, so its first chunks are already in flight; x and y may still be written by
   // the previous kernel of the stream (row clearing, x <- y / ||y|| of an iterated caller)
@@ -430,30 +408,19 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
     const uint32_t pos = i & (R - 1);
     const bool sole = (mraw.z & kChunkSole) != 0 && !force_red;
     if (pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;  // stays set until the run's first row end
-    // staged row ids: the copy started at row-map entry rank0 & ~3, so rank0 itself sits (rank0 & 3) entries in
-    const uint32_t rowbuf = ROWIDS ? ring + st * STAGE + SLOT + 4u * (mraw.x & 3u) : 0u;
-    process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red, y_policy, rowbuf);
+    process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red, y_policy,
+                            stream_policy);
     if (pos == R - 1 || i + 1 == n) {  // the row left open continues in another warp's run: hand over atomically
       if (open && lane == 0) {
         // in a `consecutive` chunk the open row follows from the rank (the flag covers it): no dependent row-map load
-        uint32_t row;
-        if (mraw.z & kChunkRowsConsecutive) {
-          row = mraw.w + (next_rank - mraw.x);
-        } else if (ROWIDS) {
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(rowbuf + 4u * (next_rank - mraw.x)));
-        } else {
-          row = rowmap[next_rank];
-        }
+        const uint32_t row = (mraw.z & kChunkRowsConsecutive) ? mraw.w + (next_rank - mraw.x) : rowmap[next_rank];
         y_add(&y[row], carry);
       }
       carry = VT(0);
       open = false;
     }
     __syncwarp();
-    if (lane == 0 && i + 2 < n) {
-      issue(t + 2, ahead(c_cur, i, 2), aux_next);
-      if (ROWIDS && i + 3 < n) aux_next = ld_aux(ahead(c_cur, i, 3));
-    }
+    if (lane == 0 && i + 2 < n) issue(t + 2, ahead(c_cur, i, 2));
     c_cur = ahead(c_cur, i, 1);
   }
 }
@@ -483,7 +450,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   // flags bit 3: "tall" matrix (x and y both larger than the L2 cache): y updates evict-last, x gathers evict-first
   const uint64_t y_policy = (flags & 8u) ? l2_policy_evict_last() : 0ull;
   const uint64_t x_policy = (flags & 8u) ? l2_policy_evict_first() : 0ull;
-  walk_chunks<VT, false>(stream, rowmap, nullptr, y, ring, bars, lane, 0u, n_chunks, blockIdx.x * WARPS + warp,
+  walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, 0u, n_chunks, blockIdx.x * WARPS + warp,
                          gridDim.x * WARPS, run_log2, (flags & 4u) != 0, t, y_policy, true,
                          [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                            gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv, x_policy);
@@ -510,14 +477,13 @@ __device__ __forceinline__ float lds_x(uint32_t a, float) {
   return v;
 }
 
-template <typename VT, int WARPS, uint32_t X_CAP, bool ROWIDS>
+template <typename VT, int WARPS, uint32_t X_CAP>
 __global__ void __launch_bounds__(WARPS * 32, 1)
-    spmv_xs_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
-                   const uint2 *__restrict__ rowaux, const VT *__restrict__ x, VT *__restrict__ y,
-                   const XsItem *__restrict__ items, const uint32_t *__restrict__ cta_first, uint32_t cdb,
-                   uint32_t run_log2, uint32_t flags) {
+    spmv_xs_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap, const VT *__restrict__ x,
+                   VT *__restrict__ y, const XsItem *__restrict__ items, const uint32_t *__restrict__ cta_first,
+                   uint32_t cdb, uint32_t run_log2, uint32_t flags) {
   constexpr uint32_t SLOT = VTraits<VT>::kGroupWords * 16 * 32 + 16;
-  constexpr uint32_t STAGE = SLOT + (ROWIDS ? kXsRowIdBytes : 0u);
+  constexpr uint32_t STAGE = SLOT;
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -545,11 +511,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
       fence_proxy_async();
       mbar_expect_tx(xbar, x_bytes);
       const uint8_t *src = reinterpret_cast<const uint8_t *>(x + x_off);
-      for (uint32_t o = 0; o < x_bytes; o += 16384u) bulk_g2s(xbuf + o, src + o, min(16384u, x_bytes - o), xbar);
+      if (y_policy) {  // tall matrix: x is streamed once per row tile - it must not displace the tile's y range in L2
+        const uint64_t xpol = l2_policy_evict_first();
+        for (uint32_t o = 0; o < x_bytes; o += 16384u) bulk_g2s_hint(xbuf + o, src + o, min(16384u, x_bytes - o), xbar, xpol);
+      } else {
+        for (uint32_t o = 0; o < x_bytes; o += 16384u) bulk_g2s(xbuf + o, src + o, min(16384u, x_bytes - o), xbar);
+      }
     }
     if (x_bytes) {
       bool waited = false;
-      walk_chunks<VT, ROWIDS>(stream, rowmap, rowaux, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
+      walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
                               (uint32_t)WARPS, run_log2, (flags & 4u) != 0, t, y_policy, false,
                               [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                                 if (!waited) {  // first chunk of the item: the window must have landed
@@ -572,7 +543,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
       if (!waited) mbar_wait(xbar, k & 1u);  // warps without work still consume the phase
       k++;
     } else {
-      walk_chunks<VT, ROWIDS>(stream, rowmap, rowaux, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
+      walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
                               (uint32_t)WARPS, run_log2, (flags & 4u) != 0, t, 0ull, false,
                               [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                                 gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv);

@@ -33,14 +33,16 @@ def _engine_vs_gold(spmvb, oracle, A, variants=(8, 7)):
             e = np.abs(y - gold) / bound
             assert np.all(e <= 1.0), "variant %d rep %d: row %d off by %g x the tolerance" % (v, rep, int(np.argmax(e)), e.max())
         worst[v] = float(e.max())
-    # linearity, a property that needs no reference: A (2x) = 2 A x exactly in binary floating point
+    # linearity, a property that needs no reference: A (2x) = 2 A x.  Scaling by 2 is exact, but rows that live in
+    # several column blocks are summed with red.global.add in whatever order the warps arrive, so two launches may
+    # round differently: the comparison carries the tolerance (twice: both sides are computed results)
     eng.set_variant(0)
     eng.set_x((2 * x).astype(vt))
     eng.spmv_dev()
     eng.set_x(x)
-    y2 = eng.get_y()
+    y2 = eng.get_y().astype(np.float64)
     eng.spmv_dev()
-    assert np.array_equal(y2, 2 * eng.get_y())
+    assert np.all(np.abs(y2 - 2 * eng.get_y().astype(np.float64)) <= 4 * bound)
     # rows without entries come out as exact zeros (empty_rows_bitmap: nothing is accumulated into them)
     empty = np.diff(A.row_ptr.astype(np.int64)) == 0
     assert not eng.get_y()[empty].any()

@@ -168,7 +168,7 @@ def test_engine_private_device_layout(spmvb, oracle, variant):
     with spmvb.options(dev_tiles=5, tall=1):       # CU-major tiles + the explicit L2 policies
         _check(spmvb, oracle, matgen.uniform(40, 30000, 9000, seed=9), 1, 1, True, variant)   # rows spanning many chunks
         _check(spmvb, oracle, matgen.laplacian2d(256, 256), 4, 1, True, variant)
-    with spmvb.options(xs_rowids=0):               # the x-window kernel without the staged row ids
+    with spmvb.options(e2e_tiles=0, dev_tiles=4):  # spmv_host without the tile pipeline
         _check(spmvb, oracle, matgen.uniform(4000, 200000, 16, seed=3), 1, 1, True, variant)
     lay = spmvb.Layout.build(*matgen.uniform(4000, 200000, 16, seed=3), 1, 1, True)
     dp = lay.device_params

@@ -108,7 +108,7 @@ def test_zero_row_list_covers_every_row_not_plainly_stored(spmvb):
 @pytest.mark.parametrize("case", ["lap", "rmat", "uniform16k", "ragged"])
 def test_xs_plan_tiles_the_stream_and_windows_cover_the_columns(spmvb, case):
     """Work plan of the shared-memory-x kernel (host side of spmv_xs_kernel): items tile the chunk range exactly, each
-    lies in one column block, is cut at block-relative multiples of run x 12 warps (fp64), and its x window (<= 128 KB,
+    lies in one column block, is cut at block-relative multiples of run x 18 warps (fp64), and its x window (<= 128 KB,
     16-byte aligned) covers every column its chunks touch.  The plan is made for what the GPU streams: an irregular fp64
     matrix with 32 768-column API blocks gets an engine-private device layout with 16 384-column blocks (x slice of a
     block = 128 KB = the kernel's window, the split on index bit 14), so every window fits."""
@@ -127,7 +127,7 @@ def test_xs_plan_tiles_the_stream_and_windows_cover_the_columns(spmvb, case):
     lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True, cdb)
     n_cta, run_log2 = 12, 1
     items, first = lay.xs_plan(n_cta, run_log2)
-    unit = (1 << run_log2) * 12
+    unit = (1 << run_log2) * 18
     dp = lay.device_params
     assert first[0] == 0 and first[-1] == len(items) and np.all(np.diff(first.astype(np.int64)) >= 0)
     pos = 0
