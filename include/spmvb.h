@@ -45,6 +45,7 @@ int spmvb_version(void);
  *   tall 0/1          explicit L2 eviction policies     autotune 1   time both kernels at engine creation
  *   dev_tiles, dev_cdb, tile_mb, xs_pairs               the engine-private device layout
  *   e2e_tiles 0       spmv_host does not pipeline the row tiles (one launch, then the copy of y)
+ *   xs_config 0/1/2   x-window kernel: 128 KB window x 1 CTA per SM / 64 KB x 2 / 32 KB x 3 (decides the device blocks' width)
  *   build_trace 1     print the time of every stage of the GPU layout builder
  * spmvb_options_from_env() applies SPMVB_<NAME>=<integer> for every option and returns how many it found: for
  * executables with no other means of configuration (the reference's run.elf is configured by -D macros only). */
@@ -191,8 +192,9 @@ int spmvb_engine_collect_steps(spmvb_engine *e, float *total_ms, float *kernel_m
 int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
 /* device time per iteration (CUDA events around the loop) of the last spmvb_engine_power_iter / spmvb_engine_cg call */
 float spmvb_engine_last_iter_ms(const spmvb_engine *e);
-/* out[10] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per
- * SpMV (UINT64_MAX = all), image bytes, row tiles spmv_host pipelines (0 = none), 1 = explicit L2 policies} */
+/* out[11] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per
+ * SpMV (UINT64_MAX = all), image bytes, row tiles spmv_host pipelines (0 = none), 1 = explicit L2 policies, x-window kernel configuration (0 wide / 1 medium /
+ * 2 narrow)} */
 int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out);
 /* Conjugate gradients for A x = b on one GPU (A symmetric positive definite, e.g. the Laplacian of BASELINE config 2):
  * the second iterated caller of SURVEY 8(f) rank 3 (the reference's caller runs spmv_hw once, main.cpp:68-75; an

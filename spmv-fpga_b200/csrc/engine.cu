@@ -38,7 +38,7 @@ struct Engine {
   // tile's rows of y to the host while the next tile is computed)
   int n_tiles = 0;
   XsItem *d_items_t = nullptr;
-  uint32_t *d_cta_first_t = nullptr;   // [n_tiles * (sms + 1)]
+  uint32_t *d_cta_first_t = nullptr;   // [n_tiles * (xs_ctas + 1)]
   std::vector<uint32_t> tile_rows_end; // rows [0, tile_rows_end[k]) are final once tiles 0..k are done
   std::vector<cudaEvent_t> ev_tile;    // [2 * n_tiles] kernel done / copy done
   cudaStream_t copy_stream = nullptr;
@@ -52,6 +52,7 @@ struct Engine {
   bool tall = false;               // x and y both exceed the L2 cache: explicit L2 eviction policies
   bool cu_major = false;           // pieces in CU-major device order (row tiles)
   bool irregular = false;          // layout_is_irregular(): x gathers are scattered, the x-window kernel pays
+  int xs_cfg = 0, xs_ctas = 148;   // configuration of the x-window kernel (xs_config) and its grid = SMs x CTAs per SM
   int auto_variant = kVariantOcc3; // what variant 0 resolves to (chosen from the layout at creation)
   float tune_ms[2] = {0.f, 0.f};   // autotune timings: OCC, XS
   uint32_t n_zero_rows = 0, run_log2 = 2;
@@ -127,24 +128,35 @@ static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, 
 }
 
 // tile < 0: the whole matrix in one launch; otherwise row tile `tile` only (per-tile plan)
-template <typename VT>
-static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile = -1) {
-  constexpr int WARPS = sizeof(VT) == 8 ? kXsWarpsF64 : kXsWarpsF32;
+template <typename VT, int WARPS, uint32_t X_CAP, int MINB>
+static int launch_xs_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
-  auto kern = spmv_xs_kernel<VT, WARPS, kXsCap>;
+  auto kern = spmv_xs_kernel<VT, WARPS, X_CAP, MINB>;
   const size_t stage = (size_t)VTraits<VT>::kGroupWords * 16 * 32 + 16;
-  const size_t smem = (size_t)kXsCap + (size_t)WARPS * 2 * stage + WARPS * 16 + 16;
+  const size_t smem = (size_t)X_CAP + (size_t)WARPS * 2 * stage + WARPS * 16 + 16;
   int &grid = E->grid_cache[kVariantXs][sizeof(VT) == 8];
   if (grid == 0) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    grid = E->sms;
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    if (per_sm < MINB) return fail(SPMVB_E_CUDA, "x-window kernel: fewer resident CTAs per SM than its work plan assumes");
+    grid = E->xs_ctas;
   }
   if (E->n_items == 0) return SPMVB_OK;
   const XsItem *items = tile < 0 ? E->d_items : E->d_items_t;
-  const uint32_t *first = tile < 0 ? E->d_cta_first : E->d_cta_first_t + (size_t)tile * (E->sms + 1);
+  const uint32_t *first = tile < 0 ? E->d_cta_first : E->d_cta_first_t + (size_t)tile * (E->xs_ctas + 1);
   CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, x, y, items, first, E->cdb,
                       E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u)));
   return SPMVB_OK;
+}
+template <typename VT>
+static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile = -1) {
+  constexpr bool D = sizeof(VT) == 8;  // the instantiations = xs_config() in layout.h
+  switch (E->xs_cfg) {
+    case 1: return launch_xs_cfg<VT, D ? 9 : 14, 64u << 10, 2>(E, x, y, st, accumulate, tile);
+    case 2: return launch_xs_cfg<VT, D ? 8 : 10, 32u << 10, 3>(E, x, y, st, accumulate, tile);
+    default: return launch_xs_cfg<VT, D ? 18 : 24, 128u << 10, 1>(E, x, y, st, accumulate, tile);
+  }
 }
 
 template <typename VT>
@@ -419,8 +431,18 @@ static int engine_adopt_layout(Engine *E, const Layout *L) {
   E->real_nnz = L->real_nnz; E->n_chunks = L->n_chunks; E->n_pairs = L->n_pairs; E->stream_bytes = L->stream_bytes;
   E->cu_major = L->cu_major; E->dev_cu = L->cu; E->dev_vf = L->vf;
   E->irregular = layout_is_irregular(L);
+  E->xs_cfg = L->xs_cfg;
+  E->xs_ctas = E->sms * xs_config(L->is_double, L->xs_cfg).ctas_per_sm;
   E->tall = (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) && (uint64_t)L->cols * L->vb > ((uint64_t)48 << 20);
   if (options().tall >= 0) E->tall = options().tall != 0;
+  if (E->tall && options().l2_persist_mb > 0) {
+    // evict-last lines only outlive the stream if the L2 has a set-aside portion for them (off by default)
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, E->device));
+    const size_t want = std::min<size_t>((size_t)options().l2_persist_mb << 20, (size_t)prop.persistingL2CacheMaxSize);
+    CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    fprintf(stderr, "[spmvb] persisting L2 set-aside: %zu MB (device maximum %d MB)\n", want >> 20, prop.persistingL2CacheMaxSize >> 20);
+  }
   E->x_touched = 0;
   for (int b = 0; b < L->blocks; b++) {
     uint64_t nz = 0;
@@ -450,7 +472,7 @@ static int engine_finish(Engine *E, const Layout *L) {
   std::vector<XsItem> items;
   std::vector<uint32_t> cta_first;
   XsTilePlan tiles;
-  build_xs_items(L, E->sms, E->xs_run_log2, items, cta_first, L->cu_major ? &tiles : nullptr);
+  build_xs_items(L, E->xs_ctas, E->xs_run_log2, items, cta_first, L->cu_major ? &tiles : nullptr);
   E->n_items = (uint32_t)items.size();
   if (tiles.n_tiles > 1 && tiles.n_tiles <= 1024 && !tiles.items.empty()) {
     E->n_tiles = tiles.n_tiles;
@@ -920,7 +942,7 @@ int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out) {
   if (!E || !out) return fail(SPMVB_E_ARG, "device_layout");
   out[0] = (uint64_t)E->dev_cu; out[1] = (uint64_t)E->dev_vf; out[2] = E->cdb; out[3] = E->cu_major ? 1u : 0u;
   out[4] = E->n_pairs; out[5] = E->n_chunks; out[6] = E->zero_all ? UINT64_MAX : (uint64_t)E->n_zero_rows;
-  out[7] = E->stream_bytes; out[8] = (uint64_t)E->n_tiles; out[9] = E->tall ? 1u : 0u;
+  out[7] = E->stream_bytes; out[8] = (uint64_t)E->n_tiles; out[9] = E->tall ? 1u : 0u; out[10] = (uint64_t)E->xs_cfg;
   return SPMVB_OK;
 }
 

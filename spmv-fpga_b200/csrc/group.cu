@@ -128,6 +128,10 @@ static int member_build(Group *G, Member &m, uint32_t n_rows, const uint64_t *ro
 static void group_destroy(Group *G) {
   if (!G) return;
   for (Member &m : G->local) {
+    if (!m.engine && !m.comm && !m.d_scalar) {  // never got as far as touching its device (e.g. a bad device index)
+      if (m.layout) spmvb_layout_free(m.layout);
+      continue;
+    }
     cudaSetDevice(m.device);
     if (m.comm && nccl()->CommDestroy) nccl()->CommDestroy(m.comm);
     if (m.engine) spmvb_engine_free(m.engine);
@@ -137,6 +141,7 @@ static void group_destroy(Group *G) {
     if (m.ev1) cudaEventDestroy(m.ev1);
   }
   if (G->h_scalar) cudaFreeHost(G->h_scalar);
+  cudaGetLastError();  // a failed creation must not leave its error behind for the next CUDA call of the process
   delete G;
 }
 

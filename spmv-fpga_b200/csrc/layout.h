@@ -45,6 +45,7 @@ struct Layout {
   std::vector<uint64_t> piece_chunk1;    // one past the last chunk index
   std::vector<uint32_t> dev_order;       // pieces (b * cu + k) in device order
   bool cu_major = false;                 // device order: CU-major instead of block-major
+  int xs_cfg = 0;                        // configuration of the x-window kernel this layout is planned for (xs_config)
   std::vector<uint32_t> piece_real_nnz;  // entries before the padding rows
 
   uint8_t *stream = nullptr;  // all pieces, each zero-padded to whole chunks
@@ -89,12 +90,20 @@ struct XsItem {
   uint32_t col_base;  // column-in-block of the window's first element
   uint32_t block, pad0, pad1;
 };
-constexpr uint32_t kXsCap = 128 * 1024;  // bytes of shared memory for the x window of an XS work item
-// warps per CTA of the XS kernel (one CTA per SM): what fits next to the x window - every warp owns two ring stages of
-// one chunk slot (2576 B fp64 / 1552 B fp32) - and into the register file.  The kernel lives on warps: its per-chunk
-// instruction chain is long and serial (measured: 12 -> 16 warps = 78 -> 69 us on the Laplacian).
-constexpr int kXsWarpsF64 = 18, kXsWarpsF32 = 24;
-inline int xs_warps(int is_double) { return is_double ? kXsWarpsF64 : kXsWarpsF32; }
+// Configurations of the x-window kernel (XS): bytes of shared memory for the x window of a work item, warps per CTA,
+// CTAs per SM.  Every warp owns two ring stages of one chunk slot (2576 B fp64 / 1552 B fp32); what is left of the
+// 227 KB next to the window(s) and the register file bound the warps.  The kernel lives on warps - its per-chunk
+// instruction chain is long and serial (measured on the Laplacian: 12 / 16 / 18 warps = 78 / 69 / 66 us) - so a narrower
+// window buys parallelism: wide = the reference's whole x slice of a 16 384-column block on chip (fp64), medium / narrow =
+// half / a quarter of it with two / three independent CTAs per SM.
+struct XsConfig { uint32_t cap; int warps, ctas_per_sm; };
+constexpr int kXsConfigs = 3;
+inline XsConfig xs_config(int is_double, int cfg) {
+  static const XsConfig f64[kXsConfigs] = {{128u << 10, 18, 1}, {64u << 10, 9, 2}, {32u << 10, 8, 3}};
+  static const XsConfig f32[kXsConfigs] = {{128u << 10, 24, 1}, {64u << 10, 14, 2}, {32u << 10, 10, 3}};
+  cfg = cfg < 0 ? 0 : (cfg >= kXsConfigs ? kXsConfigs - 1 : cfg);
+  return is_double ? f64[cfg] : f32[cfg];
+}
 // CU-major layouts only: the same work dealt tile by tile (one kernel launch per row tile)
 struct XsTilePlan {
   int n_tiles = 0;
@@ -125,6 +134,8 @@ struct Options {
   int64_t dev_cdb = -1;       // column-block width of the engine-private device layout (0 = same as the API layout)
   int64_t xs_pairs = -1;      // distinct x lines per 256-entry chunk above which the x-window kernel is preferred
   int64_t tile_mb = -1;       // target size of a row tile's y range in MB
+  int64_t xs_config = -1;     // 0 wide / 1 medium / 2 narrow x window of the XS kernel (see XsConfig)
+  int64_t l2_persist_mb = -1; // > 0: set aside that much L2 for persisting (evict-last) lines on tall matrices
   int64_t e2e_tiles = -1;     // 0: spmv_host does not pipeline row tiles (one launch, then the copy of y)
 };
 Options &options();

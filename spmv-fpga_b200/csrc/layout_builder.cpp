@@ -45,7 +45,7 @@ const OptionName kOptionNames[] = {
     {"tall", &Options::tall},                 {"occ_run_log2", &Options::occ_run_log2}, {"xs_run_log2", &Options::xs_run_log2},
     {"autotune", &Options::autotune},         {"build_trace", &Options::build_trace}, {"dev_tiles", &Options::dev_tiles},
     {"dev_cdb", &Options::dev_cdb},           {"xs_pairs", &Options::xs_pairs},       {"tile_mb", &Options::tile_mb},
-    {"e2e_tiles", &Options::e2e_tiles},
+    {"e2e_tiles", &Options::e2e_tiles},       {"xs_config", &Options::xs_config},     {"l2_persist_mb", &Options::l2_persist_mb},
 };
 }  // namespace
 
@@ -73,15 +73,16 @@ bool plan_device_params(const Layout *L, int *cu_dev, int *vf_dev, uint32_t *cdb
   int cu = L->cu, vf = L->vf;
   uint32_t cdb = L->cdb;
   const bool irregular = layout_is_irregular(L);
+  const uint32_t cap = xs_config(L->is_double, L->xs_cfg).cap;
   if (irregular) {
-    if (L->is_double && cdb > 16384) {
+    if (cdb > cap / (uint32_t)L->vb) {  // do the windows of the chunks fit the kernel's?  else: blocks of window width
       uint64_t wide = 0, used = 0;
       for (uint64_t c = 0; c < L->n_chunks; c++)
         if (L->chunk_col_lo[c] <= L->chunk_col_hi[c]) {
           used++;
-          wide += (uint64_t)(L->chunk_col_hi[c] - L->chunk_col_lo[c] + 1) * L->vb > kXsCap;
+          wide += (uint64_t)(L->chunk_col_hi[c] - L->chunk_col_lo[c] + 1) * L->vb > cap;
         }
-      if (2 * wide > used) cdb = 16384;
+      if (2 * wide > used) cdb = cap / (uint32_t)L->vb;
     }
     const uint64_t ybytes = (uint64_t)L->rows * L->vb;
     const uint64_t tile = (uint64_t)(o.tile_mb > 0 ? o.tile_mb : 32) << 20;
@@ -139,6 +140,7 @@ int layout_init_header(Layout *L, uint32_t rows, uint32_t cols, uint64_t nnz, in
   L->nr_cols.resize(blocks);
   for (int b = 0; b < blocks; b++)
     L->nr_cols[b] = (b == blocks - 1) ? L->expanded_cols - (uint32_t)b * cdb : cdb;
+  L->xs_cfg = options().xs_config >= 0 ? (int)std::min<int64_t>(options().xs_config, kXsConfigs - 1) : 0;
   // >= 1: the chunk walk prefetches two chunks ahead and a run must cover that distance (spmv_kernels.cuh)
   if (options().run_log2 >= 0) L->run_log2 = (int)std::max<int64_t>(1, std::min<int64_t>(8, options().run_log2));
   return SPMVB_OK;
@@ -694,7 +696,7 @@ static int layout_equal_impl(const Layout *A, const Layout *B, char *why, size_t
   if (A->cu != B->cu || A->vf != B->vf || A->is_double != B->is_double || A->blocks != B->blocks || A->rows != B->rows ||
       A->cols != B->cols || A->expanded_cols != B->expanded_cols || A->cdb != B->cdb || A->real_nnz != B->real_nnz ||
       A->padded_nnz != B->padded_nnz || A->n_pairs != B->n_pairs || A->stream_bytes != B->stream_bytes ||
-      A->n_chunks != B->n_chunks || A->run_log2 != B->run_log2 || A->cu_major != B->cu_major)
+      A->n_chunks != B->n_chunks || A->run_log2 != B->run_log2 || A->cu_major != B->cu_major || A->xs_cfg != B->xs_cfg)
     return say("header");
   if (A->nr_rows != B->nr_rows) return say("nr_rows");
   if (A->nr_nzeros != B->nr_nzeros) return say("nr_nzeros");

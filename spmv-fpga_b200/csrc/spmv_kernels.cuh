@@ -477,8 +477,8 @@ __device__ __forceinline__ float lds_x(uint32_t a, float) {
   return v;
 }
 
-template <typename VT, int WARPS, uint32_t X_CAP>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+template <typename VT, int WARPS, uint32_t X_CAP, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
     spmv_xs_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap, const VT *__restrict__ x,
                    VT *__restrict__ y, const XsItem *__restrict__ items, const uint32_t *__restrict__ cta_first,
                    uint32_t cdb, uint32_t run_log2, uint32_t flags) {

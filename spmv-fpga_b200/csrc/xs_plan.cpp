@@ -15,7 +15,8 @@ namespace spmvb {
 // U = run length x warps per CTA, so that every warp of the CTA gets the same number of whole runs per item.
 void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<XsItem> &items,
                     std::vector<uint32_t> &cta_first, XsTilePlan *tiles) {
-  const uint64_t U = ((uint64_t)1 << run_log2) * (uint64_t)xs_warps(L->is_double);
+  const XsConfig cfg = xs_config(L->is_double, L->xs_cfg);
+  const uint64_t U = ((uint64_t)1 << run_log2) * (uint64_t)cfg.warps;
   const uint32_t align = 16u / (uint32_t)L->vb;  // window start in elements: 16-byte aligned for the bulk copy
   // candidate cut points in global chunk indices: block starts and block-relative multiples of U
   std::vector<uint64_t> cuts;
@@ -49,7 +50,7 @@ void build_xs_items(const Layout *L, int n_cta, uint32_t run_log2, std::vector<X
           }
         const uint32_t wlo = nlo == 0xFFFF ? 0 : nlo / align * align;
         const uint64_t bytes = nlo == 0xFFFF ? 16 : ((uint64_t)(nhi - wlo + 1) * L->vb + 15) / 16 * 16;
-        if (bytes > kXsCap) {
+        if (bytes > cfg.cap) {
           if (e == ci) { fits = false; e++; }  // even one unit does not fit: gather from global memory
           break;
         }

@@ -487,11 +487,11 @@ class Engine:
 
     @property
     def device_layout(self):
-        out = (ctypes.c_uint64 * 10)()
+        out = (ctypes.c_uint64 * 11)()
         _check(lib().spmvb_engine_device_layout(self.h, out))
         v = [int(x) for x in out]
         return dict(cu=v[0], vf=v[1], cdb=v[2], cu_major=bool(v[3]), pairs=v[4], chunks=v[5],
-                    zero_rows=-1 if v[6] == 2 ** 64 - 1 else v[6], bytes=v[7], e2e_tiles=v[8], tall=bool(v[9]))
+                    zero_rows=-1 if v[6] == 2 ** 64 - 1 else v[6], bytes=v[7], e2e_tiles=v[8], tall=bool(v[9]), xs_config=v[10])
 
     def set_variant(self, v):
         _check(lib().spmvb_engine_set_variant(self.h, v))
