@@ -115,6 +115,9 @@ int spmvb_layout_chunk_cols(const spmvb_layout *l, uint64_t c, uint32_t *lo, uin
  * order, 1 = an engine-private device layout exists next to the API pieces, (row, block) pairs, chunks, rows cleared
  * per SpMV (UINT64_MAX = all), image bytes}.  The API-visible pieces (piece_info / piece_words) never change with it. */
 int spmvb_layout_device_params(const spmvb_layout *l, uint64_t *out);
+/* mean number of distinct 128-byte lines of x that the entries of a 256-entry chunk touch (API layout): the measure of
+ * irregularity that picks the kernel and the device layout (5-point Laplacian 12, R-MAT ~150-200, uniform ~250) */
+double spmvb_layout_x_lines_per_chunk(const spmvb_layout *l);
 
 /* 1 if the two layouts are identical in every table and byte (pieces, row map, chunk metadata, rows to clear, column
  * ranges), 0 if not (why receives the first difference), negative on error.  Used to check the GPU builder against
@@ -192,9 +195,10 @@ int spmvb_engine_collect_steps(spmvb_engine *e, float *total_ms, float *kernel_m
 int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
 /* device time per iteration (CUDA events around the loop) of the last spmvb_engine_power_iter / spmvb_engine_cg call */
 float spmvb_engine_last_iter_ms(const spmvb_engine *e);
-/* out[11] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per
+/* out[13] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per
  * SpMV (UINT64_MAX = all), image bytes, row tiles spmv_host pipelines (0 = none), 1 = explicit L2 policies, x-window kernel configuration (0 wide / 1 medium /
- * 2 narrow)} */
+ * 2 narrow), microseconds of one SpMV measured at creation for {the API image with global gathers, the device layout} (0 =
+ * not measured)} */
 int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out);
 /* Conjugate gradients for A x = b on one GPU (A symmetric positive definite, e.g. the Laplacian of BASELINE config 2):
  * the second iterated caller of SURVEY 8(f) rank 3 (the reference's caller runs spmv_hw once, main.cpp:68-75; an

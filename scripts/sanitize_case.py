@@ -13,6 +13,9 @@ import matgen  # noqa: E402
 import oracle_api as oa  # noqa: E402
 import spmvb  # noqa: E402
 
+for kv in os.environ.get("SANITIZE_OPTS", "").split(","):  # e.g. SANITIZE_OPTS=xs_config=1
+    if kv:
+        spmvb.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 O = oa.OracleLib()
 cases = [("ragged", matgen.ragged(1500, 70000, seed=7), 2, 2), ("uniform", matgen.uniform(1200, 70000, 16, seed=3), 1, 1),
          ("lap", matgen.laplacian2d(96, 96), 1, 1), ("rmat", matgen.rmat(11, 8, seed=5), 4, 1),

@@ -502,13 +502,9 @@ static int engine_finish(Engine *E, const Layout *L) {
   return SPMVB_OK;
 }
 
-int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_engine **out) {
-  const Layout *A = (const Layout *)l;
-  if (!A || !out) return fail(SPMVB_E_ARG, "engine_create: NULL");
+// uploads ONE layout (the device image of L itself) and makes it runnable
+static int engine_create_single(const Layout *L, int device, int variant, Engine **out) {
   *out = nullptr;
-  const Layout *L = A->dev ? A->dev : A;  // what the GPU streams: the engine-private device layout when there is one
-  if (!L->stream || !L->rowmap)
-    return fail(SPMVB_E_ARG, "engine_create: this layout was built on a GPU and lives in its engine; fetch it first");
   Engine *E = nullptr;
   int rc = engine_open(device, variant, &E);
   if (rc) return rc;
@@ -519,7 +515,7 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
     // ChunkMeta, so that a single bulk copy brings both into shared memory
     const size_t slot = (size_t)L->chunk_bytes + sizeof(ChunkMeta);
     CUDA_TRY(cudaMalloc((void **)&E->d_stream, std::max<uint64_t>(L->n_chunks * slot, 16)));
-    CUDA_TRY(cudaMalloc((void **)&E->d_rowmap, (L->n_pairs + 8) * 4));  // slack: 16-byte aligned slices are copied
+    CUDA_TRY(cudaMalloc((void **)&E->d_rowmap, (L->n_pairs + 8) * 4));
     CUDA_TRY(cudaMalloc((void **)&E->d_zero_rows, std::max<size_t>(L->zero_rows.size(), 1) * 4));
     if (L->n_chunks) {
       CUDA_TRY(cudaMemcpy2DAsync(E->d_stream, slot, L->stream, L->chunk_bytes, L->chunk_bytes, L->n_chunks,
@@ -534,6 +530,54 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   };
   rc = upload();
   if (rc) { spmvb_engine_free((spmvb_engine *)E); return rc; }
+  *out = E;
+  return SPMVB_OK;
+}
+
+// milliseconds of one y = A x (clear rows + kernel) with the engine's own kernel choice, best of `reps` after a warm-up
+static int engine_time_step(Engine *E, int reps, float *best_ms) {
+  *best_ms = 1e30f;
+  for (int rep = 0; rep <= reps; rep++) {
+    CUDA_TRY(cudaEventRecord(E->ev_t0, E->stream));
+    int rc = do_spmv(E, nullptr, nullptr, 0, E->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(E->ev_t1, E->stream));
+    CUDA_TRY(cudaEventSynchronize(E->ev_t1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, E->ev_t0, E->ev_t1));
+    if (rep) *best_ms = std::min(*best_ms, ms);
+  }
+  E->launches = 0;
+  return SPMVB_OK;
+}
+
+// What the GPU streams is the engine's choice.  A layout that carries an engine-private device layout next to its API
+// pieces (an irregular matrix: plan_device_params) offers two candidates - the API image with the global-gather kernel,
+// the device layout with the x-window kernel.  Which one is faster depends on how the matrix's scattered accesses split
+// between x (gathers) and y (updates), so the engine measures: both are uploaded, one SpMV of each is timed on the
+// actual matrix (not under a profiler: the timings are noise there), the slower one is freed.  An explicit variant or
+// option autotune = 0 skips the measurement and takes the device layout.
+int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_engine **out) {
+  const Layout *A = (const Layout *)l;
+  if (!A || !out) return fail(SPMVB_E_ARG, "engine_create: NULL");
+  *out = nullptr;
+  const Layout *L = A->dev ? A->dev : A;
+  if (!L->stream || !L->rowmap || !A->stream || !A->rowmap)
+    return fail(SPMVB_E_ARG, "engine_create: this layout was built on a GPU and lives in its engine; fetch it first");
+  Engine *E = nullptr;
+  int rc = engine_create_single(L, device, variant, &E);
+  if (rc) return rc;
+  if (A->dev && variant == kVariantDefault && options().autotune != 0) {
+    Engine *E0 = nullptr;
+    float t_dev = 0.f, t_api = 0.f;
+    rc = engine_time_step(E, 3, &t_dev);
+    if (rc == SPMVB_OK) rc = engine_create_single(A, device, variant, &E0);
+    if (rc == SPMVB_OK) rc = engine_time_step(E0, t_dev < 5.f ? 3 : 1, &t_api);
+    if (rc) { spmvb_engine_free((spmvb_engine *)E); spmvb_engine_free((spmvb_engine *)E0); return rc; }
+    E->tune_ms[0] = E0->tune_ms[0] = t_api; E->tune_ms[1] = E0->tune_ms[1] = t_dev;
+    if (t_api < t_dev) std::swap(E, E0);
+    spmvb_engine_free((spmvb_engine *)E0);
+  }
   *out = (spmvb_engine *)E;
   return SPMVB_OK;
 }
@@ -943,6 +987,7 @@ int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out) {
   out[0] = (uint64_t)E->dev_cu; out[1] = (uint64_t)E->dev_vf; out[2] = E->cdb; out[3] = E->cu_major ? 1u : 0u;
   out[4] = E->n_pairs; out[5] = E->n_chunks; out[6] = E->zero_all ? UINT64_MAX : (uint64_t)E->n_zero_rows;
   out[7] = E->stream_bytes; out[8] = (uint64_t)E->n_tiles; out[9] = E->tall ? 1u : 0u; out[10] = (uint64_t)E->xs_cfg;
+  out[11] = (uint64_t)(E->tune_ms[0] * 1000.f); out[12] = (uint64_t)(E->tune_ms[1] * 1000.f);
   return SPMVB_OK;
 }
 

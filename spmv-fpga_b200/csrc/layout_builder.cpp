@@ -85,7 +85,9 @@ bool plan_device_params(const Layout *L, int *cu_dev, int *vf_dev, uint32_t *cdb
       if (2 * wide > used) cdb = cap / (uint32_t)L->vb;
     }
     const uint64_t ybytes = (uint64_t)L->rows * L->vb;
-    const uint64_t tile = (uint64_t)(o.tile_mb > 0 ? o.tile_mb : 32) << 20;
+    // 24 MB: measured on the 1 B-nnz uniform matrix (16 / 20 / 24 / 32 / 48 / 64 MB tiles = 8.9 / 9.0 / 8.3 / 10.7 / 15.7 /
+    // 17.1 ms): the L2 keeps a tile's y range next to the stream, the x windows and the row map only up to about there
+    const uint64_t tile = (uint64_t)(o.tile_mb > 0 ? o.tile_mb : 24) << 20;
     if (ybytes > 2 * tile) cu = (int)std::min<uint64_t>(4096, (ybytes + tile - 1) / tile);
   }
   if (o.dev_cdb > 0) cdb = (uint32_t)o.dev_cdb;
@@ -734,6 +736,16 @@ static int layout_equal_impl(const Layout *A, const Layout *B, char *why, size_t
 
 int spmvb_layout_equal(const spmvb_layout *a, const spmvb_layout *b, char *why, size_t why_len) {
   return layout_equal_impl((const Layout *)a, (const Layout *)b, why, why_len, true);
+}
+
+/* mean number of distinct 128-byte lines of x per (non-empty) chunk of the API layout: the irregularity measure */
+double spmvb_layout_x_lines_per_chunk(const spmvb_layout *l) {
+  const Layout *L = (const Layout *)l;
+  if (!L) return -1.0;
+  uint64_t lines = 0, used = 0;
+  for (uint64_t c = 0; c < L->n_chunks; c++)
+    if (L->chunk_x_lines[c]) { lines += L->chunk_x_lines[c]; used++; }
+  return used ? (double)lines / (double)used : 0.0;
 }
 
 int spmvb_layout_device_params(const spmvb_layout *l, uint64_t *out) {

@@ -25,6 +25,7 @@ SYMBOLS = {
     "spmvb_get_option": (ctypes.c_int64, [ctypes.c_char_p]),
     "spmvb_options_from_env": (_int, []),
     "spmvb_layout_device_params": (_int, [_vp, _vp]),
+    "spmvb_layout_x_lines_per_chunk": (ctypes.c_double, [_vp]),
     "spmvb_engine_last_iter_ms": (ctypes.c_float, [_vp]),
     "spmvb_engine_device_layout": (_int, [_vp, _vp]),
     "spmvb_layout_build": (_int, [_u32, _u32, _vp, _vp, _vp, _int, _int, _int, _u32, _vp]),
@@ -346,6 +347,10 @@ class Layout:
         return dict(cu=v[0], vf=v[1], cdb=v[2], cu_major=bool(v[3]), private=bool(v[4]), pairs=v[5], chunks=v[6],
                     zero_rows=-1 if v[7] == 2 ** 64 - 1 else v[7], bytes=v[8])
 
+    @property
+    def x_lines_per_chunk(self):
+        return float(lib().spmvb_layout_x_lines_per_chunk(self.h))
+
     def difference(self, other):
         """'' if both layouts are identical in every table and byte, else the first component that differs."""
         why = ctypes.create_string_buffer(256)
@@ -487,11 +492,12 @@ class Engine:
 
     @property
     def device_layout(self):
-        out = (ctypes.c_uint64 * 11)()
+        out = (ctypes.c_uint64 * 13)()
         _check(lib().spmvb_engine_device_layout(self.h, out))
         v = [int(x) for x in out]
         return dict(cu=v[0], vf=v[1], cdb=v[2], cu_major=bool(v[3]), pairs=v[4], chunks=v[5],
-                    zero_rows=-1 if v[6] == 2 ** 64 - 1 else v[6], bytes=v[7], e2e_tiles=v[8], tall=bool(v[9]), xs_config=v[10])
+                    zero_rows=-1 if v[6] == 2 ** 64 - 1 else v[6], bytes=v[7], e2e_tiles=v[8], tall=bool(v[9]), xs_config=v[10],
+                    tuned_us=dict(api_image=v[11], device_layout=v[12]))
 
     def set_variant(self, v):
         _check(lib().spmvb_engine_set_variant(self.h, v))
