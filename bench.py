@@ -231,6 +231,18 @@ def ncu_traffic(workload, dtype, world, variant):
         return None
 
 
+def scatter_roofline(dev, nnz_local, k_ms):
+    """The second bound of an irregular matrix: every (row, block) pair is one scattered 8-byte
+    update of y that no blocking of this layout makes local, and a B200 sustains 193 G red.global.add.f64/s into an
+    L2-resident vector (288 G/s scattered 8-byte loads; measured with tools/access_probe.cu, profiles/r2/
+    access_probe_b200.txt).  achieved = pairs of the device layout / kernel time."""
+    peak = 193.0
+    achieved = dev["pairs"] / (k_ms * 1e-3) / 1e9
+    return {"bound": "scattered y updates (red.global.add into L2)", "achieved": achieved, "peak": peak, "unit": "G updates/s",
+            "frac": achieved / peak, "updates_per_nnz": dev["pairs"] / max(nnz_local, 1),
+            "peak_source": "measured: tools/access_probe.cu on this pool's B200 (profiles/r2/access_probe_b200.txt)"}
+
+
 KERNEL_NAMES = {7: "spmv_occ_kernel<3 CTAs/SM>", 6: "spmv_occ_kernel<4 CTAs/SM>", 8: "spmv_xs_kernel", 1: "spmv_direct_kernel"}
 
 
@@ -456,6 +468,7 @@ def measure_spmv(ctx, name, args, steps, warmup, e2e_steps, with_cpu_baseline):
                      "aggregate_frac": alg_total / (k_ms_max * 1e-3) / 1e9 / (peak * world),
                      "what": "rank 0's kernel: nnz*(2+vb) + rows*vb + x_touched*vb bytes / CUDA-event time of the launch; "
                              "aggregate_frac = all ranks' bytes / slowest rank's kernel / (N x peak)"},
+        "scatter_roofline": scatter_roofline(dev, nnz_local, k_ms),
         "check": {"max_err_over_tolerance": err_all, "e2e_accumulated_max_err_over_tolerance": err_acc_all,
                   "what": "every row of every rank against the oracle's CSR SpMV, |y - gold| <= %g x row-wise |A||x|" % TOL[is_double],
                   "seconds": t_check},

@@ -193,6 +193,10 @@ int spmvb_engine_collect_steps(spmvb_engine *e, float *total_ms, float *kernel_m
 /* Iterated SpMV on one GPU (square matrices): x <- A x / ||A x||_2, `iters` times, all on device.
  * Returns the last norm in *norm_out.  The multi-GPU version lives in the host driver (NCCL all-gather). */
 int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
+/* Bounds-checked build (make -C spmv-fpga_b200 check: lib/libspmvb_check.so): counts of out-of-range indices the kernels
+ * caught since the library was loaded, out5 = {chunk slot, row-map entry, y row, x element, x window offset}; returns 1.
+ * A release build returns -1 and leaves out5 alone. */
+int spmvb_debug_bounds_errors(uint64_t *out5);
 /* device time per iteration (CUDA events around the loop) of the last spmvb_engine_power_iter / spmvb_engine_cg call */
 float spmvb_engine_last_iter_ms(const spmvb_engine *e);
 /* out[13] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per

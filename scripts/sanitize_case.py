@@ -54,4 +54,8 @@ assert eng.power_iter(5) > 0
 grp = spmvb.Group.create(rows, cols, rp, ci, va, True, devices=[0])
 grp.set_x(np.full(cols, 1.0 / np.sqrt(cols)))
 assert grp.power_iter(3) > 0
+be = spmvb.bounds_errors()
+if be is not None:  # bounds-checked build: every index of every launch above stayed inside its array
+    print("bounds-checked kernels, violations caught:", be)
+    assert not any(be.values()), be
 print("sanitize_case: all results correct")

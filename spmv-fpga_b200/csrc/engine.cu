@@ -161,6 +161,12 @@ static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumul
 
 template <typename VT>
 static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
+#ifdef SPMVB_CHECK_BOUNDS
+  {  // the limits the bounds-checked kernels compare their indices with (stream-ordered before the launch)
+    const CheckLimits lim = {E->n_chunks, E->n_pairs, E->rows, E->x_len};
+    CUDA_TRY(cudaMemcpyToSymbolAsync(g_limits, &lim, sizeof lim, 0, cudaMemcpyHostToDevice, st));
+  }
+#endif
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
   constexpr int WARPS = 8;
   int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
@@ -977,6 +983,21 @@ int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out) {
   if (cudaEventElapsedTime(&ms, E->ev_t0, E->ev_t1) == cudaSuccess) E->last_iter_ms = ms / (float)iters;
   if (norm_out) *norm_out = std::sqrt(E->h_scalar[0]);
   return SPMVB_OK;
+}
+
+// bounds-checked build only: the violation counters of the kernels {chunk index, row-map index, y row, x index, x window
+// offset} since the library was loaded; -1 in a release build
+int spmvb_debug_bounds_errors(uint64_t *out5) {
+#ifdef SPMVB_CHECK_BOUNDS
+  unsigned long long h[5] = {0, 0, 0, 0, 0};
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(h, g_bounds_errors, sizeof h));
+  for (int i = 0; i < 5; i++) out5[i] = h[i];
+  return 1;
+#else
+  (void)out5;
+  return -1;
+#endif
 }
 
 float spmvb_engine_last_iter_ms(const spmvb_engine *e) { return e ? ((const Engine *)e)->last_iter_ms : 0.f; }

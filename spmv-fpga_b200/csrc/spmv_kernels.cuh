@@ -29,6 +29,25 @@
 
 namespace spmvb {
 
+// ---- bounds-checked build (make check: lib/libspmvb_check.so, -DSPMVB_CHECK_BOUNDS).  compute-sanitizer is not available
+// on every pool, so the kernels can check their own addresses: every index that reaches memory - chunk slot, row-map
+// entry, y row, x element (global gather) or x window offset (shared-memory gather) - is compared with the limits the
+// engine stores in g_limits before a launch; a violation is counted per class and the access is redirected to
+// element 0.  The release build compiles all of this away.
+struct CheckLimits { unsigned long long n_chunks, n_pairs, rows, x_len; };
+#ifdef SPMVB_CHECK_BOUNDS
+__device__ CheckLimits g_limits;
+__device__ unsigned long long g_bounds_errors[5];  // chunk index, row-map index, y row, x index, x window offset
+__device__ __forceinline__ uint32_t check_bound(int cls, uint32_t idx, unsigned long long limit) {
+  if ((unsigned long long)idx < limit) return idx;
+  atomicAdd(&g_bounds_errors[cls], 1ull);
+  return 0u;
+}
+#define SPMVB_BOUND(cls, idx, limit) check_bound(cls, (uint32_t)(idx), (unsigned long long)(limit))
+#else
+#define SPMVB_BOUND(cls, idx, limit) (idx)
+#endif
+
 template <typename VT> struct VTraits;
 template <> struct VTraits<double> {
   static constexpr int kValWords = 4;    // 16-byte value words per group
@@ -184,6 +203,9 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
     for (int s = 0; s < 8; s++) {
       const uint32_t e = (eor >> s) & 1u;
       rows[s] = 0;
+#ifdef SPMVB_CHECK_BOUNDS
+      if (e) rk = SPMVB_BOUND(1, rk, g_limits.n_pairs);
+#endif
       if (y_policy)  // tall matrix: the row map is read once, it must not push the y tile out of the L2 cache
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.L2::cache_hint.u32 %0, [%1], %3;\n\t}"
                      : "+r"(rows[s])
@@ -250,8 +272,9 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
       if ((eor >> s) & 1u) {
         VT v = seg[s];
         if ((first_bit >> s) & 1u) v = vadd(cin, v);
-        if ((redm >> s) & 1u) y_add(y + row, v);
-        else y[row] = v;
+        const uint32_t rr = SPMVB_BOUND(2, row, g_limits.rows);
+        if ((redm >> s) & 1u) y_add(y + rr, v);
+        else y[rr] = v;
         row++;
       }
     }
@@ -259,7 +282,7 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
 #pragma unroll
     for (int s = 0; s < 8; s++) {
       if ((eor >> s) & 1u) {
-        const uint32_t row = rows[s];
+        const uint32_t row = SPMVB_BOUND(2, rows[s], g_limits.rows);
         VT v = seg[s];
         if ((first_bit >> s) & 1u) v = vadd(cin, v);
         if ((redm >> s) & 1u) {
@@ -297,10 +320,11 @@ __device__ __forceinline__ void gather_x(const uint4 &iw, const VT *__restrict__
                                          uint64_t policy = 0) {
   if (policy) {
 #pragma unroll
-    for (int s = 0; s < 8; s++) xv[s] = ldg_x_hint(x + (xbase + (idx16(iw, s) & 0x7FFFu)), policy);
+    for (int s = 0; s < 8; s++) xv[s] = ldg_x_hint(x + SPMVB_BOUND(3, xbase + (idx16(iw, s) & 0x7FFFu), g_limits.x_len), policy);
   } else {
 #pragma unroll
-    for (int s = 0; s < 8; s++) xv[s] = ldg_x(x + (xbase + (idx16(iw, s) & 0x7FFFu)));  // 32-bit element index
+    for (int s = 0; s < 8; s++)  // 32-bit element index
+      xv[s] = ldg_x(x + SPMVB_BOUND(3, xbase + (idx16(iw, s) & 0x7FFFu), g_limits.x_len));
   }
 }
 
@@ -378,6 +402,7 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
   };
   const uint64_t stream_policy = l2_policy_evict_first();
   auto issue = [&](uint32_t slot, uint32_t chunk) {  // lane 0 only
+    chunk = SPMVB_BOUND(0, chunk, g_limits.n_chunks);
     const uint32_t bar = bars + (slot & 1u) * 8;
     mbar_expect_tx(bar, SLOT);
     bulk_g2s_hint(ring + (slot & 1u) * STAGE, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar, stream_policy);
@@ -413,7 +438,9 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
     if (pos == R - 1 || i + 1 == n) {  // the row left open continues in another warp's run: hand over atomically
       if (open && lane == 0) {
         // in a `consecutive` chunk the open row follows from the rank (the flag covers it): no dependent row-map load
-        const uint32_t row = (mraw.z & kChunkRowsConsecutive) ? mraw.w + (next_rank - mraw.x) : rowmap[next_rank];
+        uint32_t row = (mraw.z & kChunkRowsConsecutive) ? mraw.w + (next_rank - mraw.x)
+                                                        : rowmap[SPMVB_BOUND(1, next_rank, g_limits.n_pairs)];
+        row = SPMVB_BOUND(2, row, g_limits.rows);
         y_add(&y[row], carry);
       }
       carry = VT(0);
@@ -529,15 +556,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                                 }
                                 const uint32_t valid = mraw.z & 0x3FFu;
                                 const uint32_t xs = xbuf - col_base * (uint32_t)sizeof(VT);
+                                auto win = [&](uint32_t col) -> uint32_t {  // shared-memory address of x[col] of the block
+#ifdef SPMVB_CHECK_BOUNDS
+                                  const uint32_t off = (col - col_base) * (uint32_t)sizeof(VT);
+                                  return xbuf + SPMVB_BOUND(4, off, x_bytes);
+#else
+                                  return xs + col * (uint32_t)sizeof(VT);
+#endif
+                                };
                                 if (valid == (uint32_t)kChunkEntries) {
 #pragma unroll
-                                  for (int s = 0; s < 8; s++)
-                                    xv[s] = lds_x(xs + (idx16(iw, s) & 0x7FFFu) * (uint32_t)sizeof(VT), VT(0));
+                                  for (int s = 0; s < 8; s++) xv[s] = lds_x(win(idx16(iw, s) & 0x7FFFu), VT(0));
                                 } else {  // padding slots carry column 0, which may lie outside the window
                                   const int nv = min(8, max(0, (int)valid - lane * 8));
 #pragma unroll
-                                  for (int s = 0; s < 8; s++)
-                                    xv[s] = s < nv ? lds_x(xs + (idx16(iw, s) & 0x7FFFu) * (uint32_t)sizeof(VT), VT(0)) : VT(0);
+                                  for (int s = 0; s < 8; s++) xv[s] = s < nv ? lds_x(win(idx16(iw, s) & 0x7FFFu), VT(0)) : VT(0);
                                 }
                               });
       if (!waited) mbar_wait(xbar, k & 1u);  // warps without work still consume the phase

@@ -26,6 +26,7 @@ SYMBOLS = {
     "spmvb_options_from_env": (_int, []),
     "spmvb_layout_device_params": (_int, [_vp, _vp]),
     "spmvb_layout_x_lines_per_chunk": (ctypes.c_double, [_vp]),
+    "spmvb_debug_bounds_errors": (_int, [_vp]),
     "spmvb_engine_last_iter_ms": (ctypes.c_float, [_vp]),
     "spmvb_engine_device_layout": (_int, [_vp, _vp]),
     "spmvb_layout_build": (_int, [_u32, _u32, _vp, _vp, _vp, _int, _int, _int, _u32, _vp]),
@@ -177,6 +178,13 @@ def _check(rc, L=None):
 def set_option(name, value):
     """Process-wide tuning option (include/spmvb.h: spmvb_set_option); -1 restores the library's own choice."""
     _check(lib().spmvb_set_option(name.encode(), int(value)))
+
+
+def bounds_errors():
+    """Bounds-checked build only (SPMVB_LIB=.../libspmvb_check.so): the kernels' out-of-range counters, else None."""
+    out = (ctypes.c_uint64 * 5)()
+    rc = lib().spmvb_debug_bounds_errors(out)
+    return None if rc < 0 else dict(zip(("chunk", "rowmap", "y_row", "x_index", "x_window"), (int(v) for v in out)))
 
 
 def get_option(name):

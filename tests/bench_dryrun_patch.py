@@ -74,6 +74,7 @@ class FakeEngine:
         r = layout.x_ranges()
         self.x_upload_bytes = int((np.minimum(r[:, 1], layout.expanded_cols) - r[:, 0]).sum()) * (8 if layout.is_double else 4)
         self.device_layout = dict(layout.device_params)
+        self.device_layout.setdefault("pairs", layout.pairs)
         self._A = _scipy(layout._csr) if getattr(layout, "_csr", None) is not None else None
         self._x = None
 
