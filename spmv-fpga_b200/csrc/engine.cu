@@ -94,6 +94,9 @@ struct Engine {
 // 6 / 7 = OCC (TMA ring, x gathered from global memory, 4 / 3 CTAs per SM); 8 = XS (x window in shared memory).
 // Launch with programmatic dependent launch allowed: the kernel may start while the previous kernel of the stream
 // (the row-clearing kernel of the same step) is still draining; it executes griddepcontrol.wait before it touches x/y.
+// g_persist: when set, the next launch carries an access policy window - the L2 keeps the lines of [base, base + bytes)
+// as persisting (the y range of the row tile being computed), everything else of that launch is streaming.
+static thread_local struct { void *base; size_t bytes; } g_persist = {nullptr, 0};
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -101,11 +104,20 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
   cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (g_persist.base && g_persist.bytes) {
+    attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[1].val.accessPolicyWindow.base_ptr = g_persist.base;
+    attr[1].val.accessPolicyWindow.num_bytes = g_persist.bytes;
+    attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kern, (KArgs)args...);
 }
 
@@ -218,6 +230,26 @@ static int do_spmv(Engine *E, const void *x_dev, void *y_dev, int accumulate, cu
   if (!accumulate) {
     int rc = zero_y(E, y, st);
     if (rc) return rc;
+  }
+  const int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
+  if (variant == kVariantXs && E->n_tiles > 1 && options().tile_launch > 0) {
+    // one launch per row tile, each with the tile's y range as the persisting window of the L2 cache
+    uint32_t prev = 0;
+    for (int k = 0; k < E->n_tiles; k++) {
+      const uint32_t end = k + 1 == E->n_tiles ? E->rows : E->tile_rows_end[k];
+      const uint32_t slack = (end - prev) / 16 + 1024;
+      const uint32_t lo = prev > slack ? prev - slack : 0, hi = (uint64_t)end + slack < E->rows ? end + slack : E->rows;
+      g_persist.base = (uint8_t *)y + (size_t)lo * E->vb;
+      g_persist.bytes = (size_t)(hi - lo) * E->vb;
+      int rc = E->is_double ? launch_xs<double>(E, (const double *)x, (double *)y, st, accumulate, k)
+                            : launch_xs<float>(E, (const float *)x, (float *)y, st, accumulate, k);
+      g_persist.base = nullptr; g_persist.bytes = 0;
+      if (rc) return rc;
+      E->launches++;
+      prev = std::max(prev, end);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SPMVB_OK;
   }
   if (E->is_double) return launch_spmv<double>(E, (const double *)x, (double *)y, st, accumulate);
   return launch_spmv<float>(E, (const float *)x, (float *)y, st, accumulate);
