@@ -55,6 +55,8 @@ def parse_args(argv=None):
     ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (default min(steps, 5))")
     ap.add_argument("--also", default=None, help="comma list of further workloads measured at N = 1 into `also` "
                     "(default: laplacian,rmat for the default workload)")
+    ap.add_argument("--exchange", type=int, default=2, choices=[0, 1, 2], help="power iteration: 0 NCCL grouped broadcasts, "
+                    "1 peer stores to every GPU, 2 peer stores to the forwarding GPU + all-gather (default)")
     ap.add_argument("--sample-log2", type=int, default=0, help="log2(rows) of the CPU baseline's sample (default: ~2^24 non-zeros)")
     return ap.parse_args(argv)
 
@@ -541,6 +543,13 @@ def measure_poweriter(ctx, args, steps, warmup):
     grp = spmvb.Group.create_rank(n, n, bounds, csr.row_ptr, csr.col_ind, csr.values, is_double, ctx.local_rank, uid, rank,
                                   world, args.variant)
     t_build = time.perf_counter() - t0
+    if world > 1 and args.exchange:
+        # peer-memory exchange: every rank maps the other ranks' x (CUDA IPC handles travel through the launcher)
+        h = torch.from_numpy(grp.ipc_handle()).cuda()
+        allh = [torch.empty_like(h) for _ in range(world)]
+        ctx.dist.all_gather(allh, h)
+        grp.set_peer_handles(torch.stack(allh).cpu().numpy(), args.exchange)
+    exchange_mode = int(grp.exchange)
     x0 = np.full(n, 1.0 / np.sqrt(n), vt)
     grp.set_x(x0)
     grp.power_iter(max(warmup, 3))
@@ -603,9 +612,13 @@ def measure_poweriter(ctx, args, steps, warmup):
         "metric": METRIC, "value": 2.0 * nnz_total / (per * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world, "steps": steps,
         "warmup": max(warmup, 3), "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": dtype, "data": "synthetic", "config": public_config(spec, nnz_total),
-        "engine": {"row_bounds": bounds, "exchange": "one grouped NCCL call per iteration (a broadcast per row owner, in place in x) "
-                                                     "+ all-reduce of one double; spmvb_group_power_iter",
-                   "step": "clear rows + SpMV kernel + sum of squares + all-reduce + scale kernel + exchange",
+        "engine": {"row_bounds": bounds, "exchange_mode": exchange_mode,
+                   "exchange": ["one grouped NCCL call per iteration (a broadcast per row owner, in place in x)",
+                                "the normalisation kernel stores its rows into every GPU's x over NVLink (peer memory) + 8-byte "
+                                "all-reduce as barrier",
+                                "the normalisation kernel stores its rows into x of the forwarding GPU over NVLink (peer memory), "
+                                "barrier, all-gather of the equal chunks in place (NCCL)"][exchange_mode],
+                   "step": "clear rows + SpMV kernel + sum of squares + all-reduce of one double + normalisation / exchange",
                    "wall_ms_per_step": wall_ms / steps},
         "effective_gbs": alg / (per * 1e-3) / 1e9, "last_norm": nrm, "gpu_launches": launches, "clocks": sampler.summary(),
         "e2e": {"value": 2.0 * nnz_total * steps / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(world * n * vb / steps),

@@ -160,6 +160,7 @@ uint64_t spmvb_engine_launches(const spmvb_engine *e);
 uint64_t spmvb_engine_algorithmic_bytes(const spmvb_engine *e);
 /* engine-owned device vectors: x has expanded_nr_cols values, y has rows values */
 void *spmvb_engine_x_dev(spmvb_engine *e);
+uint64_t spmvb_engine_x_len(const spmvb_engine *e); /* values the device x holds (>= expanded_nr_cols, zero padded) */
 void *spmvb_engine_y_dev(spmvb_engine *e);
 void *spmvb_engine_stream(spmvb_engine *e); /* cudaStream_t */
 
@@ -259,6 +260,20 @@ int spmvb_group_get_y(spmvb_group *g, void *y_host);             /* local GPUs' 
  * group.  *norm_out = the last norm. */
 int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out);
 float spmvb_group_last_iter_ms(const spmvb_group *g); /* device time per iteration of the last call, max over local GPUs */
+/* How the power iteration moves the y slices into every GPU's x:
+ *   0  NCCL only: one grouped call of a broadcast per row owner, in place in x
+ *   1  the normalisation kernel stores its rows straight into EVERY GPU's x over NVLink (peer memory), then an 8-byte
+ *      all-reduce as barrier
+ *   2  the normalisation kernel stores its rows into x of the ONE GPU that forwards that part of the vector (x is also
+ *      cut into `world` equal chunks), barrier, then an all-gather of the equal chunks in place (NCCL; NVLS multicast
+ *      on NVSwitch): balanced whatever the row ownership looks like.  Default when the peers' x are mapped.
+ * A group made by spmvb_group_create maps the peers itself (cudaDeviceEnablePeerAccess).  A multi-process group needs
+ * the launcher's help: every rank publishes spmvb_group_ipc_handle (64 bytes = cudaIpcMemHandle_t of its x), all ranks
+ * then receive all handles (world x 64 bytes, in rank order) through spmvb_group_set_peer_handles. */
+int spmvb_group_ipc_handle(spmvb_group *g, uint8_t *out64);
+int spmvb_group_set_peer_handles(spmvb_group *g, const uint8_t *handles, int mode);
+int spmvb_group_set_exchange(spmvb_group *g, int mode);
+int spmvb_group_exchange(const spmvb_group *g);
 
 /* ------------------------------------------------------------------ matrix files and synthetic inputs */
 

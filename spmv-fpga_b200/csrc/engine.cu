@@ -783,6 +783,7 @@ uint64_t spmvb_engine_x_upload_bytes(const spmvb_engine *e) {
   return cols * E->vb;
 }
 void *spmvb_engine_x_dev(spmvb_engine *e) { return ((Engine *)e)->d_x; }
+uint64_t spmvb_engine_x_len(const spmvb_engine *e) { return ((const Engine *)e)->x_len; }
 void *spmvb_engine_y_dev(spmvb_engine *e) { return ((Engine *)e)->d_y; }
 void *spmvb_engine_stream(spmvb_engine *e) { return (void *)((Engine *)e)->stream; }
 

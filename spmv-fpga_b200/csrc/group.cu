@@ -29,6 +29,49 @@
 
 namespace spmvb {
 
+// ---- the exchange of the iterated caller over peer memory (NVLink): the normalisation kernel IS the first half of
+// the collective.  Every GPU scales its rows of y by 1 / ||y|| (the all-reduced sum of squares is on the device) and
+// stores them straight into x of a peer instead of into its own memory first:
+//   mode 1 "peer all":    into every GPU's x (one kernel, W stores per element; the biggest row owner's NVLink egress
+//                         is the bound: its rows x (W - 1) peers)
+//   mode 2 "peer + gather": into x of the ONE GPU that forwards that part of the vector - x is also cut into W equal
+//                         chunks, GPU f forwards chunk f - and an all-gather of the equal chunks, in place in x, does
+//                         the rest (NCCL, NVLS multicast on NVSwitch).  Every row crosses NVLink twice, but both steps
+//                         are balanced whatever the row ownership looks like (nnz-balanced R-MAT: one GPU owns 43 %
+//                         of the rows).
+// peers[g] = base of GPU g's x (peer-mapped or CUDA-IPC-opened pointers); r0 = first row of this GPU.
+template <typename VT, int MODE>
+__global__ void __launch_bounds__(256) scale_store_peers_kernel(const VT *__restrict__ src, uint32_t n, uint32_t r0,
+                                                                const double *__restrict__ sumsq, VT *const *__restrict__ peers,
+                                                                int world, uint32_t chunk) {
+  const double ss = *sumsq;
+  const VT s = (VT)(ss > 0.0 ? 1.0 / sqrt(ss) : 0.0);
+  constexpr int V = 16 / sizeof(VT);  // elements per 16-byte store; r0 and chunk are multiples of V
+  const uint32_t nv = n / V;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 raw = reinterpret_cast<const uint4 *>(src)[i];
+    VT *e = reinterpret_cast<VT *>(&raw);
+#pragma unroll
+    for (int k = 0; k < V; k++) e[k] *= s;
+    const size_t g = (size_t)r0 + i * V;  // global row = element of x
+    if (MODE == 1) {
+      for (int p = 0; p < world; p++) reinterpret_cast<uint4 *>(peers[p] + g)[0] = raw;
+    } else {
+      reinterpret_cast<uint4 *>(peers[g / chunk] + g)[0] = raw;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - nv * V) {  // tail shorter than one vector
+    const size_t i = (size_t)nv * V + threadIdx.x;
+    const VT v = src[i] * s;
+    const size_t g = (size_t)r0 + i;
+    if (MODE == 1) {
+      for (int p = 0; p < world; p++) peers[p][g] = v;
+    } else {
+      peers[g / chunk][g] = v;
+    }
+  }
+}
+
 namespace {
 
 struct Nccl {
@@ -41,6 +84,7 @@ struct Nccl {
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   std::string error;
 };
@@ -69,6 +113,7 @@ Nccl *nccl() {
   n.GroupEnd = (decltype(n.GroupEnd))sym("ncclGroupEnd");
   n.AllReduce = (decltype(n.AllReduce))sym("ncclAllReduce");
   n.Broadcast = (decltype(n.Broadcast))sym("ncclBroadcast");
+  n.AllGather = (decltype(n.AllGather))sym("ncclAllGather");
   n.GetErrorString = (decltype(n.GetErrorString))sym("ncclGetErrorString");
   return &n;
 }
@@ -79,6 +124,9 @@ struct Member {  // one GPU of this process
   spmvb_engine *engine = nullptr;
   ncclComm_t comm = nullptr;
   double *d_scalar = nullptr;
+  double *d_token = nullptr;   // 8 bytes all-reduced as a barrier between the peer stores and whoever reads x next
+  void **d_peers = nullptr;    // [world] base of every GPU's x as seen from this GPU
+  std::vector<void *> ipc_opened;  // pointers this process opened with cudaIpcOpenMemHandle
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -92,6 +140,8 @@ struct Group {
   double *h_scalar = nullptr;            // pinned
   float last_iter_ms = 0.f;
   uint64_t nnz_local = 0;
+  int exchange = 0;            // 0 NCCL grouped broadcasts, 1 peer stores to all, 2 peer stores to the forwarder + all-gather
+  uint32_t chunk = 0;          // mode 2: elements per forwarded chunk of x (world * chunk <= x length)
 };
 
 #define G_CUDA(expr)                                                                       \
@@ -120,15 +170,36 @@ static int member_build(Group *G, Member &m, uint32_t n_rows, const uint64_t *ro
   if (rc) return rc;
   G_CUDA(cudaSetDevice(m.device));
   G_CUDA(cudaMalloc((void **)&m.d_scalar, 64));
+  G_CUDA(cudaMalloc((void **)&m.d_token, 64));
+  G_CUDA(cudaMemset(m.d_token, 0, 64));
   G_CUDA(cudaEventCreate(&m.ev0));
   G_CUDA(cudaEventCreate(&m.ev1));
   return SPMVB_OK;
 }
 
+// installs the table of peer x pointers on one member and picks the exchange mode
+static int member_set_peers(Group *G, Member &m, const std::vector<void *> &x_of) {
+  G_CUDA(cudaSetDevice(m.device));
+  if (!m.d_peers) G_CUDA(cudaMalloc((void **)&m.d_peers, sizeof(void *) * G->world));
+  G_CUDA(cudaMemcpy(m.d_peers, x_of.data(), sizeof(void *) * G->world, cudaMemcpyHostToDevice));
+  return SPMVB_OK;
+}
+static void group_pick_exchange(Group *G, int requested) {
+  const uint32_t V = 16u / (uint32_t)G->vb;
+  bool aligned = true;  // 16-byte stores: every owner's first row must be a multiple of V
+  for (int r = 0; r < G->world; r++) aligned = aligned && G->bounds[r] % V == 0;
+  const uint64_t chunk = (((uint64_t)G->rows + G->world - 1) / G->world + V - 1) / V * V;
+  G->chunk = (uint32_t)chunk;
+  G->exchange = aligned ? requested : 0;
+  // the all-gather of mode 2 fills world * chunk elements of every x
+  for (Member &m : G->local)
+    if (G->exchange == 2 && (uint64_t)G->world * chunk > spmvb_engine_x_len(m.engine)) G->exchange = 1;
+}
+
 static void group_destroy(Group *G) {
   if (!G) return;
   for (Member &m : G->local) {
-    if (!m.engine && !m.comm && !m.d_scalar) {  // never got as far as touching its device (e.g. a bad device index)
+    if (!m.engine && !m.comm && !m.d_scalar && !m.d_peers) {  // never got as far as touching its device (e.g. a bad device index)
       if (m.layout) spmvb_layout_free(m.layout);
       continue;
     }
@@ -136,7 +207,8 @@ static void group_destroy(Group *G) {
     if (m.comm && nccl()->CommDestroy) nccl()->CommDestroy(m.comm);
     if (m.engine) spmvb_engine_free(m.engine);
     if (m.layout) spmvb_layout_free(m.layout);
-    cudaFree(m.d_scalar);
+    cudaFree(m.d_scalar); cudaFree(m.d_token); cudaFree(m.d_peers);
+    for (void *p : m.ipc_opened) cudaIpcCloseMemHandle(p);
     if (m.ev0) cudaEventDestroy(m.ev0);
     if (m.ev1) cudaEventDestroy(m.ev1);
   }
@@ -200,6 +272,28 @@ int spmvb_group_create(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, co
       for (int k = 0; k < n_devices; k++) devs[k] = G->local[k].device;
       G_NCCL(nccl()->CommInitAll(comms.data(), n_devices, devs.data()));
       for (int k = 0; k < n_devices; k++) G->local[k].comm = comms[k];
+      // peer access between all GPUs of the group: the exchange of the iterated caller stores into the peers' x
+      bool p2p = true;
+      for (int a = 0; a < n_devices && p2p; a++)
+        for (int b = 0; b < n_devices && p2p; b++) {
+          if (a == b) continue;
+          int can = 0;
+          G_CUDA(cudaDeviceCanAccessPeer(&can, devs[a], devs[b]));
+          if (!can) { p2p = false; break; }
+          G_CUDA(cudaSetDevice(devs[a]));
+          cudaError_t e = cudaDeviceEnablePeerAccess(devs[b], 0);
+          if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+          else if (e != cudaSuccess) p2p = false;
+        }
+      if (p2p) {
+        std::vector<void *> x_of(n_devices);
+        for (int k = 0; k < n_devices; k++) x_of[k] = spmvb_engine_x_dev(G->local[k].engine);
+        for (int k = 0; k < n_devices; k++) {
+          int r = member_set_peers(G, G->local[k], x_of);
+          if (r) return r;
+        }
+        group_pick_exchange(G, 2);
+      }
     }
     return SPMVB_OK;
   };
@@ -208,6 +302,50 @@ int spmvb_group_create(uint32_t rows, uint32_t cols, const uint64_t *row_ptr, co
   *out = (spmvb_group *)G;
   return SPMVB_OK;
 }
+
+// Multi-process groups: every rank publishes the CUDA IPC handle of its x (64 bytes), the launcher hands all of them
+// to every rank, which maps the peers' vectors and switches the exchange to peer stores.
+int spmvb_group_ipc_handle(spmvb_group *g, uint8_t *out64) {
+  Group *G = (Group *)g;
+  if (!G || !out64 || G->local.size() != 1) return fail(SPMVB_E_ARG, "group_ipc_handle: one local GPU per process");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  Member &m = G->local[0];
+  G_CUDA(cudaSetDevice(m.device));
+  cudaIpcMemHandle_t h;
+  G_CUDA(cudaIpcGetMemHandle(&h, spmvb_engine_x_dev(m.engine)));
+  memcpy(out64, &h, 64);
+  return SPMVB_OK;
+}
+
+int spmvb_group_set_peer_handles(spmvb_group *g, const uint8_t *handles, int mode) {
+  Group *G = (Group *)g;
+  if (!G || !handles || G->local.size() != 1 || mode < 0 || mode > 2) return fail(SPMVB_E_ARG, "group_set_peer_handles");
+  Member &m = G->local[0];
+  G_CUDA(cudaSetDevice(m.device));
+  std::vector<void *> x_of(G->world, nullptr);
+  for (int r = 0; r < G->world; r++) {
+    if (r == m.rank) { x_of[r] = spmvb_engine_x_dev(m.engine); continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, 64);
+    void *p = nullptr;
+    G_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    m.ipc_opened.push_back(p);
+    x_of[r] = p;
+  }
+  int rc = member_set_peers(G, m, x_of);
+  if (rc) return rc;
+  group_pick_exchange(G, mode);
+  return SPMVB_OK;
+}
+
+int spmvb_group_set_exchange(spmvb_group *g, int mode) {
+  Group *G = (Group *)g;
+  if (!G || mode < 0 || mode > 2) return fail(SPMVB_E_ARG, "group_set_exchange");
+  if (mode && (G->world < 2 || !G->local[0].d_peers)) return fail(SPMVB_E_ARG, "group_set_exchange: the peers' x vectors are not mapped");
+  group_pick_exchange(G, mode);
+  return SPMVB_OK;
+}
+int spmvb_group_exchange(const spmvb_group *g) { return g ? ((const Group *)g)->exchange : -1; }
 
 int spmvb_group_create_rank(uint32_t global_rows, uint32_t cols, const uint32_t *bounds, const uint64_t *row_ptr_local,
                             const uint32_t *col_ind, const void *values, int is_double, int device, int variant,
@@ -355,24 +493,59 @@ int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out) {
         G_NCCL(N->AllReduce(m.d_scalar, m.d_scalar, 1, ncclDouble, ncclSum, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
       G_NCCL(N->GroupEnd());
     }
-    for (Member &m : G->local) {
-      const uint32_t r0 = G->bounds[m.rank], n_local = G->bounds[m.rank + 1] - r0;
-      uint8_t *x = (uint8_t *)spmvb_engine_x_dev(m.engine);
-      int rc = spmvb_engine_scale_rsqrt(m.engine, spmvb_engine_y_dev(m.engine), x + (size_t)r0 * G->vb, n_local, m.d_scalar, nullptr);
-      if (rc) return rc;
-    }
-    if (multi) {  // every owner's slice into every GPU's x, in place: one NCCL launch per GPU
-      G_NCCL(N->GroupStart());
+    if (!multi || G->exchange == 0) {
       for (Member &m : G->local) {
+        const uint32_t r0 = G->bounds[m.rank], n_local = G->bounds[m.rank + 1] - r0;
         uint8_t *x = (uint8_t *)spmvb_engine_x_dev(m.engine);
-        for (int r = 0; r < G->world; r++) {
-          const uint32_t b0 = G->bounds[r], len = G->bounds[r + 1] - b0;
-          if (!len) continue;
-          void *p = x + (size_t)b0 * G->vb;
-          G_NCCL(N->Broadcast(p, p, len, dt, r, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
-        }
+        int rc = spmvb_engine_scale_rsqrt(m.engine, spmvb_engine_y_dev(m.engine), x + (size_t)r0 * G->vb, n_local, m.d_scalar, nullptr);
+        if (rc) return rc;
       }
+      if (multi) {  // every owner's slice into every GPU's x, in place: one NCCL launch per GPU
+        G_NCCL(N->GroupStart());
+        for (Member &m : G->local) {
+          uint8_t *x = (uint8_t *)spmvb_engine_x_dev(m.engine);
+          for (int r = 0; r < G->world; r++) {
+            const uint32_t b0 = G->bounds[r], len = G->bounds[r + 1] - b0;
+            if (!len) continue;
+            void *p = x + (size_t)b0 * G->vb;
+            G_NCCL(N->Broadcast(p, p, len, dt, r, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
+          }
+        }
+        G_NCCL(N->GroupEnd());
+      }
+    } else {
+      // normalise + store into the peers' x (NVLink), then a barrier: an 8-byte all-reduce that no rank leaves before
+      // every rank's store kernel has finished
+      for (Member &m : G->local) {
+        const uint32_t r0 = G->bounds[m.rank], n_local = G->bounds[m.rank + 1] - r0;
+        G_CUDA(cudaSetDevice(m.device));
+        cudaStream_t st = (cudaStream_t)spmvb_engine_stream(m.engine);
+        const int grid = 148 * 4;
+        if (G->is_double) {
+          auto k1 = scale_store_peers_kernel<double, 1>;
+          auto k2 = scale_store_peers_kernel<double, 2>;
+          (G->exchange == 1 ? k1 : k2)<<<grid, 256, 0, st>>>((const double *)spmvb_engine_y_dev(m.engine), n_local, r0, m.d_scalar,
+                                                             (double *const *)m.d_peers, G->world, G->chunk);
+        } else {
+          auto k1 = scale_store_peers_kernel<float, 1>;
+          auto k2 = scale_store_peers_kernel<float, 2>;
+          (G->exchange == 1 ? k1 : k2)<<<grid, 256, 0, st>>>((const float *)spmvb_engine_y_dev(m.engine), n_local, r0, m.d_scalar,
+                                                             (float *const *)m.d_peers, G->world, G->chunk);
+        }
+        G_CUDA(cudaGetLastError());
+      }
+      G_NCCL(N->GroupStart());
+      for (Member &m : G->local)
+        G_NCCL(N->AllReduce(m.d_token, m.d_token, 1, ncclDouble, ncclSum, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
       G_NCCL(N->GroupEnd());
+      if (G->exchange == 2) {  // every GPU forwards its equal chunk of x to all: all-gather in place
+        G_NCCL(N->GroupStart());
+        for (Member &m : G->local) {
+          uint8_t *x = (uint8_t *)spmvb_engine_x_dev(m.engine);
+          G_NCCL(N->AllGather(x + (size_t)m.rank * G->chunk * G->vb, x, G->chunk, dt, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
+        }
+        G_NCCL(N->GroupEnd());
+      }
     }
   }
   for (Member &m : G->local) {

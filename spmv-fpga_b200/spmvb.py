@@ -95,6 +95,11 @@ SYMBOLS = {
     "spmvb_group_get_y": (_int, [_vp, _vp]),
     "spmvb_group_power_iter": (_int, [_vp, _int, _vp]),
     "spmvb_group_last_iter_ms": (ctypes.c_float, [_vp]),
+    "spmvb_group_ipc_handle": (_int, [_vp, _vp]),
+    "spmvb_group_set_peer_handles": (_int, [_vp, _vp, _int]),
+    "spmvb_group_set_exchange": (_int, [_vp, _int]),
+    "spmvb_group_exchange": (_int, [_vp]),
+    "spmvb_engine_x_len": (_u64, [_vp]),
     "spmvb_csr_free": (None, [_vp]),
     "spmvb_csr_rows": (_u32, [_vp]),
     "spmvb_csr_cols": (_u32, [_vp]),
@@ -696,6 +701,26 @@ class Group:
         nrm = ctypes.c_double()
         _check(lib().spmvb_group_power_iter(self.h, iters, ctypes.byref(nrm)))
         return nrm.value
+
+    def ipc_handle(self):
+        """cudaIpcMemHandle_t (64 bytes) of this rank's x, for the other ranks of a multi-process group."""
+        out = np.zeros(64, np.uint8)
+        _check(lib().spmvb_group_ipc_handle(self.h, _ptr(out)))
+        return out
+
+    def set_peer_handles(self, handles, mode=2):
+        """handles: (world, 64) uint8, every rank's ipc_handle() in rank order; mode: see set_exchange."""
+        hh = np.ascontiguousarray(handles, np.uint8).reshape(-1)
+        assert len(hh) == 64 * self.world
+        _check(lib().spmvb_group_set_peer_handles(self.h, _ptr(hh), mode))
+
+    def set_exchange(self, mode):
+        """0 NCCL broadcasts, 1 peer stores to every GPU, 2 peer stores to the forwarding GPU + all-gather."""
+        _check(lib().spmvb_group_set_exchange(self.h, mode))
+
+    @property
+    def exchange(self):
+        return lib().spmvb_group_exchange(self.h)
 
     @property
     def last_iter_ms(self):

@@ -156,6 +156,9 @@ class FakeGroup:
         out[self.bounds[self.rank]:self.bounds[self.rank + 1]] = self.y
         return out
 
+    exchange = 0
+    def ipc_handle(self): return np.zeros(64, np.uint8)
+    def set_peer_handles(self, handles, mode=2): assert np.asarray(handles).size == 64 * self.world
     def launches(self): return self._launches
     def free(self): pass
 

@@ -45,13 +45,19 @@ def test_group_spmv_host_matches_the_oracle(spmvb, oracle, n_dev, isd):
         grp.free()
 
 
+@pytest.mark.parametrize("exchange", [0, 1, 2], ids=["nccl_broadcasts", "peer_all", "peer_forward_allgather"])
 @pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
-def test_group_power_iteration_matches_float64_numpy(spmvb, oracle, n_dev):
+def test_group_power_iteration_matches_float64_numpy(spmvb, oracle, n_dev, exchange):
     if n_dev > _ngpus():
         pytest.skip("needs %d GPUs" % n_dev)
+    if n_dev == 1 and exchange:
+        pytest.skip("one GPU exchanges nothing")
     rows, cols, rp, ci, va = matgen.rmat(12, 8, seed=3)
     va = np.abs(va).astype(np.float32)
     grp = spmvb.Group.create(rows, cols, rp, ci, va, False, devices=range(n_dev))
+    if n_dev > 1:
+        assert grp.exchange == 2          # peers mapped at creation: the balanced peer-memory exchange is the default
+        grp.set_exchange(exchange)
     x0 = np.full(cols, 1.0 / np.sqrt(cols), np.float32)
     grp.set_x(x0)
     nrm = grp.power_iter(20)
