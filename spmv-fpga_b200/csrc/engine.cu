@@ -158,7 +158,7 @@ static int launch_xs_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int acc
   const XsItem *items = tile < 0 ? E->d_items : E->d_items_t;
   const uint32_t *first = tile < 0 ? E->d_cta_first : E->d_cta_first_t + (size_t)tile * (E->xs_ctas + 1);
   CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, x, y, items, first, E->cdb,
-                      E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u)));
+                      E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u) | (uint32_t)(options().diag_flags > 0 ? options().diag_flags & 48 : 0)));
   return SPMVB_OK;
 }
 template <typename VT>

@@ -257,6 +257,7 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
 
   const uint32_t first_bit = eor & (0u - eor);  // the lane's first row end also closes what earlier lanes left open
 
+  if (y_policy == ~0ull) eor = 0;  // diagnostic (engine option diag_flags bit 5): no y updates at all, wrong results
   // which row ends must be atomics: all of them unless the chunk is `sole`; then only the run's dangling first row
   uint32_t redm = 0xFFu;
   if (sole) redm = (head_red && (seen_mask & ((2u << lane) - 1u)) == (1u << lane)) ? first_bit : 0u;
@@ -534,7 +535,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     const uint4 b = __ldg(reinterpret_cast<const uint4 *>(items + it) + 1);
     const uint32_t chunk_begin = a.x, chunk_count = a.y, x_off = a.z, x_bytes = a.w, col_base = b.x;
     __syncthreads();  // every warp is done gathering from the previous window
-    if (threadIdx.x == 0 && x_bytes) {
+    if (threadIdx.x == 0 && x_bytes && (flags & 16u)) {  // diagnostic: no window traffic (results are wrong)
+      mbar_expect_tx(xbar, 16u);
+      bulk_g2s(xbuf, x, 16u, xbar);
+    } else if (threadIdx.x == 0 && x_bytes) {
       fence_proxy_async();
       mbar_expect_tx(xbar, x_bytes);
       const uint8_t *src = reinterpret_cast<const uint8_t *>(x + x_off);
