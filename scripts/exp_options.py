@@ -40,20 +40,20 @@ for s in sets:
         t_lay = time.time() - t0
         eng = spmvb.Engine(lay, 0, variant[0] if variant else 0)
         lay.free()
-    eng.set_x(x)
-    eng.enqueue_steps(3); eng.collect_steps()
-    eng.enqueue_steps(10, False, inner_events=True)
-    total, ker = eng.collect_steps()
-    eng.spmv_dev()
-    y = eng.get_y()
-    err = float(np.max(np.abs(y.astype(np.float64) - gold.astype(np.float64)) / bound))
-    alg = eng.algorithmic_bytes
-    line = dict(workload=workload, scale=scale, dtype=dtype, options=s, variant=eng.variant, kernel_ms=float(np.mean(ker)),
+        eng.set_x(x)
+        eng.enqueue_steps(3); eng.collect_steps()
+        eng.enqueue_steps(10, False, inner_events=True)
+        total, ker = eng.collect_steps()
+        eng.spmv_dev()
+        y = eng.get_y()
+        err = float(np.max(np.abs(y.astype(np.float64) - gold.astype(np.float64)) / bound))
+        alg = eng.algorithmic_bytes
+        line = dict(workload=workload, scale=scale, dtype=dtype, options=s, variant=eng.variant, kernel_ms=float(np.mean(ker)),
                 kernel_ms_min=float(np.min(ker)), step_ms=total / 10, gbs=alg / float(np.mean(ker)) / 1e6,
                 frac=alg / float(np.mean(ker)) / 1e6 / 6547.2, err_over_tol=err, layout_s=t_lay, device_layout=eng.device_layout)
-    print(json.dumps(line), flush=True)
-    print("%-40s v%d kernel %.4f ms (min %.4f) step %.4f  %.0f GB/s frac %.3f err %.2g  %s" %
+        print(json.dumps(line), flush=True)
+        print("%-40s v%d kernel %.4f ms (min %.4f) step %.4f  %.0f GB/s frac %.3f err %.2g  %s" %
           (s, eng.variant, line["kernel_ms"], line["kernel_ms_min"], line["step_ms"], line["gbs"], line["frac"], err,
            {k: line["device_layout"][k] for k in ("cu", "cdb", "cu_major", "e2e_tiles", "tall")}), file=sys.stderr, flush=True)
-    assert err <= 1.0 or "diag_flags" in s, "wrong result"
-    eng.free()
+        assert err <= 1.0 or "diag_flags" in s, "wrong result"
+        eng.free()

@@ -161,10 +161,30 @@ static int launch_xs_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int acc
                       E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u) | (uint32_t)(options().diag_flags > 0 ? options().diag_flags & 48 : 0)));
   return SPMVB_OK;
 }
+// the continuous kernel (two 64 KB windows, rings that run across items)
+template <typename VT, int WARPS, uint32_t X_CAP>
+static int launch_xsc(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
+  const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
+  auto kern = spmv_xsc_kernel<VT, WARPS, X_CAP>;
+  const size_t slot = (size_t)VTraits<VT>::kGroupWords * 16 * 32 + 16;
+  const size_t smem = 2 * (size_t)X_CAP + (size_t)WARPS * 2 * slot + WARPS * 16 + 32;
+  int &grid = E->grid_cache[kVariantXs][sizeof(VT) == 8];
+  if (grid == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    grid = E->xs_ctas;
+  }
+  if (E->n_items == 0) return SPMVB_OK;
+  const XsItem *items = tile < 0 ? E->d_items : E->d_items_t;
+  const uint32_t *first = tile < 0 ? E->d_cta_first : E->d_cta_first_t + (size_t)tile * (E->xs_ctas + 1);
+  CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, x, y, items, first, E->cdb,
+                      E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u) | (uint32_t)(options().diag_flags > 0 ? options().diag_flags & 48 : 0)));
+  return SPMVB_OK;
+}
 template <typename VT>
 static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile = -1) {
   constexpr bool D = sizeof(VT) == 8;  // the instantiations = xs_config() in layout.h
   switch (E->xs_cfg) {
+    case 3: return launch_xsc<VT, D ? 18 : 24, 64u << 10>(E, x, y, st, accumulate, tile);
     case 1: return launch_xs_cfg<VT, D ? 9 : 14, 64u << 10, 2>(E, x, y, st, accumulate, tile);
     case 2: return launch_xs_cfg<VT, D ? 8 : 10, 32u << 10, 3>(E, x, y, st, accumulate, tile);
     default: return launch_xs_cfg<VT, D ? 18 : 24, 128u << 10, 1>(E, x, y, st, accumulate, tile);

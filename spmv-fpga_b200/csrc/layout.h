@@ -96,11 +96,12 @@ struct XsItem {
 // instruction chain is long and serial (measured on the Laplacian: 12 / 16 / 18 warps = 78 / 69 / 66 us) - so a narrower
 // window buys parallelism: wide = the reference's whole x slice of a 16 384-column block on chip (fp64), medium / narrow =
 // half / a quarter of it with two / three independent CTAs per SM.
+// Configuration 3 is the continuous kernel (spmv_xsc_kernel): two 64 KB windows, the next one copied while this one is used.
 struct XsConfig { uint32_t cap; int warps, ctas_per_sm; };
-constexpr int kXsConfigs = 3;
+constexpr int kXsConfigs = 4;
 inline XsConfig xs_config(int is_double, int cfg) {
-  static const XsConfig f64[kXsConfigs] = {{128u << 10, 18, 1}, {64u << 10, 9, 2}, {32u << 10, 8, 3}};
-  static const XsConfig f32[kXsConfigs] = {{128u << 10, 24, 1}, {64u << 10, 14, 2}, {32u << 10, 10, 3}};
+  static const XsConfig f64[kXsConfigs] = {{128u << 10, 18, 1}, {64u << 10, 9, 2}, {32u << 10, 8, 3}, {64u << 10, 18, 1}};
+  static const XsConfig f32[kXsConfigs] = {{128u << 10, 24, 1}, {64u << 10, 14, 2}, {32u << 10, 10, 3}, {64u << 10, 24, 1}};
   cfg = cfg < 0 ? 0 : (cfg >= kXsConfigs ? kXsConfigs - 1 : cfg);
   return is_double ? f64[cfg] : f32[cfg];
 }

@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     if (x_bytes) {
       bool waited = false;
       walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
-                              (uint32_t)WARPS, run_log2, (flags & 4u) != 0, t, y_policy, false,
+                              (uint32_t)WARPS, run_log2, (flags & 4u) != 0, t, (flags & 32u) ? ~0ull : y_policy, false,
                               [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                                 if (!waited) {  // first chunk of the item: the window must have landed
                                   mbar_wait(xbar, k & 1u);
@@ -586,6 +586,207 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                                 gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv);
                               });
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Variant XSC ("continuous"): the x-window kernel for row-tiled layouts, where a work item is short (one column block of
+// one row tile: a few dozen chunks) and the start-up of every item - all warps wait for the 128 KB window, then for their
+// first chunks - is what the XS kernel loses its time to.  Same arithmetic, different pipeline:
+//   * TWO x windows of X_CAP bytes each: the window of item k+2 is copied (TMA) while items k and k+1 are being
+//     processed.  Nobody waits at a barrier: the warp that is LAST to leave item k (shared-memory counter) issues the
+//     copy of item k+2 into the buffer item k used, and an mbarrier per buffer tells the warps when a window has landed.
+//   * the warps' chunk rings run ACROSS item boundaries: runs are numbered through all items of the CTA (run g belongs
+//     to warp g mod W), so every warp gets the same share whatever the items' lengths, and the chunks of the next item
+//     are already in flight while the last ones of this item are summed.
+// Every warp passes through every item in order (wait for its window, process its runs - possibly none -, count itself
+// out): a warp can run at most two items ahead of the slowest one, which is what makes the two counters and the two
+// barriers enough.
+template <typename VT, int WARPS, uint32_t X_CAP>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+    spmv_xsc_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap, const VT *__restrict__ x,
+                    VT *__restrict__ y, const XsItem *__restrict__ items, const uint32_t *__restrict__ cta_first,
+                    uint32_t cdb, uint32_t run_log2, uint32_t flags) {
+  constexpr int GW = VTraits<VT>::kGroupWords;
+  constexpr int VW = VTraits<VT>::kValWords;
+  constexpr uint32_t CHUNK_BYTES = GW * 16 * 32;
+  constexpr uint32_t SLOT = CHUNK_BYTES + 16;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t xbuf = smem_u32(smem);                                   // two windows
+  const uint32_t ring = xbuf + 2 * X_CAP + warp * 2 * SLOT;               // this warp's two chunk slots
+  const uint32_t bars = xbuf + 2 * X_CAP + WARPS * 2 * SLOT + warp * 16;  // ... and their mbarriers
+  const uint32_t wfull = xbuf + 2 * X_CAP + WARPS * 2 * SLOT + WARPS * 16;  // 2 mbarriers: window k & 1 has landed
+  const uint32_t done = wfull + 16;                                         // 2 counters: warps that left item k & 1
+  const uint32_t it0 = __ldg(cta_first + blockIdx.x), n_items = __ldg(cta_first + blockIdx.x + 1) - it0;
+  if (lane == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    if (warp == 0) {
+      mbar_init(wfull, 1);
+      mbar_init(wfull + 8, 1);
+      asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(done), "r"(0u) : "memory");
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (n_items == 0) return;
+  const bool tall = (flags & 8u) != 0;
+  const uint64_t y_policy = tall ? l2_policy_evict_last() : 0ull;
+  const uint64_t stream_policy = l2_policy_evict_first();
+  auto item = [&](uint32_t k, uint4 &a, uint4 &b) {  // descriptor of the CTA's k-th item
+    a = __ldg(reinterpret_cast<const uint4 *>(items + it0 + k));
+    b = __ldg(reinterpret_cast<const uint4 *>(items + it0 + k) + 1);
+  };
+  auto issue_window = [&](uint32_t k) {  // one thread: copy the x window of item k into buffer k & 1
+    uint4 a, b;
+    item(k, a, b);
+    const uint32_t x_off = a.z, x_bytes = (flags & 16u) ? min(a.w, 16u) : a.w, bar = wfull + (k & 1u) * 8;
+    fence_proxy_async();
+    mbar_expect_tx(bar, x_bytes);  // 0 bytes (the item gathers from global memory): the phase completes at once
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(x + x_off);
+    const uint32_t dst = xbuf + (k & 1u) * X_CAP;
+    for (uint32_t o = 0; o < x_bytes; o += 16384u) {
+      if (tall) bulk_g2s_hint(dst + o, src + o, min(16384u, x_bytes - o), bar, stream_policy);
+      else bulk_g2s(dst + o, src + o, min(16384u, x_bytes - o), bar);
+    }
+  };
+  grid_dep_wait();  // x and y may still be written by the previous kernel of the stream
+  if (threadIdx.x == 0) {
+    issue_window(0);
+    if (n_items > 1) issue_window(1);
+  }
+  const uint32_t R = 1u << run_log2, W = WARPS;
+  auto lds128 = [](uint32_t a) -> uint4 {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+  };
+  // ---- generator of this warp's chunks: (chunk index, item, position in its run, last of its run), in walk order
+  struct Desc { uint32_t chunk, item, pos, last; };
+  uint32_t g_item = 0, g_first = 0;   // item the generator is in; global index of that item's first run
+  uint32_t g_begin = 0, g_count = 0, g_runs = 0, g_q = 0, g_j = 0;  // its chunks, runs; this warp's current run / chunk in run
+  bool g_open = false;                // g_item's descriptor is loaded and g_q is a run of this warp
+  auto next = [&](Desc &d) -> bool {
+    for (;;) {
+      if (!g_open) {
+        if (g_item >= n_items) return false;
+        uint4 a, b;
+        item(g_item, a, b);
+        g_begin = a.x; g_count = a.y; g_runs = (g_count + R - 1) >> run_log2;
+        g_q = (warp + W - g_first % W) % W;  // first run of the item that is this warp's
+        g_j = 0;
+        g_open = true;
+      }
+      if (g_q < g_runs) {
+        const uint32_t len = min(R, g_count - (g_q << run_log2));
+        d.chunk = g_begin + (g_q << run_log2) + g_j; d.item = g_item; d.pos = g_j; d.last = g_j + 1 == len;
+        if (++g_j == len) { g_j = 0; g_q += W; }
+        return true;
+      }
+      g_first += g_runs; g_item++; g_open = false;
+    }
+  };
+  auto issue_chunk = [&](uint32_t slot, uint32_t chunk) {  // lane 0 only
+    chunk = SPMVB_BOUND(0, chunk, g_limits.n_chunks);
+    const uint32_t bar = bars + (slot & 1u) * 8;
+    mbar_expect_tx(bar, SLOT);
+    bulk_g2s_hint(ring + (slot & 1u) * SLOT, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar, stream_policy);
+  };
+  // ---- passing from item to item: count this warp out of item k (the last one refills k's window buffer with item
+  //      k + 2), wait for the window of the item being entered
+  auto leave = [&](uint32_t k) {
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();  // this warp's window reads are done before the count says so
+      uint32_t old;
+      asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(done + (k & 1u) * 4) : "memory");
+      if (old == W - 1) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(done + (k & 1u) * 4), "r"(0u) : "memory");
+        __threadfence_block();
+        if (k + 2 < n_items) issue_window(k + 2);
+      }
+    }
+  };
+  uint32_t col_base = 0, x_bytes = 0;
+  auto enter = [&](uint32_t k) {
+    mbar_wait(wfull + (k & 1u) * 8, (k >> 1) & 1u);
+    uint4 a, b;
+    item(k, a, b);
+    x_bytes = a.w; col_base = b.x;
+  };
+  Desc d0, d1, d2;  // current chunk and the two after it
+  bool h0 = next(d0), h1 = h0 && next(d1), h2 = h1 && next(d2);
+  uint32_t t = 0;
+  if (lane == 0) {
+    if (h0) issue_chunk(0, d0.chunk);
+    if (h1) issue_chunk(1, d1.chunk);
+  }
+  uint32_t cur = 0;  // item this warp is in
+  enter(0);
+  VT carry = VT(0);
+  bool open = false, head_red = false;
+  uint32_t next_rank = 0;
+  const uint32_t my = ring + lane * (GW * 16);
+  while (h0) {
+    while (cur < d0.item) { leave(cur); cur++; enter(cur); }
+    const uint32_t st = t & 1u;
+    mbar_wait(bars + st * 8, (t >> 1) & 1u);
+    const uint32_t g = my + st * SLOT;
+    const uint4 mraw = lds128(ring + st * SLOT + CHUNK_BYTES);
+    const uint4 iw = lds128(g);
+    VT xv[8];
+    if (x_bytes) {
+      const uint32_t valid = mraw.z & 0x3FFu;
+      const uint32_t wbase = xbuf + (cur & 1u) * X_CAP;
+      auto win = [&](uint32_t col) -> uint32_t {
+#ifdef SPMVB_CHECK_BOUNDS
+        return wbase + SPMVB_BOUND(4, (col - col_base) * (uint32_t)sizeof(VT), x_bytes);
+#else
+        return wbase + (col - col_base) * (uint32_t)sizeof(VT);
+#endif
+      };
+      if (valid == (uint32_t)kChunkEntries) {
+#pragma unroll
+        for (int s = 0; s < 8; s++) xv[s] = lds_x(win(idx16(iw, s) & 0x7FFFu), VT(0));
+      } else {  // padding slots carry column 0, which may lie outside the window
+        const int nv = min(8, max(0, (int)valid - lane * 8));
+#pragma unroll
+        for (int s = 0; s < 8; s++) xv[s] = s < nv ? lds_x(win(idx16(iw, s) & 0x7FFFu), VT(0)) : VT(0);
+      }
+    } else {
+      gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv);
+    }
+    uint4 vw[VW];
+#pragma unroll
+    for (int k = 0; k < VW; k++) vw[k] = lds128(g + 16 + k * 16);
+    const bool sole = (mraw.z & kChunkSole) != 0 && !(flags & 4u);
+    if (d0.pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;
+    process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red,
+                            (flags & 32u) ? ~0ull : y_policy, stream_policy);
+    if (d0.last) {  // the row left open continues in another warp's run: hand over atomically
+      if (open && lane == 0) {
+        uint32_t row = (mraw.z & kChunkRowsConsecutive) ? mraw.w + (next_rank - mraw.x)
+                                                        : rowmap[SPMVB_BOUND(1, next_rank, g_limits.n_pairs)];
+        row = SPMVB_BOUND(2, row, g_limits.rows);
+        y_add(&y[row], carry);
+      }
+      carry = VT(0);
+      open = false;
+    }
+    __syncwarp();
+    if (lane == 0 && h2) issue_chunk(t + 2, d2.chunk);
+    d0 = d1; h0 = h1;
+    d1 = d2; h1 = h2;
+    h2 = h2 && next(d2);
+    t++;
+  }
+  // out of chunks: still pass through the remaining items, so that the others' counters complete
+  for (;;) {
+    leave(cur);
+    if (++cur >= n_items) break;
+    enter(cur);
   }
 }
 
