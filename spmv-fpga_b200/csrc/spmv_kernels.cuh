@@ -697,14 +697,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
   // ---- passing from item to item: count this warp out of item k (the last one refills k's window buffer with item
   //      k + 2), wait for the window of the item being entered
   auto leave = [&](uint32_t k) {
+    // No memory fence here on purpose: every lane's window reads were consumed by arithmetic long before the warp
+    // gets here, and a fence would also wait for the lane's outstanding red.global updates - an L2 round trip per
+    // item and warp (measured: 17.8 instead of ~7 ms on the 1 B-nnz matrix).  The counter's reset is ordered before
+    // any later increment by the window barrier itself: warps count themselves out of item k + 2 only after its
+    // window, issued below, has landed.
     __syncwarp();
     if (lane == 0) {
-      __threadfence_block();  // this warp's window reads are done before the count says so
       uint32_t old;
       asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(done + (k & 1u) * 4) : "memory");
       if (old == W - 1) {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(done + (k & 1u) * 4), "r"(0u) : "memory");
-        __threadfence_block();
         if (k + 2 < n_items) issue_window(k + 2);
       }
     }
