@@ -52,6 +52,7 @@ struct Engine {
   bool tall = false;               // x and y both exceed the L2 cache: explicit L2 eviction policies
   bool cu_major = false;           // pieces in CU-major device order (row tiles)
   bool irregular = false;          // layout_is_irregular(): x gathers are scattered, the x-window kernel pays
+  bool stage_ids = true;           // row ids of non-consecutive chunks through shared memory (coalesced loads)
   int xs_cfg = 0, xs_ctas = 148;   // configuration of the x-window kernel (xs_config) and its grid = SMs x CTAs per SM
   int auto_variant = kVariantOcc3; // what variant 0 resolves to (chosen from the layout at creation)
   float tune_ms[2] = {0.f, 0.f};   // autotune timings: OCC, XS
@@ -121,11 +122,11 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
   return cudaLaunchKernelEx(&cfg, kern, (KArgs)args...);
 }
 
-template <typename VT, int MINB>
-static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
+template <typename VT, int MINB, bool STAGE>
+static int launch_occ_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
   constexpr int WARPS = 8;
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
-  auto kern = spmv_occ_kernel<VT, WARPS, MINB>;
+  auto kern = spmv_occ_kernel<VT, WARPS, MINB, STAGE>;
   const size_t smem = (size_t)WARPS * 2 * (VTraits<VT>::kGroupWords * 16 * 32 + 16) + (size_t)WARPS * 16;
   int &grid = E->grid_cache[slot][sizeof(VT) == 8];
   if (grid == 0) {
@@ -139,11 +140,17 @@ static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, 
   return SPMVB_OK;
 }
 
+template <typename VT, int MINB>
+static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
+  return E->stage_ids ? launch_occ_impl<VT, MINB, true>(E, x, y, st, slot, accumulate)
+                      : launch_occ_impl<VT, MINB, false>(E, x, y, st, slot, accumulate);
+}
+
 // tile < 0: the whole matrix in one launch; otherwise row tile `tile` only (per-tile plan)
-template <typename VT, int WARPS, uint32_t X_CAP, int MINB>
-static int launch_xs_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
+template <typename VT, int WARPS, uint32_t X_CAP, int MINB, bool STAGE>
+static int launch_xs_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
-  auto kern = spmv_xs_kernel<VT, WARPS, X_CAP, MINB>;
+  auto kern = spmv_xs_kernel<VT, WARPS, X_CAP, MINB, STAGE>;
   const size_t stage = (size_t)VTraits<VT>::kGroupWords * 16 * 32 + 16;
   const size_t smem = (size_t)X_CAP + (size_t)WARPS * 2 * stage + WARPS * 16 + 16;
   int &grid = E->grid_cache[kVariantXs][sizeof(VT) == 8];
@@ -161,30 +168,15 @@ static int launch_xs_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int acc
                       E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u) | (uint32_t)(options().diag_flags > 0 ? options().diag_flags & 48 : 0)));
   return SPMVB_OK;
 }
-// the continuous kernel (two 64 KB windows, rings that run across items)
-template <typename VT, int WARPS, uint32_t X_CAP>
-static int launch_xsc(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
-  const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
-  auto kern = spmv_xsc_kernel<VT, WARPS, X_CAP>;
-  const size_t slot = (size_t)VTraits<VT>::kGroupWords * 16 * 32 + 16;
-  const size_t smem = 2 * (size_t)X_CAP + (size_t)WARPS * 2 * slot + WARPS * 16 + 32;
-  int &grid = E->grid_cache[kVariantXs][sizeof(VT) == 8];
-  if (grid == 0) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    grid = E->xs_ctas;
-  }
-  if (E->n_items == 0) return SPMVB_OK;
-  const XsItem *items = tile < 0 ? E->d_items : E->d_items_t;
-  const uint32_t *first = tile < 0 ? E->d_cta_first : E->d_cta_first_t + (size_t)tile * (E->xs_ctas + 1);
-  CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, x, y, items, first, E->cdb,
-                      E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u) | (uint32_t)(options().diag_flags > 0 ? options().diag_flags & 48 : 0)));
-  return SPMVB_OK;
+template <typename VT, int WARPS, uint32_t X_CAP, int MINB>
+static int launch_xs_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
+  return E->stage_ids ? launch_xs_impl<VT, WARPS, X_CAP, MINB, true>(E, x, y, st, accumulate, tile)
+                      : launch_xs_impl<VT, WARPS, X_CAP, MINB, false>(E, x, y, st, accumulate, tile);
 }
 template <typename VT>
 static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile = -1) {
   constexpr bool D = sizeof(VT) == 8;  // the instantiations = xs_config() in layout.h
   switch (E->xs_cfg) {
-    case 3: return launch_xsc<VT, D ? 18 : 24, 64u << 10>(E, x, y, st, accumulate, tile);
     case 1: return launch_xs_cfg<VT, D ? 9 : 14, 64u << 10, 2>(E, x, y, st, accumulate, tile);
     case 2: return launch_xs_cfg<VT, D ? 8 : 10, 32u << 10, 3>(E, x, y, st, accumulate, tile);
     default: return launch_xs_cfg<VT, D ? 18 : 24, 128u << 10, 1>(E, x, y, st, accumulate, tile);
@@ -489,6 +481,13 @@ static int engine_adopt_layout(Engine *E, const Layout *L) {
   E->real_nnz = L->real_nnz; E->n_chunks = L->n_chunks; E->n_pairs = L->n_pairs; E->stream_bytes = L->stream_bytes;
   E->cu_major = L->cu_major; E->dev_cu = L->cu; E->dev_vf = L->vf;
   E->irregular = layout_is_irregular(L);
+  {  // staging only pays (and only costs registers) where some chunk's rows are not consecutive
+    bool any = false;
+#pragma omp parallel for schedule(static) reduction(| : any)
+    for (int64_t c = 0; c < (int64_t)L->n_chunks; c++)
+      any |= (L->chunks[c].valid & 0x3FFu) != 0 && !(L->chunks[c].valid & kChunkRowsConsecutive);
+    E->stage_ids = any && options().stage_ids != 0;
+  }
   E->xs_cfg = L->xs_cfg;
   E->xs_ctas = E->sms * xs_config(L->is_double, L->xs_cfg).ctas_per_sm;
   E->tall = (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) && (uint64_t)L->cols * L->vb > ((uint64_t)48 << 20);

@@ -96,12 +96,11 @@ struct XsItem {
 // instruction chain is long and serial (measured on the Laplacian: 12 / 16 / 18 warps = 78 / 69 / 66 us) - so a narrower
 // window buys parallelism: wide = the reference's whole x slice of a 16 384-column block on chip (fp64), medium / narrow =
 // half / a quarter of it with two / three independent CTAs per SM.
-// Configuration 3 is the continuous kernel (spmv_xsc_kernel): two 64 KB windows, the next one copied while this one is used.
 struct XsConfig { uint32_t cap; int warps, ctas_per_sm; };
-constexpr int kXsConfigs = 4;
+constexpr int kXsConfigs = 3;
 inline XsConfig xs_config(int is_double, int cfg) {
-  static const XsConfig f64[kXsConfigs] = {{128u << 10, 18, 1}, {64u << 10, 9, 2}, {32u << 10, 8, 3}, {64u << 10, 18, 1}};
-  static const XsConfig f32[kXsConfigs] = {{128u << 10, 24, 1}, {64u << 10, 14, 2}, {32u << 10, 10, 3}, {64u << 10, 24, 1}};
+  static const XsConfig f64[kXsConfigs] = {{128u << 10, 18, 1}, {64u << 10, 9, 2}, {32u << 10, 8, 3}};
+  static const XsConfig f32[kXsConfigs] = {{128u << 10, 24, 1}, {64u << 10, 14, 2}, {32u << 10, 10, 3}};
   cfg = cfg < 0 ? 0 : (cfg >= kXsConfigs ? kXsConfigs - 1 : cfg);
   return is_double ? f64[cfg] : f32[cfg];
 }
@@ -137,6 +136,7 @@ struct Options {
   int64_t tile_mb = -1;       // target size of a row tile's y range in MB
   int64_t xs_config = -1;     // 0 wide / 1 medium / 2 narrow x window of the XS kernel (see XsConfig)
   int64_t l2_persist_mb = -1; // > 0: set aside that much L2 for persisting (evict-last) lines on tall matrices
+  int64_t stage_ids = -1;     // 0: the lanes load their row ids themselves (8 scattered requests per chunk)
   int64_t diag_flags = -1;    // diagnostics of the x-window kernel (WRONG results): 16 = no x window traffic, 32 = no y updates
   int64_t tile_launch = -1;   // 1: one kernel launch per row tile with the tile's y range as persisting L2 window
   int64_t e2e_tiles = -1;     // 0: spmv_host does not pipeline row tiles (one launch, then the copy of y)

@@ -171,7 +171,7 @@ template <typename VT, bool MUL>
 __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw, const uint4 *vw, const VT *xv,
                                               const uint32_t *__restrict__ rowmap, VT *__restrict__ y, int lane,
                                               VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red,
-                                              uint64_t y_policy = 0, uint64_t stream_policy = 0) {
+                                              uint64_t y_policy = 0, uint64_t stream_policy = 0, uint32_t ids = 0) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t rank0 = mraw.x, valid = mraw.z & 0x3FFu, row_first = mraw.w;
   const bool consec = (mraw.z & kChunkRowsConsecutive) != 0;
@@ -196,8 +196,21 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
   // Row ids of this lane's row ends, all requested now, back to back, so that their latency overlaps the products
   // and the row sums (fetched one by one inside the update loop below they were 35 % of the XS kernel's stall time
   // on R-MAT: load -> wait -> RED -> next load ...).
+  // ids != 0: the chunk's slice of the row map already sits in shared memory (stage_row_ids: coalesced loads by the
+  // whole warp, 8 line look-ups per chunk instead of 64), entry rank0 + i at word i + i / 32
   uint32_t rows[8];
-  if (!consec) {
+  if (!consec && ids) {
+    uint32_t i = rank_t - rank0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const uint32_t e = (eor >> s) & 1u;
+      rows[s] = 0;
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
+                   : "+r"(rows[s])
+                   : "r"(ids + 4u * (i + (i >> 5))), "r"(e));
+      i += e;
+    }
+  } else if (!consec) {
     uint32_t rk = rank_t;
 #pragma unroll
     for (int s = 0; s < 8; s++) {
@@ -362,6 +375,34 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
 }
 
+// Row ids of a chunk whose rows are not consecutive (accum_results' walk of the bitmap, csr_hw.cpp:1549-1557, in its
+// compact form): entries rank0 .. rank0 + row ends of the row map (one more than the row ends: a run may leave a row
+// open).  Fetched by the whole warp with coalesced loads - lane l takes entries l, l + 32, ... : 8 requests of one or
+// two 128-byte lines each, where the per-lane loads of process_chunk touch 8 lines per request (lanes 8 ranks = 32
+// bytes apart) - and parked in the chunk's OWN ring slot, whose contents the lanes hold in registers by then; word
+// i + i / 32 keeps the lanes' later reads (8 consecutive entries per lane on a uniform matrix) free of bank conflicts.
+template <bool HINT>
+__device__ __forceinline__ void load_row_ids(const uint32_t *__restrict__ rowmap, uint32_t rank0, uint32_t n, int lane,
+                                             uint64_t policy, uint32_t *tmp) {
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    const uint32_t i = (uint32_t)lane + 32u * j;
+    tmp[j] = 0;
+    if (i < n) {
+      const uint32_t *p = rowmap + SPMVB_BOUND(1, rank0 + i, g_limits.n_pairs + 1);
+      if (HINT) asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(tmp[j]) : "l"(p), "l"(policy));
+      else asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(tmp[j]) : "l"(p));
+    }
+  }
+}
+__device__ __forceinline__ void park_row_ids(uint32_t scratch, uint32_t n, int lane, const uint32_t *tmp) {
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    const uint32_t i = (uint32_t)lane + 32u * j;
+    if (i < n) asm volatile("st.shared.u32 [%0], %1;" ::"r"(scratch + 4u * (i + (i >> 5))), "r"(tmp[j]) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // The warp-level chunk walk shared by the OCC and XS kernels: a 2-stage TMA ring per warp, no software prefetch of x.
 //   step i:  wait stage -> LDS group + meta -> 8 x gathers (functor) -> LDS values -> segmented sums / y updates
@@ -370,10 +411,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 // run q of the warp being run q*W + w of the domain, so that the W warps sweep one contiguous window of the stream
 // together (DRAM page locality) while the open row sum stays in registers inside a run.
 // `t` is the warp's running slot counter: it carries the ring stage / mbarrier phase from one domain to the next.
-// (Staging every chunk's slice of the row map with the chunk - a second bulk copy on the same mbarrier instead of the
-// lanes' eight global loads - was built and measured in round 2: no gain on the 0.5 B-nnz uniform matrix (3.74 vs 3.65
-// ms) and it cost a quarter of the warps their shared memory; the hoisted loads of process_chunk stay.)
-template <typename VT, typename Gather>
+// STAGE_IDS: the row ids of non-consecutive chunks come through shared memory (load_row_ids / park_row_ids).
+template <typename VT, bool STAGE_IDS, typename Gather>
 __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
                                             VT *__restrict__ y, uint32_t ring, uint32_t bars, int lane, uint32_t base,
                                             uint32_t n_dom, uint32_t w, uint32_t W, uint32_t run_log2, bool force_red,
@@ -426,21 +465,48 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
     const uint32_t g = my + st * STAGE;
     const uint4 mraw = lds128(ring + st * STAGE + CHUNK_BYTES);
     const uint4 iw = lds128(g);
+    // row ids of a non-consecutive chunk: requested now (coalesced), parked in the slot once the lanes hold the chunk
+    const bool stage_ids = STAGE_IDS && !(mraw.z & kChunkRowsConsecutive) && (mraw.z & 0x3FFu) != 0;
+    const uint32_t n_ids = ((mraw.y >> kMetaRowsShift) & 0x1FFu) + 1u;
+    uint32_t idtmp[9];
+    if (stage_ids) {
+      if (y_policy) load_row_ids<true>(rowmap, mraw.x, n_ids, lane, stream_policy, idtmp);
+      else load_row_ids<false>(rowmap, mraw.x, n_ids, lane, 0ull, idtmp);
+    }
     VT xv[8];
     gather(iw, mraw, xv);
     uint4 vw[VW];
 #pragma unroll
     for (int k = 0; k < VW; k++) vw[k] = lds128(g + 16 + k * 16);
+    const uint32_t scratch = ring + st * STAGE;
+    if (stage_ids) {
+      // every lane's loads of the chunk must have returned before the slot is overwritten: make each lane touch what
+      // it loaded (one XOR per register), then meet
+      uint32_t fold = iw.x ^ iw.y ^ iw.z ^ iw.w ^ mraw.x;
+#pragma unroll
+      for (int k = 0; k < VW; k++) fold ^= vw[k].x ^ vw[k].y ^ vw[k].z ^ vw[k].w;
+      asm volatile("" ::"r"(fold));
+      __syncwarp();
+      park_row_ids(scratch, n_ids, lane, idtmp);
+      __syncwarp();
+    }
     const uint32_t pos = i & (R - 1);
     const bool sole = (mraw.z & kChunkSole) != 0 && !force_red;
     if (pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;  // stays set until the run's first row end
     process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red, y_policy,
-                            stream_policy);
+                            stream_policy, stage_ids ? scratch : 0u);
     if (pos == R - 1 || i + 1 == n) {  // the row left open continues in another warp's run: hand over atomically
       if (open && lane == 0) {
         // in a `consecutive` chunk the open row follows from the rank (the flag covers it): no dependent row-map load
-        uint32_t row = (mraw.z & kChunkRowsConsecutive) ? mraw.w + (next_rank - mraw.x)
-                                                        : rowmap[SPMVB_BOUND(1, next_rank, g_limits.n_pairs)];
+        uint32_t row;
+        if (mraw.z & kChunkRowsConsecutive) {
+          row = mraw.w + (next_rank - mraw.x);
+        } else if (stage_ids) {
+          const uint32_t k = next_rank - mraw.x;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(scratch + 4u * (k + (k >> 5))));
+        } else {
+          row = rowmap[SPMVB_BOUND(1, next_rank, g_limits.n_pairs)];
+        }
         row = SPMVB_BOUND(2, row, g_limits.rows);
         y_add(&y[row], carry);
       }
@@ -448,7 +514,10 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
       open = false;
     }
     __syncwarp();
-    if (lane == 0 && i + 2 < n) issue(t + 2, ahead(c_cur, i, 2));
+    if (lane == 0 && i + 2 < n) {
+      if (STAGE_IDS) fence_proxy_async();  // the slot was written through the generic proxy (parked row ids)
+      issue(t + 2, ahead(c_cur, i, 2));
+    }
     c_cur = ahead(c_cur, i, 1);
   }
 }
@@ -457,7 +526,7 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
 // Variant OCC: x gathered from global memory (L1/L2); few enough registers for MINB resident CTAs per SM, so that
 // the gather latency of one warp is covered by the other warps of its SM sub-partition.  Nothing stays in flight in
 // registers across the row-sum code, so the kernel does not depend on how ptxas assigns scoreboard slots.
-template <typename VT, int WARPS, int MINB>
+template <typename VT, int WARPS, int MINB, bool STAGE_IDS>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     spmv_occ_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
                     const VT *__restrict__ x, VT *__restrict__ y, uint32_t n_chunks, uint32_t cdb,
@@ -478,7 +547,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   // flags bit 3: "tall" matrix (x and y both larger than the L2 cache): y updates evict-last, x gathers evict-first
   const uint64_t y_policy = (flags & 8u) ? l2_policy_evict_last() : 0ull;
   const uint64_t x_policy = (flags & 8u) ? l2_policy_evict_first() : 0ull;
-  walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, 0u, n_chunks, blockIdx.x * WARPS + warp,
+  walk_chunks<VT, STAGE_IDS>(stream, rowmap, y, ring, bars, lane, 0u, n_chunks, blockIdx.x * WARPS + warp,
                          gridDim.x * WARPS, run_log2, (flags & 4u) != 0, t, y_policy, true,
                          [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                            gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv, x_policy);
@@ -505,7 +574,7 @@ __device__ __forceinline__ float lds_x(uint32_t a, float) {
   return v;
 }
 
-template <typename VT, int WARPS, uint32_t X_CAP, int MINB>
+template <typename VT, int WARPS, uint32_t X_CAP, int MINB, bool STAGE_IDS>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     spmv_xs_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap, const VT *__restrict__ x,
                    VT *__restrict__ y, const XsItem *__restrict__ items, const uint32_t *__restrict__ cta_first,
@@ -551,7 +620,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     }
     if (x_bytes) {
       bool waited = false;
-      walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
+      walk_chunks<VT, STAGE_IDS>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
                               (uint32_t)WARPS, run_log2, (flags & 4u) != 0, t, (flags & 32u) ? ~0ull : y_policy, false,
                               [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                                 if (!waited) {  // first chunk of the item: the window must have landed
@@ -580,216 +649,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
       if (!waited) mbar_wait(xbar, k & 1u);  // warps without work still consume the phase
       k++;
     } else {
-      walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
+      walk_chunks<VT, STAGE_IDS>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
                               (uint32_t)WARPS, run_log2, (flags & 4u) != 0, t, 0ull, false,
                               [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                                 gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv);
                               });
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Variant XSC ("continuous"): the x-window kernel for row-tiled layouts, where a work item is short (one column block of
-// one row tile: a few dozen chunks) and the start-up of every item - all warps wait for the 128 KB window, then for their
-// first chunks - is what the XS kernel loses its time to.  Same arithmetic, different pipeline:
-//   * TWO x windows of X_CAP bytes each: the window of item k+2 is copied (TMA) while items k and k+1 are being
-//     processed.  Nobody waits at a barrier: the warp that is LAST to leave item k (shared-memory counter) issues the
-//     copy of item k+2 into the buffer item k used, and an mbarrier per buffer tells the warps when a window has landed.
-//   * the warps' chunk rings run ACROSS item boundaries: runs are numbered through all items of the CTA (run g belongs
-//     to warp g mod W), so every warp gets the same share whatever the items' lengths, and the chunks of the next item
-//     are already in flight while the last ones of this item are summed.
-// Every warp passes through every item in order (wait for its window, process its runs - possibly none -, count itself
-// out): a warp can run at most two items ahead of the slowest one, which is what makes the two counters and the two
-// barriers enough.
-template <typename VT, int WARPS, uint32_t X_CAP>
-__global__ void __launch_bounds__(WARPS * 32, 1)
-    spmv_xsc_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap, const VT *__restrict__ x,
-                    VT *__restrict__ y, const XsItem *__restrict__ items, const uint32_t *__restrict__ cta_first,
-                    uint32_t cdb, uint32_t run_log2, uint32_t flags) {
-  constexpr int GW = VTraits<VT>::kGroupWords;
-  constexpr int VW = VTraits<VT>::kValWords;
-  constexpr uint32_t CHUNK_BYTES = GW * 16 * 32;
-  constexpr uint32_t SLOT = CHUNK_BYTES + 16;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = threadIdx.x >> 5;
-  const uint32_t xbuf = smem_u32(smem);                                   // two windows
-  const uint32_t ring = xbuf + 2 * X_CAP + warp * 2 * SLOT;               // this warp's two chunk slots
-  const uint32_t bars = xbuf + 2 * X_CAP + WARPS * 2 * SLOT + warp * 16;  // ... and their mbarriers
-  const uint32_t wfull = xbuf + 2 * X_CAP + WARPS * 2 * SLOT + WARPS * 16;  // 2 mbarriers: window k & 1 has landed
-  const uint32_t done = wfull + 16;                                         // 2 counters: warps that left item k & 1
-  const uint32_t it0 = __ldg(cta_first + blockIdx.x), n_items = __ldg(cta_first + blockIdx.x + 1) - it0;
-  if (lane == 0) {
-    mbar_init(bars, 1);
-    mbar_init(bars + 8, 1);
-    if (warp == 0) {
-      mbar_init(wfull, 1);
-      mbar_init(wfull + 8, 1);
-      asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(done), "r"(0u) : "memory");
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-  if (n_items == 0) return;
-  const bool tall = (flags & 8u) != 0;
-  const uint64_t y_policy = tall ? l2_policy_evict_last() : 0ull;
-  const uint64_t stream_policy = l2_policy_evict_first();
-  auto item = [&](uint32_t k, uint4 &a, uint4 &b) {  // descriptor of the CTA's k-th item
-    a = __ldg(reinterpret_cast<const uint4 *>(items + it0 + k));
-    b = __ldg(reinterpret_cast<const uint4 *>(items + it0 + k) + 1);
-  };
-  auto issue_window = [&](uint32_t k) {  // one thread: copy the x window of item k into buffer k & 1
-    uint4 a, b;
-    item(k, a, b);
-    const uint32_t x_off = a.z, x_bytes = (flags & 16u) ? min(a.w, 16u) : a.w, bar = wfull + (k & 1u) * 8;
-    fence_proxy_async();
-    mbar_expect_tx(bar, x_bytes);  // 0 bytes (the item gathers from global memory): the phase completes at once
-    const uint8_t *src = reinterpret_cast<const uint8_t *>(x + x_off);
-    const uint32_t dst = xbuf + (k & 1u) * X_CAP;
-    for (uint32_t o = 0; o < x_bytes; o += 16384u) {
-      if (tall) bulk_g2s_hint(dst + o, src + o, min(16384u, x_bytes - o), bar, stream_policy);
-      else bulk_g2s(dst + o, src + o, min(16384u, x_bytes - o), bar);
-    }
-  };
-  grid_dep_wait();  // x and y may still be written by the previous kernel of the stream
-  if (threadIdx.x == 0) {
-    issue_window(0);
-    if (n_items > 1) issue_window(1);
-  }
-  const uint32_t R = 1u << run_log2, W = WARPS;
-  auto lds128 = [](uint32_t a) -> uint4 {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-  };
-  // ---- generator of this warp's chunks: (chunk index, item, position in its run, last of its run), in walk order
-  struct Desc { uint32_t chunk, item, pos, last; };
-  uint32_t g_item = 0, g_first = 0;   // item the generator is in; global index of that item's first run
-  uint32_t g_begin = 0, g_count = 0, g_runs = 0, g_q = 0, g_j = 0;  // its chunks, runs; this warp's current run / chunk in run
-  bool g_open = false;                // g_item's descriptor is loaded and g_q is a run of this warp
-  auto next = [&](Desc &d) -> bool {
-    for (;;) {
-      if (!g_open) {
-        if (g_item >= n_items) return false;
-        uint4 a, b;
-        item(g_item, a, b);
-        g_begin = a.x; g_count = a.y; g_runs = (g_count + R - 1) >> run_log2;
-        g_q = (warp + W - g_first % W) % W;  // first run of the item that is this warp's
-        g_j = 0;
-        g_open = true;
-      }
-      if (g_q < g_runs) {
-        const uint32_t len = min(R, g_count - (g_q << run_log2));
-        d.chunk = g_begin + (g_q << run_log2) + g_j; d.item = g_item; d.pos = g_j; d.last = g_j + 1 == len;
-        if (++g_j == len) { g_j = 0; g_q += W; }
-        return true;
-      }
-      g_first += g_runs; g_item++; g_open = false;
-    }
-  };
-  auto issue_chunk = [&](uint32_t slot, uint32_t chunk) {  // lane 0 only
-    chunk = SPMVB_BOUND(0, chunk, g_limits.n_chunks);
-    const uint32_t bar = bars + (slot & 1u) * 8;
-    mbar_expect_tx(bar, SLOT);
-    bulk_g2s_hint(ring + (slot & 1u) * SLOT, stream + (size_t)chunk * (32 * GW + 1), SLOT, bar, stream_policy);
-  };
-  // ---- passing from item to item: count this warp out of item k (the last one refills k's window buffer with item
-  //      k + 2), wait for the window of the item being entered
-  auto leave = [&](uint32_t k) {
-    // No memory fence here on purpose: every lane's window reads were consumed by arithmetic long before the warp
-    // gets here, and a fence would also wait for the lane's outstanding red.global updates - an L2 round trip per
-    // item and warp (measured: 17.8 instead of ~7 ms on the 1 B-nnz matrix).  The counter's reset is ordered before
-    // any later increment by the window barrier itself: warps count themselves out of item k + 2 only after its
-    // window, issued below, has landed.
-    __syncwarp();
-    if (lane == 0) {
-      uint32_t old;
-      asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(done + (k & 1u) * 4) : "memory");
-      if (old == W - 1) {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(done + (k & 1u) * 4), "r"(0u) : "memory");
-        if (k + 2 < n_items) issue_window(k + 2);
-      }
-    }
-  };
-  uint32_t col_base = 0, x_bytes = 0;
-  auto enter = [&](uint32_t k) {
-    mbar_wait(wfull + (k & 1u) * 8, (k >> 1) & 1u);
-    uint4 a, b;
-    item(k, a, b);
-    x_bytes = a.w; col_base = b.x;
-  };
-  Desc d0, d1, d2;  // current chunk and the two after it
-  bool h0 = next(d0), h1 = h0 && next(d1), h2 = h1 && next(d2);
-  uint32_t t = 0;
-  if (lane == 0) {
-    if (h0) issue_chunk(0, d0.chunk);
-    if (h1) issue_chunk(1, d1.chunk);
-  }
-  uint32_t cur = 0;  // item this warp is in
-  enter(0);
-  VT carry = VT(0);
-  bool open = false, head_red = false;
-  uint32_t next_rank = 0;
-  const uint32_t my = ring + lane * (GW * 16);
-  while (h0) {
-    while (cur < d0.item) { leave(cur); cur++; enter(cur); }
-    const uint32_t st = t & 1u;
-    mbar_wait(bars + st * 8, (t >> 1) & 1u);
-    const uint32_t g = my + st * SLOT;
-    const uint4 mraw = lds128(ring + st * SLOT + CHUNK_BYTES);
-    const uint4 iw = lds128(g);
-    VT xv[8];
-    if (x_bytes) {
-      const uint32_t valid = mraw.z & 0x3FFu;
-      const uint32_t wbase = xbuf + (cur & 1u) * X_CAP;
-      auto win = [&](uint32_t col) -> uint32_t {
-#ifdef SPMVB_CHECK_BOUNDS
-        return wbase + SPMVB_BOUND(4, (col - col_base) * (uint32_t)sizeof(VT), x_bytes);
-#else
-        return wbase + (col - col_base) * (uint32_t)sizeof(VT);
-#endif
-      };
-      if (valid == (uint32_t)kChunkEntries) {
-#pragma unroll
-        for (int s = 0; s < 8; s++) xv[s] = lds_x(win(idx16(iw, s) & 0x7FFFu), VT(0));
-      } else {  // padding slots carry column 0, which may lie outside the window
-        const int nv = min(8, max(0, (int)valid - lane * 8));
-#pragma unroll
-        for (int s = 0; s < 8; s++) xv[s] = s < nv ? lds_x(win(idx16(iw, s) & 0x7FFFu), VT(0)) : VT(0);
-      }
-    } else {
-      gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv);
-    }
-    uint4 vw[VW];
-#pragma unroll
-    for (int k = 0; k < VW; k++) vw[k] = lds128(g + 16 + k * 16);
-    const bool sole = (mraw.z & kChunkSole) != 0 && !(flags & 4u);
-    if (d0.pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;
-    process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red,
-                            (flags & 32u) ? ~0ull : y_policy, stream_policy);
-    if (d0.last) {  // the row left open continues in another warp's run: hand over atomically
-      if (open && lane == 0) {
-        uint32_t row = (mraw.z & kChunkRowsConsecutive) ? mraw.w + (next_rank - mraw.x)
-                                                        : rowmap[SPMVB_BOUND(1, next_rank, g_limits.n_pairs)];
-        row = SPMVB_BOUND(2, row, g_limits.rows);
-        y_add(&y[row], carry);
-      }
-      carry = VT(0);
-      open = false;
-    }
-    __syncwarp();
-    if (lane == 0 && h2) issue_chunk(t + 2, d2.chunk);
-    d0 = d1; h0 = h1;
-    d1 = d2; h1 = h2;
-    h2 = h2 && next(d2);
-    t++;
-  }
-  // out of chunks: still pass through the remaining items, so that the others' counters complete
-  for (;;) {
-    leave(cur);
-    if (++cur >= n_items) break;
-    enter(cur);
   }
 }
 
