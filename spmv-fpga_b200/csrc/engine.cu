@@ -52,7 +52,6 @@ struct Engine {
   bool tall = false;               // x and y both exceed the L2 cache: explicit L2 eviction policies
   bool cu_major = false;           // pieces in CU-major device order (row tiles)
   bool irregular = false;          // layout_is_irregular(): x gathers are scattered, the x-window kernel pays
-  bool stage_ids = true;           // row ids of non-consecutive chunks through shared memory (coalesced loads)
   int xs_cfg = 0, xs_ctas = 148;   // configuration of the x-window kernel (xs_config) and its grid = SMs x CTAs per SM
   int auto_variant = kVariantOcc3; // what variant 0 resolves to (chosen from the layout at creation)
   float tune_ms[2] = {0.f, 0.f};   // autotune timings: OCC, XS
@@ -122,11 +121,11 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
   return cudaLaunchKernelEx(&cfg, kern, (KArgs)args...);
 }
 
-template <typename VT, int MINB, bool STAGE>
-static int launch_occ_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
+template <typename VT, int MINB>
+static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
   constexpr int WARPS = 8;
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
-  auto kern = spmv_occ_kernel<VT, WARPS, MINB, STAGE>;
+  auto kern = spmv_occ_kernel<VT, WARPS, MINB>;
   const size_t smem = (size_t)WARPS * 2 * (VTraits<VT>::kGroupWords * 16 * 32 + 16) + (size_t)WARPS * 16;
   int &grid = E->grid_cache[slot][sizeof(VT) == 8];
   if (grid == 0) {
@@ -140,17 +139,11 @@ static int launch_occ_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int s
   return SPMVB_OK;
 }
 
-template <typename VT, int MINB>
-static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
-  return E->stage_ids ? launch_occ_impl<VT, MINB, true>(E, x, y, st, slot, accumulate)
-                      : launch_occ_impl<VT, MINB, false>(E, x, y, st, slot, accumulate);
-}
-
 // tile < 0: the whole matrix in one launch; otherwise row tile `tile` only (per-tile plan)
-template <typename VT, int WARPS, uint32_t X_CAP, int MINB, bool STAGE>
-static int launch_xs_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
+template <typename VT, int WARPS, uint32_t X_CAP, int MINB>
+static int launch_xs_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
-  auto kern = spmv_xs_kernel<VT, WARPS, X_CAP, MINB, STAGE>;
+  auto kern = spmv_xs_kernel<VT, WARPS, X_CAP, MINB>;
   const size_t stage = (size_t)VTraits<VT>::kGroupWords * 16 * 32 + 16;
   const size_t smem = (size_t)X_CAP + (size_t)WARPS * 2 * stage + WARPS * 16 + 16;
   int &grid = E->grid_cache[kVariantXs][sizeof(VT) == 8];
@@ -167,11 +160,6 @@ static int launch_xs_impl(Engine *E, const VT *x, VT *y, cudaStream_t st, int ac
   CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, x, y, items, first, E->cdb,
                       E->xs_run_log2, (accumulate ? 4u : 0u) | (E->tall ? 8u : 0u) | (uint32_t)(options().diag_flags > 0 ? options().diag_flags & 48 : 0)));
   return SPMVB_OK;
-}
-template <typename VT, int WARPS, uint32_t X_CAP, int MINB>
-static int launch_xs_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
-  return E->stage_ids ? launch_xs_impl<VT, WARPS, X_CAP, MINB, true>(E, x, y, st, accumulate, tile)
-                      : launch_xs_impl<VT, WARPS, X_CAP, MINB, false>(E, x, y, st, accumulate, tile);
 }
 template <typename VT>
 static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile = -1) {
@@ -481,13 +469,6 @@ static int engine_adopt_layout(Engine *E, const Layout *L) {
   E->real_nnz = L->real_nnz; E->n_chunks = L->n_chunks; E->n_pairs = L->n_pairs; E->stream_bytes = L->stream_bytes;
   E->cu_major = L->cu_major; E->dev_cu = L->cu; E->dev_vf = L->vf;
   E->irregular = layout_is_irregular(L);
-  {  // staging only pays (and only costs registers) where some chunk's rows are not consecutive
-    bool any = false;
-#pragma omp parallel for schedule(static) reduction(| : any)
-    for (int64_t c = 0; c < (int64_t)L->n_chunks; c++)
-      any |= (L->chunks[c].valid & 0x3FFu) != 0 && !(L->chunks[c].valid & kChunkRowsConsecutive);
-    E->stage_ids = any && options().stage_ids != 0;
-  }
   E->xs_cfg = L->xs_cfg;
   E->xs_ctas = E->sms * xs_config(L->is_double, L->xs_cfg).ctas_per_sm;
   E->tall = (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) && (uint64_t)L->cols * L->vb > ((uint64_t)48 << 20);

@@ -136,7 +136,6 @@ struct Options {
   int64_t tile_mb = -1;       // target size of a row tile's y range in MB
   int64_t xs_config = -1;     // 0 wide / 1 medium / 2 narrow x window of the XS kernel (see XsConfig)
   int64_t l2_persist_mb = -1; // > 0: set aside that much L2 for persisting (evict-last) lines on tall matrices
-  int64_t stage_ids = -1;     // 0: the lanes load their row ids themselves (8 scattered requests per chunk)
   int64_t diag_flags = -1;    // diagnostics of the x-window kernel (WRONG results): 16 = no x window traffic, 32 = no y updates
   int64_t tile_launch = -1;   // 1: one kernel launch per row tile with the tile's y range as persisting L2 window
   int64_t e2e_tiles = -1;     // 0: spmv_host does not pipeline row tiles (one launch, then the copy of y)

@@ -47,7 +47,6 @@ const OptionName kOptionNames[] = {
     {"dev_cdb", &Options::dev_cdb},           {"xs_pairs", &Options::xs_pairs},       {"tile_mb", &Options::tile_mb},
     {"e2e_tiles", &Options::e2e_tiles},       {"xs_config", &Options::xs_config},     {"l2_persist_mb", &Options::l2_persist_mb},
     {"tile_launch", &Options::tile_launch},   {"diag_flags", &Options::diag_flags},
-    {"stage_ids", &Options::stage_ids},
 };
 }  // namespace
 

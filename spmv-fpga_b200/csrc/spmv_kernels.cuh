@@ -171,7 +171,7 @@ template <typename VT, bool MUL>
 __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw, const uint4 *vw, const VT *xv,
                                               const uint32_t *__restrict__ rowmap, VT *__restrict__ y, int lane,
                                               VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red,
-                                              uint64_t y_policy = 0, uint64_t stream_policy = 0, uint32_t ids = 0) {
+                                              uint64_t y_policy = 0, uint64_t stream_policy = 0) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t rank0 = mraw.x, valid = mraw.z & 0x3FFu, row_first = mraw.w;
   const bool consec = (mraw.z & kChunkRowsConsecutive) != 0;
@@ -196,21 +196,8 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
   // Row ids of this lane's row ends, all requested now, back to back, so that their latency overlaps the products
   // and the row sums (fetched one by one inside the update loop below they were 35 % of the XS kernel's stall time
   // on R-MAT: load -> wait -> RED -> next load ...).
-  // ids != 0: the chunk's slice of the row map already sits in shared memory (stage_row_ids: coalesced loads by the
-  // whole warp, 8 line look-ups per chunk instead of 64), entry rank0 + i at word i + i / 32
   uint32_t rows[8];
-  if (!consec && ids) {
-    uint32_t i = rank_t - rank0;
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-      const uint32_t e = (eor >> s) & 1u;
-      rows[s] = 0;
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
-                   : "+r"(rows[s])
-                   : "r"(ids + 4u * (i + (i >> 5))), "r"(e));
-      i += e;
-    }
-  } else if (!consec) {
+  if (!consec) {
     uint32_t rk = rank_t;
 #pragma unroll
     for (int s = 0; s < 8; s++) {
@@ -375,34 +362,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   if (open && lane == 0) y_add(&y[rowmap[next_rank]], carry);
 }
 
-// Row ids of a chunk whose rows are not consecutive (accum_results' walk of the bitmap, csr_hw.cpp:1549-1557, in its
-// compact form): entries rank0 .. rank0 + row ends of the row map (one more than the row ends: a run may leave a row
-// open).  Fetched by the whole warp with coalesced loads - lane l takes entries l, l + 32, ... : 8 requests of one or
-// two 128-byte lines each, where the per-lane loads of process_chunk touch 8 lines per request (lanes 8 ranks = 32
-// bytes apart) - and parked in the chunk's OWN ring slot, whose contents the lanes hold in registers by then; word
-// i + i / 32 keeps the lanes' later reads (8 consecutive entries per lane on a uniform matrix) free of bank conflicts.
-template <bool HINT>
-__device__ __forceinline__ void load_row_ids(const uint32_t *__restrict__ rowmap, uint32_t rank0, uint32_t n, int lane,
-                                             uint64_t policy, uint32_t *tmp) {
-#pragma unroll
-  for (int j = 0; j < 9; j++) {
-    const uint32_t i = (uint32_t)lane + 32u * j;
-    tmp[j] = 0;
-    if (i < n) {
-      const uint32_t *p = rowmap + SPMVB_BOUND(1, rank0 + i, g_limits.n_pairs + 1);
-      if (HINT) asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(tmp[j]) : "l"(p), "l"(policy));
-      else asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(tmp[j]) : "l"(p));
-    }
-  }
-}
-__device__ __forceinline__ void park_row_ids(uint32_t scratch, uint32_t n, int lane, const uint32_t *tmp) {
-#pragma unroll
-  for (int j = 0; j < 9; j++) {
-    const uint32_t i = (uint32_t)lane + 32u * j;
-    if (i < n) asm volatile("st.shared.u32 [%0], %1;" ::"r"(scratch + 4u * (i + (i >> 5))), "r"(tmp[j]) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // The warp-level chunk walk shared by the OCC and XS kernels: a 2-stage TMA ring per warp, no software prefetch of x.
 //   step i:  wait stage -> LDS group + meta -> 8 x gathers (functor) -> LDS values -> segmented sums / y updates
@@ -411,8 +370,12 @@ __device__ __forceinline__ void park_row_ids(uint32_t scratch, uint32_t n, int l
 // run q of the warp being run q*W + w of the domain, so that the W warps sweep one contiguous window of the stream
 // together (DRAM page locality) while the open row sum stays in registers inside a run.
 // `t` is the warp's running slot counter: it carries the ring stage / mbarrier phase from one domain to the next.
-// STAGE_IDS: the row ids of non-consecutive chunks come through shared memory (load_row_ids / park_row_ids).
-template <typename VT, bool STAGE_IDS, typename Gather>
+// (Two ways of bringing a chunk's row ids through shared memory instead of the lanes' eight scattered global loads were
+// built and measured in round 2 - a second bulk copy on the chunk's mbarrier, and coalesced loads by the whole warp parked
+// in the chunk's own ring slot: 3.74 vs 3.65 ms on the 0.5 B-nnz uniform matrix for the first, 8.68 vs 8.27 ms on the
+// 1 B-nnz one and 1.73 vs 1.55 ms on R-MAT for the second.  The kernel is bound by its instruction chain, not by the
+// L1 tag stage of those loads; the hoisted loads of process_chunk stay.)
+template <typename VT, typename Gather>
 __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
                                             VT *__restrict__ y, uint32_t ring, uint32_t bars, int lane, uint32_t base,
                                             uint32_t n_dom, uint32_t w, uint32_t W, uint32_t run_log2, bool force_red,
@@ -465,48 +428,21 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
     const uint32_t g = my + st * STAGE;
     const uint4 mraw = lds128(ring + st * STAGE + CHUNK_BYTES);
     const uint4 iw = lds128(g);
-    // row ids of a non-consecutive chunk: requested now (coalesced), parked in the slot once the lanes hold the chunk
-    const bool stage_ids = STAGE_IDS && !(mraw.z & kChunkRowsConsecutive) && (mraw.z & 0x3FFu) != 0;
-    const uint32_t n_ids = ((mraw.y >> kMetaRowsShift) & 0x1FFu) + 1u;
-    uint32_t idtmp[9];
-    if (stage_ids) {
-      if (y_policy) load_row_ids<true>(rowmap, mraw.x, n_ids, lane, stream_policy, idtmp);
-      else load_row_ids<false>(rowmap, mraw.x, n_ids, lane, 0ull, idtmp);
-    }
     VT xv[8];
     gather(iw, mraw, xv);
     uint4 vw[VW];
 #pragma unroll
     for (int k = 0; k < VW; k++) vw[k] = lds128(g + 16 + k * 16);
-    const uint32_t scratch = ring + st * STAGE;
-    if (stage_ids) {
-      // every lane's loads of the chunk must have returned before the slot is overwritten: make each lane touch what
-      // it loaded (one XOR per register), then meet
-      uint32_t fold = iw.x ^ iw.y ^ iw.z ^ iw.w ^ mraw.x;
-#pragma unroll
-      for (int k = 0; k < VW; k++) fold ^= vw[k].x ^ vw[k].y ^ vw[k].z ^ vw[k].w;
-      asm volatile("" ::"r"(fold));
-      __syncwarp();
-      park_row_ids(scratch, n_ids, lane, idtmp);
-      __syncwarp();
-    }
     const uint32_t pos = i & (R - 1);
     const bool sole = (mraw.z & kChunkSole) != 0 && !force_red;
     if (pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;  // stays set until the run's first row end
     process_chunk<VT, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red, y_policy,
-                            stream_policy, stage_ids ? scratch : 0u);
+                            stream_policy);
     if (pos == R - 1 || i + 1 == n) {  // the row left open continues in another warp's run: hand over atomically
       if (open && lane == 0) {
         // in a `consecutive` chunk the open row follows from the rank (the flag covers it): no dependent row-map load
-        uint32_t row;
-        if (mraw.z & kChunkRowsConsecutive) {
-          row = mraw.w + (next_rank - mraw.x);
-        } else if (stage_ids) {
-          const uint32_t k = next_rank - mraw.x;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(scratch + 4u * (k + (k >> 5))));
-        } else {
-          row = rowmap[SPMVB_BOUND(1, next_rank, g_limits.n_pairs)];
-        }
+        uint32_t row = (mraw.z & kChunkRowsConsecutive) ? mraw.w + (next_rank - mraw.x)
+                                                        : rowmap[SPMVB_BOUND(1, next_rank, g_limits.n_pairs)];
         row = SPMVB_BOUND(2, row, g_limits.rows);
         y_add(&y[row], carry);
       }
@@ -514,10 +450,7 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
       open = false;
     }
     __syncwarp();
-    if (lane == 0 && i + 2 < n) {
-      if (STAGE_IDS) fence_proxy_async();  // the slot was written through the generic proxy (parked row ids)
-      issue(t + 2, ahead(c_cur, i, 2));
-    }
+    if (lane == 0 && i + 2 < n) issue(t + 2, ahead(c_cur, i, 2));
     c_cur = ahead(c_cur, i, 1);
   }
 }
@@ -526,7 +459,7 @@ __device__ __forceinline__ void walk_chunks(const uint4 *__restrict__ stream, co
 // Variant OCC: x gathered from global memory (L1/L2); few enough registers for MINB resident CTAs per SM, so that
 // the gather latency of one warp is covered by the other warps of its SM sub-partition.  Nothing stays in flight in
 // registers across the row-sum code, so the kernel does not depend on how ptxas assigns scoreboard slots.
-template <typename VT, int WARPS, int MINB, bool STAGE_IDS>
+template <typename VT, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     spmv_occ_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap,
                     const VT *__restrict__ x, VT *__restrict__ y, uint32_t n_chunks, uint32_t cdb,
@@ -547,7 +480,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   // flags bit 3: "tall" matrix (x and y both larger than the L2 cache): y updates evict-last, x gathers evict-first
   const uint64_t y_policy = (flags & 8u) ? l2_policy_evict_last() : 0ull;
   const uint64_t x_policy = (flags & 8u) ? l2_policy_evict_first() : 0ull;
-  walk_chunks<VT, STAGE_IDS>(stream, rowmap, y, ring, bars, lane, 0u, n_chunks, blockIdx.x * WARPS + warp,
+  walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, 0u, n_chunks, blockIdx.x * WARPS + warp,
                          gridDim.x * WARPS, run_log2, (flags & 4u) != 0, t, y_policy, true,
                          [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                            gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv, x_policy);
@@ -574,7 +507,7 @@ __device__ __forceinline__ float lds_x(uint32_t a, float) {
   return v;
 }
 
-template <typename VT, int WARPS, uint32_t X_CAP, int MINB, bool STAGE_IDS>
+template <typename VT, int WARPS, uint32_t X_CAP, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     spmv_xs_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap, const VT *__restrict__ x,
                    VT *__restrict__ y, const XsItem *__restrict__ items, const uint32_t *__restrict__ cta_first,
@@ -620,7 +553,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     }
     if (x_bytes) {
       bool waited = false;
-      walk_chunks<VT, STAGE_IDS>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
+      walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
                               (uint32_t)WARPS, run_log2, (flags & 4u) != 0, t, (flags & 32u) ? ~0ull : y_policy, false,
                               [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                                 if (!waited) {  // first chunk of the item: the window must have landed
@@ -649,7 +582,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
       if (!waited) mbar_wait(xbar, k & 1u);  // warps without work still consume the phase
       k++;
     } else {
-      walk_chunks<VT, STAGE_IDS>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
+      walk_chunks<VT>(stream, rowmap, y, ring, bars, lane, chunk_begin, chunk_count, (uint32_t)warp,
                               (uint32_t)WARPS, run_log2, (flags & 4u) != 0, t, 0ull, false,
                               [&](const uint4 &iw, const uint4 &mraw, VT *xv) {
                                 gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv);
