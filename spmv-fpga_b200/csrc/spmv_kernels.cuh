@@ -177,61 +177,6 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
   const bool consec = (mraw.z & kChunkRowsConsecutive) != 0;
   const bool partial = valid != (uint32_t)kChunkEntries;
 
-  // Fast path: every one of the 256 entries closes a row of its own (a uniform random matrix: one entry per (row, block)
-  // pair; the single-entry tail rows of a power-law matrix).  There is nothing to sum or to carry between lanes: no
-  // end-of-row extraction, no prefix scan, no running sums - y[row] (+)= value * x per entry, with the lane's 8
-  // consecutive row ids fetched as two 16-byte loads where the rank is aligned.  About a third of the instructions
-  // of the general path.
-  if (MUL && !partial && ((mraw.y >> kMetaRowsShift) & 0x1FFu) == (uint32_t)kChunkEntries) {
-    const uint32_t rk = rank0 + 8u * (uint32_t)lane;
-    uint32_t rows[8];
-    if (consec) {
-#pragma unroll
-      for (int s = 0; s < 8; s++) rows[s] = row_first + 8u * (uint32_t)lane + (uint32_t)s;
-    } else if ((rank0 & 3u) == 0u) {
-      const uint4 *p = reinterpret_cast<const uint4 *>(rowmap + SPMVB_BOUND(1, rk, g_limits.n_pairs));
-      uint4 a, b;
-      if (y_policy) {
-        asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p), "l"(stream_policy));
-        asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p + 1), "l"(stream_policy));
-      } else {
-        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p));
-        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p + 1));
-      }
-      rows[0] = a.x; rows[1] = a.y; rows[2] = a.z; rows[3] = a.w; rows[4] = b.x; rows[5] = b.y; rows[6] = b.z; rows[7] = b.w;
-    } else {
-#pragma unroll
-      for (int s = 0; s < 8; s++) {
-        const uint32_t *p = rowmap + SPMVB_BOUND(1, rk + (uint32_t)s, g_limits.n_pairs);
-        if (y_policy) asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(rows[s]) : "l"(p), "l"(stream_policy));
-        else asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(rows[s]) : "l"(p));
-      }
-    }
-    const bool skip = y_policy == ~0ull;  // diagnostic: no y updates
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-      VT v = vmul(value_of<VT>(vw, s), xv[s]);
-      bool red = !sole;
-      if (s == 0 && lane == 0) {  // the chunk's first entry closes the row the run arrived in
-        v = vadd(carry, v);
-        red = red || head_red;
-      }
-      const uint32_t row = SPMVB_BOUND(2, rows[s], g_limits.rows);
-      if (skip) continue;
-      if (red) {
-        if (y_policy) y_add_hint(y + row, v, y_policy);
-        else y_add(y + row, v);
-      } else {
-        y[row] = v;
-      }
-    }
-    head_red = false;
-    carry = VT(0);
-    open = false;
-    next_rank = rank0 + (uint32_t)kChunkEntries;
-    return;
-  }
-
   // end-of-row bits: gather the high byte of the 8 slots, then compress bit 7 of each byte with a multiply
   const uint32_t h0 = __byte_perm(iw.x, iw.y, 0x7531), h1 = __byte_perm(iw.z, iw.w, 0x7531);
   uint32_t eor = ((((h0 >> 7) & 0x01010101u) * 0x01020408u) >> 24) | (((((h1 >> 7) & 0x01010101u) * 0x01020408u) >> 20) & 0xF0u);
