@@ -82,6 +82,14 @@ struct Engine {
   float build_ms[3] = {0.f, 0.f, 0.f};
 };
 
+// CUDA events that are destroyed on every way out of a function (an early return on an error included)
+struct EventList {
+  std::vector<cudaEvent_t> ev;
+  explicit EventList(size_t n) : ev(n, nullptr) {}
+  ~EventList() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
+  cudaEvent_t &operator[](size_t i) { return ev[i]; }
+};
+
 #define CUDA_TRY(expr)                                                                       \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \
@@ -879,8 +887,8 @@ int spmvb_engine_time_spmv(spmvb_engine *e, int iters, int flush_l2, float *ms_o
     E->flush_words = (size_t)256 * 1024 * 1024 / 16;  // 256 MiB > 126 MB L2
     CUDA_TRY(cudaMalloc((void **)&E->d_flush, E->flush_words * 16));
   }
-  std::vector<cudaEvent_t> ev(2 * (size_t)iters);
-  for (auto &x : ev) CUDA_TRY(cudaEventCreate(&x));
+  EventList ev(2 * (size_t)iters);
+  for (auto &x : ev.ev) CUDA_TRY(cudaEventCreate(&x));
   int rc = SPMVB_OK;
   for (int i = 0; i < iters && rc == SPMVB_OK; i++) {
     if (flush_l2) l2_flush_kernel<<<E->sms * 4, 256, 0, E->stream>>>(E->d_flush, E->flush_words);
@@ -893,7 +901,6 @@ int spmvb_engine_time_spmv(spmvb_engine *e, int iters, int flush_l2, float *ms_o
     ms_out[i] = 0.f;
     if (ce == cudaSuccess && rc == SPMVB_OK) cudaEventElapsedTime(&ms_out[i], ev[2 * i], ev[2 * i + 1]);
   }
-  for (auto &x : ev) cudaEventDestroy(x);
   if (rc) return rc;
   if (ce != cudaSuccess) return fail(SPMVB_E_CUDA, std::string("time_spmv: ") + cudaGetErrorString(ce));
   return SPMVB_OK;

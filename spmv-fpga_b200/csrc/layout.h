@@ -80,6 +80,8 @@ struct Layout {
 // Parameters of the engine-private device layout for the API layout L; false when the API layout is what should be
 // streamed as it is.
 bool plan_device_params(const Layout *L, int *cu_dev, int *vf_dev, uint32_t *cdb_dev);
+// set (per thread) while an engine-private device layout is being built: its compute units are row tiles, walked CU-major
+bool &building_device_layout();
 bool layout_is_irregular(const Layout *L);
 
 // Work item of the XS kernel (x window in shared memory): a range of chunks of one column block.

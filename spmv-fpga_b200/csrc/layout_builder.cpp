@@ -33,6 +33,11 @@ Layout::~Layout() {
   delete dev;
 }
 
+bool &building_device_layout() {
+  static thread_local bool flag = false;
+  return flag;
+}
+
 Options &options() {
   static Options o;
   return o;
@@ -158,7 +163,7 @@ int layout_init_header(Layout *L, uint32_t rows, uint32_t cols, uint64_t nnz, in
 void layout_finish_pieces(Layout *L, const uint64_t *fp, const uint32_t *pad_rows, std::vector<uint64_t> &piece_last_rank) {
   const int cu = L->cu, blocks = L->blocks;
   const size_t KB = (size_t)cu * blocks;
-  L->cu_major = cu > 1 && (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20);
+  L->cu_major = cu > 1 && ((uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) || building_device_layout());
   if (options().cu_major >= 0) L->cu_major = cu > 1 && options().cu_major != 0;
   L->nr_ci.assign(KB, 0); L->nr_val.assign(KB, 0);
   L->piece_off.assign(KB, 0); L->piece_chunk0.assign(KB, 0); L->piece_chunk1.assign(KB, 0); L->piece_real_nnz.assign(KB, 0);
@@ -537,7 +542,9 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   int cu_dev = cu, vf_dev = vf;
   uint32_t cdb_dev = cdb;
   if (plan_device && plan_device_params(L, &cu_dev, &vf_dev, &cdb_dev)) {
+    building_device_layout() = true;
     int rc = build_impl<RP>(rows, cols, row_ptr, col_ind, values, cu_dev, vf_dev, is_double, cdb_dev, &L->dev, false);
+    building_device_layout() = false;
     if (rc) { delete L; return rc; }
   }
 

@@ -647,7 +647,9 @@ int lb_build_pair(BE &be_api, BE &be_dev, uint32_t rows, uint32_t cols, uint64_t
   int cu_dev = cu, vf_dev = vf;
   uint32_t cdb_dev = L->cdb;
   if (!plan_device_params(L, &cu_dev, &vf_dev, &cdb_dev)) return SPMVB_OK;
+  building_device_layout() = true;
   rc = lb_build(be_dev, rows, cols, nnz, d_row_ptr, d_col_ind, d_values, cu_dev, vf_dev, is_double, cdb_dev, &L->dev, dev_img);
+  building_device_layout() = false;
   if (rc) {
     be_api.release_output(api_img->image); be_api.release_output(api_img->rowmap); be_api.release_output(api_img->zero_rows);
     *api_img = LbImage();

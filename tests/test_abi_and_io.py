@@ -210,3 +210,72 @@ def test_reference_main_on_the_engine_fails_loudly_without_gpu(spmvb, tmp_path):
     spmvb.Csr.band(500, 2, 1).write(path)
     p = subprocess.run([exe, path], capture_output=True, text=True)
     assert p.returncode != 0 and "no CUDA device" in p.stderr and "Verification" not in p.stdout
+
+
+def test_options_are_explicit_and_scoped(spmvb):
+    """Tuning goes through spmvb_set_option, never through the environment of a library call; the context manager
+    restores what it changed; unknown names are errors."""
+    assert spmvb.get_option("cu_major") == -1 and spmvb.get_option("tile_mb") == -1
+    with spmvb.options(cu_major=1, tile_mb=8):
+        assert spmvb.get_option("cu_major") == 1 and spmvb.get_option("tile_mb") == 8
+    assert spmvb.get_option("cu_major") == -1 and spmvb.get_option("tile_mb") == -1
+    with pytest.raises(spmvb.SpmvbError, match="unknown option"):
+        spmvb.set_option("no_such_option", 1)
+    # an environment variable alone changes nothing: two layouts of the same matrix are identical
+    rows, cols, rp, ci, va = matgen.uniform(3000, 70000, 8, seed=2)
+    a = spmvb.Layout.build(rows, cols, rp, ci, va, 4, 1, True)
+    os.environ["SPMVB_CU_MAJOR"] = "1"
+    try:
+        b = spmvb.Layout.build(rows, cols, rp, ci, va, 4, 1, True)
+    finally:
+        del os.environ["SPMVB_CU_MAJOR"]
+    assert a.difference(b) == ""
+    # ... unless the executable asks for it (the C++ shim does, for drop-in programs)
+    os.environ["SPMVB_TILE_MB"] = "8"
+    try:
+        assert spmvb.lib().spmvb_options_from_env() >= 1 and spmvb.get_option("tile_mb") == 8
+    finally:
+        del os.environ["SPMVB_TILE_MB"]
+        spmvb.set_option("tile_mb", -1)
+
+
+def test_device_layout_is_private_to_the_engine(spmvb, oracle):
+    """The engine-private device layout (narrower column blocks, row tiles, VF 1) never shows through the API: piece
+    tables, words and bitmap stay those of the caller's CU / VF / COLS_DIV_BLOCKS, bit-exact with the oracle."""
+    rows, cols, rp, ci, va = matgen.uniform(5000, 100000, 16, seed=4)
+    with spmvb.options(dev_tiles=3):
+        lay = spmvb.Layout.build(rows, cols, rp, ci, va, 2, 2, True)
+    dp = lay.device_params
+    assert dp["private"] and dp["cu"] == 3 and dp["vf"] == 1 and dp["cdb"] == 16384 and dp["cu_major"]
+    assert lay.n_cu == 2 and lay.blocks == 4 and 150 < lay.x_lines_per_chunk <= 256
+    ho = oracle.build(rows, cols, rp, ci, va, 2, 2, True)
+    ref = oracle.snapshot(ho, rows, 2, 2, True)
+    for b in range(lay.blocks):
+        assert np.array_equal(lay.bitmap_row(b), ref.bitmap[b])
+        for k in range(2):
+            assert lay.piece_info(k, b) == ref.info[(k, b)]
+    oracle.free(ho)
+    # a banded matrix keeps its API layout as the device layout
+    lap = spmvb.Layout.build(*matgen.laplacian2d(300, 300), 1, 1, True)
+    assert not lap.device_params["private"] and lap.x_lines_per_chunk < 30
+
+
+def test_builders_reject_a_bad_row_ptr_and_the_reader_a_short_line(spmvb, tmp_path):
+    rows, cols, rp, ci, va = matgen.uniform(50, 80, 3, seed=1)
+    bad = rp.copy().astype(np.uint64)
+    bad[10] = bad[11] + 5            # decreasing
+    with pytest.raises(spmvb.SpmvbError, match="row_ptr"):
+        spmvb.Layout.build(rows, cols, bad, ci, va, 1, 1, True)
+    bad = rp.copy().astype(np.uint64)
+    bad[0] = 1                       # does not start at 0
+    with pytest.raises(spmvb.SpmvbError, match="row_ptr"):
+        spmvb.Layout.build(rows, cols, bad, ci, va, 1, 1, True)
+    # a line with a missing field is a parse error, as with the reference's per-line sscanf (csr.cpp:111-113); the
+    # value must not be taken from the next line, and a file that ends in such a line must not be read past its end
+    p = tmp_path / "short.txt"
+    p.write_text("3 3 3\n1 1 1.5\n2 2\n3 3 2.5\n")
+    with pytest.raises(spmvb.SpmvbError, match="parse error"):
+        spmvb.Csr.read(str(p))
+    p.write_text("2 2 2\n1 1 1.5\n2 2")
+    with pytest.raises(spmvb.SpmvbError, match="parse error"):
+        spmvb.Csr.read(str(p))
