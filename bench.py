@@ -589,6 +589,7 @@ def measure_poweriter(ctx, args, steps, warmup):
     wall_ms = (time.perf_counter() - t0) * 1e3
     sampler.stop()
     dev_ms = grp.last_iter_ms * steps
+    phases = [ctx.reduce([v], "max")[0] for v in grp.phase_ms]
     ms = ctx.reduce([dev_ms], "max")[0]
     wall_ms = ctx.reduce([wall_ms], "max")[0]
     nnz_total, launches = ctx.reduce([float(csr.nnz), float(grp.launches() - l0)])
@@ -619,7 +620,9 @@ def measure_poweriter(ctx, args, steps, warmup):
                                 "the normalisation kernel stores its rows into x of the forwarding GPU over NVLink (peer memory), "
                                 "barrier, all-gather of the equal chunks in place (NCCL)"][exchange_mode],
                    "step": "clear rows + SpMV kernel + sum of squares + all-reduce of one double + normalisation / exchange",
-                   "wall_ms_per_step": wall_ms / steps},
+                   "wall_ms_per_step": wall_ms / steps,
+                   "last_iteration_phase_ms_max_over_ranks": dict(zip(("spmv_and_sumsq", "norm_allreduce", "normalise_store_barrier",
+                                                                       "gather"), phases))},
         "effective_gbs": alg / (per * 1e-3) / 1e9, "last_norm": nrm, "gpu_launches": launches, "clocks": sampler.summary(),
         "e2e": {"value": 2.0 * nnz_total * steps / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(world * n * vb / steps),
                 "d2h_bytes_per_step": int(n * vb / steps), "steps": steps,

@@ -260,6 +260,9 @@ int spmvb_group_get_y(spmvb_group *g, void *y_host);             /* local GPUs' 
  * group.  *norm_out = the last norm. */
 int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out);
 float spmvb_group_last_iter_ms(const spmvb_group *g); /* device time per iteration of the last call, max over local GPUs */
+/* device time of the four phases of the LAST iteration of the last call, max over the local GPUs: {clear rows + SpMV + sum
+ * of squares, all-reduce of the norm, normalisation (+ peer stores + barrier), gather (NCCL broadcasts / all-gather)} */
+int spmvb_group_phase_ms(const spmvb_group *g, float *out4);
 /* How the power iteration moves the y slices into every GPU's x:
  *   0  NCCL only: one grouped call of a broadcast per row owner, in place in x
  *   1  the normalisation kernel stores its rows straight into EVERY GPU's x over NVLink (peer memory), then an 8-byte

@@ -128,6 +128,7 @@ struct Member {  // one GPU of this process
   void **d_peers = nullptr;    // [world] base of every GPU's x as seen from this GPU
   std::vector<void *> ipc_opened;  // pointers this process opened with cudaIpcOpenMemHandle
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ph[5] = {};      // phase marks of the last iteration of a power_iter call
 };
 
 }  // namespace
@@ -139,6 +140,7 @@ struct Group {
   std::vector<Member> local;             // the members this process drives
   double *h_scalar = nullptr;            // pinned
   float last_iter_ms = 0.f;
+  float phase_ms[4] = {0.f, 0.f, 0.f, 0.f};  // last iteration: SpMV + sum of squares, norm all-reduce, scale / stores + barrier, gather
   uint64_t nnz_local = 0;
   int exchange = 0;            // 0 NCCL grouped broadcasts, 1 peer stores to all, 2 peer stores to the forwarder + all-gather
   uint32_t chunk = 0;          // mode 2: elements per forwarded chunk of x (world * chunk <= x length)
@@ -174,6 +176,7 @@ static int member_build(Group *G, Member &m, uint32_t n_rows, const uint64_t *ro
   G_CUDA(cudaMemset(m.d_token, 0, 64));
   G_CUDA(cudaEventCreate(&m.ev0));
   G_CUDA(cudaEventCreate(&m.ev1));
+  for (auto &e : m.ph) G_CUDA(cudaEventCreate(&e));
   return SPMVB_OK;
 }
 
@@ -211,6 +214,7 @@ static void group_destroy(Group *G) {
     for (void *p : m.ipc_opened) cudaIpcCloseMemHandle(p);
     if (m.ev0) cudaEventDestroy(m.ev0);
     if (m.ev1) cudaEventDestroy(m.ev1);
+    for (auto &e : m.ph) if (e) cudaEventDestroy(e);
   }
   if (G->h_scalar) cudaFreeHost(G->h_scalar);
   cudaGetLastError();  // a failed creation must not leave its error behind for the next CUDA call of the process
@@ -407,6 +411,12 @@ int spmvb_group_rank(const spmvb_group *g, int local_index) {
   return G->local[local_index].rank;
 }
 float spmvb_group_last_iter_ms(const spmvb_group *g) { return g ? ((const Group *)g)->last_iter_ms : 0.f; }
+int spmvb_group_phase_ms(const spmvb_group *g, float *out4) {
+  const Group *G = (const Group *)g;
+  if (!G || !out4) return fail(SPMVB_E_ARG, "group_phase_ms");
+  for (int k = 0; k < 4; k++) out4[k] = G->phase_ms[k];
+  return SPMVB_OK;
+}
 
 int spmvb_group_set_x(spmvb_group *g, const void *x_host, uint32_t n) {
   Group *G = (Group *)g;
@@ -479,7 +489,16 @@ int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out) {
     G_CUDA(cudaSetDevice(m.device));
     G_CUDA(cudaEventRecord(m.ev0, (cudaStream_t)spmvb_engine_stream(m.engine)));
   }
+  auto mark = [&](int it, int k) -> int {  // phase marks, last iteration only
+    if (it != iters - 1) return SPMVB_OK;
+    for (Member &m : G->local) {
+      G_CUDA(cudaSetDevice(m.device));
+      G_CUDA(cudaEventRecord(m.ph[k], (cudaStream_t)spmvb_engine_stream(m.engine)));
+    }
+    return SPMVB_OK;
+  };
   for (int it = 0; it < iters; it++) {
+    if (int rc = mark(it, 0)) return rc;
     for (Member &m : G->local) {
       const uint32_t n_local = G->bounds[m.rank + 1] - G->bounds[m.rank];
       int rc = spmvb_engine_spmv_dev(m.engine, nullptr, nullptr, 0, nullptr);
@@ -487,12 +506,14 @@ int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out) {
       rc = spmvb_engine_sumsq(m.engine, spmvb_engine_y_dev(m.engine), n_local, m.d_scalar, nullptr);
       if (rc) return rc;
     }
+    if (int rc = mark(it, 1)) return rc;
     if (multi) {
       G_NCCL(N->GroupStart());
       for (Member &m : G->local)
         G_NCCL(N->AllReduce(m.d_scalar, m.d_scalar, 1, ncclDouble, ncclSum, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
       G_NCCL(N->GroupEnd());
     }
+    if (int rc = mark(it, 2)) return rc;
     if (!multi || G->exchange == 0) {
       for (Member &m : G->local) {
         const uint32_t r0 = G->bounds[m.rank], n_local = G->bounds[m.rank + 1] - r0;
@@ -500,6 +521,7 @@ int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out) {
         int rc = spmvb_engine_scale_rsqrt(m.engine, spmvb_engine_y_dev(m.engine), x + (size_t)r0 * G->vb, n_local, m.d_scalar, nullptr);
         if (rc) return rc;
       }
+      if (int rc = mark(it, 3)) return rc;
       if (multi) {  // every owner's slice into every GPU's x, in place: one NCCL launch per GPU
         G_NCCL(N->GroupStart());
         for (Member &m : G->local) {
@@ -538,6 +560,7 @@ int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out) {
       for (Member &m : G->local)
         G_NCCL(N->AllReduce(m.d_token, m.d_token, 1, ncclDouble, ncclSum, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
       G_NCCL(N->GroupEnd());
+      if (int rc = mark(it, 3)) return rc;
       if (G->exchange == 2) {  // every GPU forwards its equal chunk of x to all: all-gather in place
         G_NCCL(N->GroupStart());
         for (Member &m : G->local) {
@@ -547,6 +570,7 @@ int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out) {
         G_NCCL(N->GroupEnd());
       }
     }
+    if (int rc = mark(it, 4)) return rc;
   }
   for (Member &m : G->local) {
     G_CUDA(cudaSetDevice(m.device));
@@ -564,6 +588,14 @@ int spmvb_group_power_iter(spmvb_group *g, int iters, double *norm_out) {
     if (cudaEventElapsedTime(&ms, m.ev0, m.ev1) == cudaSuccess) worst = std::max(worst, ms);
   }
   G->last_iter_ms = worst / (float)iters;
+  for (int k = 0; k < 4; k++) {
+    G->phase_ms[k] = 0.f;
+    for (Member &m : G->local) {
+      float ms = 0.f;
+      G_CUDA(cudaSetDevice(m.device));
+      if (cudaEventElapsedTime(&ms, m.ph[k], m.ph[k + 1]) == cudaSuccess) G->phase_ms[k] = std::max(G->phase_ms[k], ms);
+    }
+  }
   if (norm_out) *norm_out = std::sqrt(G->h_scalar[0]);
   return SPMVB_OK;
 }

@@ -95,6 +95,7 @@ SYMBOLS = {
     "spmvb_group_get_y": (_int, [_vp, _vp]),
     "spmvb_group_power_iter": (_int, [_vp, _int, _vp]),
     "spmvb_group_last_iter_ms": (ctypes.c_float, [_vp]),
+    "spmvb_group_phase_ms": (_int, [_vp, _vp]),
     "spmvb_group_ipc_handle": (_int, [_vp, _vp]),
     "spmvb_group_set_peer_handles": (_int, [_vp, _vp, _int]),
     "spmvb_group_set_exchange": (_int, [_vp, _int]),
@@ -701,6 +702,13 @@ class Group:
         nrm = ctypes.c_double()
         _check(lib().spmvb_group_power_iter(self.h, iters, ctypes.byref(nrm)))
         return nrm.value
+
+    @property
+    def phase_ms(self):
+        """Last iteration of the last power_iter call: [SpMV + sum of squares, norm all-reduce, normalise / store, gather]."""
+        out = (ctypes.c_float * 4)()
+        _check(lib().spmvb_group_phase_ms(self.h, out))
+        return [float(v) for v in out]
 
     def ipc_handle(self):
         """cudaIpcMemHandle_t (64 bytes) of this rank's x, for the other ranks of a multi-process group."""

@@ -157,6 +157,7 @@ class FakeGroup:
         return out
 
     exchange = 0
+    phase_ms = [0.1, 0.01, 0.02, 0.05]
     def ipc_handle(self): return np.zeros(64, np.uint8)
     def set_peer_handles(self, handles, mode=2): assert np.asarray(handles).size == 64 * self.world
     def launches(self): return self._launches
