@@ -119,6 +119,15 @@ int spmvb_layout_device_params(const spmvb_layout *l, uint64_t *out);
  * irregularity that picks the kernel and the device layout (5-point Laplacian 12, R-MAT ~150-200, uniform ~250) */
 double spmvb_layout_x_lines_per_chunk(const spmvb_layout *l);
 
+/* The wide image (a second engine-private candidate): out[8] = {present, column-block width, column
+ * blocks, (row, block) pairs, chunks, rows cleared per SpMV (UINT64_MAX = all), image bytes, real entries}. */
+int spmvb_layout_wide_params(const spmvb_layout *l, uint64_t *out);
+/* Walks the wide image like the kernel does and returns its real entries in image order (row, column, value bits;
+ * any output may be NULL; at most max_entries are stored).  Returns the number of entries, negative on an
+ * inconsistent image.  For tests. */
+int64_t spmvb_layout_wide_decode(const spmvb_layout *l, uint32_t *rows_out, uint32_t *cols_out, void *vals_out,
+                                 uint64_t max_entries);
+
 /* 1 if the two layouts are identical in every table and byte (pieces, row map, chunk metadata, rows to clear, column
  * ranges), 0 if not (why receives the first difference), negative on error.  Used to check the GPU builder against
  * the host builder. */
@@ -200,10 +209,10 @@ int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
 int spmvb_debug_bounds_errors(uint64_t *out5);
 /* device time per iteration (CUDA events around the loop) of the last spmvb_engine_power_iter / spmvb_engine_cg call */
 float spmvb_engine_last_iter_ms(const spmvb_engine *e);
-/* out[13] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per
+/* out[16] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per
  * SpMV (UINT64_MAX = all), image bytes, row tiles spmv_host pipelines (0 = none), 1 = explicit L2 policies, x-window kernel configuration (0 wide / 1 medium /
  * 2 narrow), microseconds of one SpMV measured at creation for {the API image with global gathers, the device layout} (0 =
- * not measured)} */
+ * not measured), 1 = the wide image is what is streamed, microseconds of one SpMV over the wide image, column blocks} */
 int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out);
 /* Conjugate gradients for A x = b on one GPU (A symmetric positive definite, e.g. the Laplacian of BASELINE config 2):
  * the second iterated caller of SURVEY 8(f) rank 3 (the reference's caller runs spmv_hw once, main.cpp:68-75; an

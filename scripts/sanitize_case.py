@@ -37,6 +37,15 @@ for isd in (True, False):
                     eng.spmv_host(x, y, accumulate=False)
                     assert np.all(np.abs(y.astype(np.float64) - gold) <= bound), (name, isd, variant, opts)
                     eng.free()
+                for rl in (23, 16, 13):  # the wide image and its kernel: one column block, a few, many
+                    with spmvb.options(wide=1, wide_range_log2=rl, wide_hints=3 if rl == 16 else -1):
+                        layw = spmvb.Layout.build(rows, cols, rp, ci, va, cu, vf, isd)
+                        eng = spmvb.Engine(layw, 0, spmvb.VARIANT_WIDE)
+                        y = np.zeros(rows, vt)
+                        eng.spmv_host(x, y, accumulate=False)
+                        eng.spmv_host(x, y, accumulate=False)
+                        assert np.all(np.abs(y.astype(np.float64) - gold) <= bound), (name, isd, "wide", rl, opts)
+                        eng.free(); layw.free()
                 lay2, eng2 = spmvb.Engine.from_csr(rows, cols, rp, ci, va, cu, vf, isd)  # the GPU layout builder
                 y = np.zeros(rows, vt)
                 eng2.spmv_host(x, y, accumulate=False)

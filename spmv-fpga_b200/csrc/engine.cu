@@ -19,7 +19,7 @@
 
 namespace spmvb {
 
-enum Variant { kVariantDefault = 0, kVariantDirect = 1, kVariantOcc4 = 6, kVariantOcc3 = 7, kVariantXs = 8 };
+enum Variant { kVariantDefault = 0, kVariantDirect = 1, kVariantOcc4 = 6, kVariantOcc3 = 7, kVariantXs = 8, kVariantWide = 9 };
 
 
 struct Engine {
@@ -52,9 +52,10 @@ struct Engine {
   bool tall = false;               // x and y both exceed the L2 cache: explicit L2 eviction policies
   bool cu_major = false;           // pieces in CU-major device order (row tiles)
   bool irregular = false;          // layout_is_irregular(): x gathers are scattered, the x-window kernel pays
+  bool wide = false;               // the image is a wide image (Layout::is_wide): only the WIDE kernel can walk it
   int xs_cfg = 0, xs_ctas = 148;   // configuration of the x-window kernel (xs_config) and its grid = SMs x CTAs per SM
   int auto_variant = kVariantOcc3; // what variant 0 resolves to (chosen from the layout at creation)
-  float tune_ms[2] = {0.f, 0.f};   // autotune timings: OCC, XS
+  float tune_ms[3] = {0.f, 0.f, 0.f};  // measured at creation: API image, device layout, wide image
   uint32_t n_zero_rows = 0, run_log2 = 2;
   bool zero_all = true;
   void *d_x = nullptr, *d_y = nullptr;
@@ -73,7 +74,7 @@ struct Engine {
   cudaStream_t stream = nullptr;
   int sms = 148;
   uint64_t launches = 0;
-  int grid_cache[9][2] = {};  // [variant][is_double] -> grid size
+  int grid_cache[10][2] = {};  // [variant][is_double] -> grid size
   // asynchronous step timing (bench): events of the last enqueue_steps()
   std::vector<cudaEvent_t> ev;
   int ev_steps = 0;
@@ -147,6 +148,28 @@ static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, 
   return SPMVB_OK;
 }
 
+// the wide image: chunks [chunk_base, chunk_base + n_chunks) in one launch
+template <typename VT>
+static int launch_wide(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, uint64_t chunk_base, uint64_t n_chunks) {
+  constexpr int WARPS = 8, MINB = 3;
+  auto kern = spmv_wide_kernel<VT, WARPS, MINB>;
+  const size_t slot = (size_t)wide_chunk_bytes((int)sizeof(VT)) + 16;
+  const size_t smem = (size_t)WARPS * (2 * slot + (size_t)kChunkEntries * sizeof(VT)) + (size_t)WARPS * 16;
+  int &grid = E->grid_cache[kVariantWide][sizeof(VT) == 8];
+  if (grid == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    grid = E->sms * std::max(per_sm, 1);
+  }
+  if (n_chunks == 0) return SPMVB_OK;
+  const int64_t hints = options().wide_hints >= 0 ? options().wide_hints : (E->tall ? 3 : 0);
+  CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, reinterpret_cast<const uint4 *>(E->d_stream),
+                      (const uint32_t *)E->d_rowmap, x, y, (uint32_t)chunk_base, (uint32_t)n_chunks, E->cdb, E->occ_run_log2,
+                      (accumulate ? 4u : 0u) | ((hints & 1) ? 8u : 0u) | ((hints & 2) ? 16u : 0u)));
+  return SPMVB_OK;
+}
+
 // tile < 0: the whole matrix in one launch; otherwise row tile `tile` only (per-tile plan)
 template <typename VT, int WARPS, uint32_t X_CAP, int MINB>
 static int launch_xs_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, int tile) {
@@ -193,7 +216,9 @@ static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accum
   if (E->n_chunks == 0) return SPMVB_OK;
   if (E->n_chunks >= 0x7FFFFFFFull) return fail(SPMVB_E_RANGE, "too many chunks for one engine");
   int rc = SPMVB_OK;
-  if (variant == kVariantDirect) {
+  if (E->wide) {  // a wide image has one kernel
+    rc = launch_wide<VT>(E, x, y, st, accumulate, 0, E->n_chunks);
+  } else if (variant == kVariantDirect) {
     auto kern = spmv_direct_kernel<VT, WARPS, 4>;
     int &grid = E->grid_cache[kVariantDirect][sizeof(VT) == 8];
     if (grid == 0) {
@@ -271,6 +296,7 @@ static int do_spmv(Engine *E, const void *x_dev, void *y_dev, int accumulate, cu
 // windows of the chosen kernel fit.  Option autotune = 1 times both kernels on the actual matrix instead (not under a
 // profiler: the timings are noise there).
 static int autotune(Engine *E) {
+  if (E->wide) { E->auto_variant = kVariantWide; return SPMVB_OK; }
   E->auto_variant = kVariantOcc3;
   if (E->n_chunks == 0 || E->xs_windowed_frac < 0.5) return SPMVB_OK;
   if (E->cu_major || E->irregular) E->auto_variant = kVariantXs;
@@ -477,6 +503,7 @@ static int engine_adopt_layout(Engine *E, const Layout *L) {
   E->real_nnz = L->real_nnz; E->n_chunks = L->n_chunks; E->n_pairs = L->n_pairs; E->stream_bytes = L->stream_bytes;
   E->cu_major = L->cu_major; E->dev_cu = L->cu; E->dev_vf = L->vf;
   E->irregular = layout_is_irregular(L);
+  E->wide = L->is_wide;
   E->xs_cfg = L->xs_cfg;
   E->xs_ctas = E->sms * xs_config(L->is_double, L->xs_cfg).ctas_per_sm;
   E->tall = (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) && (uint64_t)L->cols * L->vb > ((uint64_t)48 << 20);
@@ -518,7 +545,8 @@ static int engine_finish(Engine *E, const Layout *L) {
   std::vector<XsItem> items;
   std::vector<uint32_t> cta_first;
   XsTilePlan tiles;
-  build_xs_items(L, E->xs_ctas, E->xs_run_log2, items, cta_first, L->cu_major ? &tiles : nullptr);
+  if (L->is_wide) cta_first.assign((size_t)E->xs_ctas + 1, 0);  // no shared-memory windows over a wide image
+  else build_xs_items(L, E->xs_ctas, E->xs_run_log2, items, cta_first, L->cu_major ? &tiles : nullptr);
   E->n_items = (uint32_t)items.size();
   if (tiles.n_tiles > 1 && tiles.n_tiles <= 1024 && !tiles.items.empty()) {
     E->n_tiles = tiles.n_tiles;
@@ -611,7 +639,15 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
   if (!L->stream || !L->rowmap || !A->stream || !A->rowmap)
     return fail(SPMVB_E_ARG, "engine_create: this layout was built on a GPU and lives in its engine; fetch it first");
   Engine *E = nullptr;
-  int rc = engine_create_single(L, device, variant, &E);
+  int rc;
+  if (variant == kVariantWide) {  // explicitly the wide image
+    if (!A->wide) return fail(SPMVB_E_ARG, "engine_create: variant 9 needs a layout with a wide image (option wide = 1)");
+    rc = engine_create_single(A->wide, device, kVariantDefault, &E);
+    if (rc) return rc;
+    *out = (spmvb_engine *)E;
+    return SPMVB_OK;
+  }
+  rc = engine_create_single(L, device, variant, &E);
   if (rc) return rc;
   if (A->dev && variant == kVariantDefault && options().autotune != 0) {
     Engine *E0 = nullptr;
@@ -623,6 +659,22 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
     E->tune_ms[0] = E0->tune_ms[0] = t_api; E->tune_ms[1] = E0->tune_ms[1] = t_dev;
     if (t_api < t_dev) std::swap(E, E0);
     spmvb_engine_free((spmvb_engine *)E0);
+  }
+  if (A->wide && variant == kVariantDefault && options().autotune != 0) {  // third candidate: the wide image
+    Engine *E2 = nullptr;
+    float t_cur = std::min(E->tune_ms[0] > 0.f ? E->tune_ms[0] : 1e30f, E->tune_ms[1] > 0.f ? E->tune_ms[1] : 1e30f), t_wide = 0.f;
+    rc = SPMVB_OK;
+    if (t_cur > 1e29f) {  // no device layout: the engine so far has not been timed yet
+      rc = engine_time_step(E, 3, &t_cur);
+      E->tune_ms[0] = t_cur;
+    }
+    if (rc == SPMVB_OK) rc = engine_create_single(A->wide, device, kVariantDefault, &E2);
+    if (rc == SPMVB_OK) rc = engine_time_step(E2, 3, &t_wide);
+    if (rc) { spmvb_engine_free((spmvb_engine *)E); spmvb_engine_free((spmvb_engine *)E2); return rc; }
+    E->tune_ms[2] = t_wide;
+    for (int i = 0; i < 3; i++) E2->tune_ms[i] = E->tune_ms[i];
+    if (t_wide < t_cur) std::swap(E, E2);
+    spmvb_engine_free((spmvb_engine *)E2);
   }
   *out = (spmvb_engine *)E;
   return SPMVB_OK;
@@ -766,7 +818,9 @@ void spmvb_engine_free(spmvb_engine *e) {
 }
 
 int spmvb_engine_set_variant(spmvb_engine *e, int variant) {
-  if (!e || variant < 0 || variant > 8) return fail(SPMVB_E_ARG, "variant");
+  if (!e || variant < 0 || variant > 9) return fail(SPMVB_E_ARG, "variant");
+  if (variant != 0 && ((Engine *)e)->wide != (variant == kVariantWide))
+    return fail(SPMVB_E_ARG, "variant: the wide image has its own kernel (9) and only that one");
   ((Engine *)e)->variant = variant;
   return SPMVB_OK;
 }
@@ -1049,6 +1103,7 @@ int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out) {
   out[4] = E->n_pairs; out[5] = E->n_chunks; out[6] = E->zero_all ? UINT64_MAX : (uint64_t)E->n_zero_rows;
   out[7] = E->stream_bytes; out[8] = (uint64_t)E->n_tiles; out[9] = E->tall ? 1u : 0u; out[10] = (uint64_t)E->xs_cfg;
   out[11] = (uint64_t)(E->tune_ms[0] * 1000.f); out[12] = (uint64_t)(E->tune_ms[1] * 1000.f);
+  out[13] = E->wide ? 1u : 0u; out[14] = (uint64_t)(E->tune_ms[2] * 1000.f); out[15] = (uint64_t)E->blocks;
   return SPMVB_OK;
 }
 

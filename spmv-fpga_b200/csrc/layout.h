@@ -74,6 +74,14 @@ struct Layout {
   // slice fits the kernel's shared-memory window, row tiles whose y range stays in the L2 cache, no VF padding.
   Layout *dev = nullptr;
 
+  // Second engine-private candidate: the "wide" image (owned; nullptr = none).  Same stream grammar (8-entry groups,
+  // 15-bit column | end-of-row bit, chunks of 32 groups, row map, chunk flags) but column blocks of up to 2^23 columns:
+  // an x range the L2 cache holds, gathered with ld.global, while the rows ascend through the range so that every
+  // (row, range) partial sum is formed in registers and y is updated by coalesced requests.  The extra column bits
+  // live in a byte plane of their own and a chunk is stored plane by plane (see kWide* below).
+  Layout *wide = nullptr;
+  bool is_wide = false;  // this layout IS a wide image
+
   ~Layout();
 };
 
@@ -83,6 +91,19 @@ bool plan_device_params(const Layout *L, int *cu_dev, int *vf_dev, uint32_t *cdb
 // set (per thread) while an engine-private device layout is being built: its compute units are row tiles, walked CU-major
 bool &building_device_layout();
 bool layout_is_irregular(const Layout *L);
+// set (per thread) while a wide image is being built: column blocks up to 2^23 columns, planar chunks
+bool &building_wide_layout();
+// Column-block width of the wide image for the API layout L (0 = none wanted)
+uint32_t plan_wide_cdb(const Layout *L);
+
+// Planar chunk of a wide image: 32 lanes x {16 B index word | 8 B high column bytes | 8 values in 16-byte words}.
+//   [0, 512)            index words, 16 B per lane (8 x (column & 0x7FFF | end-of-row bit))
+//   [512, 768)          high column bytes, 8 B per lane (column >> 15)
+//   [768 + k * 512 ...) value word k of every lane (k = 0..3 fp64, 0..1 fp32), 16 B per lane
+// so that every LDS of a warp is conflict-free.  2816 B (fp64) / 1792 B (fp32) per chunk.
+constexpr uint32_t kWideHiOff = 512, kWideValOff = 768, kWidePlane = 512;
+constexpr uint32_t kWideMaxCdb = 1u << 23;
+inline uint32_t wide_chunk_bytes(int vb) { return kWideValOff + 32u * 8u * (uint32_t)vb; }
 
 // Work item of the XS kernel (x window in shared memory): a range of chunks of one column block.
 struct XsItem {
@@ -141,6 +162,9 @@ struct Options {
   int64_t diag_flags = -1;    // diagnostics of the x-window kernel (WRONG results): 16 = no x window traffic, 32 = no y updates
   int64_t tile_launch = -1;   // 1: one kernel launch per row tile with the tile's y range as persisting L2 window
   int64_t e2e_tiles = -1;     // 0: spmv_host does not pipeline row tiles (one launch, then the copy of y)
+  int64_t wide = -1;          // wide image: 0 never, 1 always build one, -1 for irregular matrices
+  int64_t wide_range_log2 = -1;  // log2 of the column-block width of the wide image (2..23)
+  int64_t wide_hints = -1;    // L2 policies of the wide kernel: bit 0 x gathers evict-last, bit 1 y updates / row map evict-first
 };
 Options &options();
 

@@ -31,9 +31,15 @@ Layout::~Layout() {
   free(rowmap);
   free(chunks);
   delete dev;
+  delete wide;
 }
 
 bool &building_device_layout() {
+  static thread_local bool flag = false;
+  return flag;
+}
+
+bool &building_wide_layout() {
   static thread_local bool flag = false;
   return flag;
 }
@@ -51,7 +57,8 @@ const OptionName kOptionNames[] = {
     {"autotune", &Options::autotune},         {"build_trace", &Options::build_trace}, {"dev_tiles", &Options::dev_tiles},
     {"dev_cdb", &Options::dev_cdb},           {"xs_pairs", &Options::xs_pairs},       {"tile_mb", &Options::tile_mb},
     {"e2e_tiles", &Options::e2e_tiles},       {"xs_config", &Options::xs_config},     {"l2_persist_mb", &Options::l2_persist_mb},
-    {"tile_launch", &Options::tile_launch},   {"diag_flags", &Options::diag_flags},
+    {"tile_launch", &Options::tile_launch},   {"diag_flags", &Options::diag_flags},   {"wide", &Options::wide},
+    {"wide_range_log2", &Options::wide_range_log2}, {"wide_hints", &Options::wide_hints},
 };
 }  // namespace
 
@@ -104,6 +111,18 @@ bool plan_device_params(const Layout *L, int *cu_dev, int *vf_dev, uint32_t *cdb
   return true;
 }
 
+// The wide image (Layout::wide) is offered for irregular matrices: there the 15-bit blocks cost one scattered y update
+// per (row, block) pair - on a uniform matrix one per non-zero - while a block as wide as the L2 cache can hold of x
+// (2^23 columns = 64 MB fp64 / 32 MB fp32) leaves a handful of pairs per row, formed in registers.
+uint32_t plan_wide_cdb(const Layout *L) {
+  const Options &o = options();
+  if (o.wide == 0 || L->is_wide) return 0;
+  if (o.wide < 0 && !layout_is_irregular(L)) return 0;
+  int p = 23;
+  if (o.wide_range_log2 >= 2) p = (int)std::min<int64_t>(23, o.wide_range_log2);
+  return 1u << p;
+}
+
 static inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
 namespace {
@@ -127,7 +146,9 @@ int layout_init_header(Layout *L, uint32_t rows, uint32_t cols, uint64_t nnz, in
   if (!(vf == 1 || vf == 2 || vf == 4 || vf == 8)) return fail(SPMVB_E_ARG, "vf must be 1, 2, 4 or 8");
   if (rows == 0 || cols == 0) return fail(SPMVB_E_ARG, "empty matrix");
   uint32_t cdb = cdb_in ? cdb_in : ((cu == 10 || cu == 12) ? 16384u : 32768u);  // util.h:41-59
-  if (cdb > 32768 || cdb % 4 != 0) return fail(SPMVB_E_ARG, "cols_div_blocks must be a multiple of 4 and <= 32768");
+  const bool wide = building_wide_layout();
+  if (cdb > (wide ? kWideMaxCdb : 32768u) || cdb % 4 != 0)
+    return fail(SPMVB_E_ARG, "cols_div_blocks must be a multiple of 4 and <= 32768");
   if ((uint64_t)cols > (uint64_t)cdb * kMetaBlockMask) return fail(SPMVB_E_RANGE, "too many column blocks");
   L->cu = cu; L->vf = vf; L->is_double = is_double ? 1 : 0;
   L->rows = rows; L->cols = cols; L->cdb = cdb;
@@ -136,6 +157,8 @@ int layout_init_header(Layout *L, uint32_t rows, uint32_t cols, uint64_t nnz, in
   L->vb = is_double ? 8 : 4;
   L->group_bytes = L->ratio_col_val * kBusBytes;
   L->chunk_bytes = L->group_bytes * kGroupsPerChunk;
+  L->is_wide = wide;
+  if (wide) L->chunk_bytes = (int)wide_chunk_bytes(L->vb);
   L->real_nnz = nnz;
   int blocks = (int)(cols / cdb) + 1;
   if (cols % cdb == 0) blocks--;
@@ -232,6 +255,22 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   const int vb = L->vb;
   const uint32_t ratio_v = (uint32_t)L->ratio_v;
   const BlockOf block_of(cdb);
+  // where entry e of a piece lives: the reference's groups (index word + value words, csr_hw.cpp:270-318), or the
+  // planes of a wide image's chunk (layout.h: kWide*)
+  const bool wide = L->is_wide;
+  const uint64_t gbytes = (uint64_t)L->group_bytes, cbytes = (uint64_t)L->chunk_bytes;
+  struct Slot { uint8_t *idx, *hi, *val; };
+  auto slot_of = [=](uint8_t *piece, uint64_t e) -> Slot {
+    const uint32_t s = (uint32_t)(e % kRatioCi);
+    if (!wide) {
+      uint8_t *grp = piece + (e / kRatioCi) * gbytes;
+      return Slot{grp + 2 * s, nullptr, grp + kBusBytes + (size_t)s * vb};
+    }
+    uint8_t *cb = piece + (e / kChunkEntries) * cbytes;
+    const uint32_t lane = (uint32_t)(e % kChunkEntries) / kRatioCi;
+    return Slot{cb + 16 * lane + 2 * s, cb + kWideHiOff + 8 * lane + s,
+                cb + kWideValOff + (s / ratio_v) * kWidePlane + 16 * lane + (size_t)(s % ratio_v) * vb};
+  };
 
   // row ranges of (almost) equal non-zero count, one per thread
   int T = omp_get_max_threads();
@@ -407,11 +446,12 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
         const int k = piece_k[b];
         const uint64_t e = pos[b] + fill[b] - fp[(size_t)b * (cu + 1) + k];
         const uint32_t is_last = (++fill[b] == cnt[b]) && (cnt[b] % (uint32_t)vf == 0);
-        uint8_t *grp = L->stream + L->piece_off[(size_t)b * cu + k] + (e / kRatioCi) * (uint64_t)gb;
-        const uint32_t s = (uint32_t)(e % kRatioCi);
-        const uint16_t ci = (uint16_t)((c - b * cdb) | (is_last ? 0x8000u : 0u));  // csr_hw.cpp:220, :288-292
-        memcpy(grp + 2 * s, &ci, 2);
-        memcpy(grp + kBusBytes + (size_t)s * vb, vals + (size_t)j * vb, vb);       // csr_hw.cpp:300-310
+        const Slot sl = slot_of(L->stream + L->piece_off[(size_t)b * cu + k], e);
+        const uint32_t cin = c - b * cdb;
+        const uint16_t ci = (uint16_t)((cin & 0x7FFFu) | (is_last ? 0x8000u : 0u));  // csr_hw.cpp:220, :288-292
+        memcpy(sl.idx, &ci, 2);
+        if (sl.hi) *sl.hi = (uint8_t)(cin >> 15);
+        memcpy(sl.val, vals + (size_t)j * vb, vb);                                 // csr_hw.cpp:300-310
       }
       for (uint32_t b : touched) {
         const int k = piece_k[b];
@@ -421,9 +461,8 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
         const uint64_t t_e = s_e + round_up(cnt[b], (uint32_t)vf);  // VF padding: (col 0, val 0), csr_hw.cpp:229-238
         if (cnt[b] % (uint32_t)vf != 0) {
           const uint64_t e = t_e - 1;
-          uint8_t *grp = L->stream + L->piece_off[bk] + (e / kRatioCi) * (uint64_t)gb;
           const uint16_t ci = 0x8000u;
-          memcpy(grp + 2 * (e % kRatioCi), &ci, 2);
+          memcpy(slot_of(L->stream + L->piece_off[bk], e).idx, &ci, 2);
         }
         L->rowmap[rank[b]] = r;
         // chunks whose first entry lies inside this segment start at this rank
@@ -447,9 +486,8 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     const uint64_t real = L->piece_real_nnz[bk];
     for (uint32_t i = 0; i < pad_rows[b]; i++) {
       const uint64_t e = real + (uint64_t)i * vf + (vf - 1);
-      uint8_t *grp = L->stream + L->piece_off[bk] + (e / kRatioCi) * (uint64_t)gb;
       const uint16_t ci = 0x8000u;
-      memcpy(grp + 2 * (e % kRatioCi), &ci, 2);
+      memcpy(slot_of(L->stream + L->piece_off[bk], e).idx, &ci, 2);
     }
   }
 
@@ -519,20 +557,22 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
 #pragma omp parallel for schedule(static)
   for (int64_t c = 0; c < (int64_t)L->n_chunks; c++) {
     const uint32_t valid = L->chunks[c].valid & 0x3FFu;
-    const uint8_t *base = L->stream + (uint64_t)c * L->chunk_bytes;
+    uint8_t *base = L->stream + (uint64_t)c * L->chunk_bytes;
     uint16_t lo = 0xFFFF, hi = 0;
     uint32_t row_ends = 0, lines = 0;
     uint32_t seen[64] = {0};  // 32768 columns >> 4 = 2048 lines at most
     for (uint32_t e = 0; e < valid; e++) {
       uint16_t ci;
-      memcpy(&ci, base + (size_t)(e / kRatioCi) * gb + 2 * (e % kRatioCi), 2);
+      memcpy(&ci, slot_of(base, e).idx, 2);
       row_ends += ci >> 15;
       ci &= 0x7FFF;
+      if (wide) continue;  // no shared-memory windows over a wide image: its column statistics are not used
       lo = std::min(lo, ci); hi = std::max(hi, ci);
       const uint32_t ln = (uint32_t)ci >> line_shift, bit = 1u << (ln & 31);
       lines += !(seen[ln >> 5] & bit);
       seen[ln >> 5] |= bit;
     }
+    if (wide) { lo = 0; hi = 0; }
     L->chunk_col_lo[c] = lo; L->chunk_col_hi[c] = hi; L->chunk_x_lines[c] = (uint16_t)lines;
     L->chunks[c].block = (L->chunks[c].block & kMetaBlockMask) | (row_ends << kMetaRowsShift);
   }
@@ -546,6 +586,15 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     int rc = build_impl<RP>(rows, cols, row_ptr, col_ind, values, cu_dev, vf_dev, is_double, cdb_dev, &L->dev, false);
     building_device_layout() = false;
     if (rc) { delete L; return rc; }
+  }
+  // the wide image: the same builder with one column block per L2-sized range of x, one compute unit, no VF padding
+  if (const uint32_t cdb_wide = plan_device ? plan_wide_cdb(L) : 0u) {
+    phase("device layout");
+    building_wide_layout() = true;
+    int rc = build_impl<RP>(rows, cols, row_ptr, col_ind, values, 1, 1, is_double, cdb_wide, &L->wide, false);
+    building_wide_layout() = false;
+    if (rc) { delete L; return rc; }
+    phase("wide image");
   }
 
   *out = L;
@@ -764,6 +813,68 @@ int spmvb_layout_device_params(const spmvb_layout *l, uint64_t *out) {
   out[4] = L->dev ? 1u : 0u; out[5] = D->n_pairs; out[6] = D->n_chunks;
   out[7] = D->zero_all ? UINT64_MAX : (uint64_t)D->zero_rows.size(); out[8] = D->stream_bytes;
   return SPMVB_OK;
+}
+
+/* The wide image of this layout (engine-private, like the device layout): out[8] = {present, column-block width,
+ * column blocks, (row, block) pairs, chunks, rows cleared per SpMV (UINT64_MAX = all), image bytes, real entries}. */
+int spmvb_layout_wide_params(const spmvb_layout *l, uint64_t *out) {
+  const Layout *L = (const Layout *)l;
+  if (!L || !out) return fail(SPMVB_E_ARG, "wide_params");
+  const Layout *W = L->wide;
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  if (!W) return SPMVB_OK;
+  out[0] = 1; out[1] = W->cdb; out[2] = (uint64_t)W->blocks; out[3] = W->n_pairs; out[4] = W->n_chunks;
+  out[5] = W->zero_all ? UINT64_MAX : (uint64_t)W->zero_rows.size(); out[6] = W->stream_bytes; out[7] = W->real_nnz;
+  return SPMVB_OK;
+}
+
+/* Walks the wide image the way the kernel does - planes of every chunk, end-of-row bits, row map - and returns its
+ * real entries in image order as (row, column, value bits).  For tests: the image must hold exactly the CSR's entries,
+ * ordered by (column block, row, CSR position). */
+int64_t spmvb_layout_wide_decode(const spmvb_layout *l, uint32_t *rows_out, uint32_t *cols_out, void *vals_out,
+                                 uint64_t max_entries) {
+  const Layout *L = (const Layout *)l;
+  if (!L || !L->wide) return fail(SPMVB_E_ARG, "wide_decode: no wide image");
+  const Layout *W = L->wide;
+  if (!W->stream || !W->rowmap) return fail(SPMVB_E_ARG, "wide_decode: image not on the host");
+  uint64_t n = 0;
+  const uint32_t ratio_v = (uint32_t)W->ratio_v;
+  for (int b = 0; b < W->blocks; b++) {
+    const uint8_t *piece = W->stream + W->piece_off[b];
+    uint64_t rank = W->rank_base[b];
+    const uint32_t real = W->piece_real_nnz[b];
+    for (uint64_t c = W->piece_chunk0[b]; c < W->piece_chunk1[b]; c++) {
+      const ChunkMeta &m = W->chunks[c];
+      const uint64_t first = (c - W->piece_chunk0[b]) * kChunkEntries;
+      const uint32_t valid = m.valid & 0x3FFu;
+      if (valid != (first >= real ? 0u : (uint32_t)std::min<uint64_t>(kChunkEntries, real - first)))
+        return fail(SPMVB_E_ARG, "wide_decode: chunk entry count");
+      if (valid && m.rank0 != rank) return fail(SPMVB_E_ARG, "wide_decode: chunk rank0");
+      if (valid && (m.block & kMetaBlockMask) != (uint32_t)b) return fail(SPMVB_E_ARG, "wide_decode: chunk block");
+      if (valid && m.row_first != W->rowmap[rank]) return fail(SPMVB_E_ARG, "wide_decode: chunk row_first");
+      const uint8_t *cb = piece + (c - W->piece_chunk0[b]) * (uint64_t)W->chunk_bytes;
+      uint32_t row_ends = 0;
+      for (uint32_t e = 0; e < valid; e++) {
+        const uint32_t lane = e / kRatioCi, s = e % kRatioCi;
+        uint16_t ci;
+        memcpy(&ci, cb + 16 * lane + 2 * s, 2);
+        const uint32_t col = (uint32_t)b * W->cdb + (((uint32_t)cb[kWideHiOff + 8 * lane + s] << 15) | (ci & 0x7FFFu));
+        if (rank >= W->rank_base[b + 1]) return fail(SPMVB_E_ARG, "wide_decode: rank runs past the block");
+        if (n < max_entries) {
+          if (rows_out) rows_out[n] = W->rowmap[rank];
+          if (cols_out) cols_out[n] = col;
+          if (vals_out)
+            memcpy((uint8_t *)vals_out + n * W->vb,
+                   cb + kWideValOff + (s / ratio_v) * kWidePlane + 16 * lane + (size_t)(s % ratio_v) * W->vb, W->vb);
+        }
+        n++;
+        if (ci & 0x8000u) { rank++; row_ends++; }
+      }
+      if (valid && (m.block >> kMetaRowsShift) != row_ends) return fail(SPMVB_E_ARG, "wide_decode: chunk row ends");
+    }
+    if (rank != W->rank_base[b + 1]) return fail(SPMVB_E_ARG, "wide_decode: pairs of the block");
+  }
+  return (int64_t)n;
 }
 
 int spmvb_partition_rows(uint32_t rows, const uint64_t *row_ptr, int parts, int ratio_v, uint32_t *bounds) {

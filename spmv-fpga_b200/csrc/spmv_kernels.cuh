@@ -167,11 +167,28 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ends closed.  `consec`: the chunk's rows are row_first, row_first + 1, ... (no row-map loads).
 // `sole` chunks (every row lives in one column block only) write y with plain stores: nothing else ever touches
 // those rows, so they need no zero-fill and no read-modify-write.
-template <typename VT, bool MUL>
+// COAL (wide images, whose rows ascend through a chunk): the row sums are parked in `scratch` (shared memory, one
+// VT per row end of the chunk, in rank order) and written out by the whole warp, lane q taking row ends q, q + 32, ...:
+// consecutive rows per request - 4 fp64 rows per 32-byte sector - instead of one sector per lane, and the row ids of
+// non-consecutive chunks come as coalesced loads.
+__device__ __forceinline__ void sts_v(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_v(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ double lds_v(uint32_t a, double) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_v(uint32_t a, float) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+
+template <typename VT, bool MUL, bool COAL = false>
 __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw, const uint4 *vw, const VT *xv,
                                               const uint32_t *__restrict__ rowmap, VT *__restrict__ y, int lane,
                                               VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red,
-                                              uint64_t y_policy = 0, uint64_t stream_policy = 0) {
+                                              uint64_t y_policy = 0, uint64_t stream_policy = 0, uint32_t scratch = 0) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t rank0 = mraw.x, valid = mraw.z & 0x3FFu, row_first = mraw.w;
   const bool consec = (mraw.z & kChunkRowsConsecutive) != 0;
@@ -197,7 +214,7 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
   // and the row sums (fetched one by one inside the update loop below they were 35 % of the XS kernel's stall time
   // on R-MAT: load -> wait -> RED -> next load ...).
   uint32_t rows[8];
-  if (!consec) {
+  if (!COAL && !consec) {
     uint32_t rk = rank_t;
 #pragma unroll
     for (int s = 0; s < 8; s++) {
@@ -256,6 +273,45 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
   if (lane == 0) cin = VT(0);  // lane 0 already absorbed the incoming carry
 
   const uint32_t first_bit = eor & (0u - eor);  // the lane's first row end also closes what earlier lanes left open
+
+  if (COAL) {
+    const bool head = head_red;  // the chunk's first row end closes the row the run started in: an atomic even if `sole`
+    if (seen_mask) head_red = false;
+    uint32_t q = (uint32_t)(pre - n_eor);
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      if ((eor >> s) & 1u) {
+        VT v = seg[s];
+        if ((first_bit >> s) & 1u) v = vadd(cin, v);
+        sts_v(scratch + q * (uint32_t)sizeof(VT), v);
+        q++;
+      }
+    }
+    __syncwarp();
+    for (q = (uint32_t)lane; q < total_eor; q += 32u) {
+      const VT v = lds_v(scratch + q * (uint32_t)sizeof(VT), VT(0));
+      uint32_t row;
+      if (consec) {
+        row = row_first + q;
+      } else {
+        const uint32_t rk = SPMVB_BOUND(1, rank0 + q, g_limits.n_pairs);
+        if (stream_policy) asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(row) : "l"(rowmap + rk), "l"(stream_policy));
+        else row = __ldg(rowmap + rk);
+      }
+      row = SPMVB_BOUND(2, row, g_limits.rows);
+      if (!sole || (q == 0 && head)) {
+        if (y_policy) y_add_hint(y + row, v, y_policy);
+        else y_add(y + row, v);
+      } else {
+        y[row] = v;
+      }
+    }
+    __syncwarp();  // the scratch is free for the next chunk
+    open = !partial && ((__shfl_sync(FULL, eor, 31) >> 7) & 1u) == 0;
+    if (partial) carry = VT(0);
+    next_rank = rank0 + total_eor;
+    return;
+  }
 
   if (y_policy == ~0ull) eor = 0;  // diagnostic (engine option diag_flags bit 5): no y updates at all, wrong results
   // which row ends must be atomics: all of them unless the chunk is `sole`; then only the run's dangling first row
@@ -588,6 +644,124 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                                 gather_x<VT>(iw, x, (mraw.y & kMetaBlockMask) * cdb, xv);
                               });
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Variant WIDE: the kernel of the wide image (layout.h: Layout::wide).  The column blocks are as wide as the L2 cache
+// can hold of x (up to 2^23 columns) and the rows ascend through a block, so the scattered 8-byte access of every
+// entry is the x gather - ld.global.nc out of an L2-resident range, the cheapest scattered access a B200 has
+// (tools/access_probe.cu: 288 G/s against 193 G/s for red.global.add) - while the row sums of a (row, block) pair are
+// formed in registers and leave as coalesced requests (process_chunk<COAL>).  Same machinery otherwise: per-warp TMA
+// ring of chunk slots, runs of chunks with the open row carried in registers.  A slot is the planar chunk of
+// layout.h (kWide*) + its ChunkMeta; lane l reads its index word, its 8 high column bytes and its value words with
+// conflict-free LDS.128 / LDS.64.
+//   flags bit 2: accumulate (all updates atomics); bit 3: x gathers evict-last; bit 4: y updates + row map evict-first
+template <typename VT, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+    spmv_wide_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap, const VT *__restrict__ x,
+                     VT *__restrict__ y, uint32_t chunk_base, uint32_t n_chunks, uint32_t cdb, uint32_t run_log2,
+                     uint32_t flags) {
+  constexpr int VW = VTraits<VT>::kValWords;
+  constexpr uint32_t CHUNK_BYTES = kWideValOff + 32u * 8u * (uint32_t)sizeof(VT);
+  constexpr uint32_t SLOT = CHUNK_BYTES + 16u;
+  constexpr uint32_t SCRATCH = (uint32_t)kChunkEntries * (uint32_t)sizeof(VT);
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t ring = smem_u32(smem) + (uint32_t)warp * 2 * SLOT;
+  const uint32_t scratch = smem_u32(smem) + WARPS * 2 * SLOT + (uint32_t)warp * SCRATCH;
+  const uint32_t bars = smem_u32(smem) + WARPS * (2 * SLOT + SCRATCH) + (uint32_t)warp * 16;
+  if (lane == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  const uint64_t x_policy = (flags & 8u) ? l2_policy_evict_last() : 0ull;
+  const uint64_t y_policy = (flags & 16u) ? l2_policy_evict_first() : 0ull;
+  const uint64_t stream_policy = l2_policy_evict_first();
+  const bool force_red = (flags & 4u) != 0;
+
+  // the walk of walk_chunks: warp w of W takes run q*W + w of the domain [chunk_base, chunk_base + n_chunks)
+  const uint32_t w = blockIdx.x * WARPS + warp, W = gridDim.x * WARPS;
+  const uint32_t R = 1u << run_log2;
+  const uint32_t total_runs = (n_chunks + R - 1) >> run_log2;
+  if (w >= total_runs) return;
+  const uint32_t my_runs = (total_runs - w + W - 1) / W;
+  uint32_t n = my_runs << run_log2;
+  {
+    const uint32_t over = ((my_runs - 1) * W + w + 1) << run_log2;
+    if (over > n_chunks) n -= over - n_chunks;
+  }
+  const uint32_t jump = (W - 1) << run_log2;
+  auto ahead = [&](uint32_t ci, uint32_t i, uint32_t k) -> uint32_t {
+    return ci + k + ((((i & (R - 1)) + k) >> run_log2) * jump);
+  };
+  auto lds128 = [](uint32_t a) -> uint4 {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+  };
+  auto issue = [&](uint32_t slot, uint32_t chunk) {  // lane 0 only
+    chunk = SPMVB_BOUND(0, chunk, g_limits.n_chunks);
+    const uint32_t bar = bars + (slot & 1u) * 8;
+    mbar_expect_tx(bar, SLOT);
+    bulk_g2s_hint(ring + (slot & 1u) * SLOT, reinterpret_cast<const uint8_t *>(stream) + (size_t)chunk * SLOT, SLOT, bar,
+                  stream_policy);
+  };
+  uint32_t c_cur = chunk_base + (w << run_log2);
+  uint32_t t = 0;
+  if (lane == 0) {
+    issue(t, c_cur);
+    if (1 < n) issue(t + 1, ahead(c_cur, 0, 1));
+  }
+  grid_dep_wait();  // x and y may still be written by the previous kernel of the stream
+  VT carry = VT(0);
+  bool open = false, head_red = false;
+  uint32_t next_rank = 0;
+  for (uint32_t i = 0; i < n; i++, t++) {
+    const uint32_t st = t & 1u;
+    mbar_wait(bars + st * 8, (t >> 1) & 1u);
+    const uint32_t slot = ring + st * SLOT;
+    const uint4 mraw = lds128(slot + CHUNK_BYTES);
+    const uint4 iw = lds128(slot + 16u * (uint32_t)lane);
+    uint2 hb;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(hb.x), "=r"(hb.y) : "r"(slot + kWideHiOff + 8u * (uint32_t)lane));
+    const VT *xb = x + (size_t)(mraw.y & kMetaBlockMask) * cdb;
+    VT xv[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const uint32_t hi = ((s < 4 ? hb.x : hb.y) >> (8 * (s & 3))) & 0xFFu;
+      const uint32_t col = (hi << 15) | (idx16(iw, s) & 0x7FFFu);
+#ifdef SPMVB_CHECK_BOUNDS
+      const VT *p = x + SPMVB_BOUND(3, (uint32_t)((size_t)(mraw.y & kMetaBlockMask) * cdb + col), g_limits.x_len);
+#else
+      const VT *p = xb + col;
+#endif
+      xv[s] = x_policy ? ldg_x_hint(p, x_policy) : ldg_x(p);
+    }
+    uint4 vw[VW];
+#pragma unroll
+    for (int k = 0; k < VW; k++) vw[k] = lds128(slot + kWideValOff + (uint32_t)k * kWidePlane + 16u * (uint32_t)lane);
+    const uint32_t pos = i & (R - 1);
+    const bool sole = (mraw.z & kChunkSole) != 0 && !force_red;
+    if (pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;
+    process_chunk<VT, true, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red, y_policy,
+                                  y_policy ? stream_policy : 0ull, scratch);
+    if (pos == R - 1 || i + 1 == n) {  // the row left open continues in another warp's run: hand over atomically
+      if (open && lane == 0) {
+        uint32_t row = (mraw.z & kChunkRowsConsecutive) ? mraw.w + (next_rank - mraw.x)
+                                                        : rowmap[SPMVB_BOUND(1, next_rank, g_limits.n_pairs)];
+        row = SPMVB_BOUND(2, row, g_limits.rows);
+        y_add(&y[row], carry);
+      }
+      carry = VT(0);
+      open = false;
+    }
+    __syncwarp();
+    if (lane == 0 && i + 2 < n) issue(t + 2, ahead(c_cur, i, 2));
+    c_cur = ahead(c_cur, i, 1);
   }
 }
 

@@ -26,6 +26,8 @@ SYMBOLS = {
     "spmvb_options_from_env": (_int, []),
     "spmvb_layout_device_params": (_int, [_vp, _vp]),
     "spmvb_layout_x_lines_per_chunk": (ctypes.c_double, [_vp]),
+    "spmvb_layout_wide_params": (_int, [_vp, _vp]),
+    "spmvb_layout_wide_decode": (ctypes.c_int64, [_vp, _vp, _vp, _vp, ctypes.c_uint64]),
     "spmvb_debug_bounds_errors": (_int, [_vp]),
     "spmvb_engine_last_iter_ms": (ctypes.c_float, [_vp]),
     "spmvb_engine_device_layout": (_int, [_vp, _vp]),
@@ -362,6 +364,31 @@ class Layout:
                     zero_rows=-1 if v[7] == 2 ** 64 - 1 else v[7], bytes=v[8])
 
     @property
+    def wide_params(self):
+        """The wide image: dict(present, cdb, blocks, pairs, chunks, zero_rows (-1 = all), bytes, nnz)."""
+        out = (ctypes.c_uint64 * 8)()
+        _check(lib().spmvb_layout_wide_params(self.h, out))
+        v = [int(x) for x in out]
+        return dict(present=bool(v[0]), cdb=v[1], blocks=v[2], pairs=v[3], chunks=v[4],
+                    zero_rows=-1 if v[5] == 2 ** 64 - 1 else v[5], bytes=v[6], nnz=v[7])
+
+    def wide_decode(self):
+        """(rows, cols, values) of the wide image's entries in image order, after the library's own consistency walk."""
+        w = self.wide_params
+        if not w["present"]:
+            raise SpmvbError(-1, "no wide image")
+        n = w["nnz"]
+        rows = np.zeros(max(n, 1), np.uint32)
+        cols = np.zeros(max(n, 1), np.uint32)
+        vals = np.zeros(max(n, 1), np.float64 if self.is_double else np.float32)
+        got = lib().spmvb_layout_wide_decode(self.h, _ptr(rows), _ptr(cols), _ptr(vals), n)
+        if got < 0:
+            raise SpmvbError(int(got), lib().spmvb_last_error().decode(errors="replace"))
+        if got != n:
+            raise SpmvbError(-1, "wide image holds %d entries, expected %d" % (got, n))
+        return rows[:n], cols[:n], vals[:n]
+
+    @property
     def x_lines_per_chunk(self):
         return float(lib().spmvb_layout_x_lines_per_chunk(self.h))
 
@@ -451,7 +478,7 @@ def partition_rows(rows, row_ptr, parts, ratio_v=2):
     return bounds
 
 
-VARIANT_AUTO, VARIANT_DIRECT, VARIANT_OCC4, VARIANT_OCC3, VARIANT_XS = 0, 1, 6, 7, 8
+VARIANT_AUTO, VARIANT_DIRECT, VARIANT_OCC4, VARIANT_OCC3, VARIANT_XS, VARIANT_WIDE = 0, 1, 6, 7, 8, 9
 
 
 class Engine:
@@ -506,12 +533,12 @@ class Engine:
 
     @property
     def device_layout(self):
-        out = (ctypes.c_uint64 * 13)()
+        out = (ctypes.c_uint64 * 16)()
         _check(lib().spmvb_engine_device_layout(self.h, out))
         v = [int(x) for x in out]
         return dict(cu=v[0], vf=v[1], cdb=v[2], cu_major=bool(v[3]), pairs=v[4], chunks=v[5],
                     zero_rows=-1 if v[6] == 2 ** 64 - 1 else v[6], bytes=v[7], e2e_tiles=v[8], tall=bool(v[9]), xs_config=v[10],
-                    tuned_us=dict(api_image=v[11], device_layout=v[12]))
+                    wide=bool(v[13]), blocks=v[15], tuned_us=dict(api_image=v[11], device_layout=v[12], wide_image=v[14]))
 
     def set_variant(self, v):
         _check(lib().spmvb_engine_set_variant(self.h, v))

@@ -73,6 +73,61 @@ def test_small_column_blocks(spmvb, oracle, variant):
     _check(spmvb, oracle, matgen.uniform(3000, 9000, 12, seed=4), 2, 2, True, variant, cdb=256)
 
 
+@pytest.mark.parametrize("range_log2", [23, 16, 12])
+@pytest.mark.parametrize("isd", [True, False], ids=["f64", "f32"])
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_wide_image_kernel_matches_oracle(spmvb, oracle, case, isd, range_log2):
+    """The wide image (column blocks of 2^range_log2 columns, rows ascending through a block) and its kernel (variant
+    9): one block, a few blocks, many blocks; the API pieces next to it are the reference's as ever."""
+    with spmvb.options(wide=1, wide_range_log2=range_log2):
+        _check(spmvb, oracle, CASES[case](), 1, 1, isd, 9)
+
+
+@pytest.mark.parametrize("opts", [dict(occ_run_log2=1), dict(occ_run_log2=5), dict(wide_hints=3), dict(wide_hints=1),
+                                  dict(run_log2=3, zero_all=1)], ids=lambda o: ",".join("%s=%d" % kv for kv in o.items()))
+def test_wide_image_kernel_options(spmvb, oracle, opts):
+    with spmvb.options(wide=1, wide_range_log2=14, **opts):
+        _check(spmvb, oracle, matgen.uniform(6000, 100000, 12, seed=8), 8, 4, True, 9)
+        _check(spmvb, oracle, matgen.rmat(13, 8, seed=5), 2, 2, False, 9)
+        _check(spmvb, oracle, matgen.uniform(40, 30000, 9000, seed=9), 1, 1, True, 9)
+
+
+def test_wide_image_device_accumulate_and_variant_rules(spmvb, oracle):
+    rows, cols, rp, ci, va = matgen.ragged(5000, 100000, seed=7)
+    x = np.random.default_rng(0).random(cols)
+    gold = oracle.spmv_gold(rows, rp, ci, va, x, True)
+    scale = oracle.abs_ax(rows, rp, ci, va, x, True) + 1e-300
+    with spmvb.options(wide=1, wide_range_log2=15):
+        lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True)
+    eng = spmvb.Engine(lay, 0, 9)
+    assert eng.variant == 9 and eng.device_layout["wide"] and eng.device_layout["cdb"] == 32768
+    eng.set_x(x)
+    eng.spmv_dev()
+    y1 = eng.get_y()
+    eng.spmv_dev(accumulate=True)   # every update an atomic on top of the first result
+    y2 = eng.get_y()
+    assert np.all(np.abs(y1 - gold) <= 1e-12 * scale)
+    assert np.all(np.abs(y2 - 2 * gold) <= 4e-12 * scale)
+    with pytest.raises(spmvb.SpmvbError):
+        eng.set_variant(7)            # a wide image has one kernel
+    eng.free()
+    plain = spmvb.Engine(lay, 0, 7)
+    with pytest.raises(spmvb.SpmvbError):
+        plain.set_variant(9)
+    plain.free()
+    with spmvb.options(wide=0):
+        nowide = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True)
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Engine(nowide, 0, 9)
+    # the engine's own choice (variant 0): whichever candidate it measured fastest, the result is the same
+    auto = spmvb.Engine(lay, 0)
+    y = np.zeros(rows)
+    auto.spmv_host(x, y, accumulate=False)
+    assert np.all(np.abs(y - gold) <= 1e-12 * scale)
+    assert auto.device_layout["tuned_us"]["wide_image"] > 0
+    auto.free()
+
+
 def test_device_api_and_determinism_of_inputs(spmvb, oracle):
     rows, cols, rp, ci, va = matgen.laplacian2d(512, 512)
     lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True)
