@@ -238,6 +238,15 @@ def scatter_roofline(dev, nnz_local, k_ms):
     update of y that no blocking of this layout makes local, and a B200 sustains 193 G red.global.add.f64/s into an
     L2-resident vector (288 G/s scattered 8-byte loads; measured with tools/access_probe.cu, profiles/r2/
     access_probe_b200.txt).  achieved = pairs of the device layout / kernel time."""
+    if dev.get("ell"):  # sliced ELLPACK of a regular matrix: no scattered access at all
+        return None
+    if dev.get("wide"):  # the wide image: the scattered access of every entry is the x gather out of an L2-resident range
+        peak = 288.0
+        achieved = nnz_local / (k_ms * 1e-3) / 1e9
+        return {"bound": "scattered x gathers (ld.global.nc out of an L2-resident column block)", "achieved": achieved,
+                "peak": peak, "unit": "G gathers/s", "frac": achieved / peak, "gathers_per_nnz": 1.0,
+                "y_updates_per_nnz": dev["pairs"] / max(nnz_local, 1),
+                "peak_source": "measured: tools/access_probe.cu on this pool's B200 (profiles/r2/access_probe_b200.txt)"}
     peak = 193.0
     achieved = dev["pairs"] / (k_ms * 1e-3) / 1e9
     return {"bound": "scattered y updates (red.global.add into L2)", "achieved": achieved, "peak": peak, "unit": "G updates/s",
@@ -245,7 +254,8 @@ def scatter_roofline(dev, nnz_local, k_ms):
             "peak_source": "measured: tools/access_probe.cu on this pool's B200 (profiles/r2/access_probe_b200.txt)"}
 
 
-KERNEL_NAMES = {7: "spmv_occ_kernel<3 CTAs/SM>", 6: "spmv_occ_kernel<4 CTAs/SM>", 8: "spmv_xs_kernel", 1: "spmv_direct_kernel"}
+KERNEL_NAMES = {7: "spmv_occ_kernel<3 CTAs/SM>", 6: "spmv_occ_kernel<4 CTAs/SM>", 8: "spmv_xs_kernel", 1: "spmv_direct_kernel",
+                9: "spmv_wide_kernel", 10: "spmv_ell_kernel"}
 
 
 def time_reference_gold(csr, x, is_double, steps, warmup, budget_s=None):

@@ -119,6 +119,14 @@ int spmvb_layout_device_params(const spmvb_layout *l, uint64_t *out);
  * irregularity that picks the kernel and the device layout (5-point Laplacian 12, R-MAT ~150-200, uniform ~250) */
 double spmvb_layout_x_lines_per_chunk(const spmvb_layout *l);
 
+/* The sliced-ELLPACK image (engine-private candidate for regular matrices - rows of almost equal length whose columns
+ * stay within 65 536 of each other per 32 rows): out[8] = {present, width = slots per row, slices of 32
+ * rows, bytes per slice, slots, image bytes, real entries, 0}. */
+int spmvb_layout_ell_params(const spmvb_layout *l, uint64_t *out);
+/* Every slot of the ELL image, row-major (slices * 32 rows x width): absolute column and value bits; padding slots carry
+ * the row's first column and value 0.  Returns the number of slots.  For tests. */
+int64_t spmvb_layout_ell_decode(const spmvb_layout *l, uint32_t *cols_out, void *vals_out, uint64_t max_slots);
+
 /* The wide image (a second engine-private candidate): out[8] = {present, column-block width, column
  * blocks, (row, block) pairs, chunks, rows cleared per SpMV (UINT64_MAX = all), image bytes, real entries}. */
 int spmvb_layout_wide_params(const spmvb_layout *l, uint64_t *out);
@@ -209,10 +217,12 @@ int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
 int spmvb_debug_bounds_errors(uint64_t *out5);
 /* device time per iteration (CUDA events around the loop) of the last spmvb_engine_power_iter / spmvb_engine_cg call */
 float spmvb_engine_last_iter_ms(const spmvb_engine *e);
-/* out[16] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per
+/* out[20] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per
  * SpMV (UINT64_MAX = all), image bytes, row tiles spmv_host pipelines (0 = none), 1 = explicit L2 policies, x-window kernel configuration (0 wide / 1 medium /
  * 2 narrow), microseconds of one SpMV measured at creation for {the API image with global gathers, the device layout} (0 =
- * not measured), 1 = the wide image is what is streamed, microseconds of one SpMV over the wide image, column blocks} */
+ * not measured), 1 = the wide image is what is streamed, microseconds of one SpMV over the wide image, column blocks,
+ * 1 = the sliced-ELLPACK image is what is streamed, microseconds of one SpMV over it, its width (slots per row), row tiles of
+ * its end-to-end pipeline} */
 int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out);
 /* Conjugate gradients for A x = b on one GPU (A symmetric positive definite, e.g. the Laplacian of BASELINE config 2):
  * the second iterated caller of SURVEY 8(f) rank 3 (the reference's caller runs spmv_hw once, main.cpp:68-75; an

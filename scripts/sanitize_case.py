@@ -46,6 +46,15 @@ for isd in (True, False):
                         eng.spmv_host(x, y, accumulate=False)
                         assert np.all(np.abs(y.astype(np.float64) - gold) <= bound), (name, isd, "wide", rl, opts)
                         eng.free(); layw.free()
+                if lay.ell_params["present"]:  # regular matrix: the sliced-ELLPACK image, one launch and the pipeline
+                    for tiles in (1, 5):
+                        with spmvb.options(ell_tiles=tiles):
+                            eng = spmvb.Engine(lay, 0, spmvb.VARIANT_ELL)
+                            y = np.zeros(rows, vt)
+                            eng.spmv_host(x, y, accumulate=False)
+                            eng.spmv_host(x, y, accumulate=False)
+                            assert np.all(np.abs(y.astype(np.float64) - gold) <= bound), (name, isd, "ell", tiles, opts)
+                            eng.free()
                 lay2, eng2 = spmvb.Engine.from_csr(rows, cols, rp, ci, va, cu, vf, isd)  # the GPU layout builder
                 y = np.zeros(rows, vt)
                 eng2.spmv_host(x, y, accumulate=False)

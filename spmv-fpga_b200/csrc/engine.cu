@@ -13,13 +13,14 @@
 #include <vector>
 
 #include "../../include/spmvb.h"
+#include "ell.h"
 #include "layout.h"
 #include "layout_gpu.cuh"
 #include "spmv_kernels.cuh"
 
 namespace spmvb {
 
-enum Variant { kVariantDefault = 0, kVariantDirect = 1, kVariantOcc4 = 6, kVariantOcc3 = 7, kVariantXs = 8, kVariantWide = 9 };
+enum Variant { kVariantDefault = 0, kVariantDirect = 1, kVariantOcc4 = 6, kVariantOcc3 = 7, kVariantXs = 8, kVariantWide = 9, kVariantEll = 10 };
 
 
 struct Engine {
@@ -53,9 +54,19 @@ struct Engine {
   bool cu_major = false;           // pieces in CU-major device order (row tiles)
   bool irregular = false;          // layout_is_irregular(): x gathers are scattered, the x-window kernel pays
   bool wide = false;               // the image is a wide image (Layout::is_wide): only the WIDE kernel can walk it
+  // sliced-ELLPACK image (ell.h): regular matrices, one row per lane; nothing of the hw_matrix stream is on the device then
+  bool ell = false;
+  uint8_t *d_ell = nullptr;
+  uint32_t ell_slices = 0, ell_width = 0, ell_slice_bytes = 0;
+  std::vector<uint32_t> ell_tile_slice;   // [tiles + 1] slice ranges of the end-to-end pipeline
+  std::vector<uint64_t> ell_tile_x_end;   // [tiles] x[0, end) must be on the device before the tile runs
+  uint64_t ell_x_begin = 0;               // first column any slice reads
+  cudaStream_t down_stream = nullptr;     // y tiles travel to the host while x tiles still arrive
+  std::vector<uint64_t> block_chunk0;  // wide image: [blocks + 1] first chunk of every column block
+  std::vector<cudaEvent_t> ev_block;   // wide image: x range of block b is on the device
   int xs_cfg = 0, xs_ctas = 148;   // configuration of the x-window kernel (xs_config) and its grid = SMs x CTAs per SM
   int auto_variant = kVariantOcc3; // what variant 0 resolves to (chosen from the layout at creation)
-  float tune_ms[3] = {0.f, 0.f, 0.f};  // measured at creation: API image, device layout, wide image
+  float tune_ms[4] = {0.f, 0.f, 0.f, 0.f};  // measured at creation: API image, device layout, wide image, ELL image
   uint32_t n_zero_rows = 0, run_log2 = 2;
   bool zero_all = true;
   void *d_x = nullptr, *d_y = nullptr;
@@ -74,7 +85,7 @@ struct Engine {
   cudaStream_t stream = nullptr;
   int sms = 148;
   uint64_t launches = 0;
-  int grid_cache[10][2] = {};  // [variant][is_double] -> grid size
+  int grid_cache[11][2] = {};  // [variant][is_double] -> grid size
   // asynchronous step timing (bench): events of the last enqueue_steps()
   std::vector<cudaEvent_t> ev;
   int ev_steps = 0;
@@ -130,6 +141,18 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
   return cudaLaunchKernelEx(&cfg, kern, (KArgs)args...);
 }
 
+// bounds-checked build: the limits the kernels compare their indices with, stream-ordered before EVERY launch (the
+// end-to-end paths launch the kernels per row tile / per column block without going through launch_spmv)
+static int upload_check_limits(Engine *E, cudaStream_t st) {
+#ifdef SPMVB_CHECK_BOUNDS
+  const CheckLimits lim = {E->n_chunks, E->n_pairs, E->rows, E->x_len};
+  CUDA_TRY(cudaMemcpyToSymbolAsync(g_limits, &lim, sizeof lim, 0, cudaMemcpyHostToDevice, st));
+#else
+  (void)E; (void)st;
+#endif
+  return SPMVB_OK;
+}
+
 template <typename VT, int MINB>
 static int launch_occ(Engine *E, const VT *x, VT *y, cudaStream_t st, int slot, int accumulate) {
   constexpr int WARPS = 8;
@@ -163,11 +186,39 @@ static int launch_wide(Engine *E, const VT *x, VT *y, cudaStream_t st, int accum
     grid = E->sms * std::max(per_sm, 1);
   }
   if (n_chunks == 0) return SPMVB_OK;
+  if (int rcl = upload_check_limits(E, st)) return rcl;
   const int64_t hints = options().wide_hints >= 0 ? options().wide_hints : (E->tall ? 3 : 0);
   CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, reinterpret_cast<const uint4 *>(E->d_stream),
                       (const uint32_t *)E->d_rowmap, x, y, (uint32_t)chunk_base, (uint32_t)n_chunks, E->cdb, E->occ_run_log2,
-                      (accumulate ? 4u : 0u) | ((hints & 1) ? 8u : 0u) | ((hints & 2) ? 16u : 0u)));
+                      (accumulate ? 4u : 0u) | ((hints & 1) ? 8u : 0u) | ((hints & 2) ? 16u : 0u) |
+                          (uint32_t)(options().diag_flags > 0 ? options().diag_flags & 96 : 0)));
   return SPMVB_OK;
+}
+
+// the ELL image: slices [slice_begin, slice_begin + n_slices) in one launch.  Two instantiations: rows of up to 8 entries
+// (4 ring stages, 4 CTAs per SM) and of up to kEllMaxWidth = 16
+template <typename VT, int STAGES, int WMAX, int MINB>
+static int launch_ell_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, uint32_t slice_begin, uint32_t n_slices) {
+  constexpr int WARPS = 8;
+  auto kern = spmv_ell_kernel<VT, WARPS, STAGES, WMAX, MINB>;
+  const size_t smem = (size_t)WARPS * STAGES * E->ell_slice_bytes + (size_t)WARPS * STAGES * 8;
+  int &grid = E->grid_cache[kVariantEll][sizeof(VT) == 8];
+  if (grid == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    grid = E->sms * std::max(per_sm, 1);
+  }
+  if (n_slices == 0) return SPMVB_OK;
+  if (int rcl = upload_check_limits(E, st)) return rcl;
+  CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, (const uint8_t *)E->d_ell, x, y, E->rows, slice_begin, n_slices,
+                      E->ell_width, E->ell_slice_bytes, accumulate ? 4u : 0u));
+  return SPMVB_OK;
+}
+template <typename VT>
+static int launch_ell(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate, uint32_t slice_begin, uint32_t n_slices) {
+  if (E->ell_width <= 8) return launch_ell_cfg<VT, 4, 8, 4>(E, x, y, st, accumulate, slice_begin, n_slices);
+  return launch_ell_cfg<VT, 3, kEllMaxWidth, 1>(E, x, y, st, accumulate, slice_begin, n_slices);
 }
 
 // tile < 0: the whole matrix in one launch; otherwise row tile `tile` only (per-tile plan)
@@ -186,6 +237,7 @@ static int launch_xs_cfg(Engine *E, const VT *x, VT *y, cudaStream_t st, int acc
     grid = E->xs_ctas;
   }
   if (E->n_items == 0) return SPMVB_OK;
+  if (int rcl = upload_check_limits(E, st)) return rcl;
   const XsItem *items = tile < 0 ? E->d_items : E->d_items_t;
   const uint32_t *first = tile < 0 ? E->d_cta_first : E->d_cta_first_t + (size_t)tile * (E->xs_ctas + 1);
   CUDA_TRY(launch_pdl(kern, grid, WARPS * 32, smem, st, stream, (const uint32_t *)E->d_rowmap, x, y, items, first, E->cdb,
@@ -204,15 +256,17 @@ static int launch_xs(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumul
 
 template <typename VT>
 static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accumulate) {
-#ifdef SPMVB_CHECK_BOUNDS
-  {  // the limits the bounds-checked kernels compare their indices with (stream-ordered before the launch)
-    const CheckLimits lim = {E->n_chunks, E->n_pairs, E->rows, E->x_len};
-    CUDA_TRY(cudaMemcpyToSymbolAsync(g_limits, &lim, sizeof lim, 0, cudaMemcpyHostToDevice, st));
-  }
-#endif
+  if (int rcl = upload_check_limits(E, st)) return rcl;
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
   constexpr int WARPS = 8;
   int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
+  if (E->ell) {  // an ELL image has one kernel; every row is written, nothing needs clearing
+    int rce = launch_ell<VT>(E, x, y, st, accumulate, 0, E->ell_slices);
+    if (rce) return rce;
+    E->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SPMVB_OK;
+  }
   if (E->n_chunks == 0) return SPMVB_OK;
   if (E->n_chunks >= 0x7FFFFFFFull) return fail(SPMVB_E_RANGE, "too many chunks for one engine");
   int rc = SPMVB_OK;
@@ -244,6 +298,7 @@ static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accum
 
 // y = A x needs y prepared only where the kernel uses atomics or writes nothing: either the listed rows or all of y
 static int zero_y(Engine *E, void *y, cudaStream_t st) {
+  if (E->ell) return SPMVB_OK;  // the ELL kernel writes every row
   const int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
   if (E->zero_all || variant == kVariantDirect) {
     CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)E->rows * E->vb, st));
@@ -296,6 +351,7 @@ static int do_spmv(Engine *E, const void *x_dev, void *y_dev, int accumulate, cu
 // windows of the chosen kernel fit.  Option autotune = 1 times both kernels on the actual matrix instead (not under a
 // profiler: the timings are noise there).
 static int autotune(Engine *E) {
+  if (E->ell) { E->auto_variant = kVariantEll; return SPMVB_OK; }
   if (E->wide) { E->auto_variant = kVariantWide; return SPMVB_OK; }
   E->auto_variant = kVariantOcc3;
   if (E->n_chunks == 0 || E->xs_windowed_frac < 0.5) return SPMVB_OK;
@@ -381,6 +437,109 @@ static int spmv_host_tiled(Engine *E, void *y_host, int accumulate) {
     prev = std::max(prev, end);
   }
   if (werr != cudaSuccess) return fail(SPMVB_E_CUDA, std::string("spmv_host: ") + cudaGetErrorString(werr));
+  return SPMVB_OK;
+}
+
+// spmv_hw end to end over an ELL image.  Slices are rows: tile k of the slices can run as soon as the columns ITS rows
+// read are on the device (a band or a stencil reads a window of x that moves with the rows), and its rows of y are final
+// when it is done.  Three streams: x pieces go up, kernels run, y tiles come down - PCIe carries both directions at
+// once - and the host adds the tiles that have arrived (accumulate) while the rest is still on its way.
+template <typename VT>
+static int spmv_host_ell(Engine *E, const void *x_host, uint32_t n, void *y_host, int accumulate) {
+  const int T = (int)E->ell_tile_slice.size() - 1;
+  if (!E->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
+  if (!E->down_stream) CUDA_TRY(cudaStreamCreateWithFlags(&E->down_stream, cudaStreamNonBlocking));
+  while (E->ev_block.size() < (size_t)3 * T + 1) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    E->ev_block.push_back(e);
+  }
+  const size_t bytes = (size_t)E->rows * E->vb;
+  if (accumulate && E->h_stage_bytes < bytes) {
+    if (E->h_stage) cudaFreeHost(E->h_stage);
+    E->h_stage = nullptr; E->h_stage_bytes = 0;
+    CUDA_TRY(cudaMallocHost(&E->h_stage, bytes));
+    E->h_stage_bytes = bytes;
+  }
+  uint8_t *dst = accumulate ? (uint8_t *)E->h_stage : (uint8_t *)y_host;
+  const uint64_t m = std::min<uint32_t>(n, E->expanded_cols);
+  // the upload must not overtake a kernel of an earlier call that still reads x
+  CUDA_TRY(cudaEventRecord(E->ev_block[3 * T], E->stream));
+  CUDA_TRY(cudaStreamWaitEvent(E->copy_stream, E->ev_block[3 * T], 0));
+  uint64_t have = E->ell_x_begin;  // x[ell_x_begin, have) is on its way
+  for (int k = 0; k < T; k++) {
+    const uint64_t want = std::min<uint64_t>(E->ell_tile_x_end[k], E->x_len);
+    if (want > have) {
+      const uint64_t up = std::min(want, m);
+      if (up > have)
+        CUDA_TRY(cudaMemcpyAsync((uint8_t *)E->d_x + have * E->vb, (const uint8_t *)x_host + have * E->vb,
+                                 (size_t)(up - have) * E->vb, cudaMemcpyHostToDevice, E->copy_stream));
+      if (up < want)  // zero padding behind a short x (csr_hw.cpp:1478-1481)
+        CUDA_TRY(cudaMemsetAsync((uint8_t *)E->d_x + std::max(up, have) * E->vb, 0, (size_t)(want - std::max(up, have)) * E->vb,
+                                 E->copy_stream));
+      have = want;
+    }
+    CUDA_TRY(cudaEventRecord(E->ev_block[3 * k], E->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(E->stream, E->ev_block[3 * k], 0));
+    const uint32_t s0 = E->ell_tile_slice[k], s1 = E->ell_tile_slice[k + 1];
+    int rc = launch_ell<VT>(E, (const VT *)E->d_x, (VT *)E->d_y, E->stream, 0, s0, s1 - s0);
+    if (rc) return rc;
+    E->launches++;
+    CUDA_TRY(cudaEventRecord(E->ev_block[3 * k + 1], E->stream));
+    CUDA_TRY(cudaStreamWaitEvent(E->down_stream, E->ev_block[3 * k + 1], 0));
+    const uint64_t r0 = (uint64_t)s0 * kEllSliceRows, r1 = std::min<uint64_t>((uint64_t)s1 * kEllSliceRows, E->rows);
+    if (r1 > r0)
+      CUDA_TRY(cudaMemcpyAsync(dst + r0 * E->vb, (const uint8_t *)E->d_y + r0 * E->vb, (size_t)(r1 - r0) * E->vb,
+                               cudaMemcpyDeviceToHost, E->down_stream));
+    CUDA_TRY(cudaEventRecord(E->ev_block[3 * k + 2], E->down_stream));
+  }
+  CUDA_TRY(cudaGetLastError());
+  cudaError_t werr = cudaSuccess;
+  for (int k = 0; k < T; k++) {
+    cudaError_t r = cudaEventSynchronize(E->ev_block[3 * k + 2]);
+    if (r != cudaSuccess) werr = r;
+    const int64_t r0 = (int64_t)E->ell_tile_slice[k] * kEllSliceRows;
+    const int64_t r1 = std::min<int64_t>((int64_t)E->ell_tile_slice[k + 1] * kEllSliceRows, E->rows);
+    if (werr == cudaSuccess && accumulate && r1 > r0) host_accumulate(E, y_host, r0, r1);
+  }
+  if (werr != cudaSuccess) return fail(SPMVB_E_CUDA, std::string("spmv_host: ") + cudaGetErrorString(werr));
+  return SPMVB_OK;
+}
+
+// spmv_hw end to end over a wide image: the column blocks are walked one after the other, so block b can be computed
+// as soon as ITS range of x has arrived - the upload of the next ranges runs on a second stream under the kernels.
+template <typename VT>
+static int spmv_host_wide(Engine *E, const void *x_host, uint32_t n) {
+  if (!E->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
+  while (E->ev_block.size() < (size_t)E->blocks + 1) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    E->ev_block.push_back(e);
+  }
+  const uint64_t m = std::min<uint32_t>(n, E->expanded_cols);
+  // the copy stream must not overtake a kernel of the previous call that still reads x
+  CUDA_TRY(cudaEventRecord(E->ev_block[E->blocks], E->stream));
+  CUDA_TRY(cudaStreamWaitEvent(E->copy_stream, E->ev_block[E->blocks], 0));
+  int rc = zero_y(E, E->d_y, E->stream);
+  if (rc) return rc;
+  for (int b = 0; b < E->blocks; b++) {
+    const uint64_t first = (uint64_t)b * E->cdb, end = first + E->cdb;
+    const uint64_t c0 = E->block_chunk0[b], c1 = E->block_chunk0[b + 1];
+    if (c1 == c0) continue;  // nothing reads this range
+    const uint64_t up = std::min(end, m);
+    if (up > first)
+      CUDA_TRY(cudaMemcpyAsync((uint8_t *)E->d_x + first * E->vb, (const uint8_t *)x_host + first * E->vb,
+                               (size_t)(up - first) * E->vb, cudaMemcpyHostToDevice, E->copy_stream));
+    if (up < end)  // zero padding behind a short x (csr_hw.cpp:1478-1481)
+      CUDA_TRY(cudaMemsetAsync((uint8_t *)E->d_x + std::max(up, first) * E->vb, 0, (size_t)(end - std::max(up, first)) * E->vb,
+                               E->copy_stream));
+    CUDA_TRY(cudaEventRecord(E->ev_block[b], E->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(E->stream, E->ev_block[b], 0));
+    rc = launch_wide<VT>(E, (const VT *)E->d_x, (VT *)E->d_y, E->stream, 0, c0, c1 - c0);
+    if (rc) return rc;
+    E->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
   return SPMVB_OK;
 }
 
@@ -504,6 +663,10 @@ static int engine_adopt_layout(Engine *E, const Layout *L) {
   E->cu_major = L->cu_major; E->dev_cu = L->cu; E->dev_vf = L->vf;
   E->irregular = layout_is_irregular(L);
   E->wide = L->is_wide;
+  if (L->is_wide) {
+    E->block_chunk0.assign((size_t)L->blocks + 1, L->n_chunks);
+    for (int b = 0; b < L->blocks; b++) E->block_chunk0[b] = L->piece_chunk0[b];
+  }
   E->xs_cfg = L->xs_cfg;
   E->xs_ctas = E->sms * xs_config(L->is_double, L->xs_cfg).ctas_per_sm;
   E->tall = (uint64_t)L->rows * L->vb > ((uint64_t)48 << 20) && (uint64_t)L->cols * L->vb > ((uint64_t)48 << 20);
@@ -608,6 +771,50 @@ static int engine_create_single(const Layout *L, int device, int variant, Engine
   return SPMVB_OK;
 }
 
+// an engine over the ELL image of layout A (sizes, x ranges and vectors follow the API layout; the hw_matrix stream
+// itself is not uploaded)
+static int engine_create_ell(const Layout *A, int device, Engine **out) {
+  *out = nullptr;
+  const EllImage *I = A->ell;
+  Engine *E = nullptr;
+  int rc = engine_open(device, kVariantDefault, &E);
+  if (rc) return rc;
+  auto upload = [&]() -> int {
+    int r = engine_adopt_layout(E, A);
+    if (r) return r;
+    E->ell = true; E->wide = false; E->cu_major = false; E->irregular = false; E->tall = false;
+    E->ell_slices = I->n_slices; E->ell_width = I->width; E->ell_slice_bytes = I->slice_bytes;
+    E->n_chunks = I->n_slices; E->n_pairs = 0; E->stream_bytes = I->bytes; E->zero_all = false; E->n_zero_rows = 0;
+    E->dev_cu = 1; E->dev_vf = 1; E->auto_variant = kVariantEll;
+    CUDA_TRY(cudaMalloc((void **)&E->d_ell, std::max<uint64_t>(I->bytes, 16)));
+    CUDA_TRY(cudaMemcpyAsync(E->d_ell, I->image, I->bytes, cudaMemcpyHostToDevice, E->stream));
+    // row tiles of the end-to-end pipeline: equal slice counts; x[.., end) each tile needs = running maximum of the
+    // slices' last columns (whatever lies below the window of a later tile is on the device by then)
+    int T = options().ell_tiles > 0 ? (int)std::min<int64_t>(options().ell_tiles, 256) : 8;
+    T = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)T, I->n_slices));
+    E->ell_tile_slice.assign((size_t)T + 1, 0);
+    for (int k = 0; k <= T; k++) E->ell_tile_slice[k] = (uint32_t)((uint64_t)I->n_slices * k / T);
+    E->ell_tile_x_end.assign((size_t)T, 0);
+    uint64_t lo_all = E->x_len, hi_run = 0;
+    for (uint32_t s = 0; s < I->n_slices; s++)
+      if (I->col_lo[s] <= I->col_hi[s]) lo_all = std::min<uint64_t>(lo_all, I->col_lo[s]);
+    for (int k = 0; k < T; k++) {
+      for (uint32_t s = E->ell_tile_slice[k]; s < E->ell_tile_slice[k + 1]; s++)
+        if (I->col_lo[s] <= I->col_hi[s]) hi_run = std::max<uint64_t>(hi_run, (uint64_t)I->col_hi[s] + 1);
+      E->ell_tile_x_end[k] = (hi_run + 63) & ~(uint64_t)63;  // whole 512-byte pieces
+    }
+    E->ell_x_begin = lo_all == E->x_len ? 0 : (lo_all & ~(uint64_t)63);
+    CUDA_TRY(cudaMemsetAsync(E->d_x, 0, E->x_len * E->vb, E->stream));
+    CUDA_TRY(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    return SPMVB_OK;
+  };
+  rc = upload();
+  if (rc) { spmvb_engine_free((spmvb_engine *)E); return rc; }
+  *out = E;
+  return SPMVB_OK;
+}
+
 // milliseconds of one y = A x (clear rows + kernel) with the engine's own kernel choice, best of `reps` after a warm-up
 static int engine_time_step(Engine *E, int reps, float *best_ms) {
   *best_ms = 1e30f;
@@ -647,6 +854,13 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
     *out = (spmvb_engine *)E;
     return SPMVB_OK;
   }
+  if (variant == kVariantEll) {  // explicitly the ELL image
+    if (!A->ell) return fail(SPMVB_E_ARG, "engine_create: variant 10 needs a layout with an ELL image (a regular matrix)");
+    rc = engine_create_ell(A, device, &E);
+    if (rc) return rc;
+    *out = (spmvb_engine *)E;
+    return SPMVB_OK;
+  }
   rc = engine_create_single(L, device, variant, &E);
   if (rc) return rc;
   if (A->dev && variant == kVariantDefault && options().autotune != 0) {
@@ -672,9 +886,27 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
     if (rc == SPMVB_OK) rc = engine_time_step(E2, 3, &t_wide);
     if (rc) { spmvb_engine_free((spmvb_engine *)E); spmvb_engine_free((spmvb_engine *)E2); return rc; }
     E->tune_ms[2] = t_wide;
-    for (int i = 0; i < 3; i++) E2->tune_ms[i] = E->tune_ms[i];
+    for (int i = 0; i < 4; i++) E2->tune_ms[i] = E->tune_ms[i];
     if (t_wide < t_cur) std::swap(E, E2);
     spmvb_engine_free((spmvb_engine *)E2);
+  }
+  if (A->ell && variant == kVariantDefault && options().autotune != 0) {  // regular matrix: the ELL image against the best so far
+    Engine *E3 = nullptr;
+    float t_cur = 1e30f, t_ell = 0.f;
+    for (int i = 0; i < 3; i++)
+      if (E->tune_ms[i] > 0.f) t_cur = std::min(t_cur, E->tune_ms[i]);
+    rc = SPMVB_OK;
+    if (t_cur > 1e29f) {
+      rc = engine_time_step(E, 5, &t_cur);
+      E->tune_ms[E->wide ? 2 : 0] = t_cur;
+    }
+    if (rc == SPMVB_OK) rc = engine_create_ell(A, device, &E3);
+    if (rc == SPMVB_OK) rc = engine_time_step(E3, 5, &t_ell);
+    if (rc) { spmvb_engine_free((spmvb_engine *)E); spmvb_engine_free((spmvb_engine *)E3); return rc; }
+    E->tune_ms[3] = t_ell;
+    for (int i = 0; i < 4; i++) E3->tune_ms[i] = E->tune_ms[i];
+    if (t_ell < t_cur) std::swap(E, E3);
+    spmvb_engine_free((spmvb_engine *)E3);
   }
   *out = (spmvb_engine *)E;
   return SPMVB_OK;
@@ -803,8 +1035,10 @@ void spmvb_engine_free(spmvb_engine *e) {
   if (E->stream) cudaStreamSynchronize(E->stream);
   cudaFree(E->d_stream); cudaFree(E->d_rowmap); cudaFree(E->d_zero_rows); cudaFree(E->d_items); cudaFree(E->d_cta_first);
   cudaFree(E->d_x); cudaFree(E->d_y); cudaFree(E->d_scalar); cudaFree(E->d_flush);
-  cudaFree(E->d_items_t); cudaFree(E->d_cta_first_t);
+  cudaFree(E->d_items_t); cudaFree(E->d_cta_first_t); cudaFree(E->d_ell);
+  if (E->down_stream) cudaStreamDestroy(E->down_stream);
   for (auto &x : E->ev_tile) if (x) cudaEventDestroy(x);
+  for (auto &x : E->ev_block) if (x) cudaEventDestroy(x);
   if (E->copy_stream) cudaStreamDestroy(E->copy_stream);
   cudaFree(E->d_api_stream); cudaFree(E->d_api_rowmap); cudaFree(E->d_cg);
   if (E->h_stage) cudaFreeHost(E->h_stage);
@@ -818,9 +1052,9 @@ void spmvb_engine_free(spmvb_engine *e) {
 }
 
 int spmvb_engine_set_variant(spmvb_engine *e, int variant) {
-  if (!e || variant < 0 || variant > 9) return fail(SPMVB_E_ARG, "variant");
-  if (variant != 0 && ((Engine *)e)->wide != (variant == kVariantWide))
-    return fail(SPMVB_E_ARG, "variant: the wide image has its own kernel (9) and only that one");
+  if (!e || variant < 0 || variant > 10) return fail(SPMVB_E_ARG, "variant");
+  if (variant != 0 && (((Engine *)e)->wide != (variant == kVariantWide) || ((Engine *)e)->ell != (variant == kVariantEll)))
+    return fail(SPMVB_E_ARG, "variant: the wide image and the ELL image have their own kernels (9, 10) and only those");
   ((Engine *)e)->variant = variant;
   return SPMVB_OK;
 }
@@ -923,6 +1157,16 @@ int spmvb_engine_get_y(spmvb_engine *e, void *y_host, uint32_t n, int accumulate
 int spmvb_engine_spmv_host(spmvb_engine *e, const void *x_host, uint32_t n, void *y_host, int accumulate) {
   Engine *E = (Engine *)e;
   if (!E) return fail(SPMVB_E_ARG, "spmv_host");
+  if (E->ell && x_host && y_host && options().e2e_tiles != 0 && E->ell_tile_slice.size() > 2) {
+    CUDA_TRY(cudaSetDevice(E->device));
+    return E->is_double ? spmv_host_ell<double>(E, x_host, n, y_host, accumulate) : spmv_host_ell<float>(E, x_host, n, y_host, accumulate);
+  }
+  if (E->wide && E->blocks > 1 && x_host && options().e2e_tiles != 0) {
+    CUDA_TRY(cudaSetDevice(E->device));
+    int rcw = E->is_double ? spmv_host_wide<double>(E, x_host, n) : spmv_host_wide<float>(E, x_host, n);
+    if (rcw) return rcw;
+    return spmvb_engine_get_y(e, y_host, E->rows, accumulate);
+  }
   int rc = spmvb_engine_set_x(e, x_host, n);
   if (rc) return rc;
   const int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
@@ -1104,6 +1348,8 @@ int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out) {
   out[7] = E->stream_bytes; out[8] = (uint64_t)E->n_tiles; out[9] = E->tall ? 1u : 0u; out[10] = (uint64_t)E->xs_cfg;
   out[11] = (uint64_t)(E->tune_ms[0] * 1000.f); out[12] = (uint64_t)(E->tune_ms[1] * 1000.f);
   out[13] = E->wide ? 1u : 0u; out[14] = (uint64_t)(E->tune_ms[2] * 1000.f); out[15] = (uint64_t)E->blocks;
+  out[16] = E->ell ? 1u : 0u; out[17] = (uint64_t)(E->tune_ms[3] * 1000.f); out[18] = E->ell_width;
+  out[19] = (uint64_t)(E->ell_tile_slice.empty() ? 0 : E->ell_tile_slice.size() - 1);
   return SPMVB_OK;
 }
 

@@ -30,6 +30,8 @@ constexpr uint32_t kChunkRowsConsecutive = 0x80000000u;  // rows of the chunk's 
 constexpr uint32_t kChunkSole = 0x40000000u;       // every row touched by the chunk lives in exactly one column block
 constexpr uint32_t kChunkStartsMid = 0x20000000u;  // the chunk's first entry continues a row begun in the previous chunk
 
+struct EllImage;
+
 struct Layout {
   int cu = 1, vf = 1, is_double = 1, blocks = 0;
   uint32_t rows = 0, cols = 0, expanded_cols = 0, cdb = 32768;
@@ -81,6 +83,8 @@ struct Layout {
   // live in a byte plane of their own and a chunk is stored plane by plane (see kWide* below).
   Layout *wide = nullptr;
   bool is_wide = false;  // this layout IS a wide image
+  // Third engine-private candidate, for regular matrices only (ell.h): sliced ELLPACK, one row per lane
+  EllImage *ell = nullptr;
 
   ~Layout();
 };
@@ -162,7 +166,9 @@ struct Options {
   int64_t diag_flags = -1;    // diagnostics of the x-window kernel (WRONG results): 16 = no x window traffic, 32 = no y updates
   int64_t tile_launch = -1;   // 1: one kernel launch per row tile with the tile's y range as persisting L2 window
   int64_t e2e_tiles = -1;     // 0: spmv_host does not pipeline row tiles (one launch, then the copy of y)
-  int64_t wide = -1;          // wide image: 0 never, 1 always build one, -1 for irregular matrices
+  int64_t wide = -1;          // wide image: 1 build one (a third candidate for the engine), otherwise none
+  int64_t ell = -1;           // sliced-ELLPACK image: 0 never, 1 whenever the format can hold the matrix, -1 when it is (almost) free
+  int64_t ell_tiles = -1;     // row tiles of the end-to-end pipeline over an ELL image (x up / kernel / y down overlapped)
   int64_t wide_range_log2 = -1;  // log2 of the column-block width of the wide image (2..23)
   int64_t wide_hints = -1;    // L2 policies of the wide kernel: bit 0 x gathers evict-last, bit 1 y updates / row map evict-first
 };

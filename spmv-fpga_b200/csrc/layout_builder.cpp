@@ -22,11 +22,13 @@
 #include <vector>
 
 #include "../../include/spmvb.h"
+#include "ell.h"
 #include "layout.h"
 
 namespace spmvb {
 
 Layout::~Layout() {
+  delete ell;
   free(stream);
   free(rowmap);
   free(chunks);
@@ -58,7 +60,8 @@ const OptionName kOptionNames[] = {
     {"dev_cdb", &Options::dev_cdb},           {"xs_pairs", &Options::xs_pairs},       {"tile_mb", &Options::tile_mb},
     {"e2e_tiles", &Options::e2e_tiles},       {"xs_config", &Options::xs_config},     {"l2_persist_mb", &Options::l2_persist_mb},
     {"tile_launch", &Options::tile_launch},   {"diag_flags", &Options::diag_flags},   {"wide", &Options::wide},
-    {"wide_range_log2", &Options::wide_range_log2}, {"wide_hints", &Options::wide_hints},
+    {"wide_range_log2", &Options::wide_range_log2}, {"wide_hints", &Options::wide_hints},   {"ell", &Options::ell},
+    {"ell_tiles", &Options::ell_tiles},
 };
 }  // namespace
 
@@ -111,13 +114,15 @@ bool plan_device_params(const Layout *L, int *cu_dev, int *vf_dev, uint32_t *cdb
   return true;
 }
 
-// The wide image (Layout::wide) is offered for irregular matrices: there the 15-bit blocks cost one scattered y update
-// per (row, block) pair - on a uniform matrix one per non-zero - while a block as wide as the L2 cache can hold of x
-// (2^23 columns = 64 MB fp64 / 32 MB fp32) leaves a handful of pairs per row, formed in registers.
+// The wide image (Layout::wide): with 15-bit blocks an irregular matrix costs one scattered y update per (row, block)
+// pair - on a uniform matrix one per non-zero - while a block as wide as the L2 cache can hold of x (2^23 columns = 64 MB
+// fp64 / 32 MB fp32) leaves a handful of pairs per row, formed in registers, and moves the scattered access to the x
+// gather.  Measured on B200 it loses to the row-tiled device layout on every configuration of
+// BASELINE.json - under the stream the L2 does not keep a 16-64 MB range of x resident, and gathers that miss run at a
+// third of the rate of the updates they replace - so it is built on request only (option wide = 1).
 uint32_t plan_wide_cdb(const Layout *L) {
   const Options &o = options();
-  if (o.wide == 0 || L->is_wide) return 0;
-  if (o.wide < 0 && !layout_is_irregular(L)) return 0;
+  if (o.wide <= 0 || L->is_wide) return 0;
   int p = 23;
   if (o.wide_range_log2 >= 2) p = (int)std::min<int64_t>(23, o.wide_range_log2);
   return 1u << p;
@@ -595,6 +600,11 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     building_wide_layout() = false;
     if (rc) { delete L; return rc; }
     phase("wide image");
+  }
+  // the sliced-ELLPACK image, when the matrix is regular enough for it to cost nothing (ell.h)
+  if (plan_device) {
+    L->ell = build_ell<RP>(rows, cols, row_ptr, col_ind, values, is_double);
+    phase("ELL image");
   }
 
   *out = L;

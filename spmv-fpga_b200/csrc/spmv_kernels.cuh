@@ -25,6 +25,7 @@
 
 #include <type_traits>
 
+#include "ell.h"
 #include "layout.h"
 
 namespace spmvb {
@@ -188,7 +189,8 @@ template <typename VT, bool MUL, bool COAL = false>
 __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw, const uint4 *vw, const VT *xv,
                                               const uint32_t *__restrict__ rowmap, VT *__restrict__ y, int lane,
                                               VT &carry, bool &open, uint32_t &next_rank, bool sole, bool &head_red,
-                                              uint64_t y_policy = 0, uint64_t stream_policy = 0, uint32_t scratch = 0) {
+                                              uint64_t y_policy = 0, uint64_t stream_policy = 0, uint32_t scratch = 0,
+                                              const uint32_t *rows_pre = nullptr) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t rank0 = mraw.x, valid = mraw.z & 0x3FFu, row_first = mraw.w;
   const bool consec = (mraw.z & kChunkRowsConsecutive) != 0;
@@ -277,6 +279,7 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
   if (COAL) {
     const bool head = head_red;  // the chunk's first row end closes the row the run started in: an atomic even if `sole`
     if (seen_mask) head_red = false;
+    uint32_t total_eor_emit = total_eor;
     uint32_t q = (uint32_t)(pre - n_eor);
 #pragma unroll
     for (int s = 0; s < 8; s++) {
@@ -288,22 +291,21 @@ __device__ __forceinline__ void process_chunk(const uint4 &iw, const uint4 &mraw
       }
     }
     __syncwarp();
-    for (q = (uint32_t)lane; q < total_eor; q += 32u) {
-      const VT v = lds_v(scratch + q * (uint32_t)sizeof(VT), VT(0));
-      uint32_t row;
-      if (consec) {
-        row = row_first + q;
-      } else {
-        const uint32_t rk = SPMVB_BOUND(1, rank0 + q, g_limits.n_pairs);
-        if (stream_policy) asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(row) : "l"(rowmap + rk), "l"(stream_policy));
-        else row = __ldg(rowmap + rk);
-      }
-      row = SPMVB_BOUND(2, row, g_limits.rows);
-      if (!sole || (q == 0 && head)) {
-        if (y_policy) y_add_hint(y + row, v, y_policy);
-        else y_add(y + row, v);
-      } else {
-        y[row] = v;
+    if (stream_policy == ~0ull) total_eor_emit = 0;  // diagnostic (diag_flags 32): no y updates, wrong results
+    // rows_pre[j] = row id of row end lane + 32 j, requested by the caller together with the x gathers (a load inside
+    // this loop would put one memory latency between every two updates)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      q = (uint32_t)lane + 32u * (uint32_t)j;
+      if (q < total_eor_emit) {
+        const VT v = lds_v(scratch + q * (uint32_t)sizeof(VT), VT(0));
+        const uint32_t row = SPMVB_BOUND(2, consec ? row_first + q : rows_pre[j], g_limits.rows);
+        if (!sole || (q == 0 && head)) {
+          if (y_policy) y_add_hint(y + row, v, y_policy);
+          else y_add(y + row, v);
+        } else {
+          y[row] = v;
+        }
       }
     }
     __syncwarp();  // the scratch is free for the next chunk
@@ -656,7 +658,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 // ring of chunk slots, runs of chunks with the open row carried in registers.  A slot is the planar chunk of
 // layout.h (kWide*) + its ChunkMeta; lane l reads its index word, its 8 high column bytes and its value words with
 // conflict-free LDS.128 / LDS.64.
-//   flags bit 2: accumulate (all updates atomics); bit 3: x gathers evict-last; bit 4: y updates + row map evict-first
+//   flags bit 2: accumulate (all updates atomics); bit 3: x gathers evict-last; bit 4: y updates + row map evict-first;
+//   bits 5, 6: diagnostics (no y updates / gathers confined to a small window of x)
 template <typename VT, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     spmv_wide_kernel(const uint4 *__restrict__ stream, const uint32_t *__restrict__ rowmap, const VT *__restrict__ x,
@@ -733,13 +736,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 #pragma unroll
     for (int s = 0; s < 8; s++) {
       const uint32_t hi = ((s < 4 ? hb.x : hb.y) >> (8 * (s & 3))) & 0xFFu;
-      const uint32_t col = (hi << 15) | (idx16(iw, s) & 0x7FFFu);
+      uint32_t col = (hi << 15) | (idx16(iw, s) & 0x7FFFu);
+      if (flags & 64u) col &= 0xFFFFu;  // diagnostic (diag_flags 64): every gather hits a 512 KB window, wrong results
 #ifdef SPMVB_CHECK_BOUNDS
       const VT *p = x + SPMVB_BOUND(3, (uint32_t)((size_t)(mraw.y & kMetaBlockMask) * cdb + col), g_limits.x_len);
 #else
       const VT *p = xb + col;
 #endif
       xv[s] = x_policy ? ldg_x_hint(p, x_policy) : ldg_x(p);
+    }
+    // row ids of the chunk's row ends (lane + 32 j of them), in flight together with the gathers
+    uint32_t rows_pre[8];
+    if (!(mraw.z & kChunkRowsConsecutive)) {
+      const uint32_t n_ends = mraw.y >> kMetaRowsShift;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t q = (uint32_t)lane + 32u * (uint32_t)j;
+        rows_pre[j] = 0;
+        if (q < n_ends) {
+          const uint32_t rk = SPMVB_BOUND(1, mraw.x + q, g_limits.n_pairs);
+          if (y_policy) asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(rows_pre[j]) : "l"(rowmap + rk), "l"(stream_policy));
+          else asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(rows_pre[j]) : "l"(rowmap + rk));
+        }
+      }
     }
     uint4 vw[VW];
 #pragma unroll
@@ -748,7 +767,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     const bool sole = (mraw.z & kChunkSole) != 0 && !force_red;
     if (pos == 0) head_red = (mraw.z & kChunkStartsMid) != 0;
     process_chunk<VT, true, true>(iw, mraw, vw, xv, rowmap, y, lane, carry, open, next_rank, sole, head_red, y_policy,
-                                  y_policy ? stream_policy : 0ull, scratch);
+                                  (flags & 32u) ? ~0ull : 0ull, scratch, rows_pre);
     if (pos == R - 1 || i + 1 == n) {  // the row left open continues in another warp's run: hand over atomically
       if (open && lane == 0) {
         uint32_t row = (mraw.z & kChunkRowsConsecutive) ? mraw.w + (next_rank - mraw.x)
@@ -762,6 +781,87 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     __syncwarp();
     if (lane == 0 && i + 2 < n) issue(t + 2, ahead(c_cur, i, 2));
     c_cur = ahead(c_cur, i, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Variant ELL: the kernel of the sliced-ELLPACK image (ell.h) for regular matrices.  One warp per slice of 32
+// consecutive rows, lane l owns row l: slot s of the 32 rows is ONE gather request over neighbouring columns (2-3
+// distinct lines of x on a stencil instead of 12 with the reference's row-after-row groups), the row sum never leaves
+// the lane's registers (left to right, multiply and add separately rounded like compute_results, spmv.cpp:84-97), and
+// y is written once, 32 consecutive rows per store.  Slices arrive through a per-warp ring of STAGES TMA bulk copies
+// (cp.async.bulk + mbarrier, evict-first); warp w of W takes slices w, w + W, ... so that all warps sweep the stream
+// together.  flags bit 2: accumulate (y += A x; rows are exclusive, so a plain read-modify-write).
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
+template <typename VT, int WARPS, int STAGES, int WMAX, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+    spmv_ell_kernel(const uint8_t *__restrict__ image, const VT *__restrict__ x, VT *__restrict__ y, uint32_t rows,
+                    uint32_t slice_begin, uint32_t n_slices, uint32_t width, uint32_t slice_bytes, uint32_t flags) {
+  static_assert(STAGES >= 3, "slices i and i + 1 are both in use while the next ones arrive");
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t ring = smem_u32(smem) + (uint32_t)warp * STAGES * slice_bytes;
+  const uint32_t bars = smem_u32(smem) + (uint32_t)WARPS * STAGES * slice_bytes + (uint32_t)warp * STAGES * 8;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) mbar_init(bars + s * 8, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  const uint32_t w = blockIdx.x * WARPS + warp, W = gridDim.x * WARPS;
+  if (w >= n_slices) return;
+  const uint32_t n = (n_slices - w + W - 1) / W;
+  const uint64_t stream_policy = l2_policy_evict_first();
+  auto issue = [&](uint32_t k) {  // lane 0 only: the warp's k-th slice into stage k % STAGES
+    const uint32_t st = k % STAGES;
+    const uint64_t slice = (uint64_t)slice_begin + w + (uint64_t)k * W;
+    mbar_expect_tx(bars + st * 8, slice_bytes);
+    bulk_g2s_hint(ring + st * slice_bytes, image + slice * slice_bytes, slice_bytes, bars + st * 8, stream_policy);
+  };
+  if (lane == 0)
+    for (uint32_t k = 0; k < (uint32_t)STAGES && k < n; k++) issue(k);
+  grid_dep_wait();  // x and y may still be written by the previous kernel of the stream
+  // the warp's k-th slice has landed: its header, and the x gathers of this lane's row (one request per slot)
+  auto fetch = [&](uint32_t k, uint4 &head, VT *xv) {
+    const uint32_t st = k % STAGES;
+    mbar_wait(bars + st * 8, (k / STAGES) & 1u);
+    const uint32_t rec = ring + st * slice_bytes;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(head.x), "=r"(head.y), "=r"(head.z), "=r"(head.w) : "r"(rec));
+#pragma unroll
+    for (int s = 0; s < WMAX; s++)
+      if ((uint32_t)s < width) {
+        const uint32_t off = lds_u16(rec + 16u + (uint32_t)s * 64u + 2u * (uint32_t)lane);
+        xv[s] = ldg_x(x + SPMVB_BOUND(3, head.x + off, g_limits.x_len));
+      }
+  };
+  // software pipeline: the gathers of slice i + 1 are in flight while slice i is summed and stored
+  uint4 head_n;
+  VT xn[WMAX];
+  fetch(0, head_n, xn);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint4 head = head_n;
+    VT xc[WMAX];
+#pragma unroll
+    for (int s = 0; s < WMAX; s++) xc[s] = xn[s];
+    if (i + 1 < n) fetch(i + 1, head_n, xn);
+    const uint32_t vals = ring + (i % STAGES) * slice_bytes + 16u + width * 64u + (uint32_t)lane * (uint32_t)sizeof(VT);
+    VT acc = VT(0);
+#pragma unroll
+    for (int s = 0; s < WMAX; s++)
+      if ((uint32_t)s < width) acc = vadd(acc, vmul(lds_v(vals + (uint32_t)s * 32u * (uint32_t)sizeof(VT), VT(0)), xc[s]));
+    const uint32_t row = head.z + (uint32_t)lane;
+    if (row < rows) {
+      const uint32_t rr = SPMVB_BOUND(2, row, g_limits.rows);
+      y[rr] = (flags & 4u) ? vadd(y[rr], acc) : acc;
+    }
+    __syncwarp();  // every lane's loads from this stage have been consumed: it can be refilled
+    if (lane == 0 && i + STAGES < n) issue(i + STAGES);
   }
 }
 

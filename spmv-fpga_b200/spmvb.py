@@ -26,6 +26,8 @@ SYMBOLS = {
     "spmvb_options_from_env": (_int, []),
     "spmvb_layout_device_params": (_int, [_vp, _vp]),
     "spmvb_layout_x_lines_per_chunk": (ctypes.c_double, [_vp]),
+    "spmvb_layout_ell_params": (_int, [_vp, _vp]),
+    "spmvb_layout_ell_decode": (ctypes.c_int64, [_vp, _vp, _vp, ctypes.c_uint64]),
     "spmvb_layout_wide_params": (_int, [_vp, _vp]),
     "spmvb_layout_wide_decode": (ctypes.c_int64, [_vp, _vp, _vp, _vp, ctypes.c_uint64]),
     "spmvb_debug_bounds_errors": (_int, [_vp]),
@@ -364,6 +366,27 @@ class Layout:
                     zero_rows=-1 if v[7] == 2 ** 64 - 1 else v[7], bytes=v[8])
 
     @property
+    def ell_params(self):
+        """The sliced-ELLPACK image (regular matrices): dict(present, width, slices, slice_bytes, slots, bytes, nnz)."""
+        out = (ctypes.c_uint64 * 8)()
+        _check(lib().spmvb_layout_ell_params(self.h, out))
+        v = [int(x) for x in out]
+        return dict(present=bool(v[0]), width=v[1], slices=v[2], slice_bytes=v[3], slots=v[4], bytes=v[5], nnz=v[6])
+
+    def ell_decode(self):
+        """(cols, values) of every slot of the ELL image, row-major: arrays of shape (slices * 32, width)."""
+        e = self.ell_params
+        if not e["present"]:
+            raise SpmvbError(-1, "no ELL image")
+        n = e["slots"]
+        cols = np.zeros(n, np.uint32)
+        vals = np.zeros(n, np.float64 if self.is_double else np.float32)
+        got = lib().spmvb_layout_ell_decode(self.h, _ptr(cols), _ptr(vals), n)
+        if got != n:
+            raise SpmvbError(int(got), lib().spmvb_last_error().decode(errors="replace"))
+        return cols.reshape(-1, e["width"]), vals.reshape(-1, e["width"])
+
+    @property
     def wide_params(self):
         """The wide image: dict(present, cdb, blocks, pairs, chunks, zero_rows (-1 = all), bytes, nnz)."""
         out = (ctypes.c_uint64 * 8)()
@@ -478,7 +501,7 @@ def partition_rows(rows, row_ptr, parts, ratio_v=2):
     return bounds
 
 
-VARIANT_AUTO, VARIANT_DIRECT, VARIANT_OCC4, VARIANT_OCC3, VARIANT_XS, VARIANT_WIDE = 0, 1, 6, 7, 8, 9
+VARIANT_AUTO, VARIANT_DIRECT, VARIANT_OCC4, VARIANT_OCC3, VARIANT_XS, VARIANT_WIDE, VARIANT_ELL = 0, 1, 6, 7, 8, 9, 10
 
 
 class Engine:
@@ -533,12 +556,13 @@ class Engine:
 
     @property
     def device_layout(self):
-        out = (ctypes.c_uint64 * 16)()
+        out = (ctypes.c_uint64 * 20)()
         _check(lib().spmvb_engine_device_layout(self.h, out))
         v = [int(x) for x in out]
         return dict(cu=v[0], vf=v[1], cdb=v[2], cu_major=bool(v[3]), pairs=v[4], chunks=v[5],
                     zero_rows=-1 if v[6] == 2 ** 64 - 1 else v[6], bytes=v[7], e2e_tiles=v[8], tall=bool(v[9]), xs_config=v[10],
-                    wide=bool(v[13]), blocks=v[15], tuned_us=dict(api_image=v[11], device_layout=v[12], wide_image=v[14]))
+                    wide=bool(v[13]), blocks=v[15], ell=bool(v[16]), ell_width=v[18], ell_e2e_tiles=v[19],
+                    tuned_us=dict(api_image=v[11], device_layout=v[12], wide_image=v[14], ell_image=v[17]))
 
     def set_variant(self, v):
         _check(lib().spmvb_engine_set_variant(self.h, v))

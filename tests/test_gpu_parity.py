@@ -128,6 +128,64 @@ def test_wide_image_device_accumulate_and_variant_rules(spmvb, oracle):
     auto.free()
 
 
+ELL_CASES = ["kat6x6", "band10k", "lap256", "lap_wide"]   # rows of <= 16 entries whose columns stay close together
+
+
+@pytest.mark.parametrize("tiles", [-1, 1, 3, 64])
+@pytest.mark.parametrize("cfg", [(1, 1, True), (1, 1, False), (8, 4, True)], ids=lambda c: "cu%d_vf%d_%s" % (c[0], c[1], "f64" if c[2] else "f32"))
+@pytest.mark.parametrize("case", ELL_CASES)
+def test_ell_image_kernel_matches_oracle(spmvb, oracle, case, cfg, tiles):
+    """The sliced-ELLPACK image of a regular matrix and its kernel (variant 10), through the end-to-end pipeline of
+    spmv_host (x pieces up / kernel per row tile / y tiles down, overlapped) with several tile counts."""
+    cu, vf, isd = cfg
+    with spmvb.options(ell=1, ell_tiles=tiles):
+        _check(spmvb, oracle, CASES[case](), cu, vf, isd, 10)
+
+
+def test_ell_image_device_calls_and_variant_rules(spmvb, oracle):
+    rows, cols, rp, ci, va = matgen.laplacian2d(300, 200)
+    x = np.random.default_rng(0).random(cols)
+    gold = oracle.spmv_gold(rows, rp, ci, va, x, True)
+    scale = oracle.abs_ax(rows, rp, ci, va, x, True) + 1e-300
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True)
+    eng = spmvb.Engine(lay, 0, 10)
+    info = eng.device_layout
+    assert eng.variant == 10 and info["ell"] and info["ell_width"] == 5 and info["zero_rows"] == 0
+    eng.set_x(x)
+    eng.spmv_dev()
+    y1 = eng.get_y()
+    eng.spmv_dev(accumulate=True)
+    y2 = eng.get_y()
+    assert np.all(np.abs(y1 - gold) <= 1e-12 * scale)
+    assert np.all(np.abs(y2 - 2 * gold) <= 4e-12 * scale)
+    with pytest.raises(spmvb.SpmvbError):
+        eng.set_variant(7)
+    # a short x is zero padded (csr_hw.cpp:1478-1481), also through the pipeline
+    xs = x[: cols - 1000]
+    xfull = np.zeros(cols); xfull[: len(xs)] = xs
+    y = np.zeros(rows)
+    eng.spmv_host(xs, y, accumulate=False)
+    g2 = oracle.spmv_gold(rows, rp, ci, va, xfull, True)
+    assert np.all(np.abs(y - g2) <= 1e-12 * scale)
+    eng.spmv_host(x, y, accumulate=False)       # and a full one after it replaces every column
+    assert np.all(np.abs(y - gold) <= 1e-12 * scale)
+    nrm = None
+    eng.set_x(np.full(cols, 1.0 / np.sqrt(cols)))
+    nrm = eng.power_iter(3)
+    assert nrm > 0
+    eng.free()
+    # the engine's own choice on a regular matrix: whichever it measured fastest gives the same result
+    auto = spmvb.Engine(lay, 0)
+    assert auto.device_layout["tuned_us"]["ell_image"] > 0
+    y = np.zeros(rows)
+    auto.spmv_host(x, y, accumulate=False)
+    assert np.all(np.abs(y - gold) <= 1e-12 * scale)
+    auto.free()
+    rows, cols, rp, ci, va = matgen.uniform(2000, 200000, 8, seed=1)
+    with pytest.raises(spmvb.SpmvbError):
+        spmvb.Engine(spmvb.Layout.build(rows, cols, rp, ci, va), 0, 10)   # not a regular matrix: no ELL image
+
+
 def test_device_api_and_determinism_of_inputs(spmvb, oracle):
     rows, cols, rp, ci, va = matgen.laplacian2d(512, 512)
     lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True)
@@ -185,7 +243,7 @@ def test_power_iteration_matches_numpy(spmvb, oracle):
     assert abs(nrm - n) <= 1e-3 * n
 
 
-@pytest.mark.parametrize("variant", [0, 1, 7, 8])
+@pytest.mark.parametrize("variant", [0, 1, 7, 8, 10])
 def test_config2_scale_every_variant_repeated(spmvb, oracle, variant):
     """BASELINE config 2 at full size against the gold CSR SpMV, several launches per variant: every warp walks
     many chunks here, which is what exposes pipeline races that the small cases cannot."""

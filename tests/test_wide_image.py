@@ -56,15 +56,14 @@ def test_wide_image_leaves_the_api_pieces_alone(spmvb):
     assert plain.difference(withw) == ""  # every API table and byte
 
 
-def test_wide_image_only_for_irregular_matrices(spmvb):
-    rows, cols, rp, ci, va = matgen.laplacian2d(64, 64)
-    assert not spmvb.Layout.build(rows, cols, rp, ci, va).wide_params["present"]
+def test_wide_image_only_on_request(spmvb):
+    """It lost every measurement on B200: built only with option wide = 1."""
     rows, cols, rp, ci, va = matgen.uniform(4000, 60000, 16, seed=2)
-    assert spmvb.Layout.build(rows, cols, rp, ci, va).wide_params["present"]
+    assert not spmvb.Layout.build(rows, cols, rp, ci, va).wide_params["present"]
     with spmvb.options(wide=0):
         assert not spmvb.Layout.build(rows, cols, rp, ci, va).wide_params["present"]
-    lay = spmvb.Layout.build(rows, cols, rp, ci, va)
     with pytest.raises(spmvb.SpmvbError):
-        with spmvb.options(wide=0):
-            spmvb.Layout.build(rows, cols, rp, ci, va).wide_decode()
-    assert lay.wide_params["zero_rows"] >= -1
+        spmvb.Layout.build(rows, cols, rp, ci, va).wide_decode()
+    with spmvb.options(wide=1):
+        lay = spmvb.Layout.build(rows, cols, rp, ci, va)
+    assert lay.wide_params["present"] and lay.wide_params["zero_rows"] >= -1
