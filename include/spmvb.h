@@ -123,6 +123,8 @@ double spmvb_layout_x_lines_per_chunk(const spmvb_layout *l);
  * stay within 65 536 of each other per 32 rows): out[8] = {present, width = slots per row, slices of 32
  * rows, bytes per slice, slots, image bytes, real entries, 0}. */
 int spmvb_layout_ell_params(const spmvb_layout *l, uint64_t *out);
+/* The bytes of the (host-built) ELL image: copied to `out` when max_bytes suffices; returns their number, 0 without an image. */
+int64_t spmvb_layout_ell_image(const spmvb_layout *l, void *out, uint64_t max_bytes);
 /* Every slot of the ELL image, row-major (slices * 32 rows x width): absolute column and value bits; padding slots carry
  * the row's first column and value 0.  Returns the number of slots.  For tests. */
 int64_t spmvb_layout_ell_decode(const spmvb_layout *l, uint32_t *cols_out, void *vals_out, uint64_t max_slots);
@@ -215,6 +217,9 @@ int spmvb_engine_power_iter(spmvb_engine *e, int iters, double *norm_out);
  * caught since the library was loaded, out5 = {chunk slot, row-map entry, y row, x element, x window offset}; returns 1.
  * A release build returns -1 and leaves out5 alone. */
 int spmvb_debug_bounds_errors(uint64_t *out5);
+/* For tests: copies the sliced-ELLPACK image the engine streams to `out` (when max_bytes suffices) and returns its size in
+ * bytes; 0 when the engine streams something else. */
+int64_t spmvb_engine_ell_image(spmvb_engine *e, void *out, uint64_t max_bytes);
 /* device time per iteration (CUDA events around the loop) of the last spmvb_engine_power_iter / spmvb_engine_cg call */
 float spmvb_engine_last_iter_ms(const spmvb_engine *e);
 /* out[20] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per

@@ -88,6 +88,14 @@ int spmvb_layout_ell_params(const spmvb_layout *l, uint64_t *out) {
   return SPMVB_OK;
 }
 
+int64_t spmvb_layout_ell_image(const spmvb_layout *l, void *out, uint64_t max_bytes) {
+  const Layout *L = (const Layout *)l;
+  if (!L) return fail(SPMVB_E_ARG, "ell_image");
+  if (!L->ell) return 0;
+  if (out && max_bytes >= L->ell->bytes) memcpy(out, L->ell->image, (size_t)L->ell->bytes);
+  return (int64_t)L->ell->bytes;
+}
+
 int64_t spmvb_layout_ell_decode(const spmvb_layout *l, uint32_t *cols_out, void *vals_out, uint64_t max_slots) {
   const Layout *L = (const Layout *)l;
   if (!L || !L->ell) return fail(SPMVB_E_ARG, "ell_decode: no ELL image");

@@ -14,6 +14,7 @@
 
 #include "../../include/spmvb.h"
 #include "ell.h"
+#include "ell_gpu.cuh"
 #include "layout.h"
 #include "layout_gpu.cuh"
 #include "spmv_kernels.cuh"
@@ -54,7 +55,8 @@ struct Engine {
   bool cu_major = false;           // pieces in CU-major device order (row tiles)
   bool irregular = false;          // layout_is_irregular(): x gathers are scattered, the x-window kernel pays
   bool wide = false;               // the image is a wide image (Layout::is_wide): only the WIDE kernel can walk it
-  // sliced-ELLPACK image (ell.h): regular matrices, one row per lane; nothing of the hw_matrix stream is on the device then
+  // sliced-ELLPACK image (ell.h): regular matrices, one row per lane.  ell = the engine holds one (see ell_on()); a
+  // host-built engine then holds nothing of the hw_matrix stream, a GPU-built one keeps both
   bool ell = false;
   uint8_t *d_ell = nullptr;
   uint32_t ell_slices = 0, ell_width = 0, ell_slice_bytes = 0;
@@ -93,6 +95,12 @@ struct Engine {
   // events) and of the whole call (host clock)
   float build_ms[3] = {0.f, 0.f, 0.f};
 };
+
+// the ELL image is what the next SpMV streams (an engine may hold it next to the hw_matrix stream: GPU-built engines
+// keep both, and spmvb_engine_set_variant switches between them)
+static inline bool ell_on(const Engine *E) {
+  return E->ell && (E->variant == kVariantDefault ? E->auto_variant : E->variant) == kVariantEll;
+}
 
 // CUDA events that are destroyed on every way out of a function (an early return on an error included)
 struct EventList {
@@ -260,7 +268,7 @@ static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accum
   const uint4 *stream = reinterpret_cast<const uint4 *>(E->d_stream);
   constexpr int WARPS = 8;
   int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
-  if (E->ell) {  // an ELL image has one kernel; every row is written, nothing needs clearing
+  if (ell_on(E)) {  // an ELL image has one kernel; every row is written, nothing needs clearing
     int rce = launch_ell<VT>(E, x, y, st, accumulate, 0, E->ell_slices);
     if (rce) return rce;
     E->launches++;
@@ -298,7 +306,7 @@ static int launch_spmv(Engine *E, const VT *x, VT *y, cudaStream_t st, int accum
 
 // y = A x needs y prepared only where the kernel uses atomics or writes nothing: either the listed rows or all of y
 static int zero_y(Engine *E, void *y, cudaStream_t st) {
-  if (E->ell) return SPMVB_OK;  // the ELL kernel writes every row
+  if (ell_on(E)) return SPMVB_OK;  // the ELL kernel writes every row
   const int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
   if (E->zero_all || variant == kVariantDirect) {
     CUDA_TRY(cudaMemsetAsync(y, 0, (size_t)E->rows * E->vb, st));
@@ -351,7 +359,6 @@ static int do_spmv(Engine *E, const void *x_dev, void *y_dev, int accumulate, cu
 // windows of the chosen kernel fit.  Option autotune = 1 times both kernels on the actual matrix instead (not under a
 // profiler: the timings are noise there).
 static int autotune(Engine *E) {
-  if (E->ell) { E->auto_variant = kVariantEll; return SPMVB_OK; }
   if (E->wide) { E->auto_variant = kVariantWide; return SPMVB_OK; }
   E->auto_variant = kVariantOcc3;
   if (E->n_chunks == 0 || E->xs_windowed_frac < 0.5) return SPMVB_OK;
@@ -771,8 +778,35 @@ static int engine_create_single(const Layout *L, int device, int variant, Engine
   return SPMVB_OK;
 }
 
-// an engine over the ELL image of layout A (sizes, x ranges and vectors follow the API layout; the hw_matrix stream
-// itself is not uploaded)
+static int engine_time_step(Engine *E, int reps, float *best_ms);
+
+// switches an engine whose vectors and sizes are set up (engine_adopt_layout) over to an ELL image that is on the device
+// already: kernel choice, row tiles of the end-to-end pipeline (equal slice counts; x[.., end) each tile needs = running
+// maximum of the slices' last columns - whatever lies below the window of a later tile is on the device by then)
+static void engine_set_ell(Engine *E, uint8_t *d_image, uint32_t n_slices, uint32_t width, uint32_t slice_bytes,
+                           const uint32_t *col_lo, const uint32_t *col_hi) {
+  E->ell = true;
+  E->d_ell = d_image;
+  E->ell_slices = n_slices; E->ell_width = width; E->ell_slice_bytes = slice_bytes;
+  E->auto_variant = kVariantEll;
+  int T = options().ell_tiles > 0 ? (int)std::min<int64_t>(options().ell_tiles, 256) : 8;
+  T = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)T, n_slices));
+  E->ell_tile_slice.assign((size_t)T + 1, 0);
+  for (int k = 0; k <= T; k++) E->ell_tile_slice[k] = (uint32_t)((uint64_t)n_slices * k / T);
+  E->ell_tile_x_end.assign((size_t)T, 0);
+  uint64_t lo_all = E->x_len, hi_run = 0;
+  for (uint32_t s = 0; s < n_slices; s++)
+    if (col_lo[s] <= col_hi[s]) lo_all = std::min<uint64_t>(lo_all, col_lo[s]);
+  for (int k = 0; k < T; k++) {
+    for (uint32_t s = E->ell_tile_slice[k]; s < E->ell_tile_slice[k + 1]; s++)
+      if (col_lo[s] <= col_hi[s]) hi_run = std::max<uint64_t>(hi_run, (uint64_t)col_hi[s] + 1);
+    E->ell_tile_x_end[k] = (hi_run + 63) & ~(uint64_t)63;  // whole 512-byte pieces
+  }
+  E->ell_x_begin = lo_all == E->x_len ? 0 : (lo_all & ~(uint64_t)63);
+}
+
+// an engine over the host-built ELL image of layout A (sizes, x ranges and vectors follow the API layout; the hw_matrix
+// stream itself is not uploaded)
 static int engine_create_ell(const Layout *A, int device, Engine **out) {
   *out = nullptr;
   const EllImage *I = A->ell;
@@ -782,28 +816,10 @@ static int engine_create_ell(const Layout *A, int device, Engine **out) {
   auto upload = [&]() -> int {
     int r = engine_adopt_layout(E, A);
     if (r) return r;
-    E->ell = true; E->wide = false; E->cu_major = false; E->irregular = false; E->tall = false;
-    E->ell_slices = I->n_slices; E->ell_width = I->width; E->ell_slice_bytes = I->slice_bytes;
-    E->n_chunks = I->n_slices; E->n_pairs = 0; E->stream_bytes = I->bytes; E->zero_all = false; E->n_zero_rows = 0;
-    E->dev_cu = 1; E->dev_vf = 1; E->auto_variant = kVariantEll;
-    CUDA_TRY(cudaMalloc((void **)&E->d_ell, std::max<uint64_t>(I->bytes, 16)));
+    uint8_t *d_image = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d_image, std::max<uint64_t>(I->bytes, 16)));
+    engine_set_ell(E, d_image, I->n_slices, I->width, I->slice_bytes, I->col_lo.data(), I->col_hi.data());
     CUDA_TRY(cudaMemcpyAsync(E->d_ell, I->image, I->bytes, cudaMemcpyHostToDevice, E->stream));
-    // row tiles of the end-to-end pipeline: equal slice counts; x[.., end) each tile needs = running maximum of the
-    // slices' last columns (whatever lies below the window of a later tile is on the device by then)
-    int T = options().ell_tiles > 0 ? (int)std::min<int64_t>(options().ell_tiles, 256) : 8;
-    T = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)T, I->n_slices));
-    E->ell_tile_slice.assign((size_t)T + 1, 0);
-    for (int k = 0; k <= T; k++) E->ell_tile_slice[k] = (uint32_t)((uint64_t)I->n_slices * k / T);
-    E->ell_tile_x_end.assign((size_t)T, 0);
-    uint64_t lo_all = E->x_len, hi_run = 0;
-    for (uint32_t s = 0; s < I->n_slices; s++)
-      if (I->col_lo[s] <= I->col_hi[s]) lo_all = std::min<uint64_t>(lo_all, I->col_lo[s]);
-    for (int k = 0; k < T; k++) {
-      for (uint32_t s = E->ell_tile_slice[k]; s < E->ell_tile_slice[k + 1]; s++)
-        if (I->col_lo[s] <= I->col_hi[s]) hi_run = std::max<uint64_t>(hi_run, (uint64_t)I->col_hi[s] + 1);
-      E->ell_tile_x_end[k] = (hi_run + 63) & ~(uint64_t)63;  // whole 512-byte pieces
-    }
-    E->ell_x_begin = lo_all == E->x_len ? 0 : (lo_all & ~(uint64_t)63);
     CUDA_TRY(cudaMemsetAsync(E->d_x, 0, E->x_len * E->vb, E->stream));
     CUDA_TRY(cudaMemsetAsync(E->d_y, 0, (size_t)E->rows * E->vb, E->stream));
     CUDA_TRY(cudaStreamSynchronize(E->stream));
@@ -813,6 +829,60 @@ static int engine_create_ell(const Layout *A, int device, Engine **out) {
   if (rc) { spmvb_engine_free((spmvb_engine *)E); return rc; }
   *out = E;
   return SPMVB_OK;
+}
+
+// GPU-built engines (spmvb_engine_create_from_csr): the ELL image built on the device from the device-resident CSR
+// (ell_gpu.cuh), timed against the stream image the engine already runs; the faster stays.  The API image is kept for
+// spmvb_engine_fetch_layout either way.
+static int engine_try_ell_gpu(Engine *E, const Layout *L, uint32_t rows, uint64_t nnz, const uint64_t *rp, const uint32_t *ci,
+                              const void *va) {
+  if (options().ell == 0 || nnz == 0) return SPMVB_OK;
+  const uint32_t n_slices = (rows + kEllSliceRows - 1) / kEllSliceRows;
+  uint32_t *d_lohi = nullptr; EllScan *d_scan = nullptr; uint8_t *d_image = nullptr;
+  auto run = [&]() -> int {
+    CUDA_TRY(cudaMalloc((void **)&d_lohi, (size_t)n_slices * 8));
+    CUDA_TRY(cudaMalloc((void **)&d_scan, sizeof(EllScan)));
+    CUDA_TRY(cudaMemsetAsync(d_scan, 0, sizeof(EllScan), E->stream));
+    const int grid = (int)(((uint64_t)n_slices * 32 + 255) / 256);
+    ell_scan_kernel<<<grid, 256, 0, E->stream>>>(rows, rp, ci, n_slices, d_lohi, d_lohi + n_slices, d_scan);
+    EllScan scan;
+    CUDA_TRY(cudaMemcpyAsync(&scan, d_scan, sizeof scan, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    const uint64_t slots = (uint64_t)n_slices * kEllSliceRows * scan.width;
+    if (scan.width == 0 || scan.width > (uint32_t)kEllMaxWidth || scan.bad) return SPMVB_OK;
+    if (options().ell < 1 && (double)slots > 1.04 * (double)nnz) return SPMVB_OK;
+    const uint32_t sb = ell_slice_bytes(scan.width, E->vb);
+    CUDA_TRY(cudaMalloc((void **)&d_image, std::max<uint64_t>((uint64_t)n_slices * sb, 16)));
+    if (E->is_double)
+      ell_fill_kernel<double><<<grid, 256, 0, E->stream>>>(rows, rp, ci, (const double *)va, n_slices, scan.width, sb, d_lohi,
+                                                            d_lohi + n_slices, d_image);
+    else
+      ell_fill_kernel<float><<<grid, 256, 0, E->stream>>>(rows, rp, ci, (const float *)va, n_slices, scan.width, sb, d_lohi,
+                                                           d_lohi + n_slices, d_image);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<uint32_t> lohi((size_t)n_slices * 2);
+    CUDA_TRY(cudaMemcpyAsync(lohi.data(), d_lohi, lohi.size() * 4, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+    float t_cur = 0.f, t_ell = 0.f;
+    int rc = engine_time_step(E, 5, &t_cur);
+    if (rc) return rc;
+    const int auto_before = E->auto_variant;
+    engine_set_ell(E, d_image, n_slices, scan.width, sb, lohi.data(), lohi.data() + n_slices);
+    rc = engine_time_step(E, 5, &t_ell);
+    if (rc) return rc;
+    E->tune_ms[E->wide ? 2 : (L->dev ? 1 : 0)] = t_cur; E->tune_ms[3] = t_ell;
+    if (t_ell < t_cur || options().ell == 1) {
+      d_image = nullptr;  // owned by the engine now; the stream image stays (spmvb_engine_set_variant, fetch_layout)
+    } else {
+      E->ell = false; E->d_ell = nullptr; E->ell_slices = 0; E->ell_width = 0; E->ell_slice_bytes = 0;
+      E->auto_variant = auto_before;
+      E->ell_tile_slice.clear(); E->ell_tile_x_end.clear();
+    }
+    return SPMVB_OK;
+  };
+  const int rc = run();
+  cudaFree(d_lohi); cudaFree(d_scan); cudaFree(d_image);
+  return rc;
 }
 
 // milliseconds of one y = A x (clear rows + kernel) with the engine's own kernel choice, best of `reps` after a warm-up
@@ -905,7 +975,7 @@ int spmvb_engine_create(const spmvb_layout *l, int device, int variant, spmvb_en
     if (rc) { spmvb_engine_free((spmvb_engine *)E); spmvb_engine_free((spmvb_engine *)E3); return rc; }
     E->tune_ms[3] = t_ell;
     for (int i = 0; i < 4; i++) E3->tune_ms[i] = E->tune_ms[i];
-    if (t_ell < t_cur) std::swap(E, E3);
+    if (t_ell < t_cur || options().ell == 1) std::swap(E, E3);
     spmvb_engine_free((spmvb_engine *)E3);
   }
   *out = (spmvb_engine *)E;
@@ -983,6 +1053,10 @@ int spmvb_engine_create_from_csr(uint32_t rows, uint32_t cols, const uint64_t *r
     if (r) return r;
     r = engine_finish(E, D);
     if (r) return r;
+    if (variant == kVariantDefault && options().autotune != 0) {  // regular matrix: the sliced-ELLPACK image as well
+      r = engine_try_ell_gpu(E, L, rows, nnz, rp, ci, va);
+      if (r) return r;
+    }
     CUDA_TRY(cudaEventElapsedTime(&E->build_ms[0], ev[0], ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&E->build_ms[1], ev[1], ev[2]));
     return SPMVB_OK;
@@ -1053,8 +1127,11 @@ void spmvb_engine_free(spmvb_engine *e) {
 
 int spmvb_engine_set_variant(spmvb_engine *e, int variant) {
   if (!e || variant < 0 || variant > 10) return fail(SPMVB_E_ARG, "variant");
-  if (variant != 0 && (((Engine *)e)->wide != (variant == kVariantWide) || ((Engine *)e)->ell != (variant == kVariantEll)))
-    return fail(SPMVB_E_ARG, "variant: the wide image and the ELL image have their own kernels (9, 10) and only those");
+  const Engine *E0 = (const Engine *)e;
+  if (variant == kVariantEll && !E0->ell) return fail(SPMVB_E_ARG, "variant 10: this engine holds no ELL image");
+  if (variant != 0 && variant != kVariantEll && (!E0->d_stream || E0->wide != (variant == kVariantWide)))
+    return fail(SPMVB_E_ARG, "variant: this engine holds no image that kernel can walk (the wide image has its own kernel, 9; "
+                             "a host-built ELL engine holds the ELL image only)");
   ((Engine *)e)->variant = variant;
   return SPMVB_OK;
 }
@@ -1157,7 +1234,7 @@ int spmvb_engine_get_y(spmvb_engine *e, void *y_host, uint32_t n, int accumulate
 int spmvb_engine_spmv_host(spmvb_engine *e, const void *x_host, uint32_t n, void *y_host, int accumulate) {
   Engine *E = (Engine *)e;
   if (!E) return fail(SPMVB_E_ARG, "spmv_host");
-  if (E->ell && x_host && y_host && options().e2e_tiles != 0 && E->ell_tile_slice.size() > 2) {
+  if (ell_on(E) && x_host && y_host && options().e2e_tiles != 0 && E->ell_tile_slice.size() > 2) {
     CUDA_TRY(cudaSetDevice(E->device));
     return E->is_double ? spmv_host_ell<double>(E, x_host, n, y_host, accumulate) : spmv_host_ell<float>(E, x_host, n, y_host, accumulate);
   }
@@ -1338,6 +1415,21 @@ int spmvb_debug_bounds_errors(uint64_t *out5) {
 #endif
 }
 
+// for tests: the ELL image the engine streams (device -> host); returns its size in bytes, 0 when the engine streams
+// something else
+int64_t spmvb_engine_ell_image(spmvb_engine *e, void *out, uint64_t max_bytes) {
+  Engine *E = (Engine *)e;
+  if (!E) return fail(SPMVB_E_ARG, "ell_image");
+  if (!E->ell) return 0;
+  const uint64_t bytes = (uint64_t)E->ell_slices * E->ell_slice_bytes;
+  if (out && max_bytes >= bytes) {
+    CUDA_TRY(cudaSetDevice(E->device));
+    CUDA_TRY(cudaMemcpyAsync(out, E->d_ell, bytes, cudaMemcpyDeviceToHost, E->stream));
+    CUDA_TRY(cudaStreamSynchronize(E->stream));
+  }
+  return (int64_t)bytes;
+}
+
 float spmvb_engine_last_iter_ms(const spmvb_engine *e) { return e ? ((const Engine *)e)->last_iter_ms : 0.f; }
 
 int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out) {
@@ -1345,10 +1437,13 @@ int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out) {
   if (!E || !out) return fail(SPMVB_E_ARG, "device_layout");
   out[0] = (uint64_t)E->dev_cu; out[1] = (uint64_t)E->dev_vf; out[2] = E->cdb; out[3] = E->cu_major ? 1u : 0u;
   out[4] = E->n_pairs; out[5] = E->n_chunks; out[6] = E->zero_all ? UINT64_MAX : (uint64_t)E->n_zero_rows;
-  out[7] = E->stream_bytes; out[8] = (uint64_t)E->n_tiles; out[9] = E->tall ? 1u : 0u; out[10] = (uint64_t)E->xs_cfg;
+  out[7] = E->stream_bytes;
+  if (ell_on(E)) {  // no pairs, no chunks, no rows to clear: slices
+    out[0] = 1; out[1] = 1; out[4] = 0; out[5] = E->ell_slices; out[6] = 0; out[7] = (uint64_t)E->ell_slices * E->ell_slice_bytes;
+  } out[8] = (uint64_t)E->n_tiles; out[9] = E->tall ? 1u : 0u; out[10] = (uint64_t)E->xs_cfg;
   out[11] = (uint64_t)(E->tune_ms[0] * 1000.f); out[12] = (uint64_t)(E->tune_ms[1] * 1000.f);
   out[13] = E->wide ? 1u : 0u; out[14] = (uint64_t)(E->tune_ms[2] * 1000.f); out[15] = (uint64_t)E->blocks;
-  out[16] = E->ell ? 1u : 0u; out[17] = (uint64_t)(E->tune_ms[3] * 1000.f); out[18] = E->ell_width;
+  out[16] = ell_on(E) ? 1u : 0u; out[17] = (uint64_t)(E->tune_ms[3] * 1000.f); out[18] = E->ell_width;
   out[19] = (uint64_t)(E->ell_tile_slice.empty() ? 0 : E->ell_tile_slice.size() - 1);
   return SPMVB_OK;
 }

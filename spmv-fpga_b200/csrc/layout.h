@@ -167,7 +167,8 @@ struct Options {
   int64_t tile_launch = -1;   // 1: one kernel launch per row tile with the tile's y range as persisting L2 window
   int64_t e2e_tiles = -1;     // 0: spmv_host does not pipeline row tiles (one launch, then the copy of y)
   int64_t wide = -1;          // wide image: 1 build one (a third candidate for the engine), otherwise none
-  int64_t ell = -1;           // sliced-ELLPACK image: 0 never, 1 whenever the format can hold the matrix, -1 when it is (almost) free
+  int64_t ell = -1;           // sliced-ELLPACK image: 0 never; 1 build and use it whenever the format can hold the matrix;
+                              // -1 build it when its padding is (almost) free and use it when it measures faster
   int64_t ell_tiles = -1;     // row tiles of the end-to-end pipeline over an ELL image (x up / kernel / y down overlapped)
   int64_t wide_range_log2 = -1;  // log2 of the column-block width of the wide image (2..23)
   int64_t wide_hints = -1;    // L2 policies of the wide kernel: bit 0 x gathers evict-last, bit 1 y updates / row map evict-first

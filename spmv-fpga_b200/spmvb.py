@@ -27,12 +27,14 @@ SYMBOLS = {
     "spmvb_layout_device_params": (_int, [_vp, _vp]),
     "spmvb_layout_x_lines_per_chunk": (ctypes.c_double, [_vp]),
     "spmvb_layout_ell_params": (_int, [_vp, _vp]),
+    "spmvb_layout_ell_image": (ctypes.c_int64, [_vp, _vp, ctypes.c_uint64]),
     "spmvb_layout_ell_decode": (ctypes.c_int64, [_vp, _vp, _vp, ctypes.c_uint64]),
     "spmvb_layout_wide_params": (_int, [_vp, _vp]),
     "spmvb_layout_wide_decode": (ctypes.c_int64, [_vp, _vp, _vp, _vp, ctypes.c_uint64]),
     "spmvb_debug_bounds_errors": (_int, [_vp]),
     "spmvb_engine_last_iter_ms": (ctypes.c_float, [_vp]),
     "spmvb_engine_device_layout": (_int, [_vp, _vp]),
+    "spmvb_engine_ell_image": (ctypes.c_int64, [_vp, _vp, ctypes.c_uint64]),
     "spmvb_layout_build": (_int, [_u32, _u32, _vp, _vp, _vp, _int, _int, _int, _u32, _vp]),
     "spmvb_layout_build_u32": (_int, [_u32, _u32, _vp, _vp, _vp, _int, _int, _int, _u32, _vp]),
     "spmvb_layout_free": (None, [_vp]),
@@ -373,6 +375,15 @@ class Layout:
         v = [int(x) for x in out]
         return dict(present=bool(v[0]), width=v[1], slices=v[2], slice_bytes=v[3], slots=v[4], bytes=v[5], nnz=v[6])
 
+    def ell_image(self):
+        """The bytes of the host-built ELL image (None without one)."""
+        n = lib().spmvb_layout_ell_image(self.h, None, 0)
+        if n <= 0:
+            return None
+        out = np.zeros(n, np.uint8)
+        assert lib().spmvb_layout_ell_image(self.h, _ptr(out), n) == n
+        return out
+
     def ell_decode(self):
         """(cols, values) of every slot of the ELL image, row-major: arrays of shape (slices * 32, width)."""
         e = self.ell_params
@@ -563,6 +574,15 @@ class Engine:
                     zero_rows=-1 if v[6] == 2 ** 64 - 1 else v[6], bytes=v[7], e2e_tiles=v[8], tall=bool(v[9]), xs_config=v[10],
                     wide=bool(v[13]), blocks=v[15], ell=bool(v[16]), ell_width=v[18], ell_e2e_tiles=v[19],
                     tuned_us=dict(api_image=v[11], device_layout=v[12], wide_image=v[14], ell_image=v[17]))
+
+    def ell_image(self):
+        """The bytes of the sliced-ELLPACK image the engine streams (None when it streams something else)."""
+        n = lib().spmvb_engine_ell_image(self.h, None, 0)
+        if n <= 0:
+            return None
+        out = np.zeros(n, np.uint8)
+        assert lib().spmvb_engine_ell_image(self.h, _ptr(out), n) == n
+        return out
 
     def set_variant(self, v):
         _check(lib().spmvb_engine_set_variant(self.h, v))

@@ -133,3 +133,32 @@ def test_gpu_builder_rmat_scale20(spmvb, cu):
     eng.fetch_layout()
     assert host.difference(lay) == ""
     print("\nR-MAT scale 20 CU=%d: GPU build kernels %.2f ms" % (cu, eng.build_ms()["build_ms"]))
+
+
+@pytest.mark.parametrize("isd", [True, False], ids=["f64", "f32"])
+@pytest.mark.parametrize("case", ["kat6x6", "band10k", "lap_wide"])
+def test_gpu_built_ell_image_equals_host_built(spmvb, oracle, case, isd):
+    """Regular matrices: the sliced-ELLPACK image built by CUDA kernels from the device-resident CSR (ell_gpu.cuh) is
+    the host builder's, byte for byte; a GPU-built engine keeps it NEXT to the hw_matrix stream, so every kernel
+    variant stays available and the API image can still be fetched."""
+    M = CASES[case]()
+    rows, cols, rp, ci, va = M
+    va = va.astype(oa.vdtype(isd))
+    with spmvb.options(ell=1):                      # use it whenever the format can hold the matrix
+        host = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, isd)
+        lay, eng = spmvb.Engine.from_csr(rows, cols, rp, ci, va, 1, 1, isd)
+    assert eng.variant == 10 and eng.device_layout["ell"]
+    assert np.array_equal(eng.ell_image(), host.ell_image())
+    _parity(oracle, eng, M, isd)
+    for variant in (7, 8, 10, 0):
+        eng.set_variant(variant)
+        _parity(oracle, eng, M, isd)
+    eng.fetch_layout()
+    assert host.difference(lay) == ""
+    eng.free(); lay.free(); host.free()
+    with spmvb.options(ell=0):
+        lay, eng = spmvb.Engine.from_csr(rows, cols, rp, ci, va, 1, 1, isd)
+    assert eng.ell_image() is None and eng.variant != 10
+    with pytest.raises(spmvb.SpmvbError):
+        eng.set_variant(10)
+    eng.free(); lay.free()
