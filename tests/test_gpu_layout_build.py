@@ -113,7 +113,8 @@ def test_gpu_builder_at_config2_scale(spmvb, oracle):
     ms = eng.build_ms()
     eng.fetch_layout()
     assert host.difference(lay) == ""
-    assert eng.variant == 7
+    # a regular matrix: the engine also builds the sliced-ELLPACK image on the GPU and keeps whichever kernel it measured faster
+    assert eng.variant in (7, 10) and eng.device_layout["tuned_us"]["ell_image"] > 0
     x = np.random.default_rng(5).random(cols)
     y = np.zeros(rows)
     eng.spmv_host(x, y, accumulate=True)
