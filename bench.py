@@ -85,11 +85,14 @@ def workload_spec(name, args, world):
     return spec
 
 
-def rmat_row_bounds(scale, world, p_one=0.24):
-    """Row ranges with (almost) equal expected non-zero count for an R-MAT matrix without vertex permutation: every row
-    bit is 1 with probability c + d independently, so the row CDF has a closed form (no need to generate the matrix on
-    every rank just to balance it)."""
+def rmat_row_bounds(scale, world, p_one=0.24, row_weight=0.0, edge_factor=16):
+    """Row ranges with (almost) equal expected COST for an R-MAT matrix without vertex permutation: every row bit is 1
+    with probability c + d independently, so the row CDF of the non-zeros has a closed form (no need to generate the
+    matrix on every rank just to balance it).  cost = non-zeros + row_weight x rows: the sparse end of the matrix costs
+    more per non-zero than the dense end (one y update and one row-map entry per (row, block) pair), see
+    scripts/exp_partition.py; row_weight = 0 balances the non-zeros alone."""
     n = 1 << scale
+    nnz_total = float(edge_factor) * n
 
     def cdf(r):  # P(row < r)
         acc, pref = 0.0, 1.0
@@ -106,7 +109,7 @@ def rmat_row_bounds(scale, world, p_one=0.24):
         lo, hi = 0, n
         while lo < hi:
             mid = (lo + hi) // 2
-            if cdf(mid) < j / world:
+            if (cdf(mid) * nnz_total + row_weight * mid) / (nnz_total + row_weight * n) < j / world:
                 lo = mid + 1
             else:
                 hi = mid

@@ -224,8 +224,8 @@ int64_t spmvb_engine_ell_image(spmvb_engine *e, void *out, uint64_t max_bytes);
 float spmvb_engine_last_iter_ms(const spmvb_engine *e);
 /* out[20] = the device layout in use: {compute units, VF, column-block width, CU-major, pairs, chunks, rows cleared per
  * SpMV (UINT64_MAX = all), image bytes, row tiles spmv_host pipelines (0 = none), 1 = explicit L2 policies, x-window kernel configuration (0 wide / 1 medium /
- * 2 narrow), microseconds of one SpMV measured at creation for {the API image with global gathers, the device layout} (0 =
- * not measured), 1 = the wide image is what is streamed, microseconds of one SpMV over the wide image, column blocks,
+ * 2 narrow), microseconds of one SpMV measured at creation for {the API image with global gathers, the device layout - or, for an
+ * irregular matrix without one, the x-window kernel on the same image} (0 = not measured), 1 = the wide image is what is streamed, microseconds of one SpMV over the wide image, column blocks,
  * 1 = the sliced-ELLPACK image is what is streamed, microseconds of one SpMV over it, its width (slots per row), row tiles of
  * its end-to-end pipeline} */
 int spmvb_engine_device_layout(const spmvb_engine *e, uint64_t *out);

@@ -356,14 +356,17 @@ static int do_spmv(Engine *E, const void *x_dev, void *y_dev, int accumulate, cu
 // gathers touch one 128-byte line per entry, 2 cycles of L1 tag time each - and it is required for tall matrices
 // (CU-major order, x streamed once per row tile).  Banded matrices keep the global gathers with more resident warps.
 // The same criterion (layout_is_irregular: distinct x lines per chunk) decides the engine-private device layout (plan_device_params), so that the
-// windows of the chosen kernel fit.  Option autotune = 1 times both kernels on the actual matrix instead (not under a
-// profiler: the timings are noise there).
+// windows of the chosen kernel fit.  Where that rule would take the x-window kernel the two kernels are also TIMED on the
+// actual matrix (three SpMVs each; option autotune = 0 keeps the rule's choice, e.g. under a profiler where timings are
+// noise): the rule is right for whole matrices, but a row shard of an irregular matrix - one GPU's part of a group - has
+// to load every x window for an eighth of the entries, and the global-gather kernel is the faster one there (R-MAT scale
+// 24 in fp32, 8 shards: 0.25-0.33 ms per shard with the x-window kernel against 1.07 ms for the whole matrix).
 static int autotune(Engine *E) {
   if (E->wide) { E->auto_variant = kVariantWide; return SPMVB_OK; }
   E->auto_variant = kVariantOcc3;
   if (E->n_chunks == 0 || E->xs_windowed_frac < 0.5) return SPMVB_OK;
   if (E->cu_major || E->irregular) E->auto_variant = kVariantXs;
-  if (options().autotune <= 0) return SPMVB_OK;
+  if (options().autotune == 0 || E->auto_variant != kVariantXs || E->variant != kVariantDefault) return SPMVB_OK;
   const int cand[2] = {kVariantOcc3, kVariantXs};
   cudaEvent_t a, b;
   CUDA_TRY(cudaEventCreate(&a));
