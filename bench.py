@@ -85,31 +85,49 @@ def workload_spec(name, args, world):
     return spec
 
 
-def rmat_row_bounds(scale, world, p_one=0.24, row_weight=0.0, edge_factor=16):
-    """Row ranges with (almost) equal expected COST for an R-MAT matrix without vertex permutation: every row bit is 1
-    with probability c + d independently, so the row CDF of the non-zeros has a closed form (no need to generate the
-    matrix on every rank just to balance it).  cost = non-zeros + row_weight x rows: the sparse end of the matrix costs
-    more per non-zero than the dense end (one y update and one row-map entry per (row, block) pair), see
-    scripts/exp_partition.py; row_weight = 0 balances the non-zeros alone."""
+def rmat_row_bounds(scale, world, p_one=0.24, pair_weight=0.0, edge_factor=16, cdb=32768):
+    """Row ranges of (almost) equal expected COST for an R-MAT matrix without vertex permutation.  Every row bit is 1
+    with probability c + d independently, so a row's expected length depends on its number of 1-bits only and prefix
+    sums over rows have a closed form (no need to generate the matrix on every rank just to balance it).
+    cost(row) = non-zeros + pair_weight x (row, column block) pairs: the sparse end of the matrix costs more per non-zero
+    than the dense end - one y update and one row-map entry per pair (measured on the 8 shards of scale 24, each timed by
+    itself on one GPU, scripts/exp_partition.py: t = 2.75 ns/Mnnz + 5.1 ns/Mpair in fp32, 3.8 + 5.2 in fp64).  The
+    expected number of distinct column blocks a row of expected length L touches is sum_b 1 - (1 - q_b)^L with q_b the
+    probability of block b (column bits are 1 with probability b + d); it agrees with the built layouts within 3 %.
+    pair_weight = 0 balances the non-zeros alone."""
+    from math import comb
     n = 1 << scale
     nnz_total = float(edge_factor) * n
+    q_one = 0.24  # b + d
+    block_bits = max(0, scale - (cdb.bit_length() - 1))
+    q = [(q_one ** j) * ((1.0 - q_one) ** (block_bits - j)) for j in range(block_bits + 1)]
 
-    def cdf(r):  # P(row < r)
-        acc, pref = 0.0, 1.0
+    def row_cost(ones):
+        length = nnz_total * (p_one ** ones) * ((1.0 - p_one) ** (scale - ones))
+        if pair_weight == 0.0:
+            return length
+        pairs = sum(comb(block_bits, j) * (1.0 - (1.0 - q[j]) ** length) for j in range(block_bits + 1))
+        return length + pair_weight * pairs
+
+    cost_of = [row_cost(o) for o in range(scale + 1)]
+
+    def prefix(r):  # cost of rows [0, r): r splits into aligned cubes whose rows share their leading bits
+        if r >= n:
+            return sum(comb(scale, o) * cost_of[o] for o in range(scale + 1))
+        acc, ones = 0.0, 0
         for k in range(scale - 1, -1, -1):
             if (r >> k) & 1:
-                acc += pref * (1.0 - p_one)
-                pref *= p_one
-            else:
-                pref *= (1.0 - p_one)
+                acc += sum(comb(k, j) * cost_of[ones + j] for j in range(k + 1))
+                ones += 1
         return acc
 
+    total = prefix(n)
     bounds = [0]
     for j in range(1, world):
         lo, hi = 0, n
         while lo < hi:
             mid = (lo + hi) // 2
-            if (cdf(mid) * nnz_total + row_weight * mid) / (nnz_total + row_weight * n) < j / world:
+            if prefix(mid) < total * j / world:
                 lo = mid + 1
             else:
                 hi = mid
@@ -118,9 +136,13 @@ def rmat_row_bounds(scale, world, p_one=0.24, row_weight=0.0, edge_factor=16):
     return bounds
 
 
-def shard_bounds(spec, world):
+# pairs cost 1.85 (fp32) / 1.37 (fp64) non-zeros each on B200 (see rmat_row_bounds)
+RMAT_PAIR_WEIGHT = {True: 1.37, False: 1.85}
+
+
+def shard_bounds(spec, world, is_double=True):
     if spec["kind"] == "rmat":
-        return rmat_row_bounds(spec["scale"], world)
+        return rmat_row_bounds(spec["scale"], world, pair_weight=RMAT_PAIR_WEIGHT[bool(is_double)])
     rows = spec["rows"]
     return [rows * r // world // 4 * 4 for r in range(world)] + [rows]
 
@@ -363,7 +385,7 @@ def measure_spmv(ctx, name, args, steps, warmup, e2e_steps, with_cpu_baseline):
     vt = np.float64 if is_double else np.float32
     vb = 8 if is_double else 4
     spec = workload_spec(name, args, world)
-    bounds = shard_bounds(spec, world)
+    bounds = shard_bounds(spec, world, is_double)
     rb, re = bounds[rank], bounds[rank + 1]
 
     t0 = time.perf_counter()
@@ -542,7 +564,7 @@ def measure_poweriter(ctx, args, steps, warmup):
     vb = 8 if is_double else 4
     spec = workload_spec("poweriter", args, world)
     n = spec["rows"]
-    bounds = rmat_row_bounds(spec["scale"], world)
+    bounds = shard_bounds(spec, world, is_double)   # equal expected cost (non-zeros + weighted pairs), not equal non-zeros
     rb, re = bounds[rank], bounds[rank + 1]
     t0 = time.perf_counter()
     csr = make_matrix(spmvb, spec, is_double, rb, re)

@@ -1,6 +1,6 @@
 """Row partitions of the R-MAT matrix for 8 GPUs, evaluated on ONE GPU: every shard's SpMV step (clear rows + kernel) is
 timed by itself, the slowest shard is what an 8-GPU iteration waits for.  Partitions: equal expected cost
-nnz + w x rows for several w (w = 0: the non-zero balance of round 1).
+non-zeros + w x (row, block) pairs for several w (w = 0: the non-zero balance of round 1; see bench.rmat_row_bounds).
     python scripts/exp_partition.py <scale> <f32|f64> <parts> w0 w1 ...        JSON lines on stdout"""
 import json
 import os
@@ -22,7 +22,7 @@ vt = np.float64 if isd else np.float32
 n = 1 << scale
 x = np.random.default_rng(1).random(n).astype(vt)
 for w in weights:
-    bounds = rmat_row_bounds(scale, parts, row_weight=w)
+    bounds = rmat_row_bounds(scale, parts, pair_weight=w)
     shards = []
     for k in range(parts):
         rb, re = bounds[k], bounds[k + 1]
@@ -41,7 +41,7 @@ for w in weights:
         eng.free()
         print("w=%g shard %d rows %d nnz %d pairs %d variant %d: %.4f ms" % (w, k, re - rb, A.nnz, pairs, shards[-1]["variant"],
                                                                                shards[-1]["step_ms"]), file=sys.stderr, flush=True)
-    line = dict(scale=scale, dtype=dtype, parts=parts, row_weight=w, bounds=bounds, shards=shards,
+    line = dict(scale=scale, dtype=dtype, parts=parts, pair_weight=w, bounds=bounds, shards=shards,
                 slowest_ms=max(s["step_ms"] for s in shards), mean_ms=float(np.mean([s["step_ms"] for s in shards])))
     print(json.dumps(line), flush=True)
     print("w=%g: slowest %.4f ms, mean %.4f ms" % (w, line["slowest_ms"], line["mean_ms"]), file=sys.stderr, flush=True)
