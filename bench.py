@@ -506,6 +506,11 @@ def measure_spmv(ctx, name, args, steps, warmup, e2e_steps, with_cpu_baseline):
                      "what": "rank 0's kernel: nnz*(2+vb) + rows*vb + x_touched*vb bytes / CUDA-event time of the launch; "
                              "aggregate_frac = all ranks' bytes / slowest rank's kernel / (N x peak)"},
         "scatter_roofline": scatter_roofline(dev, nnz_local, k_ms),
+        "l2_note": ("back-to-back steps run faster than the measured DRAM copy rate would allow for the algorithmic bytes: x and y "
+                    "(%d MB of them) fit the 126 MB L2 next to the evict-first stream and are partly reused from one step to the "
+                    "next, and the next launch's prologue overlaps the previous kernel's tail (programmatic dependent launch); "
+                    "roofline.achieved uses the per-launch event time instead, roofline.traffic is what one launch moves in DRAM"
+                    % (int((csr.rows + csr.cols) * vb) >> 20)) if eff_gbs > peak * world else None,
         "check": {"max_err_over_tolerance": err_all, "e2e_accumulated_max_err_over_tolerance": err_acc_all,
                   "what": "every row of every rank against the oracle's CSR SpMV, |y - gold| <= %g x row-wise |A||x|" % TOL[is_double],
                   "seconds": t_check},
