@@ -438,15 +438,36 @@ def measure_spmv(ctx, name, args, steps, warmup, e2e_steps, with_cpu_baseline):
     eff_gbs = alg_total / (ms_per_step * 1e-3) / 1e9
 
     # ---- end to end through the C-ABI call with host buffers (spmv_hw semantics: H2D x, SpMV, D2H y, y_host += y)
+    #      On several GPUs the call is the multi-GPU one of the C ABI (spmvb_group_spmv_host_rows): the group decides how x
+    #      reaches the GPUs - 1/N of it per PCIe link + one in-place NCCL all-gather over NVLink when every shard reads all
+    #      of x, the band each shard reads otherwise.
     xp = (x_host.data_ptr(), csr.cols)
     yp = y_host.data_ptr()
+    grp = None
+    if world > 1:
+        u = torch.from_numpy(spmvb.Group.unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+        ctx.dist.broadcast(u, src=0)
+        grp = spmvb.Group.adopt(eng, spec["rows"], csr.cols, bounds, ctx.local_rank, u.cpu().numpy(), rank, world)
+
+    def e2e_call():
+        if grp is not None:
+            grp.spmv_host_rows(xp, yp, accumulate=True)
+        else:
+            eng.spmv_host(xp, yp, accumulate=True)
+
     for _ in range(2):
-        eng.spmv_host(xp, yp, accumulate=True)
+        e2e_call()
     ctx.barrier(eng)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.spmv_host(xp, yp, accumulate=True)
+        e2e_call()
     ctx.barrier(eng)
+    x_links = grp is not None and grp.x_over_links == 1
+    if x_links:  # x crosses the host links once in total, not once per GPU
+        x_upload_local = int(-(-csr.cols // world) * vb)
+        x_upload_total = ctx.reduce([x_upload_local])[0]
+    if grp is not None:
+        grp.free()
     e2e_s = ctx.reduce([time.perf_counter() - t0], "max")[0]
     e2e_gflops = 2.0 * nnz_total * e2e_steps / e2e_s / 1e9
 
@@ -495,7 +516,11 @@ def measure_spmv(ctx, name, args, steps, warmup, e2e_steps, with_cpu_baseline):
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": int(x_upload_total),
                 "d2h_bytes_per_step": int(spec["rows"] * vb), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                "what": "spmvb_engine_spmv_host: pinned x -> GPU, kernel, y -> pinned host, y_host += y (spmv_hw semantics)"},
+                "what": ("spmvb_group_spmv_host_rows: every GPU uploads 1/N of the pinned x over its own PCIe link, one in-place "
+                         "ncclAllGather over NVLink replicates it, kernels, y slices -> pinned host, y_host += y (spmv_hw semantics)")
+                if x_links else
+                ("spmvb_group_spmv_host_rows" if world > 1 else "spmvb_engine_spmv_host") +
+                ": pinned x -> GPU, kernel, y -> pinned host, y_host += y (spmv_hw semantics)"},
         "gpu_launches": int(launches_total),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(name, dtype, world, variant), "peak_source": peak_src,

@@ -275,6 +275,16 @@ int spmvb_group_rank(const spmvb_group *g, int local_index);
 /* spmv_hw (csr_hw_wrapper.cpp:193-288) over the group with HOST buffers: x (n values) to every GPU, all kernels
  * concurrently, every local GPU's rows of y into their place of y_host (global row index; accumulate like spmv_hw). */
 int spmvb_group_spmv_host(spmvb_group *g, const void *x_host, uint32_t n, void *y_host, int accumulate);
+/* The same with y_rows holding the rows of this process's GPUs only (y_rows[0] = first row of the first local GPU).
+ * How x reaches the GPUs is decided once per group, collectively: when every GPU reads (almost) all of x - an irregular
+ * matrix - each GPU uploads 1/world of x over its own PCIe link and one in-place ncclAllGather over NVLink fills every
+ * GPU's x (world x fewer host bytes); row shards of a banded matrix keep uploading the band they read.
+ * spmvb_group_x_over_links: 1 / 0 once decided, -1 before the first call.  Collective across a multi-process group. */
+int spmvb_group_spmv_host_rows(spmvb_group *g, const void *x_host, uint32_t n, void *y_rows, int accumulate);
+int spmvb_group_x_over_links(const spmvb_group *g);
+/* One rank of a multi-process group around an engine the caller created and keeps (spmvb_group_free leaves it alone). */
+int spmvb_group_adopt_engine(uint32_t global_rows, uint32_t cols, const uint32_t *bounds, spmvb_engine *engine, int is_double,
+                             int device, const uint8_t *unique_id128, int rank, int world, spmvb_group **out);
 int spmvb_group_set_x(spmvb_group *g, const void *x_host, uint32_t n);
 int spmvb_group_get_x(spmvb_group *g, void *x_host, uint32_t n); /* from the first local GPU */
 int spmvb_group_get_y(spmvb_group *g, void *y_host);             /* local GPUs' rows into their place of y_host */

@@ -122,6 +122,7 @@ struct Member {  // one GPU of this process
   int rank = 0, device = 0;
   spmvb_layout *layout = nullptr;
   spmvb_engine *engine = nullptr;
+  bool engine_borrowed = false;  // spmvb_group_adopt_engine: the caller keeps the engine
   ncclComm_t comm = nullptr;
   double *d_scalar = nullptr;
   double *d_token = nullptr;   // 8 bytes all-reduced as a barrier between the peer stores and whoever reads x next
@@ -144,6 +145,10 @@ struct Group {
   uint64_t nnz_local = 0;
   int exchange = 0;            // 0 NCCL grouped broadcasts, 1 peer stores to all, 2 peer stores to the forwarder + all-gather
   uint32_t chunk = 0;          // mode 2: elements per forwarded chunk of x (world * chunk <= x length)
+  // spmv_host: x over the links.  -1 = not decided yet; 1 = every GPU uploads 1/world of x over its own PCIe link and the
+  // chunks are all-gathered in place over NVLink (NCCL); 0 = every GPU uploads what its rows read (banded matrices)
+  int x_links = -1;
+  uint32_t x_chunk = 0;        // elements per uploaded chunk of x (world * x_chunk <= x length of every engine)
 };
 
 #define G_CUDA(expr)                                                                       \
@@ -163,6 +168,8 @@ static int need_nccl() {
   return SPMVB_OK;
 }
 
+static int member_resources(Group *G, Member &m);
+
 // layout + engine of one member from its row slice (row_ptr rebased to 0)
 static int member_build(Group *G, Member &m, uint32_t n_rows, const uint64_t *row_ptr, const uint32_t *col_ind,
                         const void *values, int variant) {
@@ -170,6 +177,11 @@ static int member_build(Group *G, Member &m, uint32_t n_rows, const uint64_t *ro
   if (rc) return rc;
   rc = spmvb_engine_create(m.layout, m.device, variant, &m.engine);
   if (rc) return rc;
+  return member_resources(G, m);
+}
+
+// what a member needs next to its engine: scalars, events
+static int member_resources(Group *G, Member &m) {
   G_CUDA(cudaSetDevice(m.device));
   G_CUDA(cudaMalloc((void **)&m.d_scalar, 64));
   G_CUDA(cudaMalloc((void **)&m.d_token, 64));
@@ -208,7 +220,7 @@ static void group_destroy(Group *G) {
     }
     cudaSetDevice(m.device);
     if (m.comm && nccl()->CommDestroy) nccl()->CommDestroy(m.comm);
-    if (m.engine) spmvb_engine_free(m.engine);
+    if (m.engine && !m.engine_borrowed) spmvb_engine_free(m.engine);
     if (m.layout) spmvb_layout_free(m.layout);
     cudaFree(m.d_scalar); cudaFree(m.d_token); cudaFree(m.d_peers);
     for (void *p : m.ipc_opened) cudaIpcCloseMemHandle(p);
@@ -390,6 +402,44 @@ int spmvb_group_create_rank(uint32_t global_rows, uint32_t cols, const uint32_t 
   return SPMVB_OK;
 }
 
+// One rank of a multi-process group around an engine the caller has created (and keeps): for callers that build their
+// layout / engine themselves and want the group's collectives (x over the links in spmv_host).  No iterated caller on
+// such a group unless the peers' handles are installed as well.
+int spmvb_group_adopt_engine(uint32_t global_rows, uint32_t cols, const uint32_t *bounds, spmvb_engine *engine, int is_double,
+                             int device, const uint8_t *unique_id128, int rank, int world, spmvb_group **out) {
+  if (!out || !bounds || !engine || world < 1 || rank < 0 || rank >= world || (world > 1 && !unique_id128))
+    return fail(SPMVB_E_ARG, "group_adopt_engine");
+  *out = nullptr;
+  if (bounds[0] != 0 || bounds[world] != global_rows) return fail(SPMVB_E_ARG, "group_adopt_engine: bounds must cover the rows");
+  for (int k = 0; k < world; k++)
+    if (bounds[k + 1] < bounds[k]) return fail(SPMVB_E_ARG, "group_adopt_engine: bounds must ascend");
+  Group *G = new Group();
+  G->world = world; G->is_double = is_double ? 1 : 0; G->vb = is_double ? 8 : 4;
+  G->rows = global_rows; G->cols = cols;
+  G->bounds.assign(bounds, bounds + world + 1);
+  G->local.resize(1);
+  Member &m = G->local[0];
+  m.rank = rank; m.device = device; m.engine = engine; m.engine_borrowed = true;
+  auto build = [&]() -> int {
+    int r = member_resources(G, m);
+    if (r) return r;
+    G_CUDA(cudaMallocHost((void **)&G->h_scalar, 64));
+    if (world > 1) {
+      r = need_nccl();
+      if (r) return r;
+      ncclUniqueId id;
+      memcpy(&id, unique_id128, 128);
+      G_CUDA(cudaSetDevice(device));
+      G_NCCL(nccl()->CommInitRank(&m.comm, world, id, rank));
+    }
+    return SPMVB_OK;
+  };
+  int rc = build();
+  if (rc) { group_destroy(G); return rc; }
+  *out = (spmvb_group *)G;
+  return SPMVB_OK;
+}
+
 void spmvb_group_free(spmvb_group *g) { group_destroy((Group *)g); }
 
 int spmvb_group_world(const spmvb_group *g) { return g ? ((const Group *)g)->world : 0; }
@@ -443,25 +493,116 @@ int spmvb_group_get_x(spmvb_group *g, void *x_host, uint32_t n) {
   return spmvb_engine_sync(m.engine);
 }
 
-// spmv_hw over the group: x goes to every GPU, all kernels run concurrently (one stream per GPU), every GPU's slice of
-// y comes back into its place of y_host.  The local members' rows only: in a multi-process group every rank fills its
-// own slice of its own y_host.
-int spmvb_group_spmv_host(spmvb_group *g, const void *x_host, uint32_t n, void *y_host, int accumulate) {
-  Group *G = (Group *)g;
-  if (!G || !x_host || !y_host) return fail(SPMVB_E_ARG, "group_spmv_host");
-  for (Member &m : G->local) {  // uploads and kernels of all GPUs are queued before anything is waited for
-    int rc = spmvb_engine_set_x(m.engine, x_host, n);
-    if (rc) return rc;
-    rc = spmvb_engine_spmv_dev(m.engine, nullptr, nullptr, 0, nullptr);
-    if (rc) return rc;
+// Collective, once per group: does every GPU read (almost) all of x?  Then replicating x is an exchange that belongs on
+// the NVLink fabric: each GPU uploads 1/world of x over its own PCIe link and ONE in-place ncclAllGather fills every
+// GPU's x - 8 x fewer host bytes than 8 full uploads, which is what bounds the end-to-end call on 8 GPUs (round 1:
+// the host side of the links carries ~64-75 GB/s whatever the number of GPUs).  A banded matrix, whose row shards read a
+// band of x each, keeps the per-GPU uploads of exactly that band.
+static int group_decide_x_links(Group *G) {
+  if (G->x_links >= 0) return SPMVB_OK;
+  const uint32_t V = 16u / (uint32_t)G->vb;
+  const uint64_t chunk = (((uint64_t)G->cols + G->world - 1) / G->world + V - 1) / V * V;
+  int want = G->world > 1 ? 1 : 0;
+  for (Member &m : G->local) {
+    if (!m.comm) want = 0;
+    if (spmvb_engine_x_upload_bytes(m.engine) * 2 < (uint64_t)G->cols * G->vb) want = 0;       // reads a band only
+    if ((uint64_t)G->world * chunk > spmvb_engine_x_len(m.engine)) want = 0;                   // the gather would not fit
+  }
+  if (G->world > 1 && G->local[0].comm) {  // all ranks must take the same path: minimum over the group
+    Nccl *N = nccl();
+    for (Member &m : G->local) {
+      G_CUDA(cudaSetDevice(m.device));
+      const double v = (double)want;
+      G_CUDA(cudaMemcpyAsync(m.d_scalar, &v, 8, cudaMemcpyHostToDevice, (cudaStream_t)spmvb_engine_stream(m.engine)));
+    }
+    G_NCCL(N->GroupStart());
+    for (Member &m : G->local)
+      G_NCCL(N->AllReduce(m.d_scalar, m.d_scalar, 1, ncclDouble, ncclMin, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
+    G_NCCL(N->GroupEnd());
+    Member &m0 = G->local[0];
+    G_CUDA(cudaSetDevice(m0.device));
+    G_CUDA(cudaMemcpyAsync(G->h_scalar, m0.d_scalar, 8, cudaMemcpyDeviceToHost, (cudaStream_t)spmvb_engine_stream(m0.engine)));
+    for (Member &m : G->local) {
+      int rc = spmvb_engine_sync(m.engine);
+      if (rc) return rc;
+    }
+    want = G->h_scalar[0] > 0.5 ? 1 : 0;
+  }
+  G->x_chunk = (uint32_t)chunk;
+  G->x_links = want;
+  if (want)  // nothing ever writes x behind the gathered chunks: clear it once
+    for (Member &m : G->local) {
+      G_CUDA(cudaSetDevice(m.device));
+      const uint64_t end = (uint64_t)G->world * chunk, len = spmvb_engine_x_len(m.engine);
+      if (len > end)
+        G_CUDA(cudaMemsetAsync((uint8_t *)spmvb_engine_x_dev(m.engine) + end * G->vb, 0, (len - end) * G->vb,
+                               (cudaStream_t)spmvb_engine_stream(m.engine)));
+    }
+  return SPMVB_OK;
+}
+
+// spmv_hw over the group: x reaches every GPU (see group_decide_x_links), all kernels run concurrently (one stream per
+// GPU), every GPU's slice of y comes back into its place of y_host.  The local members' rows only: in a multi-process
+// group every rank fills its own slice of its own y_host.  y_base_row = global row that y_host[0] stands for.
+static int group_spmv_host(Group *G, const void *x_host, uint32_t n, void *y_host, uint32_t y_base_row, int accumulate) {
+  int rc = group_decide_x_links(G);
+  if (rc) return rc;
+  if (G->x_links == 1) {
+    Nccl *N = nccl();
+    const ncclDataType_t dt = G->is_double ? ncclDouble : ncclFloat;
+    const uint64_t chunk = G->x_chunk, m_cols = std::min<uint64_t>(n, G->cols);
+    for (Member &m : G->local) {  // this GPU's chunk of x over this GPU's link
+      G_CUDA(cudaSetDevice(m.device));
+      cudaStream_t st = (cudaStream_t)spmvb_engine_stream(m.engine);
+      uint8_t *x = (uint8_t *)spmvb_engine_x_dev(m.engine);
+      const uint64_t first = (uint64_t)m.rank * chunk, end = first + chunk, up = std::min(end, m_cols);
+      if (up > first)
+        G_CUDA(cudaMemcpyAsync(x + first * G->vb, (const uint8_t *)x_host + first * G->vb, (size_t)(up - first) * G->vb,
+                               cudaMemcpyHostToDevice, st));
+      if (up < end)  // zero padding behind a short x (csr_hw.cpp:1478-1481)
+        G_CUDA(cudaMemsetAsync(x + std::max(up, first) * G->vb, 0, (size_t)(end - std::max(up, first)) * G->vb, st));
+    }
+    G_NCCL(N->GroupStart());
+    for (Member &m : G->local) {
+      uint8_t *x = (uint8_t *)spmvb_engine_x_dev(m.engine);
+      G_NCCL(N->AllGather(x + (size_t)m.rank * chunk * G->vb, x, chunk, dt, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
+    }
+    G_NCCL(N->GroupEnd());
+    for (Member &m : G->local) {
+      rc = spmvb_engine_spmv_dev(m.engine, nullptr, nullptr, 0, nullptr);
+      if (rc) return rc;
+    }
+  } else {
+    for (Member &m : G->local) {  // uploads and kernels of all GPUs are queued before anything is waited for
+      rc = spmvb_engine_set_x(m.engine, x_host, n);
+      if (rc) return rc;
+      rc = spmvb_engine_spmv_dev(m.engine, nullptr, nullptr, 0, nullptr);
+      if (rc) return rc;
+    }
   }
   for (Member &m : G->local) {
     const uint32_t r0 = G->bounds[m.rank], r1 = G->bounds[m.rank + 1];
-    int rc = spmvb_engine_get_y(m.engine, (uint8_t *)y_host + (size_t)r0 * G->vb, r1 - r0, accumulate);
+    if (r0 < y_base_row) return fail(SPMVB_E_ARG, "group_spmv_host: y does not start at the first local row");
+    rc = spmvb_engine_get_y(m.engine, (uint8_t *)y_host + (size_t)(r0 - y_base_row) * G->vb, r1 - r0, accumulate);
     if (rc) return rc;
   }
   return SPMVB_OK;
 }
+
+int spmvb_group_spmv_host(spmvb_group *g, const void *x_host, uint32_t n, void *y_host, int accumulate) {
+  Group *G = (Group *)g;
+  if (!G || !x_host || !y_host) return fail(SPMVB_E_ARG, "group_spmv_host");
+  return group_spmv_host(G, x_host, n, y_host, 0, accumulate);
+}
+
+// the same with y_rows = the rows of this process's GPUs only (y_rows[0] = the first local GPU's first row)
+int spmvb_group_spmv_host_rows(spmvb_group *g, const void *x_host, uint32_t n, void *y_rows, int accumulate) {
+  Group *G = (Group *)g;
+  if (!G || !x_host || !y_rows || G->local.empty()) return fail(SPMVB_E_ARG, "group_spmv_host_rows");
+  return group_spmv_host(G, x_host, n, y_rows, G->bounds[G->local[0].rank], accumulate);
+}
+
+int spmvb_group_x_over_links(const spmvb_group *g) { return g ? ((const Group *)g)->x_links : -1; }
 
 // y slices of the local members after the last SpMV / iteration, into their places of y_host (diagnostics, tests)
 int spmvb_group_get_y(spmvb_group *g, void *y_host) {

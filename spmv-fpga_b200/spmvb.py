@@ -96,6 +96,9 @@ SYMBOLS = {
     "spmvb_group_engine": (_vp, [_vp, _int]),
     "spmvb_group_rank": (_int, [_vp, _int]),
     "spmvb_group_spmv_host": (_int, [_vp, _vp, _u32, _vp, _int]),
+    "spmvb_group_spmv_host_rows": (_int, [_vp, _vp, _u32, _vp, _int]),
+    "spmvb_group_x_over_links": (_int, [_vp]),
+    "spmvb_group_adopt_engine": (_int, [_u32, _u32, _vp, _vp, _int, _int, _vp, _int, _int, _vp]),
     "spmvb_group_set_x": (_int, [_vp, _vp, _u32]),
     "spmvb_group_get_x": (_int, [_vp, _vp, _u32]),
     "spmvb_group_get_y": (_int, [_vp, _vp]),
@@ -742,6 +745,32 @@ class Group:
         _check(lib().spmvb_group_create_rank(global_rows, cols, _ptr(b), _ptr(rp), _ptr(ci), _ptr(va), int(is_double), device,
                                              variant, _ptr(uid), rank, world, ctypes.byref(out)))
         return Group(out.value, is_double, global_rows, cols)
+
+    @staticmethod
+    def adopt(engine, global_rows, cols, bounds, device, unique_id, rank, world):
+        """One rank of a multi-process group around an Engine this process created (and keeps)."""
+        b = np.ascontiguousarray(bounds, np.uint32)
+        uid = np.ascontiguousarray(unique_id, np.uint8) if unique_id is not None else None
+        out = _vp()
+        _check(lib().spmvb_group_adopt_engine(global_rows, cols, _ptr(b), engine.h, int(engine.is_double), device, _ptr(uid),
+                                              rank, world, ctypes.byref(out)))
+        return Group(out.value, engine.is_double, global_rows, cols)
+
+    def spmv_host_rows(self, x, y_rows, accumulate=True):
+        """spmv_hw over the group with y_rows = this process's rows only (x, y_rows numpy arrays or raw host pointers)."""
+        if isinstance(x, np.ndarray):
+            assert x.dtype == vdtype(self.is_double) and x.flags.c_contiguous
+            xp, n = _ptr(x), len(x)
+        else:
+            xp, n = x
+        yp = _ptr(y_rows) if isinstance(y_rows, np.ndarray) else y_rows
+        _check(lib().spmvb_group_spmv_host_rows(self.h, xp, n, yp, int(accumulate)))
+        return y_rows
+
+    @property
+    def x_over_links(self):
+        """1: spmv_host uploads 1/world of x per GPU and all-gathers over NVLink; 0: per-GPU uploads; -1: not decided yet."""
+        return lib().spmvb_group_x_over_links(self.h)
 
     def engine_handle(self, i=0):
         return lib().spmvb_group_engine(self.h, i)

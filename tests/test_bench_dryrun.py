@@ -99,7 +99,8 @@ def test_two_rank_strong_scaling_of_the_default_workload_over_gloo():
     d = _check_line(p.stdout, 2, 3)
     assert d["scaling"] == "strong" and d["config"]["rows"] == 1 << 14 and d["config"]["nnz"] == 16 << 14
     assert d["engine"]["rows_per_gpu"] == [1 << 13, 1 << 13]
-    assert d["e2e"]["h2d_bytes_per_step"] == 2 * (1 << 14) * 8   # x replicated: every rank uploads all of it
+    # x is replicated over the GPU links: every rank uploads 1/N of it, so it crosses the host links once in total
+    assert d["e2e"]["h2d_bytes_per_step"] == (1 << 14) * 8 and "ncclAllGather" in d["e2e"]["what"]
 
 
 def test_power_iteration_line_over_gloo():

@@ -41,8 +41,38 @@ def test_group_spmv_host_matches_the_oracle(spmvb, oracle, n_dev, isd):
         grp = spmvb.Group.create(rows, cols, rp, ci, va.astype(oa.vdtype(isd)), isd, devices=range(n_dev))
         assert grp.world == n_dev and grp.local_count == n_dev and grp.bounds[0] == 0 and grp.bounds[-1] == rows
         assert np.all(np.diff(grp.bounds.astype(np.int64)) > 0)
+        assert grp.x_over_links == -1     # decided (collectively) at the first spmv_host
         _parity(oracle, grp, M, isd)
+        if cols == 150000:  # every shard of the uniform matrix reads all of x: 1/N per PCIe link + all-gather over NVLink
+            assert grp.x_over_links == (1 if n_dev > 1 else 0)
+            # a short x is zero padded (csr_hw.cpp:1478-1481) on that path as well
+            vt = oa.vdtype(isd)
+            xs = np.random.default_rng(5).random(cols - 40001).astype(vt)
+            xfull = np.zeros(cols, vt); xfull[: len(xs)] = xs
+            y = np.zeros(rows, vt)
+            grp.spmv_host(xs, y, accumulate=False)
+            gold = oracle.spmv_gold(rows, rp, ci, va.astype(vt), xfull, isd).astype(np.float64)
+            bound = oracle.abs_ax(rows, rp, ci, va.astype(vt), np.abs(xfull) + 1e-3, isd) * TOL[isd] + np.finfo(vt).tiny
+            assert np.all(np.abs(y.astype(np.float64) - gold) <= bound)
         grp.free()
+
+
+def test_group_around_an_engine_of_the_caller(spmvb, oracle):
+    """spmvb_group_adopt_engine: a group rank around an engine the caller made and keeps; y_rows = the local rows."""
+    rows, cols, rp, ci, va = matgen.uniform(3000, 90000, 12, seed=2)
+    lay = spmvb.Layout.build(rows, cols, rp, ci, va, 1, 1, True)
+    eng = spmvb.Engine(lay, 0)
+    grp = spmvb.Group.adopt(eng, rows, cols, [0, rows], 0, None, 0, 1)
+    x = np.random.default_rng(3).random(cols)
+    y = np.zeros(rows)
+    grp.spmv_host_rows(x, y, accumulate=False)
+    gold = oracle.spmv_gold(rows, rp, ci, va, x, True)
+    assert np.all(np.abs(y - gold) <= 1e-12 * oracle.abs_ax(rows, rp, ci, va, x, True) + 1e-300)
+    assert grp.x_over_links == 0          # one GPU: nothing to replicate
+    grp.free()
+    eng.spmv_host(x, y, accumulate=False)  # the engine outlives the group
+    assert np.all(np.abs(y - gold) <= 1e-12 * oracle.abs_ax(rows, rp, ci, va, x, True) + 1e-300)
+    eng.free()
 
 
 @pytest.mark.parametrize("exchange", [0, 1, 2], ids=["nccl_broadcasts", "peer_all", "peer_forward_allgather"])
