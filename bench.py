@@ -462,13 +462,13 @@ def measure_spmv(ctx, name, args, steps, warmup, e2e_steps, with_cpu_baseline):
     for _ in range(e2e_steps):
         e2e_call()
     ctx.barrier(eng)
+    e2e_s = ctx.reduce([time.perf_counter() - t0], "max")[0]
     x_links = grp is not None and grp.x_over_links == 1
     if x_links:  # x crosses the host links once in total, not once per GPU
         x_upload_local = int(-(-csr.cols // world) * vb)
         x_upload_total = ctx.reduce([x_upload_local])[0]
     if grp is not None:
         grp.free()
-    e2e_s = ctx.reduce([time.perf_counter() - t0], "max")[0]
     e2e_gflops = 2.0 * nnz_total * e2e_steps / e2e_s / 1e9
 
     # ---- result check, every row of every rank, per-row tolerance: a wrong result is an error, not a number.  The

@@ -200,6 +200,10 @@ int spmvb_engine_get_y(spmvb_engine *e, void *y_host, uint32_t n, int accumulate
 /* Replaces spmv_hw (csr_hw_wrapper.cpp:193-288) end to end with HOST buffers: H2D x, SpMV, D2H y,
  * y_host (+)= result.  Synchronous. */
 int spmvb_engine_spmv_host(spmvb_engine *e, const void *x_host, uint32_t n, void *y_host, int accumulate);
+/* The second half of spmvb_engine_spmv_host - kernel(s) and y to the host, pipelined by row tiles where the device layout
+ * has them - for a caller that has put x on the device itself (spmvb_engine_x_dev; the multi-GPU group replicates x over
+ * NVLink). */
+int spmvb_engine_spmv_host_x_resident(spmvb_engine *e, void *y_host, int accumulate);
 /* Times `iters` device SpMVs (y = A x, engine vectors) with CUDA events on the engine stream;
  * ms_out[iters] per-iteration milliseconds.  flush_l2 1 writes a >L2 scratch buffer between iterations. */
 int spmvb_engine_time_spmv(spmvb_engine *e, int iters, int flush_l2, float *ms_out);

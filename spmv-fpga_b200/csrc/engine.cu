@@ -1249,10 +1249,19 @@ int spmvb_engine_spmv_host(spmvb_engine *e, const void *x_host, uint32_t n, void
   }
   int rc = spmvb_engine_set_x(e, x_host, n);
   if (rc) return rc;
+  return spmvb_engine_spmv_host_x_resident(e, y_host, accumulate);
+}
+
+// the second half of spmv_host for callers that brought x to the device themselves (the group replicates it over NVLink):
+// kernel(s) + y down, with the row-tile pipeline where the layout has one
+int spmvb_engine_spmv_host_x_resident(spmvb_engine *e, void *y_host, int accumulate) {
+  Engine *E = (Engine *)e;
+  if (!E || !y_host) return fail(SPMVB_E_ARG, "spmv_host_x_resident");
+  CUDA_TRY(cudaSetDevice(E->device));
   const int variant = E->variant == kVariantDefault ? E->auto_variant : E->variant;
-  if (variant == kVariantXs && E->n_tiles > 1 && y_host && options().e2e_tiles != 0)
+  if (variant == kVariantXs && E->n_tiles > 1 && options().e2e_tiles != 0 && !ell_on(E))
     return E->is_double ? spmv_host_tiled<double>(E, y_host, accumulate) : spmv_host_tiled<float>(E, y_host, accumulate);
-  rc = do_spmv(E, nullptr, nullptr, 0, E->stream);
+  int rc = do_spmv(E, nullptr, nullptr, 0, E->stream);
   if (rc) return rc;
   return spmvb_engine_get_y(e, y_host, E->rows, accumulate);
 }

@@ -14,6 +14,9 @@
 // process one rank of a multi-process group (one process per GPU, e.g. under torchrun; the NCCL unique id travels
 // through the launcher).  NCCL is loaded with dlopen on first use: libspmvb.so itself does not depend on it.
 #include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
 #include <dlfcn.h>
 #include <nccl.h>
 #include <omp.h>
@@ -547,6 +550,17 @@ static int group_decide_x_links(Group *G) {
 static int group_spmv_host(Group *G, const void *x_host, uint32_t n, void *y_host, uint32_t y_base_row, int accumulate) {
   int rc = group_decide_x_links(G);
   if (rc) return rc;
+  // option build_trace: wall-clock time of every stage (with a synchronisation after each: diagnostics only)
+  const bool trace = spmvb_get_option("build_trace") > 0;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_mark = now();
+  auto stage = [&](const char *what) {
+    if (!trace) return;
+    for (Member &m : G->local) spmvb_engine_sync(m.engine);
+    const double t = now();
+    fprintf(stderr, "[group spmv_host rank %d] %-22s %8.3f ms\n", G->local[0].rank, what, t - t_mark);
+    t_mark = t;
+  };
   if (G->x_links == 1) {
     Nccl *N = nccl();
     const ncclDataType_t dt = G->is_double ? ncclDouble : ncclFloat;
@@ -562,16 +576,27 @@ static int group_spmv_host(Group *G, const void *x_host, uint32_t n, void *y_hos
       if (up < end)  // zero padding behind a short x (csr_hw.cpp:1478-1481)
         G_CUDA(cudaMemsetAsync(x + std::max(up, first) * G->vb, 0, (size_t)(end - std::max(up, first)) * G->vb, st));
     }
+    stage("x chunk upload");
     G_NCCL(N->GroupStart());
     for (Member &m : G->local) {
       uint8_t *x = (uint8_t *)spmvb_engine_x_dev(m.engine);
       G_NCCL(N->AllGather(x + (size_t)m.rank * chunk * G->vb, x, chunk, dt, m.comm, (cudaStream_t)spmvb_engine_stream(m.engine)));
     }
     G_NCCL(N->GroupEnd());
+    stage("all-gather of x");
+    if (G->local.size() == 1) {  // one GPU per process: kernel(s) + y down through the engine's row-tile pipeline
+      Member &m = G->local[0];
+      const uint32_t r0 = G->bounds[m.rank];
+      if (r0 < y_base_row) return fail(SPMVB_E_ARG, "group_spmv_host: y does not start at the first local row");
+      rc = spmvb_engine_spmv_host_x_resident(m.engine, (uint8_t *)y_host + (size_t)(r0 - y_base_row) * G->vb, accumulate);
+      stage("SpMV + y down");
+      return rc;
+    }
     for (Member &m : G->local) {
       rc = spmvb_engine_spmv_dev(m.engine, nullptr, nullptr, 0, nullptr);
       if (rc) return rc;
     }
+    stage("SpMV");
   } else {
     for (Member &m : G->local) {  // uploads and kernels of all GPUs are queued before anything is waited for
       rc = spmvb_engine_set_x(m.engine, x_host, n);
@@ -586,6 +611,7 @@ static int group_spmv_host(Group *G, const void *x_host, uint32_t n, void *y_hos
     rc = spmvb_engine_get_y(m.engine, (uint8_t *)y_host + (size_t)(r0 - y_base_row) * G->vb, r1 - r0, accumulate);
     if (rc) return rc;
   }
+  stage("y down (+ host add)");
   return SPMVB_OK;
 }
 

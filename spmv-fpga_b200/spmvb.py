@@ -77,6 +77,7 @@ SYMBOLS = {
     "spmvb_engine_sync": (_int, [_vp]),
     "spmvb_engine_get_y": (_int, [_vp, _vp, _u32, _int]),
     "spmvb_engine_spmv_host": (_int, [_vp, _vp, _u32, _vp, _int]),
+    "spmvb_engine_spmv_host_x_resident": (_int, [_vp, _vp, _int]),
     "spmvb_engine_time_spmv": (_int, [_vp, _int, _int, _vp]),
     "spmvb_engine_enqueue_steps": (_int, [_vp, _int, _int]),
     "spmvb_engine_steps_done": (_int, [_vp]),
