@@ -44,6 +44,20 @@ def test_engine_fails_loudly_without_gpu(spmvb):
     assert ei.value.code == -3
 
 
+def test_host_calls_reject_null_handles(spmvb):
+    """The end-to-end entry points return SPMVB_E_ARG (and say where) instead of touching a null engine / group / buffer."""
+    import ctypes
+    L = spmvb.lib()
+    y = np.zeros(4)
+    yp = y.ctypes.data_as(ctypes.c_void_p)
+    for rc in (L.spmvb_engine_spmv_host(None, yp, 4, yp, 1), L.spmvb_engine_spmv_host_x_resident(None, yp, 1),
+               L.spmvb_group_spmv_host(None, yp, 4, yp, 1), L.spmvb_group_spmv_host_rows(None, yp, 4, yp, 1)):
+        assert rc == -1, rc  # SPMVB_E_ARG
+        assert "spmv_host" in L.spmvb_last_error().decode()
+    assert L.spmvb_group_x_over_links(None) == -1
+    assert y.sum() == 0.0
+
+
 def test_matrix_file_roundtrip_and_reference_reader(spmvb, tmp_path):
     rows, cols, rp, ci, va = matgen.ragged(300, 500, seed=4)
     path = str(tmp_path / "m.txt")
