@@ -11,6 +11,7 @@
 // per block; here three passes over the CSR (count, [segment lengths], scatter) with per-thread per-block cursors
 // write every entry straight to its final byte, and the empty_rows_bitmap is kept as a rank -> row map.
 #include <omp.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <cctype>
@@ -26,6 +27,25 @@
 #include "layout.h"
 
 namespace spmvb {
+
+// Large host arrays of the layout (stream, row map): 2 MB-aligned, huge pages requested (the scatter of pass 3 writes
+// through thousands of streams at once - one per column block - and would otherwise miss the TLB on every entry and
+// fault in 4 KB pages one by one), pages touched by all cores.  Released with free().
+void *layout_big_alloc(uint64_t bytes, bool zero) {
+  const uint64_t huge = 2ull << 20;
+  if (bytes < 8 * huge) return zero ? calloc((size_t)std::max<uint64_t>(bytes, 16), 1) : malloc((size_t)std::max<uint64_t>(bytes, 16));
+  const uint64_t rounded = (bytes + huge - 1) / huge * huge;
+  uint8_t *p = (uint8_t *)aligned_alloc((size_t)huge, (size_t)rounded);
+  if (!p) return nullptr;
+  madvise(p, (size_t)rounded, MADV_HUGEPAGE);  // advisory: plain pages if the kernel declines
+  const int64_t n = (int64_t)(rounded / huge);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; i++) {
+    if (zero) memset(p + (uint64_t)i * huge, 0, (size_t)huge);
+    else for (uint64_t o = 0; o < huge; o += 4096) p[(uint64_t)i * huge + o] = 0;
+  }
+  return p;
+}
 
 Layout::~Layout() {
   delete ell;
@@ -332,7 +352,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   for (int b = 0; b < blocks; b++) L->rank_base[b + 1] = L->rank_base[b] + P[b];
   L->n_pairs = L->rank_base[blocks];
   if (L->n_pairs >= 0xFFFFFFF0ull) { delete L; return fail(SPMVB_E_RANGE, "too many (row, block) pairs for a 32-bit rank"); }
-  L->rowmap = (uint32_t *)malloc((size_t)std::max<uint64_t>(L->n_pairs, 1) * 4);
+  L->rowmap = (uint32_t *)layout_big_alloc(std::max<uint64_t>(L->n_pairs, 1) * 4, false);
   if (!L->rowmap) { delete L; return fail(SPMVB_E_NOMEM, "rowmap"); }
 
   // ---- pass 2 (CU > 1 only): row map + padded segment lengths, needed by the sequential split rule
@@ -402,7 +422,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   std::vector<uint64_t> piece_last_rank;
   layout_finish_pieces(L, fp.data(), pad_rows.data(), piece_last_rank);
   const uint64_t off = L->stream_bytes, chunk0 = L->n_chunks;
-  L->stream = (uint8_t *)calloc((size_t)std::max<uint64_t>(off, 16), 1);
+  L->stream = (uint8_t *)layout_big_alloc(off, true);
   L->chunks = (ChunkMeta *)calloc((size_t)std::max<uint64_t>(chunk0, 1), sizeof(ChunkMeta));
   if (!L->stream || !L->chunks) { delete L; return fail(SPMVB_E_NOMEM, "stream"); }
 #pragma omp parallel for schedule(static)
