@@ -356,9 +356,12 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   if (!L->rowmap) { delete L; return fail(SPMVB_E_NOMEM, "rowmap"); }
 
   // ---- pass 2 (CU > 1 only): row map + padded segment lengths, needed by the sequential split rule
-  std::vector<uint32_t> seglen;
+  struct FreeOnExit { void *p = nullptr; ~FreeOnExit() { free(p); } } seglen_mem;  // every return path releases it
+  uint32_t *seglen = nullptr;
   if (cu > 1) {
-    seglen.resize((size_t)L->n_pairs);
+    seglen_mem.p = layout_big_alloc(std::max<uint64_t>(L->n_pairs, 1) * 4, false);  // every entry is written below
+    seglen = (uint32_t *)seglen_mem.p;
+    if (!seglen) { delete L; return fail(SPMVB_E_NOMEM, "segment lengths"); }
 #pragma omp parallel num_threads(T)
     {
       const int t = omp_get_thread_num();
@@ -415,7 +418,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
     L->nr_rows[(size_t)(cu - 1) * blocks + b] = (uint32_t)rc;
     L->nr_nzeros[(size_t)(cu - 1) * blocks + b] = (uint32_t)nz;
   }
-  std::vector<uint32_t>().swap(seglen);
+  free(seglen_mem.p); seglen_mem.p = nullptr; seglen = nullptr;
 
   phase("split");
   // ---- hw_matrix_alloc + device image offsets
