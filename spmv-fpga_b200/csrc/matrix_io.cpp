@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <charconv>
 #include <cerrno>
 #include <cmath>
 #include <cstdio>
@@ -39,10 +40,16 @@ static bool parse_entry(const char *p, const char *e, unsigned long &r, unsigned
   };
   if (!index(r) || !index(c)) return false;
   skip();
+  const char *t0 = p;
+  while (p < e && *p != ' ' && *p != '\t' && *p != '\r') p++;
+  const size_t n = (size_t)(p - t0);
+  if (n == 0 || n + 1 >= 64) return false;
+  // plain decimal tokens (all a matrix file normally holds) in place, correctly rounded like strtod; anything else
+  // that sscanf's %lf accepts - a leading '+', hex floats, out-of-range magnitudes - through strtod on a bounded copy
+  const std::from_chars_result fr = std::from_chars(t0, p, v);
+  if (fr.ec == std::errc() && fr.ptr == p) return true;
   char tok[64];
-  size_t n = 0;
-  while (p < e && n + 1 < sizeof tok && *p != ' ' && *p != '\t' && *p != '\r') tok[n++] = *p++;
-  if (n == 0 || n + 1 >= sizeof tok) return false;
+  memcpy(tok, t0, n);
   tok[n] = 0;
   char *end = nullptr;
   v = strtod(tok, &end);

@@ -94,6 +94,26 @@ def test_matrix_file_errors(spmvb, tmp_path):
     assert list(A.row_ptr) == [0, 1, 1, 1]
 
 
+def test_reader_accepts_what_sscanf_lf_accepts(spmvb, tmp_path):
+    """Value tokens are parsed in place (from_chars) with strtod behind it: everything the reference's "%lf" takes
+    (csr.cpp:111) gives the same double - signs, exponents, hex floats, infinities, overflow and underflow."""
+    toks = ["1", "-2.5", "+3.25", "1e-3", "-4.E+2", ".5", "5.", "0x1.8p1", "inf", "-INF", "1e400", "1e-400",
+            "0.1", "-0.30000000000000004", "2.2250738585072011e-308", "1.7976931348623157e308", "123456789012345678901234567890"]
+    p = tmp_path / "tok.txt"
+    p.write_text("%d 1 %d\n" % (len(toks), len(toks)) + "".join("%d 1 %s\n" % (i + 1, t) for i, t in enumerate(toks)))
+    A = spmvb.Csr.read(str(p), True)
+    want = np.array([float.fromhex(t) if "x" in t else float(t) for t in toks])
+    assert np.array_equal(A.values, want), (A.values, want)
+    for bad in ("1.5x", "--1", "e5", "1 .5e", ""):
+        p.write_text("1 1 1\n1 1 %s\n" % bad)
+        if bad == "1 .5e":  # the value token is "1": what follows it on the line is ignored, like sscanf does
+            B = spmvb.Csr.read(str(p), True)  # (views are valid while the object lives: keep it)
+            assert B.values[0] == 1.0
+            continue
+        with pytest.raises(spmvb.SpmvbError):
+            spmvb.Csr.read(str(p), True)
+
+
 def test_generators_match_numpy_twins(spmvb):
     A = spmvb.Csr.laplacian2d(37, 23)
     rows, cols, rp, ci, va = matgen.laplacian2d(37, 23)
