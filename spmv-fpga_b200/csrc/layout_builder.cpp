@@ -355,7 +355,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
   L->rowmap = (uint32_t *)layout_big_alloc(std::max<uint64_t>(L->n_pairs, 1) * 4, false);
   if (!L->rowmap) { delete L; return fail(SPMVB_E_NOMEM, "rowmap"); }
 
-  // ---- pass 2 (CU > 1 only): row map + padded segment lengths, needed by the sequential split rule
+  // ---- pass 2 (CU > 1 only): padded segment lengths in rank order, needed by the sequential split rule
   struct FreeOnExit { void *p = nullptr; ~FreeOnExit() { free(p); } } seglen_mem;  // every return path releases it
   uint32_t *seglen = nullptr;
   if (cu > 1) {
@@ -374,7 +374,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
           if (cnt[b]++ == 0) touched.push_back(b);
         }
         for (uint32_t b : touched) {
-          L->rowmap[rank[b]] = r; seglen[rank[b]] = round_up(cnt[b], (uint32_t)vf);
+          seglen[rank[b]] = round_up(cnt[b], (uint32_t)vf);  // (the row map itself is written by pass 3)
           rank[b]++; cnt[b] = 0;
         }
         touched.clear();
@@ -448,60 +448,78 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
 #pragma omp parallel num_threads(T)
   {
     const int t = omp_get_thread_num();
-    std::vector<uint32_t> cnt(blocks, 0), fill(blocks, 0), touched;
-    std::vector<uint64_t> rank(blocks), pos(blocks);
+    // everything the scatter needs to know about a column block in ONE cache line: with thousands of blocks the
+    // per-block tables (counts, cursors, piece bounds, piece addresses) otherwise cost five or six misses per entry
+    struct alignas(64) Cursor {
+      uint32_t cnt, fill;     // entries of the current row in this block: counted / written
+      int32_t k;              // CU piece that holds pos (monotone)
+      uint32_t unused;
+      uint64_t pos, rank;     // block position of the row's first entry; rank of the (row, block) pair
+      uint64_t piece_start;   // fp[b][k]
+      uint8_t *piece;         // stream + piece_off[b][k]
+      uint64_t chunk0;        // piece_chunk0[b][k]
+    };
+    std::vector<Cursor> cur((size_t)blocks);
+    std::vector<uint32_t> touched;
+    auto enter_piece = [&](Cursor &c, uint32_t b, int k) {
+      c.k = k;
+      c.piece_start = fp[(size_t)b * (cu + 1) + k];
+      c.piece = L->stream + L->piece_off[(size_t)b * cu + k];
+      c.chunk0 = L->piece_chunk0[(size_t)b * cu + k];
+    };
     for (int b = 0; b < blocks; b++) {
-      rank[b] = L->rank_base[b] + pairs_t[(size_t)t * blocks + b];
-      pos[b] = zpad_t[(size_t)t * blocks + b];
+      Cursor &c = cur[b];
+      c.cnt = 0; c.fill = 0; c.unused = 0;
+      c.rank = L->rank_base[b] + pairs_t[(size_t)t * blocks + b];
+      c.pos = zpad_t[(size_t)t * blocks + b];
+      enter_piece(c, (uint32_t)b, 0);
     }
-    std::vector<int> piece_k(blocks, 0);  // monotone cursor: CU piece that holds pos[b]
     for (uint32_t r = rb[t]; r < rb[t + 1]; r++) {
       const uint64_t j0 = row_ptr[r], j1 = row_ptr[r + 1];
       for (uint64_t j = j0; j < j1; j++) {
         uint32_t b = block_of(col_ind[j]);
-        if (cnt[b]++ == 0) touched.push_back(b);
+        if (cur[b].cnt++ == 0) touched.push_back(b);
       }
       // a segment never straddles pieces: resolve the piece once per (row, block)
       for (uint32_t b : touched) {
+        Cursor &c = cur[b];
         const uint64_t *f = &fp[(size_t)b * (cu + 1)];
-        int k = piece_k[b];
-        while (k < cu - 1 && pos[b] >= f[k + 1]) k++;
-        piece_k[b] = k;
+        int k = c.k;
+        while (k < cu - 1 && c.pos >= f[k + 1]) k++;
+        if (k != c.k) enter_piece(c, b, k);
       }
       for (uint64_t j = j0; j < j1; j++) {
-        const uint32_t c = col_ind[j];
-        const uint32_t b = block_of(c);
-        const int k = piece_k[b];
-        const uint64_t e = pos[b] + fill[b] - fp[(size_t)b * (cu + 1) + k];
-        const uint32_t is_last = (++fill[b] == cnt[b]) && (cnt[b] % (uint32_t)vf == 0);
-        const Slot sl = slot_of(L->stream + L->piece_off[(size_t)b * cu + k], e);
-        const uint32_t cin = c - b * cdb;
+        const uint32_t col = col_ind[j];
+        const uint32_t b = block_of(col);
+        Cursor &c = cur[b];
+        const uint64_t e = c.pos + c.fill - c.piece_start;
+        const uint32_t is_last = (++c.fill == c.cnt) && (c.cnt % (uint32_t)vf == 0);
+        const Slot sl = slot_of(c.piece, e);
+        const uint32_t cin = col - b * cdb;
         const uint16_t ci = (uint16_t)((cin & 0x7FFFu) | (is_last ? 0x8000u : 0u));  // csr_hw.cpp:220, :288-292
         memcpy(sl.idx, &ci, 2);
         if (sl.hi) *sl.hi = (uint8_t)(cin >> 15);
         memcpy(sl.val, vals + (size_t)j * vb, vb);                                 // csr_hw.cpp:300-310
       }
       for (uint32_t b : touched) {
-        const int k = piece_k[b];
-        const size_t bk = (size_t)b * cu + k;
-        const uint64_t pstart = fp[(size_t)b * (cu + 1) + k];
-        const uint64_t s_e = pos[b] - pstart;
-        const uint64_t t_e = s_e + round_up(cnt[b], (uint32_t)vf);  // VF padding: (col 0, val 0), csr_hw.cpp:229-238
-        if (cnt[b] % (uint32_t)vf != 0) {
+        Cursor &c = cur[b];
+        const uint64_t s_e = c.pos - c.piece_start;
+        const uint64_t t_e = s_e + round_up(c.cnt, (uint32_t)vf);  // VF padding: (col 0, val 0), csr_hw.cpp:229-238
+        if (c.cnt % (uint32_t)vf != 0) {
           const uint64_t e = t_e - 1;
           const uint16_t ci = 0x8000u;
-          memcpy(slot_of(L->stream + L->piece_off[bk], e).idx, &ci, 2);
+          memcpy(slot_of(c.piece, e).idx, &ci, 2);
         }
-        L->rowmap[rank[b]] = r;
+        L->rowmap[c.rank] = r;
         // chunks whose first entry lies inside this segment start at this rank
-        for (uint64_t c = (s_e + kChunkEntries - 1) / kChunkEntries; c * kChunkEntries < t_e; c++) {
-          ChunkMeta &cm = L->chunks[L->piece_chunk0[bk] + c];
-          cm.rank0 = (uint32_t)rank[b];
-          if (c * kChunkEntries > s_e) cm.valid |= kChunkStartsMid;
+        for (uint64_t ch = (s_e + kChunkEntries - 1) / kChunkEntries; ch * kChunkEntries < t_e; ch++) {
+          ChunkMeta &cm = L->chunks[c.chunk0 + ch];
+          cm.rank0 = (uint32_t)c.rank;
+          if (ch * kChunkEntries > s_e) cm.valid |= kChunkStartsMid;
         }
-        pos[b] = pstart + t_e;
-        rank[b]++;
-        cnt[b] = 0; fill[b] = 0;
+        c.pos = c.piece_start + t_e;
+        c.rank++;
+        c.cnt = 0; c.fill = 0;
       }
       touched.clear();
     }
