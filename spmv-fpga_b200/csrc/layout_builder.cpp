@@ -371,7 +371,7 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
       for (uint32_t r = rb[t]; r < rb[t + 1]; r++) {
         for (uint64_t j = row_ptr[r]; j < (uint64_t)row_ptr[r + 1]; j++) {
           uint32_t b = block_of(col_ind[j]);
-          if (cnt[b]++ == 0) touched.push_back(b);
+          if (cnt[b]++ == 0) { touched.push_back(b); __builtin_prefetch(&seglen[rank[b]], 1); }
         }
         for (uint32_t b : touched) {
           seglen[rank[b]] = round_up(cnt[b], (uint32_t)vf);  // (the row map itself is written by pass 3)
@@ -487,6 +487,11 @@ int build_impl(uint32_t rows, uint32_t cols, const RP *row_ptr, const uint32_t *
         int k = c.k;
         while (k < cu - 1 && c.pos >= f[k + 1]) k++;
         if (k != c.k) enter_piece(c, b, k);
+        // the row's first slot in this block and its row-map entry are written a few hundred instructions from now
+        const Slot first = slot_of(c.piece, c.pos - c.piece_start);
+        __builtin_prefetch(first.idx, 1);
+        __builtin_prefetch(first.val, 1);
+        __builtin_prefetch(&L->rowmap[c.rank], 1);
       }
       for (uint64_t j = j0; j < j1; j++) {
         const uint32_t col = col_ind[j];
