@@ -82,6 +82,19 @@ def test_gpu_builder_steps_cu_major_and_run_granularity(spmvb, emu):
             host.free(); dev.free()
 
 
+def test_host_builder_large_allocation_path_against_the_gpu_steps(spmvb, emu):
+    """Above 16 MB the host builder puts the stream and the row map into 2 MB-aligned, huge-page-advised memory touched
+    by all cores (layout_big_alloc) - a path the small cases never take.  2 M non-zeros over 128 narrow blocks, CU = 1
+    and CU = 4 (pass 2 + split), every table and byte against the independent builder."""
+    rows, cols, rp, ci, va = matgen.uniform(1 << 17, 1 << 17, 16, seed=11)
+    for cu, vf, isd in ((1, 1, True), (4, 2, True)):
+        host = spmvb.Layout.build(rows, cols, rp, ci, va, cu, vf, isd, 1024)
+        assert host.stream_bytes > (16 << 20)
+        dev = emu(rows, cols, rp, ci, va, cu, vf, isd, 1024)
+        assert host.difference(dev) == ""
+        host.free(); dev.free()
+
+
 def test_gpu_builder_steps_degenerate_inputs(spmvb, emu):
     # one entry; one row; empty matrix (no non-zeros at all); duplicates inside a row
     cases = [
