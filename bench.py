@@ -562,18 +562,19 @@ def measure_spmv(ctx, name, args, steps, warmup, e2e_steps, with_cpu_baseline):
         # the reference's own CPU loop on this box, single thread, on a bounded sample: a row prefix of the same matrix
         S = sample_rows(spec, args)
         sub = csr if S >= csr.rows else make_matrix(spmvb, spec, is_double, 0, S)
-        kind, times, _ = time_reference_gold(sub, x_np, is_double, steps=50, warmup=1, budget_s=12.0)
+        x_cpu = np.array(x_np)  # a pageable copy first touched by this thread, like the reference arm's x (x_np is pinned)
+        kind, times, _ = time_reference_gold(sub, x_cpu, is_double, steps=50, warmup=1, budget_s=12.0)
         t = float(np.mean(times))
         line["cpu_baseline"] = {"value": 2.0 * sub.nnz / t / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": kind,
                                 "sample": "rows [0, %d) of the workload matrix = %d nnz, x full length, %d passes of spmv_gold "
                                           "(csr.cpp:184-194), single thread as the reference runs it" % (sub.rows, sub.nnz, len(times)),
                                 "ms_per_pass": t * 1e3}
         try:  # the same loop over all host cores (oracle port, OpenMP over rows)
-            O.spmv_gold_omp(sub.rows, sub.row_ptr, sub.col_ind, sub.values, x_np, is_double)
+            O.spmv_gold_omp(sub.rows, sub.row_ptr, sub.col_ind, sub.values, x_cpu, is_double)
             ts = []
             for _ in range(5):
                 t0 = time.perf_counter()
-                _, threads = O.spmv_gold_omp(sub.rows, sub.row_ptr, sub.col_ind, sub.values, x_np, is_double)
+                _, threads = O.spmv_gold_omp(sub.rows, sub.row_ptr, sub.col_ind, sub.values, x_cpu, is_double)
                 ts.append(time.perf_counter() - t0)
             line["cpu_baseline_all_cores"] = {"value": 2.0 * sub.nnz / min(ts) / 1e9, "unit": "GFLOP/s", "cores": int(threads),
                                               "kind": "port", "sample": "same sample, best of 5 passes, OpenMP over rows"}
